@@ -1,0 +1,217 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by running the reference's OWN source text.
+
+Runs only in the build container (needs /root/reference; the GPU box has none).
+It never copies reference source into this repository: the text of
+``models/dgcnn-hais-concat-direct-4.py`` lines 30-205 (knn / get_graph_feature*)
+and 455-534 (DGCNNEncoderGn) is read from where it lies, compiled and executed
+in memory with one substitution -- ``torch.device('cuda')`` -> ``x.device`` --
+because the file hard-codes the CUDA device (M4:101,138,175) and cannot be
+imported here (spconv, softgroup.ops, models/backbone.py are absent).
+
+For every function it (1) asserts that oracle/dgcnn_oracle.py returns
+bit-identical tensors (the oracle's parity pin) and (2) stores the seeded inputs
+and the reference outputs as fixtures.  The hand-written golden vectors of
+``models/search_knn.py:180-304`` are extracted with ``ast`` (data, not code) into
+tests/golden/search_knn_golden.json.
+
+Usage:  python oracle/make_golden.py [--reference /root/reference]
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import dgcnn_oracle as orc            # noqa: E402
+from gcanet_b200.synth import abc_like_batch      # noqa: E402
+
+M4 = "models/dgcnn-hais-concat-direct-4.py"
+
+
+def load_reference_namespace(ref_root: str) -> dict:
+    with open(os.path.join(ref_root, M4)) as f:
+        lines = f.read().split("\n")
+    text = "\n".join(lines[29:205]) + "\n" + "\n".join(lines[454:534]) + "\n"
+    assert text.count("torch.device('cuda')") == 3
+    text = text.replace("torch.device('cuda')", "x.device")
+    ns = {"torch": torch, "np": np, "nn": nn, "F": F}
+    exec(compile(text, os.path.join(ref_root, M4), "exec"), ns)
+    return ns
+
+
+def same(a: torch.Tensor, b: torch.Tensor, what: str):
+    assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+    assert torch.equal(a, b), f"oracle differs from the reference: {what} (max abs {(a - b).abs().max()})"
+    print(f"  oracle == reference   {what:46s} {tuple(a.shape)}")
+
+
+def randomise_affine(mod: nn.Module, gen: torch.Generator):
+    """GroupNorm defaults (gamma=1, beta=0) would hide the sign(gamma) handling of the
+    max-over-k shortcut, so the fixtures use random affine parameters of both signs."""
+    with torch.no_grad():
+        for m in mod.modules():
+            if isinstance(m, nn.GroupNorm):
+                m.weight.copy_(torch.randn(m.weight.shape, generator=gen) * 0.7 + 0.2)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=gen) * 0.3)
+
+
+def hot_state(mod: nn.Module) -> dict:
+    keep = ("conv1.0.weight", "conv2.0.weight", "conv3.0.weight", "bn1.weight", "bn1.bias",
+            "bn2.weight", "bn2.bias", "bn3.weight", "bn3.bias")
+    sd = mod.state_dict()
+    return {k: sd[k].clone() for k in keep}
+
+
+def make_knn_fixture(ns, out_dir):
+    print("[knn / graph features]")
+    B, N, k = 2, 257, 20
+    x6 = torch.from_numpy(abc_like_batch(B, N, seed=4321, with_normals=True))
+    x3 = x6[:, 0:3].contiguous()
+    g = torch.Generator().manual_seed(7)
+    xf = torch.randn(B, 64, 131, generator=g)
+    fix = {"x6": x6.numpy(), "xf": xf.numpy(), "k": np.int64(k), "kf": np.int64(12)}
+
+    r = ns["knn"](x3, k, k)
+    same(orc.knn(x3, k, k), r, "knn C=3")
+    fix["idx_l2_c3"] = r.numpy().astype(np.int16)
+    r = ns["knn"](x3, 10, 20)                       # dilation k2 > k1
+    same(orc.knn(x3, 10, 20), r, "knn C=3 k1=10 k2=20 (dilated)")
+    fix["idx_l2_c3_dil"] = r.numpy().astype(np.int16)
+    r = ns["knn"](xf, 12, 12)
+    same(orc.knn(xf, 12, 12), r, "knn C=64")
+    fix["idx_l2_c64"] = r.numpy().astype(np.int16)
+    r = ns["knn_points_normals"](x6, k, k)
+    same(orc.knn_points_normals(x6, k, k), r, "knn_points_normals")
+    fix["idx_pn"] = r.numpy().astype(np.int16)
+
+    r = ns["get_graph_feature"](x3, k, k)
+    same(orc.get_graph_feature(x3, k, k), r, "get_graph_feature C=3")
+    assert r.stride() == (N * k * 6, 1, k * 6, 6)    # permuted view over [B,N,k,2C]
+    fix["gf_c3"] = r.contiguous().numpy()
+    r = ns["get_graph_feature"](xf, 12, 12)
+    same(orc.get_graph_feature(xf, 12, 12), r, "get_graph_feature C=64")
+    fix["gf_c64_rows"] = r[:, :, ::13, :].contiguous().numpy()
+    r = ns["get_graph_feature_with_normals"](x6, k, k)
+    same(orc.get_graph_feature_with_normals(x6, k, k), r, "get_graph_feature_with_normals")
+    fix["gf_pn"] = r.contiguous().numpy()
+    r = ns["get_graph_feature_with_normals_g"](x6, k, k)
+    same(orc.get_graph_feature_with_normals_g(x6, k, k), r, "get_graph_feature_with_normals_g")
+    fix["gf_png"] = r.contiguous().numpy()
+    # explicit idx argument (M4:93 idx=)
+    ext = torch.from_numpy(fix["idx_l2_c3"].astype(np.int64))
+    same(orc.get_graph_feature(x3, k, k, idx=ext), ns["get_graph_feature"](x3, k, k, idx=ext),
+         "get_graph_feature idx=given")
+    np.savez_compressed(os.path.join(out_dir, "graph_small.npz"), **fix)
+
+
+def make_encoder_fixture(ns, out_dir):
+    print("[DGCNNEncoderGn edge stack, forward + backward]")
+    B, N, k = 2, 192, 16
+    x6 = torch.from_numpy(abc_like_batch(B, N, seed=99, with_normals=True))
+    fix = {"x6": x6.numpy(), "k": np.int64(k)}
+    for mode in (0, 5):
+        torch.manual_seed(0)
+        ref = ns["DGCNNEncoderGn"](mode=mode, nn_nb=k, input_channels=6)
+        randomise_affine(ref, torch.Generator().manual_seed(11 + mode))
+        mine = orc.DGCNNEncoderGn(mode=mode, nn_nb=k, input_channels=6)
+        mine.load_state_dict(ref.state_dict())
+        x = (x6 if mode == 5 else x6[:, 0:3]).contiguous()
+
+        out_ref = ref(x)
+        out_mine = mine(x)
+        same(out_mine, out_ref, f"DGCNNEncoderGn mode={mode} forward")
+        x1, x2, x3 = mine.edge_stack(x)
+        same(torch.cat((x1, x2, x3), 1), out_ref[:, 1024:], f"edge_stack mode={mode} == output[:,1024:]")
+
+        gen = torch.Generator().manual_seed(5)
+        cot = torch.randn(out_ref[:, 1024:].shape, generator=gen)
+        (out_ref[:, 1024:] * cot).sum().backward()
+        (torch.cat(mine.edge_stack(x), 1) * cot).sum().backward()
+        for name in hot_state(ref):
+            gr = dict(ref.named_parameters())[name].grad
+            gm = dict(mine.named_parameters())[name].grad
+            same(gm, gr, f"grad {name} mode={mode}")
+            fix[f"m{mode}.grad.{name}"] = gr.numpy()
+        for name, v in hot_state(ref).items():
+            fix[f"m{mode}.param.{name}"] = v.numpy()
+        fix[f"m{mode}.x123"] = out_ref[:, 1024:].detach().numpy()
+        fix[f"m{mode}.cot"] = cot.numpy()
+    np.savez_compressed(os.path.join(out_dir, "encoder_small.npz"), **fix)
+
+
+def make_normal_head_fixture(ns, out_dir):
+    print("[conv_normal head]")
+    B, N, k = 2, 192, 16
+    x6 = torch.from_numpy(abc_like_batch(B, N, seed=77, with_normals=True))
+    torch.manual_seed(3)
+    head = orc.NormalEdgeHead(nn_nb=k)
+    randomise_affine(head, torch.Generator().manual_seed(13))
+    # reference: M4:691-693 = graph feature (reference text) -> Sequential(Conv2d(7,64,1,bias=False), GN(2,64), LeakyReLU(0.2)) -> max
+    feat = ns["get_graph_feature_with_normals_g"](x6, k1=k, k2=k)
+    out_ref = head.conv_normal(feat).max(dim=-1, keepdim=False)[0]
+    out = head(x6)
+    same(out, out_ref, "conv_normal head forward")
+    gen = torch.Generator().manual_seed(6)
+    cot = torch.randn(out.shape, generator=gen)
+    (out * cot).sum().backward()
+    fix = {"x6": x6.numpy(), "k": np.int64(k), "out": out.detach().numpy(), "cot": cot.numpy()}
+    for name, p in head.named_parameters():
+        fix[f"param.{name}"] = p.detach().numpy()
+        fix[f"grad.{name}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(out_dir, "normal_head_small.npz"), **fix)
+
+
+def extract_search_knn_golden(ref_root, out_dir):
+    print("[search_knn.py hand-written golden vectors]")
+    path = os.path.join(ref_root, "models/search_knn.py")
+    tree = ast.parse(open(path).read())
+    want = {"query_cloud", "point_cloud", "point_features", "expected_nn_cloud",
+            "expected_features_nn_1", "expected_features_nn_3"}
+    found = {}
+    main = [n for n in tree.body if isinstance(n, ast.If)][-1]
+    for node in main.body:
+        if isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Name) \
+                and node.targets[0].id in want and node.targets[0].id not in found:
+            call = node.value
+            assert isinstance(call, ast.Call) and call.func.attr == "array"
+            found[node.targets[0].id] = ast.literal_eval(call.args[0])
+    assert set(found) == want, sorted(found)
+    found["source"] = "models/search_knn.py:180-244 (SoftProjection self-test; temperature 1.0 for " \
+                      "propagate, sigma forced to 0.1**2 for project with roles swapped, :282-283)"
+    with open(os.path.join(out_dir, "search_knn_golden.json"), "w") as f:
+        json.dump(found, f, indent=1)
+    print("  wrote", len(found) - 1, "arrays")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="/root/reference")
+    args = ap.parse_args()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    torch.set_num_threads(1)          # fixed reduction order inside ATen for reproducible fixtures
+    ns = load_reference_namespace(args.reference)
+    make_knn_fixture(ns, out_dir)
+    make_encoder_fixture(ns, out_dir)
+    make_normal_head_fixture(ns, out_dir)
+    extract_search_knn_golden(args.reference, out_dir)
+    meta = {"torch": torch.__version__, "numpy": np.__version__, "threads": 1,
+            "reference_files": [M4 + ":30-205", M4 + ":455-534", "models/search_knn.py:180-244"]}
+    with open(os.path.join(out_dir, "META.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("done ->", out_dir)
+
+
+if __name__ == "__main__":
+    main()
