@@ -1,0 +1,28 @@
+"""gcanet_b200 -- B200-native kNN-graph + EdgeConv path of GCANet's DGCNN backbone.
+
+Public surface = the reference's own call signatures (see functional.py / modules.py);
+all compute is in libgcanet_b200.so behind the C-ABI of include/gcanet_b200.h.
+"""
+from .functional import (  # noqa: F401
+    KNN,
+    GroupingOperation,
+    edgeconv,
+    get_graph_feature,
+    get_graph_feature_with_normals,
+    get_graph_feature_with_normals_g,
+    group_points,
+    grouping_operation,
+    knn,
+    knn_cuda,
+    knn_cuda_pair,
+    knn_graph,
+    knn_point,
+    knn_points_normals,
+    splinenet_get_graph_feature,
+    splinenet_knn,
+    to_channel_major,
+    to_point_major,
+)
+from .modules import DGCNNEncoderGn, SoftProjection  # noqa: F401
+
+__version__ = "0.1.0"

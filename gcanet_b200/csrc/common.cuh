@@ -1,0 +1,72 @@
+// Shared helpers for the gcanet_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/gcanet_b200.h"
+
+namespace gcanet {
+
+void set_error(const char *fmt, ...);
+void count_launch();   // statistics only: bumps the counter gcanet_launch_count() reports
+
+#define GCANET_REQUIRE(cond, ...)                         \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            ::gcanet::set_error(__VA_ARGS__);             \
+            return GCANET_ERR_INVALID_ARGUMENT;           \
+        }                                                 \
+    } while (0)
+
+#define GCANET_CUDA_OK(expr)                                                            \
+    do {                                                                                \
+        cudaError_t err__ = (expr);                                                     \
+        if (err__ != cudaSuccess) {                                                     \
+            ::gcanet::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                                __FILE__, __LINE__);                                    \
+            return GCANET_ERR_CUDA;                                                     \
+        }                                                                               \
+    } while (0)
+
+#define GCANET_LAUNCH_OK(name)                                                          \
+    do {                                                                                \
+        cudaError_t err__ = cudaGetLastError();                                         \
+        ::gcanet::count_launch();                                                       \
+        if (err__ != cudaSuccess) {                                                     \
+            ::gcanet::set_error("launch of %s failed: %s", name, cudaGetErrorString(err__)); \
+            return GCANET_ERR_CUDA;                                                     \
+        }                                                                               \
+    } while (0)
+
+constexpr int kNumSMs = 148;          // B200
+constexpr size_t kAlign = 256;        // every workspace sub-buffer starts on this boundary
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Bump allocator over a caller-provided workspace (base may be null when only sizing).
+struct Carver {
+    uintptr_t base;
+    size_t off = 0;
+    explicit Carver(void *p) : base(reinterpret_cast<uintptr_t>(p)) {}
+    template <typename T>
+    T *take(size_t count) {
+        T *p = reinterpret_cast<T *>(base + off);
+        off += align_up(count * sizeof(T));
+        return p;
+    }
+};
+
+inline cudaStream_t as_stream(gcanet_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+// layout.cu
+int launch_cn_to_nc(const float *x_cn, float *x_nc, int B, int C, int N, int ld, cudaStream_t st);
+int launch_nc_to_cn(const float *x_nc, float *x_cn, int B, int C, int N, int ld, cudaStream_t st);
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+}  // namespace gcanet

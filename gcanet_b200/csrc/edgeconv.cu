@@ -1,0 +1,733 @@
+// Fused EdgeConv block: graph feature -> 1x1 conv -> GroupNorm -> LeakyReLU -> max over k,
+// forward and backward, without the [B][2C][N][k] edge tensor or the [B][Cout][N][k]
+// activation ever existing in memory.
+//
+// Identities (DESIGN.md section 3 derives them; tests check them against autograd):
+//   (1) W [x_j - x_i ; x_i] = W1 x_j + (W2 - W1) x_i  =: P_j + Q_i,  so the per-edge conv
+//       output is y_ik = P[idx(i,k)] + Q[i] with [P|Q] = X Wcat one small GEMM per layer.
+//   (2) GroupNorm is a per-(sample,channel) affine map a*y + b with sign(a) = sign(gamma) and
+//       LeakyReLU is increasing, so  max_k LReLU(GN(y_ik)) = LReLU(GN(a >= 0 ? max_k y : min_k y)).
+//       One gather pass therefore yields everything: max, min (+ their k), sum_k y, and the
+//       group moments sum y, sum y^2 for the GroupNorm statistics.
+//   (3) backward: dy_ik = [k = k*] rstd gamma du + A_g + K_g y_ik  (the last two terms are the
+//       GroupNorm mean/variance paths, dense over all edges but affine in y), hence
+//         dQ_i = rstd gamma du_i + k A_g + K_g sum_k y_ik
+//         dP_j = sum_{(i,k)->j} ([k = k*] rstd gamma du_i + A_g + K_g Q_i) + deg_j K_g P_j
+//       i.e. one scatter pass over the edges (vector atomics into an L2-resident buffer), then
+//       dX = [dP|dQ] Wcat^T and dWcat = X^T [dP|dQ] as two small GEMMs.
+//
+// Rooflines: the gather/scatter passes move B*N*k rows of Cout*4 bytes through L2 (the cloud's
+// P matrix is N*Cout*4 bytes, L2-resident) and B*N*Cout*~14 bytes through HBM; the GEMMs are
+// 2*B*N*C*2Cout FLOP, k times fewer than the per-edge formulation.
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace gcanet {
+
+constexpr unsigned FULLM = 0xffffffffu;
+constexpr int kGWarps = 8;           // warps per CTA in the per-point kernels
+constexpr int kPtsPerWarp = 4;       // points each warp handles
+constexpr int kPtsPerCta = kGWarps * kPtsPerWarp;
+
+// ---------------------------------------------------------------------------------
+// weights:  Wcat[c][o] = W[o][c],  Wcat[c][Cout+o] = W[o][C+c] - W[o][c]   (rows c >= C zero)
+//           WcatT[n][c] = Wcat[c][n]
+// ---------------------------------------------------------------------------------
+__global__ void prep_wcat_kernel(const float *__restrict__ W, float *__restrict__ wcat, float *__restrict__ wcatT,
+                                 int C, int ldx, int Cout) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = ldx * 2 * Cout;
+    if (t >= total) return;
+    int c = t / (2 * Cout), n = t % (2 * Cout);
+    float v = 0.f;
+    if (c < C) {
+        if (n < Cout) v = W[(size_t)n * 2 * C + c];
+        else { int o = n - Cout; v = W[(size_t)o * 2 * C + C + c] - W[(size_t)o * 2 * C + c]; }
+    }
+    if (wcat) wcat[t] = v;
+    if (wcatT) wcatT[(size_t)n * ldx + c] = v;
+}
+
+// dW[o][c] = dWcat[c][o] - dWcat[c][Cout+o];  dW[o][C+c] = dWcat[c][Cout+o]
+__global__ void unprep_dw_kernel(const float *__restrict__ dwcat, float *__restrict__ dW, int C, int Cout) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Cout * C) return;
+    int o = t / C, c = t % C;
+    float dp = dwcat[(size_t)c * 2 * Cout + o], dq = dwcat[(size_t)c * 2 * Cout + Cout + o];
+    dW[(size_t)o * 2 * C + c] = dp - dq;
+    dW[(size_t)o * 2 * C + C + c] = dq;
+}
+
+// ---------------------------------------------------------------------------------
+// fp32 GEMM on CUDA cores.   TA = false: C[M][N] = A[M][K] B[K][N]
+//                            TA = true : C[K][N] (+= over M-splits) = A[M][K]^T B[M][N]
+// Tile 128 x 64 x 16, 256 threads, 8 x 4 outputs per thread.  K, N, lda, ldb, ldc % 4 == 0.
+// ---------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 64, BK = 16;
+
+template <bool TA>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A, const float *__restrict__ Bm,
+                                                    float *__restrict__ Cm, int M, int N, int K, int lda, int ldb,
+                                                    int ldc, int rows_per_split) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.x * BN;
+    const int r0 = blockIdx.y * BM;            // output-row tile (M for NN, K for TN)
+    int red_lo = 0, red_hi = TA ? M : K;       // reduction range
+    if (TA) { red_lo = blockIdx.z * rows_per_split; red_hi = min(M, red_lo + rows_per_split); }
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = red_lo; k0 < red_hi; k0 += BK) {
+        if (!TA) {
+            // A tile: rows r0..r0+127, cols k0..k0+15 -> As[k][row]
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                int f = tid + i * 256;
+                int row = f >> 2, kq = f & 3;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + row < M && k0 + kq * 4 < red_hi)
+                    v = *reinterpret_cast<const float4 *>(A + (size_t)(r0 + row) * lda + k0 + kq * 4);
+                As[kq * 4 + 0][row] = v.x; As[kq * 4 + 1][row] = v.y;
+                As[kq * 4 + 2][row] = v.z; As[kq * 4 + 3][row] = v.w;
+            }
+        } else {
+            // A tile: reduction rows k0..k0+15, output rows (columns of A) r0..r0+127 -> As[k][row]
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                int f = tid + i * 256;
+                int kr = f >> 5, cq = f & 31;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k0 + kr < red_hi && r0 + cq * 4 < K)
+                    v = *reinterpret_cast<const float4 *>(A + (size_t)(k0 + kr) * lda + r0 + cq * 4);
+                *reinterpret_cast<float4 *>(&As[kr][cq * 4]) = v;
+            }
+        }
+        {
+            int kr = tid >> 4, nq = tid & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + kr < red_hi && n0 + nq * 4 < N)
+                v = *reinterpret_cast<const float4 *>(Bm + (size_t)(k0 + kr) * ldb + n0 + nq * 4);
+            *reinterpret_cast<float4 *>(&Bs[kr][nq * 4]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8 + 4]);
+            float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const int out_rows = TA ? K : M;
+    float *Cbase = Cm + (TA ? (size_t)blockIdx.z * K * ldc : 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int r = r0 + ty * 8 + i;
+        int c = n0 + tx * 4;
+        if (r < out_rows && c < N)
+            *reinterpret_cast<float4 *>(Cbase + (size_t)r * ldc + c) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+// sums `splits` partial [rows][ld] matrices
+__global__ void reduce_splits_kernel(const float *__restrict__ part, float *__restrict__ out, int count, int splits) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    double s = 0.0;
+    for (int z = 0; z < splits; ++z) s += (double)part[(size_t)z * count + t];
+    out[t] = (float)s;
+}
+
+static int launch_sgemm_nn(const float *A, const float *Bm, float *Cm, int M, int N, int K, int lda, int ldb, int ldc,
+                           cudaStream_t st) {
+    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), 1);
+    sgemm_kernel<false><<<grid, 256, 0, st>>>(A, Bm, Cm, M, N, K, lda, ldb, ldc, 0);
+    GCANET_LAUNCH_OK("sgemm_kernel<NN>");
+    return GCANET_OK;
+}
+
+static int tn_splits(int M, int N, int K) {
+    int tiles = ceil_div(N, BN) * ceil_div(K, BM);
+    int splits = (2 * kNumSMs + tiles - 1) / tiles;
+    int max_splits = ceil_div(M, 4 * BK);
+    if (splits > max_splits) splits = max_splits;
+    return splits < 1 ? 1 : splits;
+}
+
+// out[K][N] = A[M][K]^T B[M][N]; part must hold tn_splits * K * N floats
+static int launch_sgemm_tn(const float *A, const float *Bm, float *out, float *part, int M, int N, int K, int lda,
+                           int ldb, cudaStream_t st) {
+    int splits = tn_splits(M, N, K);
+    int rows = ceil_div(ceil_div(M, splits), BK) * BK;
+    splits = ceil_div(M, rows);
+    dim3 grid(ceil_div(N, BN), ceil_div(K, BM), splits);
+    sgemm_kernel<true><<<grid, 256, 0, st>>>(A, Bm, part, M, N, K, lda, ldb, N, rows);
+    GCANET_LAUNCH_OK("sgemm_kernel<TN>");
+    int count = K * N;
+    reduce_splits_kernel<<<ceil_div(count, 256), 256, 0, st>>>(part, out, count, splits);
+    GCANET_LAUNCH_OK("reduce_splits_kernel");
+    return GCANET_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// forward gather pass
+// ---------------------------------------------------------------------------------
+template <int VEC>
+struct VecIO;
+template <>
+struct VecIO<1> {
+    static __device__ __forceinline__ void ld(const float *p, float *v) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void st(float *p, const float *v) { p[0] = v[0]; }
+    static __device__ __forceinline__ void red(float *p, const float *v) { atomicAdd(p, v[0]); }
+};
+template <>
+struct VecIO<2> {
+    static __device__ __forceinline__ void ld(const float *p, float *v) {
+        float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void st(float *p, const float *v) { *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]); }
+    static __device__ __forceinline__ void red(float *p, const float *v) { atomicAdd(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1])); }
+};
+template <>
+struct VecIO<4> {
+    static __device__ __forceinline__ void ld(const float *p, float *v) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void st(float *p, const float *v) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+    static __device__ __forceinline__ void red(float *p, const float *v) { atomicAdd(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <>
+struct VecIO<8> {
+    static __device__ __forceinline__ void ld(const float *p, float *v) { VecIO<4>::ld(p, v); VecIO<4>::ld(p + 4, v + 4); }
+    static __device__ __forceinline__ void st(float *p, const float *v) { VecIO<4>::st(p, v); VecIO<4>::st(p + 4, v + 4); }
+    static __device__ __forceinline__ void red(float *p, const float *v) { VecIO<4>::red(p, v); VecIO<4>::red(p + 4, v + 4); }
+};
+
+struct FwdArgs {
+    const float *pq;       // [B][N][2*Cout]
+    const int32_t *idx;    // [B][N][k]
+    float *ymax, *ymin, *ysum;           // [B][N][Cout]
+    unsigned char *amax, *amin;          // [B][N][Cout]
+    double *part;          // [B][nblk][G][2]
+    int N, Cout, k, G;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArgs a) {
+    __shared__ double red[kGWarps * 32][2];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cout = a.Cout, k = a.k;
+    const int c0 = lane * VEC;
+    const float *pq = a.pq + (size_t)b * a.N * 2 * Cout;
+    double s1 = 0.0, s2 = 0.0;
+
+    for (int pi = 0; pi < kPtsPerWarp; ++pi) {
+        const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
+        if (i >= a.N) break;
+        float q[VEC], vmax[VEC], vmin[VEC], vsum[VEC], vsq[VEC];
+        int kmax[VEC], kmin[VEC];
+        VecIO<VEC>::ld(pq + (size_t)i * 2 * Cout + Cout + c0, q);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { vmax[v] = -CUDART_INF_F; vmin[v] = CUDART_INF_F; vsum[v] = 0.f; vsq[v] = 0.f; kmax[v] = 0; kmin[v] = 0; }
+        const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
+        for (int base = 0; base < k; base += 32) {
+            const int cnt = min(32, k - base);
+            const int myj = lane < cnt ? ip[base + lane] : 0;
+            int t = 0;
+            for (; t + 4 <= cnt; t += 4) {
+                float p[4][VEC];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int j = __shfl_sync(FULLM, myj, t + u);
+                    VecIO<VEC>::ld(pq + (size_t)j * 2 * Cout + c0, p[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        float y = p[u][v] + q[v];
+                        if (y > vmax[v]) { vmax[v] = y; kmax[v] = base + t + u; }
+                        if (y < vmin[v]) { vmin[v] = y; kmin[v] = base + t + u; }
+                        vsum[v] += y;
+                        vsq[v] = fmaf(y, y, vsq[v]);
+                    }
+            }
+            for (; t < cnt; ++t) {
+                float p[VEC];
+                int j = __shfl_sync(FULLM, myj, t);
+                VecIO<VEC>::ld(pq + (size_t)j * 2 * Cout + c0, p);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    float y = p[v] + q[v];
+                    if (y > vmax[v]) { vmax[v] = y; kmax[v] = base + t; }
+                    if (y < vmin[v]) { vmin[v] = y; kmin[v] = base + t; }
+                    vsum[v] += y;
+                    vsq[v] = fmaf(y, y, vsq[v]);
+                }
+            }
+        }
+        const size_t o = ((size_t)b * a.N + i) * Cout + c0;
+        VecIO<VEC>::st(a.ymax + o, vmax);
+        VecIO<VEC>::st(a.ymin + o, vmin);
+        VecIO<VEC>::st(a.ysum + o, vsum);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            a.amax[o + v] = (unsigned char)kmax[v];
+            a.amin[o + v] = (unsigned char)kmin[v];
+            s1 += (double)vsum[v];
+            s2 += (double)vsq[v];
+        }
+    }
+    red[threadIdx.x][0] = s1;
+    red[threadIdx.x][1] = s2;
+    __syncthreads();
+    if (threadIdx.x < a.G * 2) {
+        const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const int lanes_per_group = 32 / a.G;      // channels of a lane never straddle a group
+        double s = 0.0;
+        for (int w = 0; w < kGWarps; ++w)
+            for (int l = g * lanes_per_group; l < (g + 1) * lanes_per_group; ++l) s += red[w * 32 + l][which];
+        a.part[(((size_t)b * gridDim.x + blockIdx.x) * a.G + g) * 2 + which] = s;
+    }
+}
+
+// stats[b][g] = (mean, rstd)
+__global__ void gn_stats_kernel(const double *__restrict__ part, float *__restrict__ stats, int nblk, int G,
+                                double count, float eps) {
+    const int b = blockIdx.x, g = threadIdx.x;
+    if (g >= G) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < nblk; ++i) {
+        s1 += part[(((size_t)b * nblk + i) * G + g) * 2 + 0];
+        s2 += part[(((size_t)b * nblk + i) * G + g) * 2 + 1];
+    }
+    double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((size_t)b * G + g) * 2 + 0] = (float)mean;
+    stats[((size_t)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// picks max or min by the sign of gamma, applies GroupNorm + LeakyReLU; ymax/amax become ysel/arg
+__global__ void edge_finish_kernel(float *__restrict__ ymax, const float *__restrict__ ymin,
+                                   unsigned char *__restrict__ amax, const unsigned char *__restrict__ amin,
+                                   const float *__restrict__ stats, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, float *__restrict__ out_nc,
+                                   float *__restrict__ out_cn, int N, int Cout, int G, float slope) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int cpg = Cout / G;
+    {
+        const int c = c0 + threadIdx.x;
+        const float gm = gamma[c], bt = beta[c];
+        const float mean = stats[((size_t)b * G + c / cpg) * 2 + 0], rstd = stats[((size_t)b * G + c / cpg) * 2 + 1];
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            const int n = n0 + r;
+            float o = 0.f;
+            if (n < N) {
+                const size_t e = ((size_t)b * N + n) * Cout + c;
+                float ys = ymax[e];
+                if (gm < 0.f) { ys = ymin[e]; ymax[e] = ys; amax[e] = amin[e]; }
+                o = lrelu((ys - mean) * rstd * gm + bt, slope);
+                out_nc[e] = o;
+            }
+            tile[r][threadIdx.x] = o;
+        }
+    }
+    if (out_cn == nullptr) return;
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, n = n0 + threadIdx.x;
+        if (n < N) out_cn[((size_t)b * Cout + c) * N + n] = tile[threadIdx.x][r];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------
+struct BwdArgs {
+    const float *pq, *ysel, *ysum, *stats, *gamma, *beta, *gout;
+    const unsigned char *arg;
+    const int32_t *idx;
+    float *part;       // [B][nblk][Cout][2]  per-CTA sums of du, du*yhat
+    const float *coef; // [B][G][2] = (A_g, K_g)
+    float *dpq;        // [B][N][2*Cout]
+    int *deg;          // [B][N]
+    int N, Cout, k, G;
+    float slope;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kGWarps * 32) edge_bwd_reduce_kernel(BwdArgs a) {
+    __shared__ float red[kGWarps][32 * VEC][2];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cout = a.Cout, c0 = lane * VEC;
+    const int cpg = Cout / a.G;
+    const float mean = a.stats[((size_t)b * a.G + c0 / cpg) * 2 + 0], rstd = a.stats[((size_t)b * a.G + c0 / cpg) * 2 + 1];
+    float gm[VEC], bt[VEC], s1[VEC], s2[VEC];
+    VecIO<VEC>::ld(a.gamma + c0, gm);
+    VecIO<VEC>::ld(a.beta + c0, bt);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { s1[v] = 0.f; s2[v] = 0.f; }
+    for (int pi = 0; pi < kPtsPerWarp; ++pi) {
+        const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
+        if (i >= a.N) break;
+        const size_t o = ((size_t)b * a.N + i) * Cout + c0;
+        float ys[VEC], g[VEC];
+        VecIO<VEC>::ld(a.ysel + o, ys);
+        VecIO<VEC>::ld(a.gout + o, g);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float yh = (ys[v] - mean) * rstd;
+            float u = yh * gm[v] + bt[v];
+            float du = u > 0.f ? g[v] : g[v] * a.slope;
+            s1[v] += du;
+            s2[v] = fmaf(du, yh, s2[v]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { red[warp][c0 + v][0] = s1[v]; red[warp][c0 + v][1] = s2[v]; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < Cout * 2; e += blockDim.x) {
+        const int c = e >> 1, which = e & 1;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kGWarps; ++w) s += red[w][c][which];
+        a.part[(((size_t)b * gridDim.x + blockIdx.x) * Cout + c) * 2 + which] = s;
+    }
+}
+
+// per cloud: S1[c] = sum_i du, S2[c] = sum_i du*yhat  ->  sbc[b][c][2] (double) and coef[b][g] = (A_g, K_g)
+__global__ void edge_bwd_coef_kernel(const float *__restrict__ part, const float *__restrict__ stats,
+                                     const float *__restrict__ gamma, double *__restrict__ sbc,
+                                     float *__restrict__ coef, int nblk, int Cout, int G, double count) {
+    extern __shared__ double sh[];      // [Cout][2] weighted by gamma
+    const int b = blockIdx.x;
+    const int cpg = Cout / G;
+    for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int i = 0; i < nblk; ++i) {
+            s1 += (double)part[(((size_t)b * nblk + i) * Cout + c) * 2 + 0];
+            s2 += (double)part[(((size_t)b * nblk + i) * Cout + c) * 2 + 1];
+        }
+        sbc[((size_t)b * Cout + c) * 2 + 0] = s1;
+        sbc[((size_t)b * Cout + c) * 2 + 1] = s2;
+        sh[c * 2 + 0] = s1 * (double)gamma[c];
+        sh[c * 2 + 1] = s2 * (double)gamma[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        const int g = threadIdx.x;
+        double m1 = 0.0, m2 = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { m1 += sh[c * 2]; m2 += sh[c * 2 + 1]; }
+        m1 /= count; m2 /= count;
+        const double mean = stats[((size_t)b * G + g) * 2 + 0], rstd = stats[((size_t)b * G + g) * 2 + 1];
+        coef[((size_t)b * G + g) * 2 + 0] = (float)(-rstd * m1 + rstd * rstd * m2 * mean);
+        coef[((size_t)b * G + g) * 2 + 1] = (float)(-rstd * rstd * m2);
+    }
+}
+
+// dgamma[c] = sum_b S2, dbeta[c] = sum_b S1
+__global__ void edge_bwd_affine_kernel(const double *__restrict__ sbc, float *__restrict__ dgamma,
+                                       float *__restrict__ dbeta, int B, int Cout) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cout) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < B; ++b) { s1 += sbc[((size_t)b * Cout + c) * 2]; s2 += sbc[((size_t)b * Cout + c) * 2 + 1]; }
+    dbeta[c] = (float)s1;
+    dgamma[c] = (float)s2;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_kernel(BwdArgs a) {
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cout = a.Cout, k = a.k, c0 = lane * VEC;
+    const int cpg = Cout / a.G;
+    const int g = c0 / cpg;
+    const float mean = a.stats[((size_t)b * a.G + g) * 2 + 0], rstd = a.stats[((size_t)b * a.G + g) * 2 + 1];
+    const float Ag = a.coef[((size_t)b * a.G + g) * 2 + 0], Kg = a.coef[((size_t)b * a.G + g) * 2 + 1];
+    float gm[VEC], bt[VEC];
+    VecIO<VEC>::ld(a.gamma + c0, gm);
+    VecIO<VEC>::ld(a.beta + c0, bt);
+    float *dpq = a.dpq + (size_t)b * a.N * 2 * Cout;
+    const float *pq = a.pq + (size_t)b * a.N * 2 * Cout;
+    for (int pi = 0; pi < kPtsPerWarp; ++pi) {
+        const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
+        if (i >= a.N) break;
+        const size_t o = ((size_t)b * a.N + i) * Cout + c0;
+        float ys[VEC], gg[VEC], ysum[VEC], q[VEC], s[VEC], T[VEC], dq[VEC];
+        int ak[VEC];
+        VecIO<VEC>::ld(a.ysel + o, ys);
+        VecIO<VEC>::ld(a.gout + o, gg);
+        VecIO<VEC>::ld(a.ysum + o, ysum);
+        VecIO<VEC>::ld(pq + (size_t)i * 2 * Cout + Cout + c0, q);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            ak[v] = a.arg[o + v];
+            float yh = (ys[v] - mean) * rstd;
+            float u = yh * gm[v] + bt[v];
+            float du = u > 0.f ? gg[v] : gg[v] * a.slope;
+            s[v] = rstd * gm[v] * du;
+            dq[v] = s[v] + (float)k * Ag + Kg * ysum[v];
+            T[v] = fmaf(Kg, q[v], Ag);
+        }
+        VecIO<VEC>::st(dpq + (size_t)i * 2 * Cout + Cout + c0, dq);
+        const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
+        for (int base = 0; base < k; base += 32) {
+            const int cnt = min(32, k - base);
+            const int myj = lane < cnt ? ip[base + lane] : 0;
+            if (lane < cnt) atomicAdd(a.deg + (size_t)b * a.N + myj, 1);
+            for (int t = 0; t < cnt; ++t) {
+                const int j = __shfl_sync(FULLM, myj, t);
+                float val[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) val[v] = T[v] + (ak[v] == base + t ? s[v] : 0.f);
+                VecIO<VEC>::red(dpq + (size_t)j * 2 * Cout + c0, val);
+            }
+        }
+    }
+}
+
+// dP[j][c] += deg_j * K_g * P[j][c]
+__global__ void edge_bwd_degfix_kernel(float *__restrict__ dpq, const float *__restrict__ pq, const int *__restrict__ deg,
+                                       const float *__restrict__ coef, int N, int Cout, int G, long long total4) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total4) return;
+    const int c4 = Cout / 4;
+    long long bn = t / c4;
+    int c = (int)(t % c4) * 4;
+    int b = (int)(bn / N);
+    const float Kg = coef[((size_t)b * G + c / (Cout / G)) * 2 + 1];
+    const float d = (float)deg[bn] * Kg;
+    float4 p = *reinterpret_cast<const float4 *>(pq + bn * 2 * Cout + c);
+    float4 *o = reinterpret_cast<float4 *>(dpq + bn * 2 * Cout + c);
+    float4 v = *o;
+    v.x = fmaf(d, p.x, v.x); v.y = fmaf(d, p.y, v.y); v.z = fmaf(d, p.z, v.z); v.w = fmaf(d, p.w, v.w);
+    *o = v;
+}
+
+// ---------------------------------------------------------------------------------
+// buffer plans
+// ---------------------------------------------------------------------------------
+struct Saved {
+    float *pq, *ysel, *ysum, *stats;
+    unsigned char *arg;
+};
+
+static size_t plan_saved(const gcanet_edgeconv_desc *d, void *base, Saved *s) {
+    Carver cv(base);
+    size_t bn = (size_t)d->B * d->N;
+    float *pq = cv.take<float>(bn * 2 * d->Cout);
+    float *ysel = cv.take<float>(bn * d->Cout);
+    float *ysum = cv.take<float>(bn * d->Cout);
+    unsigned char *arg = cv.take<unsigned char>(bn * d->Cout);
+    float *stats = cv.take<float>((size_t)d->B * d->groups * 2);
+    if (s) { s->pq = pq; s->ysel = ysel; s->ysum = ysum; s->arg = arg; s->stats = stats; }
+    return cv.off;
+}
+
+struct FwdWs {
+    float *wcat, *ymin;
+    unsigned char *amin;
+    double *part;
+};
+
+static size_t plan_fwd(const gcanet_edgeconv_desc *d, void *base, FwdWs *w) {
+    Carver cv(base);
+    size_t bn = (size_t)d->B * d->N;
+    int nblk = ceil_div(d->N, kPtsPerCta);
+    float *wcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
+    float *ymin = cv.take<float>(bn * d->Cout);
+    unsigned char *amin = cv.take<unsigned char>(bn * d->Cout);
+    double *part = cv.take<double>((size_t)d->B * nblk * d->groups * 2);
+    if (w) { w->wcat = wcat; w->ymin = ymin; w->amin = amin; w->part = part; }
+    return cv.off;
+}
+
+struct BwdWs {
+    float *wcatT, *dpq, *part, *coef, *dwcat, *dwpart;
+    int *deg;
+    double *sbc;
+};
+
+static size_t plan_bwd(const gcanet_edgeconv_desc *d, void *base, BwdWs *w) {
+    Carver cv(base);
+    size_t bn = (size_t)d->B * d->N;
+    int nblk = ceil_div(d->N, kPtsPerCta);
+    int M = (int)bn;
+    float *wcatT = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
+    float *dpq = cv.take<float>(bn * 2 * d->Cout);
+    int *deg = cv.take<int>(bn);
+    float *part = cv.take<float>((size_t)d->B * nblk * d->Cout * 2);
+    double *sbc = cv.take<double>((size_t)d->B * d->Cout * 2);
+    float *coef = cv.take<float>((size_t)d->B * d->groups * 2);
+    float *dwcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
+    float *dwpart = cv.take<float>((size_t)tn_splits(M, 2 * d->Cout, d->ldx) * d->ldx * 2 * d->Cout);
+    if (w) { w->wcatT = wcatT; w->dpq = dpq; w->deg = deg; w->part = part; w->sbc = sbc; w->coef = coef; w->dwcat = dwcat; w->dwpart = dwpart; }
+    return cv.off;
+}
+
+static int check_desc(const gcanet_edgeconv_desc *d) {
+    GCANET_REQUIRE(d != nullptr, "edgeconv: null descriptor");
+    GCANET_REQUIRE(d->B >= 1 && d->N >= 1 && d->C >= 1 && d->k >= 1, "edgeconv: bad shape B=%d N=%d C=%d k=%d", d->B, d->N, d->C, d->k);
+    GCANET_REQUIRE(d->B <= 65535, "edgeconv: B > 65535");
+    GCANET_REQUIRE(d->k <= 255, "edgeconv: k=%d > 255 (arg index is one byte)", d->k);
+    GCANET_REQUIRE(d->ldx >= d->C && d->ldx % 4 == 0 && d->ldx <= 256, "edgeconv: ldx=%d must be a multiple of 4 in [C, 256]", d->ldx);
+    GCANET_REQUIRE(d->Cout % 32 == 0 && d->Cout >= 32 && d->Cout <= 256, "edgeconv: Cout=%d must be a multiple of 32 in [32, 256]", d->Cout);
+    int vec = d->Cout / 32;
+    GCANET_REQUIRE(vec == 1 || vec == 2 || vec == 4 || vec == 8, "edgeconv: Cout=%d unsupported (Cout/32 must be 1, 2, 4 or 8)", d->Cout);
+    GCANET_REQUIRE(d->groups >= 1 && d->Cout % d->groups == 0 && 32 % d->groups == 0,
+                   "edgeconv: groups=%d must divide 32 and Cout=%d", d->groups, d->Cout);
+    GCANET_REQUIRE(d->eps > 0.f, "edgeconv: eps must be positive");
+    return GCANET_OK;
+}
+
+template <int VEC>
+static int run_forward(const gcanet_edgeconv_desc *d, const float *x_nc, const int32_t *idx, const float *weight,
+                       const float *gamma, const float *beta, float *out_nc, float *out_cn, const Saved &sv,
+                       const FwdWs &w, cudaStream_t st) {
+    const int M = d->B * d->N, Cout = d->Cout;
+    int total = d->ldx * 2 * Cout;
+    prep_wcat_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, w.wcat, nullptr, d->C, d->ldx, Cout);
+    GCANET_LAUNCH_OK("prep_wcat_kernel");
+    int rc = launch_sgemm_nn(x_nc, w.wcat, sv.pq, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, 2 * Cout, st);
+    if (rc) return rc;
+    FwdArgs fa{sv.pq, idx, sv.ysel, w.ymin, sv.ysum, sv.arg, w.amin, w.part, d->N, Cout, d->k, d->groups};
+    const int nblk = ceil_div(d->N, kPtsPerCta);
+    edge_gather_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(fa);
+    GCANET_LAUNCH_OK("edge_gather_reduce_kernel");
+    double count = (double)(Cout / d->groups) * d->N * d->k;
+    gn_stats_kernel<<<d->B, 32, 0, st>>>(w.part, sv.stats, nblk, d->groups, count, d->eps);
+    GCANET_LAUNCH_OK("gn_stats_kernel");
+    dim3 fg(ceil_div(d->N, 32), Cout / 32, d->B), fb(32, 8);
+    edge_finish_kernel<<<fg, fb, 0, st>>>(sv.ysel, w.ymin, sv.arg, w.amin, sv.stats, gamma, beta, out_nc, out_cn, d->N,
+                                          Cout, d->groups, d->slope);
+    GCANET_LAUNCH_OK("edge_finish_kernel");
+    return GCANET_OK;
+}
+
+template <int VEC>
+static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const int32_t *idx, const float *weight,
+                        const float *gamma, const float *beta, const float *gout, const Saved &sv, float *grad_x_nc,
+                        float *grad_weight, float *grad_gamma, float *grad_beta, const BwdWs &w, cudaStream_t st) {
+    const int M = d->B * d->N, Cout = d->Cout;
+    const size_t bn = (size_t)M;
+    const int nblk = ceil_div(d->N, kPtsPerCta);
+    int total = d->ldx * 2 * Cout;
+    prep_wcat_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, nullptr, w.wcatT, d->C, d->ldx, Cout);
+    GCANET_LAUNCH_OK("prep_wcat_kernel");
+    GCANET_CUDA_OK(cudaMemsetAsync(w.dpq, 0, bn * 2 * Cout * sizeof(float), st));
+    GCANET_CUDA_OK(cudaMemsetAsync(w.deg, 0, bn * sizeof(int), st));
+
+    BwdArgs ba{sv.pq, sv.ysel, sv.ysum, sv.stats, gamma, beta, gout, sv.arg, idx, w.part, w.coef, w.dpq, w.deg,
+               d->N, Cout, d->k, d->groups, d->slope};
+    edge_bwd_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
+    GCANET_LAUNCH_OK("edge_bwd_reduce_kernel");
+    double count = (double)(Cout / d->groups) * d->N * d->k;
+    edge_bwd_coef_kernel<<<d->B, 128, Cout * 2 * sizeof(double), st>>>(w.part, sv.stats, gamma, w.sbc, w.coef, nblk, Cout,
+                                                                      d->groups, count);
+    GCANET_LAUNCH_OK("edge_bwd_coef_kernel");
+    edge_bwd_affine_kernel<<<ceil_div(Cout, 128), 128, 0, st>>>(w.sbc, grad_gamma, grad_beta, d->B, Cout);
+    GCANET_LAUNCH_OK("edge_bwd_affine_kernel");
+    edge_bwd_scatter_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
+    GCANET_LAUNCH_OK("edge_bwd_scatter_kernel");
+    long long total4 = (long long)bn * (Cout / 4);
+    edge_bwd_degfix_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, d->N, Cout,
+                                                                            d->groups, total4);
+    GCANET_LAUNCH_OK("edge_bwd_degfix_kernel");
+    // dWcat[ldx][2Cout] = X^T dPQ ; dW from it
+    int rc = launch_sgemm_tn(x_nc, w.dpq, w.dwcat, w.dwpart, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, st);
+    if (rc) return rc;
+    unprep_dw_kernel<<<ceil_div(Cout * d->C, 256), 256, 0, st>>>(w.dwcat, grad_weight, d->C, Cout);
+    GCANET_LAUNCH_OK("unprep_dw_kernel");
+    if (grad_x_nc) {
+        rc = launch_sgemm_nn(w.dpq, w.wcatT, grad_x_nc, M, d->ldx, 2 * Cout, 2 * Cout, d->ldx, d->ldx, st);
+        if (rc) return rc;
+    }
+    return GCANET_OK;
+}
+
+}  // namespace gcanet
+
+using namespace gcanet;
+
+extern "C" size_t gcanet_edgeconv_saved_bytes(const gcanet_edgeconv_desc *d) {
+    if (check_desc(d) != GCANET_OK) return 0;
+    return plan_saved(d, nullptr, nullptr);
+}
+
+extern "C" size_t gcanet_edgeconv_workspace_bytes(const gcanet_edgeconv_desc *d) {
+    if (check_desc(d) != GCANET_OK) return 0;
+    size_t f = plan_fwd(d, nullptr, nullptr), b = plan_bwd(d, nullptr, nullptr);
+    return f > b ? f : b;
+}
+
+static int check_ws(const char *who, const void *p, size_t have, size_t need) {
+    if (p == nullptr || have < need || reinterpret_cast<uintptr_t>(p) % kAlign) {
+        set_error("%s: workspace too small or misaligned (%zu given, %zu needed)", who, have, need);
+        return GCANET_ERR_WORKSPACE;
+    }
+    return GCANET_OK;
+}
+
+extern "C" int gcanet_edgeconv_forward(const gcanet_edgeconv_desc *d, const float *x_nc, const int32_t *idx,
+                                       const float *weight, const float *gamma, const float *beta, float *out_nc,
+                                       float *out_cn, void *saved, void *ws, size_t ws_bytes, gcanet_stream_t stream) {
+    int rc = check_desc(d);
+    if (rc) return rc;
+    GCANET_REQUIRE(x_nc && idx && weight && gamma && beta && out_nc && saved, "edgeconv_forward: null pointer");
+    GCANET_REQUIRE(reinterpret_cast<uintptr_t>(saved) % kAlign == 0, "edgeconv_forward: saved buffer must be 256-byte aligned");
+    rc = check_ws("edgeconv_forward", ws, ws_bytes, plan_fwd(d, nullptr, nullptr));
+    if (rc) return rc;
+    Saved sv; FwdWs w;
+    plan_saved(d, saved, &sv);
+    plan_fwd(d, ws, &w);
+    cudaStream_t st = as_stream(stream);
+    switch (d->Cout / 32) {
+        case 1: return run_forward<1>(d, x_nc, idx, weight, gamma, beta, out_nc, out_cn, sv, w, st);
+        case 2: return run_forward<2>(d, x_nc, idx, weight, gamma, beta, out_nc, out_cn, sv, w, st);
+        case 4: return run_forward<4>(d, x_nc, idx, weight, gamma, beta, out_nc, out_cn, sv, w, st);
+        default: return run_forward<8>(d, x_nc, idx, weight, gamma, beta, out_nc, out_cn, sv, w, st);
+    }
+}
+
+extern "C" int gcanet_edgeconv_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const int32_t *idx,
+                                        const float *weight, const float *gamma, const float *beta,
+                                        const float *grad_out_nc, const void *saved, float *grad_x_nc,
+                                        float *grad_weight, float *grad_gamma, float *grad_beta, void *ws,
+                                        size_t ws_bytes, gcanet_stream_t stream) {
+    int rc = check_desc(d);
+    if (rc) return rc;
+    GCANET_REQUIRE(x_nc && idx && weight && gamma && beta && grad_out_nc && saved && grad_weight && grad_gamma && grad_beta,
+                   "edgeconv_backward: null pointer");
+    rc = check_ws("edgeconv_backward", ws, ws_bytes, plan_bwd(d, nullptr, nullptr));
+    if (rc) return rc;
+    Saved sv; BwdWs w;
+    plan_saved(d, const_cast<void *>(saved), &sv);
+    plan_bwd(d, ws, &w);
+    cudaStream_t st = as_stream(stream);
+    switch (d->Cout / 32) {
+        case 1: return run_backward<1>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_x_nc, grad_weight, grad_gamma, grad_beta, w, st);
+        case 2: return run_backward<2>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_x_nc, grad_weight, grad_gamma, grad_beta, w, st);
+        case 4: return run_backward<4>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_x_nc, grad_weight, grad_gamma, grad_beta, w, st);
+        default: return run_backward<8>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_x_nc, grad_weight, grad_gamma, grad_beta, w, st);
+    }
+}

@@ -1,0 +1,519 @@
+// CUDA-core brute-force kNN with a fused streaming top-k (no N x N matrix in memory).
+//
+// One warp owns R queries; the 32 lanes each take one reference point of the current
+// group, so a group of 32 candidates costs C*R FMAs per lane plus one compare per query.
+// The running k-best of every query is an ascending list distributed over the warp's
+// registers (position p lives in slot p/32 of lane p%32); a candidate is inserted with
+// two ballots (rank) and a shuffle-up (shift).  Only candidates that beat the current
+// k-th distance reach the insertion, which after the first few hundred references is
+// rare, so the scan is FMA/compare bound.
+//
+// Arithmetic follows the reference so that index sets agree up to fp32 ties:
+//   L2   (M4:36-38)  d = fl(fl(|x_j|^2 - 2 x_i.x_j) + |x_i|^2), norms summed without FMA
+//   PN   (M4:61-73)  d = d_p * (1 + (2 - 2 n_i.n_j)),  d_p as above on channels 0..2
+//   SSD  (KNN/csrc/cuda/knn.cu:73-76)  d = sum_c fma(t, t, d), t = ref_c - query_c
+// Ties: a candidate equal to the current k-th is rejected and an equal candidate is
+// placed after its equals, so the lower reference index wins (knn.cu:125,149).
+#include "common.cuh"
+
+#include <math_constants.h>
+#include <type_traits>
+
+namespace gcanet {
+
+enum { METRIC_L2 = 0, METRIC_PN = 1, METRIC_SSD = 2 };
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kWarps = 8;               // warps per CTA
+constexpr int kThreads = kWarps * 32;
+
+// ---------------------------------------------------------------------------------
+// squared norms, reference order: sum_c fl(x_c * x_c), sequential, no FMA contraction
+// ---------------------------------------------------------------------------------
+__global__ void sqnorm_kernel(const float *__restrict__ x, float *__restrict__ out, int C, int Cuse, int N) {
+    int b = blockIdx.y;
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float *p = x + (size_t)b * C * N + n;
+    float s = 0.f;
+    for (int c = 0; c < Cuse; ++c) {
+        float v = p[(size_t)c * N];
+        s = __fadd_rn(s, __fmul_rn(v, v));
+    }
+    out[(size_t)b * N + n] = s;
+}
+
+// ---------------------------------------------------------------------------------
+// warp-distributed ascending list
+// ---------------------------------------------------------------------------------
+template <int KS>
+struct WarpList {
+    float v[KS];
+    int id[KS];
+
+    // The list has 32*KS positions but only the last k are real: the first 32*KS - k hold
+    // -inf sentinels that never move, so the k-th best always sits in the last position
+    // and the threshold is one shuffle from a fixed register.
+    __device__ __forceinline__ void init(int k, int lane) {
+#pragma unroll
+        for (int s = 0; s < KS; ++s) { v[s] = (s * 32 + lane < 32 * KS - k) ? -CUDART_INF_F : CUDART_INF_F; id[s] = 0; }
+    }
+    // All lanes pass the same (d, j).
+    __device__ __forceinline__ void insert(float d, int j, int lane) {
+        int pos = 0;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) pos += __popc(__ballot_sync(FULL, v[s] <= d));
+#pragma unroll
+        for (int t = 0; t < KS; ++t) {
+            const int s = KS - 1 - t;   // high slots first: slot s reads the old slot s-1
+            float uv = __shfl_up_sync(FULL, v[s], 1);
+            int ui = __shfl_up_sync(FULL, id[s], 1);
+            if (s > 0) {
+                float cv = __shfl_sync(FULL, v[s - 1], 31);
+                int ci = __shfl_sync(FULL, id[s - 1], 31);
+                if (lane == 0) { uv = cv; ui = ci; }
+            }
+            int p = s * 32 + lane;
+            if (p == pos) { v[s] = d; id[s] = j; }
+            else if (p > pos) { v[s] = uv; id[s] = ui; }
+        }
+    }
+    __device__ __forceinline__ float kth() const { return __shfl_sync(FULL, v[KS - 1], 31); }
+};
+
+// compile-time loop: keeps per-query state indexed by constants so it stays in registers
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+template <int KS>
+__device__ __forceinline__ void offer(WarpList<KS> &L, float &thr, float d, int j0, int lane) {
+    unsigned m = __ballot_sync(FULL, d < thr);
+    while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        float dd = __shfl_sync(FULL, d, src);
+        if (dd < thr) {
+            L.insert(dd, j0 + src, lane);
+            thr = L.kth();
+        }
+    }
+}
+
+struct ScanArgs {
+    const float *ref;       // [B][C][Nr]
+    const float *qry;       // [B][C][Nq]
+    const float *ref_norm;  // [B][Nr]   (L2 / PN)
+    const float *qry_norm;  // [B][Nq]
+    int C, Nr, Nq, k;
+    int step, kout;         // dilation: list position p is written to column p/step when p % step == 0
+    int64_t *idx64;
+    int32_t *idx32;
+    float *dist;            // optional; sqrt(d) is written (KNN_CUDA path)
+    int k_major;            // 0: out[b][q][col]   1: out[b][col][q]
+    int index_base;
+    int TR;                 // reference tile (multiple of 32)
+};
+
+// CDIM > 0: compile-time dimension, queries in registers.  CDIM == 0: runtime C, queries in smem.
+template <int CDIM, int METRIC, int KS, int R>
+__global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
+    extern __shared__ float smem[];
+    const int C = CDIM > 0 ? CDIM : a.C;
+    const int TR = a.TR;
+    constexpr int QPB = kWarps * R;
+    float *rs = smem;                 // [C][TR]
+    float *rn = rs + (size_t)C * TR;  // [TR]
+    float *qs = rn + TR;              // [C][QPB]
+
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * QPB + warp * R;
+    const float *ref = a.ref + (size_t)b * C * a.Nr;
+    const float *qry = a.qry + (size_t)b * C * a.Nq;
+
+    // stage this CTA's queries (zero for out-of-range ones)
+    for (int e = threadIdx.x; e < C * QPB; e += kThreads) {
+        int c = e / QPB, qq = e % QPB;
+        int q = blockIdx.x * QPB + qq;
+        qs[e] = q < a.Nq ? qry[(size_t)c * a.Nq + q] : 0.f;
+    }
+    __syncthreads();
+
+    float qreg[R][CDIM > 0 ? CDIM : 1];
+    float qn[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (CDIM > 0) {
+#pragma unroll
+            for (int c = 0; c < (CDIM > 0 ? CDIM : 1); ++c) qreg[r][c] = qs[c * QPB + warp * R + r];
+        }
+        qn[r] = 0.f;
+        if (METRIC != METRIC_SSD) {
+            int q = q0 + r;
+            qn[r] = q < a.Nq ? a.qry_norm[(size_t)b * a.Nq + q] : 0.f;
+        }
+    }
+
+    WarpList<KS> L[R];
+    float thr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { L[r].init(a.k, lane); thr[r] = CUDART_INF_F; }
+
+    for (int t0 = 0; t0 < a.Nr; t0 += TR) {
+        __syncthreads();   // previous tile fully consumed
+        for (int e = threadIdx.x; e < C * TR; e += kThreads) {
+            int c = e / TR, jj = e % TR;
+            int j = t0 + jj;
+            rs[e] = j < a.Nr ? ref[(size_t)c * a.Nr + j] : 0.f;
+        }
+        if (METRIC != METRIC_SSD) {
+            for (int jj = threadIdx.x; jj < TR; jj += kThreads) {
+                int j = t0 + jj;
+                rn[jj] = j < a.Nr ? a.ref_norm[(size_t)b * a.Nr + j] : 0.f;
+            }
+        }
+        __syncthreads();
+
+        const int groups = min(TR, a.Nr - t0 + 31) >> 5;
+        for (int g = 0; g < groups; ++g) {
+            const int jj = g * 32 + lane;
+            const int j = t0 + jj;
+            float d[R];
+            if (CDIM > 0) {
+                float rv[CDIM > 0 ? CDIM : 1];
+#pragma unroll
+                for (int c = 0; c < (CDIM > 0 ? CDIM : 1); ++c) rv[c] = rs[c * TR + jj];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (METRIC == METRIC_SSD) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int c = 0; c < (CDIM > 0 ? CDIM : 1); ++c) {
+                            float t = rv[c] - qreg[r][c];
+                            s = fmaf(t, t, s);
+                        }
+                        d[r] = s;
+                    } else if (METRIC == METRIC_L2) {
+                        float t = __fmul_rn(qreg[r][0], rv[0]);
+#pragma unroll
+                        for (int c = 1; c < (CDIM > 0 ? CDIM : 1); ++c) t = fmaf(qreg[r][c], rv[c], t);
+                        d[r] = __fadd_rn(fmaf(-2.f, t, rn[jj]), qn[r]);
+                    } else {   // METRIC_PN, CDIM == 6
+                        float tp = __fmul_rn(qreg[r][0], rv[0]);
+                        tp = fmaf(qreg[r][1 % (CDIM > 0 ? CDIM : 1)], rv[1 % (CDIM > 0 ? CDIM : 1)], tp);
+                        tp = fmaf(qreg[r][2 % (CDIM > 0 ? CDIM : 1)], rv[2 % (CDIM > 0 ? CDIM : 1)], tp);
+                        float tn = __fmul_rn(qreg[r][3 % (CDIM > 0 ? CDIM : 1)], rv[3 % (CDIM > 0 ? CDIM : 1)]);
+                        tn = fmaf(qreg[r][4 % (CDIM > 0 ? CDIM : 1)], rv[4 % (CDIM > 0 ? CDIM : 1)], tn);
+                        tn = fmaf(qreg[r][5 % (CDIM > 0 ? CDIM : 1)], rv[5 % (CDIM > 0 ? CDIM : 1)], tn);
+                        float dp = __fadd_rn(fmaf(-2.f, tp, rn[jj]), qn[r]);
+                        float dn = fmaf(-2.f, tn, 2.f);
+                        d[r] = __fmul_rn(dp, __fadd_rn(1.f, dn));
+                    }
+                }
+            } else {
+                float acc[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = 0.f;
+                const float *rp = rs + jj;
+                const float *qp = qs + warp * R;
+#pragma unroll 4
+                for (int c = 0; c < C; ++c) {
+                    float rvv = rp[(size_t)c * TR];
+                    float qv[R];
+                    if (R % 4 == 0) {
+#pragma unroll
+                        for (int r4 = 0; r4 < R / 4; ++r4) {
+                            float4 q4 = *reinterpret_cast<const float4 *>(qp + c * QPB + r4 * 4);
+                            qv[r4 * 4 + 0] = q4.x; qv[r4 * 4 + 1] = q4.y; qv[r4 * 4 + 2] = q4.z; qv[r4 * 4 + 3] = q4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) qv[r] = qp[c * QPB + r];
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (METRIC == METRIC_SSD) {
+                            float t = rvv - qv[r];
+                            acc[r] = fmaf(t, t, acc[r]);
+                        } else {
+                            acc[r] = fmaf(qv[r], rvv, acc[r]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    d[r] = METRIC == METRIC_SSD ? acc[r] : __fadd_rn(fmaf(-2.f, acc[r], rn[jj]), qn[r]);
+            }
+            const bool valid = j < a.Nr;
+            static_for<0, R>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                float dr = valid ? d[r] : CUDART_INF_F;
+                offer<KS>(L[r], thr[r], dr, t0 + g * 32, lane);
+            });
+        }
+    }
+
+    // write the lists
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int q = q0 + r;
+        if (q >= a.Nq) continue;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            int p = s * 32 + lane - (32 * KS - a.k);   // rank among the k real entries
+            if (p >= 0 && p % a.step == 0) {
+                int col = p / a.step;
+                size_t o = a.k_major ? ((size_t)b * a.kout + col) * a.Nq + q
+                                     : ((size_t)b * a.Nq + q) * a.kout + col;
+                int id = L[r].id[s] + a.index_base;
+                if (a.idx64) a.idx64[o] = id;
+                if (a.idx32) a.idx32[o] = id;
+                if (a.dist) a.dist[o] = sqrtf(L[r].v[s]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// k > 128: one query per warp, the list lives in shared memory.  Generic and slow;
+// exists so the KNN_CUDA entry point covers the reference's own test grid (k = 400).
+// ---------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads) knn_scan_bigk_kernel(ScanArgs a) {
+    extern __shared__ float smem[];
+    const int C = a.C, TR = a.TR, k = a.k;
+    float *rs = smem;                        // [C][TR]
+    float *rn = rs + (size_t)C * TR;         // [TR]
+    float *qs = rn + TR;                     // [kWarps][C]
+    float *lv = qs + kWarps * C;             // [kWarps][k]
+    int *li = reinterpret_cast<int *>(lv + (size_t)kWarps * k);
+
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * kWarps + warp;
+    const float *ref = a.ref + (size_t)b * C * a.Nr;
+    const float *qry = a.qry + (size_t)b * C * a.Nq;
+    float *mv = lv + (size_t)warp * k;
+    int *mi = li + (size_t)warp * k;
+
+    for (int c = lane; c < C; c += 32) qs[warp * C + c] = q < a.Nq ? qry[(size_t)c * a.Nq + q] : 0.f;
+    for (int p = lane; p < k; p += 32) { mv[p] = CUDART_INF_F; mi[p] = 0; }
+    float qn = 0.f;
+    if (METRIC != METRIC_SSD && q < a.Nq) qn = a.qry_norm[(size_t)b * a.Nq + q];
+    float thr = CUDART_INF_F;
+
+    for (int t0 = 0; t0 < a.Nr; t0 += TR) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < C * TR; e += kThreads) {
+            int c = e / TR, jj = e % TR;
+            int j = t0 + jj;
+            rs[e] = j < a.Nr ? ref[(size_t)c * a.Nr + j] : 0.f;
+        }
+        if (METRIC != METRIC_SSD)
+            for (int jj = threadIdx.x; jj < TR; jj += kThreads) {
+                int j = t0 + jj;
+                rn[jj] = j < a.Nr ? a.ref_norm[(size_t)b * a.Nr + j] : 0.f;
+            }
+        __syncthreads();
+        const int groups = min(TR, a.Nr - t0 + 31) >> 5;
+        for (int g = 0; g < groups; ++g) {
+            const int jj = g * 32 + lane;
+            float d;
+            if (METRIC == METRIC_PN) {
+                const float *qq = qs + warp * C;
+                float tp = __fmul_rn(qq[0], rs[jj]);
+                tp = fmaf(qq[1], rs[TR + jj], tp);
+                tp = fmaf(qq[2], rs[2 * TR + jj], tp);
+                float tn = __fmul_rn(qq[3], rs[3 * TR + jj]);
+                tn = fmaf(qq[4], rs[4 * TR + jj], tn);
+                tn = fmaf(qq[5], rs[5 * TR + jj], tn);
+                float dp = __fadd_rn(fmaf(-2.f, tp, rn[jj]), qn);
+                d = __fmul_rn(dp, __fadd_rn(1.f, fmaf(-2.f, tn, 2.f)));
+            } else {
+                float acc = 0.f;
+                for (int c = 0; c < C; ++c) {
+                    float rv = rs[(size_t)c * TR + jj], qv = qs[warp * C + c];
+                    if (METRIC == METRIC_SSD) { float t = rv - qv; acc = fmaf(t, t, acc); }
+                    else acc = fmaf(qv, rv, acc);
+                }
+                d = METRIC == METRIC_SSD ? acc : __fadd_rn(fmaf(-2.f, acc, rn[jj]), qn);
+            }
+            if (t0 + jj >= a.Nr) d = CUDART_INF_F;
+            unsigned m = __ballot_sync(FULL, d < thr);
+            while (m) {
+                int src = __ffs(m) - 1;
+                m &= m - 1;
+                float dd = __shfl_sync(FULL, d, src);
+                if (!(dd < thr)) continue;
+                int jnew = t0 + g * 32 + src;
+                int pos = 0;
+                for (int base = 0; base < k; base += 32) {
+                    int p = base + lane;
+                    pos += __popc(__ballot_sync(FULL, p < k && mv[p] <= dd));
+                }
+                for (int base = ((k - 1) >> 5) << 5; base >= 0; base -= 32) {
+                    int p = base + lane;
+                    float nv = 0.f; int ni = 0; bool w = false;
+                    if (p < k && p > pos) { nv = mv[p - 1]; ni = mi[p - 1]; w = true; }
+                    else if (p == pos) { nv = dd; ni = jnew; w = true; }
+                    __syncwarp();
+                    if (w) { mv[p] = nv; mi[p] = ni; }
+                    __syncwarp();
+                    if (base <= pos) break;
+                }
+                thr = mv[k - 1];
+            }
+        }
+    }
+    __syncwarp();
+    if (q < a.Nq) {
+        for (int p = lane; p < k; p += 32) {
+            if (p % a.step) continue;
+            int col = p / a.step;
+            size_t o = a.k_major ? ((size_t)b * a.kout + col) * a.Nq + q : ((size_t)b * a.Nq + q) * a.kout + col;
+            int id = mi[p] + a.index_base;
+            if (a.idx64) a.idx64[o] = id;
+            if (a.idx32) a.idx32[o] = id;
+            if (a.dist) a.dist[o] = sqrtf(mv[p]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host dispatch
+// ---------------------------------------------------------------------------------
+static int pick_tile(int C, int Nr) {
+    int tr = 16384 / (C > 0 ? C : 1);     // <= 64 KB of reference rows
+    tr = tr / 32 * 32;
+    if (tr > 1024) tr = 1024;
+    if (tr < 32) tr = 32;
+    int need = (Nr + 31) / 32 * 32;
+    return tr < need ? tr : need;
+}
+
+template <int CDIM, int METRIC, int KS, int R>
+static int launch_scan(ScanArgs a, int B, cudaStream_t st) {
+    constexpr int QPB = kWarps * R;
+    size_t smem = ((size_t)a.C * a.TR + a.TR + (size_t)a.C * QPB) * sizeof(float);
+    auto kern = knn_scan_kernel<CDIM, METRIC, KS, R>;
+    if (smem > 48 * 1024) GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(a.Nq, QPB), B);
+    kern<<<grid, kThreads, smem, st>>>(a);
+    GCANET_LAUNCH_OK("knn_scan_kernel");
+    return GCANET_OK;
+}
+
+template <int CDIM, int METRIC, int R>
+static int launch_scan_k(ScanArgs a, int B, cudaStream_t st) {
+    if (a.k <= 32) return launch_scan<CDIM, METRIC, 1, R>(a, B, st);
+    if (a.k <= 64) return launch_scan<CDIM, METRIC, 2, R>(a, B, st);
+    return launch_scan<CDIM, METRIC, 4, R>(a, B, st);
+}
+
+template <int METRIC>
+static int launch_bigk(ScanArgs a, int B, cudaStream_t st) {
+    // shrink the reference tile so tile + lists fit in 200 KB
+    size_t list_bytes = (size_t)kWarps * a.k * 8 + (size_t)kWarps * a.C * 4;
+    int tr = a.TR;
+    while (tr > 32 && ((size_t)a.C * tr + tr) * 4 + list_bytes > 200 * 1024) tr -= 32;
+    a.TR = tr;
+    size_t smem = ((size_t)a.C * tr + tr) * 4 + list_bytes;
+    if (smem > 220 * 1024) { set_error("knn: C=%d with k=%d does not fit in shared memory", a.C, a.k); return GCANET_ERR_INVALID_ARGUMENT; }
+    auto kern = knn_scan_bigk_kernel<METRIC>;
+    GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(a.Nq, kWarps), B);
+    kern<<<grid, kThreads, smem, st>>>(a);
+    GCANET_LAUNCH_OK("knn_scan_bigk_kernel");
+    return GCANET_OK;
+}
+
+static int launch_sqnorm(const float *x, float *out, int B, int C, int Cuse, int N, cudaStream_t st) {
+    dim3 grid(ceil_div(N, 256), B);
+    sqnorm_kernel<<<grid, 256, 0, st>>>(x, out, C, Cuse, N);
+    GCANET_LAUNCH_OK("sqnorm_kernel");
+    return GCANET_OK;
+}
+
+int knn_graph_cuda_cores(const float *x, int B, int C, int N, int k1, int k2, int metric, int64_t *idx64,
+                         int32_t *idx32, float *norms, cudaStream_t st) {
+    int rc = launch_sqnorm(x, norms, B, C, metric == GCANET_METRIC_POINTS_NORMALS ? 3 : C, N, st);
+    if (rc) return rc;
+    ScanArgs a{};
+    a.ref = x; a.qry = x; a.ref_norm = norms; a.qry_norm = norms;
+    a.C = C; a.Nr = N; a.Nq = N; a.k = k2;
+    a.step = k2 / k1; a.kout = gcanet_knn_graph_columns(k1, k2);
+    a.idx64 = idx64; a.idx32 = idx32; a.dist = nullptr; a.k_major = 0; a.index_base = 0;
+    a.TR = pick_tile(C, N);
+    if (metric == GCANET_METRIC_POINTS_NORMALS) {
+        if (k2 > 128) return launch_bigk<METRIC_PN>(a, B, st);
+        return launch_scan_k<6, METRIC_PN, 4>(a, B, st);
+    }
+    if (k2 > 128) return launch_bigk<METRIC_L2>(a, B, st);
+    if (C == 3) return launch_scan_k<3, METRIC_L2, 4>(a, B, st);
+    return launch_scan_k<0, METRIC_L2, 4>(a, B, st);
+}
+
+}  // namespace gcanet
+
+using namespace gcanet;
+
+extern "C" int gcanet_knn_graph_columns(int k1, int k2) {
+    if (k1 < 1 || k2 < k1) return 0;
+    int step = k2 / k1;
+    return (k2 + step - 1) / step;
+}
+
+extern "C" size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric) {
+    (void)C; (void)k2; (void)metric;
+    return align_up((size_t)B * N * sizeof(float));
+}
+
+extern "C" int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int k2, int metric,
+                                int64_t *idx64, int32_t *idx32, void *ws, size_t ws_bytes,
+                                gcanet_stream_t stream) {
+    GCANET_REQUIRE(x != nullptr && (idx64 != nullptr || idx32 != nullptr), "knn_graph: null pointer");
+    GCANET_REQUIRE(B >= 1 && C >= 1 && N >= 1, "knn_graph: bad shape B=%d C=%d N=%d", B, C, N);
+    GCANET_REQUIRE(k1 >= 1 && k2 >= k1, "knn_graph: need 1 <= k1 <= k2 (k1=%d k2=%d)", k1, k2);
+    GCANET_REQUIRE(k2 <= N, "knn_graph: k2=%d exceeds the number of points N=%d (topk would raise, M4:43)", k2, N);
+    GCANET_REQUIRE(k2 <= 1024, "knn_graph: k2=%d > 1024 unsupported", k2);
+    GCANET_REQUIRE(metric == GCANET_METRIC_L2 || metric == GCANET_METRIC_POINTS_NORMALS, "knn_graph: bad metric %d", metric);
+    GCANET_REQUIRE(metric != GCANET_METRIC_POINTS_NORMALS || C == 6,
+                   "knn_graph: the points x normals metric needs C = 6 (got %d)", C);
+    GCANET_REQUIRE(C <= 1024, "knn_graph: C=%d > 1024 unsupported", C);
+    if (ws == nullptr || ws_bytes < gcanet_knn_graph_workspace_bytes(B, C, N, k2, metric) ||
+        (reinterpret_cast<uintptr_t>(ws) % kAlign) != 0) {
+        set_error("knn_graph: workspace too small or misaligned (%zu bytes given)", ws_bytes);
+        return GCANET_ERR_WORKSPACE;
+    }
+    return knn_graph_cuda_cores(x, B, C, N, k1, k2, metric, idx64, idx32, static_cast<float *>(ws), as_stream(stream));
+}
+
+extern "C" size_t gcanet_knn_cuda_workspace_bytes(int batch, int dim, int ref_nb, int query_nb, int k) {
+    (void)batch; (void)dim; (void)ref_nb; (void)query_nb; (void)k;
+    return kAlign;   // the direct-difference metric needs no norms; kept for ABI symmetry
+}
+
+extern "C" int gcanet_knn_cuda(const float *ref, int ref_nb, const float *query, int query_nb, int dim, int k,
+                               int batch, int index_base, float *dist, int64_t *ind, void *ws, size_t ws_bytes,
+                               gcanet_stream_t stream) {
+    (void)ws; (void)ws_bytes;
+    GCANET_REQUIRE(ref && query && dist && ind, "knn_cuda: null pointer");
+    GCANET_REQUIRE(batch >= 1 && dim >= 1 && ref_nb >= 1 && query_nb >= 1, "knn_cuda: bad shape");
+    GCANET_REQUIRE(k >= 1 && k <= ref_nb, "knn_cuda: need 1 <= k <= ref_nb (k=%d ref_nb=%d)", k, ref_nb);
+    GCANET_REQUIRE(k <= 1024 && dim <= 1024, "knn_cuda: k or dim > 1024 unsupported");
+    GCANET_REQUIRE(index_base == 0 || index_base == 1, "knn_cuda: index_base must be 0 or 1");
+    ScanArgs a{};
+    a.ref = ref; a.qry = query; a.ref_norm = nullptr; a.qry_norm = nullptr;
+    a.C = dim; a.Nr = ref_nb; a.Nq = query_nb; a.k = k; a.step = 1; a.kout = k;
+    a.idx64 = ind; a.idx32 = nullptr; a.dist = dist; a.k_major = 1; a.index_base = index_base;
+    a.TR = pick_tile(dim, ref_nb);
+    cudaStream_t st = as_stream(stream);
+    if (k > 128) return launch_bigk<METRIC_SSD>(a, batch, st);
+    if (dim == 3) return launch_scan_k<3, METRIC_SSD, 4>(a, batch, st);
+    return launch_scan_k<0, METRIC_SSD, 4>(a, batch, st);
+}

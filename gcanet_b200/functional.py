@@ -1,0 +1,392 @@
+"""Reference-signature front end of the B200 kNN-graph + EdgeConv path.
+
+Every public function keeps the name, argument order, defaults, return arity, dtypes
+and tensor layouts of the reference function it replaces (cited per function; paths are
+relative to the reference root, M4 = models/dgcnn-hais-concat-direct-4.py), so a call
+site can switch by changing its import.  All compute goes through the C-ABI of
+libgcanet_b200.so; there is no CPU or eager fallback -- CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as _ct
+
+import torch
+
+from . import _cabi
+from ._cabi import EdgeConvDesc, call, ptr, require_cuda, stream, workspace
+
+METRIC_L2 = 0
+METRIC_POINTS_NORMALS = 1
+EDGE_DIFF_CENTER = 0
+EDGE_NORMAL_ANGLE = 1
+
+
+
+# Optional per-call device timing (bench.py): CUDA events on the launching stream around
+# each C-ABI compute call.  Off by default; costs two event records per call when on.
+_timing = None
+
+
+def enable_kernel_timing(flag: bool = True) -> None:
+    global _timing
+    _timing = [] if flag else None
+
+
+def kernel_timings_ms() -> dict:
+    """{tag: [ms, ...]} for the calls recorded since the last enable; call after a synchronize."""
+    out = {}
+    for tag, a, b in (_timing or []):
+        out.setdefault(tag, []).append(a.elapsed_time(b))
+    return out
+
+
+class _timed:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if _timing is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timing is not None:
+            self.b.record()
+            _timing.append((self.tag, self.a, self.b))
+        return False
+
+
+def _as_f32_contig(x: torch.Tensor, name: str) -> torch.Tensor:
+    require_cuda(x, name, contiguous=False)
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous()
+
+
+# ----------------------------------------------------------------------------------
+# kNN graph (torch path)
+# ----------------------------------------------------------------------------------
+def knn_graph(x: torch.Tensor, k1: int, k2: int, metric: int = METRIC_L2, want64: bool = True,
+              want32: bool = False):
+    """x [B, C, N] -> (idx64 or None, idx32 or None), each [B, N, kout]."""
+    x = _as_f32_contig(x.detach(), "x")
+    if x.dim() != 3:
+        raise RuntimeError(f"x must be [B, C, N] (got {tuple(x.shape)})")
+    B, C, N = x.shape
+    k1, k2 = int(k1), int(k2)
+    L = _cabi.lib()
+    kout = L.gcanet_knn_graph_columns(k1, k2)
+    if kout <= 0:
+        raise RuntimeError(f"need 1 <= k1 <= k2 (k1={k1}, k2={k2})")
+    with torch.cuda.device(x.device):
+        i64 = torch.empty((B, N, kout), dtype=torch.int64, device=x.device) if want64 else None
+        i32 = torch.empty((B, N, kout), dtype=torch.int32, device=x.device) if want32 else None
+        ws_bytes = L.gcanet_knn_graph_workspace_bytes(B, C, N, k2, metric)
+        ws = workspace(ws_bytes, x.device)
+        with _timed(f"knn_graph[C={C},metric={metric}]"):
+            call("gcanet_knn_graph", ptr(x), B, C, N, k1, k2, metric, ptr(i64), ptr(i32), ptr(ws), ws.numel(), stream())
+    return i64, i32
+
+
+def knn(x, k1, k2=None):
+    """Replaces ``knn(x, k1, k2)`` (M4:30-47) and, called with two arguments, ``knn(x, k)``
+    of models/splinenet.py:9-22.  x [B, C, N] -> idx [B, N, k1] int64, nearest first, the
+    point itself included, reference dilation columns ``arange(0, k2, k2 // k1)``."""
+    if k2 is None:
+        k2 = k1
+    return knn_graph(x, k1, k2, METRIC_L2)[0]
+
+
+def knn_points_normals(x, k1, k2):
+    """Replaces ``knn_points_normals`` (M4:50-90); x is [B, 6, N] (xyz + unit normals)."""
+    return knn_graph(x, k1, k2, METRIC_POINTS_NORMALS)[0]
+
+
+# ----------------------------------------------------------------------------------
+# materialised graph features
+# ----------------------------------------------------------------------------------
+class _GraphFeature(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, variant):
+        B, C, N = x.shape
+        k = idx.shape[2]
+        L = _cabi.lib()
+        F = L.gcanet_graph_feature_channels(C, variant)
+        with torch.cuda.device(x.device):
+            out = torch.empty((B, N, k, F), dtype=torch.float32, device=x.device)
+            ws = workspace(L.gcanet_graph_feature_workspace_bytes(B, C, N, k, variant), x.device)
+            call("gcanet_graph_feature", ptr(x), ptr(idx), ptr(out), B, C, N, k, variant, ptr(ws), ws.numel(), stream())
+        ctx.save_for_backward(x, idx)
+        ctx.variant = variant
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, idx = ctx.saved_tensors
+        B, C, N = x.shape
+        k = idx.shape[2]
+        L = _cabi.lib()
+        g = grad_out.contiguous().float()
+        with torch.cuda.device(x.device):
+            gx = torch.empty_like(x)
+            ws = workspace(L.gcanet_graph_feature_grad_workspace_bytes(B, C, N, k, ctx.variant), x.device)
+            call("gcanet_graph_feature_grad", ptr(g), ptr(x), ptr(idx), ptr(gx), B, C, N, k, ctx.variant,
+                 ptr(ws), ws.numel(), stream())
+        return gx, None, None
+
+
+def _graph_feature(x, k1, k2, idx, metric, variant):
+    B, N = x.size(0), x.size(2)
+    x = _as_f32_contig(x.reshape(B, -1, N), "x")
+    if idx is None:
+        idx = knn_graph(x, k1, k2, metric)[0]
+    else:
+        require_cuda(idx, "idx", contiguous=False)
+        idx = idx.to(torch.int64).contiguous()
+        if idx.dim() != 3 or idx.shape[0] != B or idx.shape[1] != N:
+            raise RuntimeError(f"idx must be [B, N, k] (got {tuple(idx.shape)})")
+        if idx.shape[2] != k1:
+            # the reference's view(batch, num_points, k1, dims) fails the same way (M4:120)
+            raise RuntimeError(f"idx has {idx.shape[2]} columns but k1={k1}")
+    out = _GraphFeature.apply(x, idx, variant)
+    return out.permute(0, 3, 1, 2)          # the reference returns this permuted view (M4:123)
+
+
+def get_graph_feature(x, k1=20, k2=20, idx=None):
+    """Replaces ``get_graph_feature`` (M4:93-124): [B, C, N] -> [B, 2C, N, k1], a permuted view
+    of a contiguous [B, N, k1, 2C] buffer holding (x_j - x_i, x_i); differentiable in x."""
+    return _graph_feature(x, k1, k2, idx, METRIC_L2, EDGE_DIFF_CENTER)
+
+
+def get_graph_feature_with_normals(x, k1=20, k2=20, idx=None):
+    """Replaces ``get_graph_feature_with_normals`` (M4:127-161): neighbours under the
+    points x normals metric, same (x_j - x_i, x_i) feature on all 6 channels."""
+    return _graph_feature(x, k1, k2, idx, METRIC_POINTS_NORMALS, EDGE_DIFF_CENTER)
+
+
+def get_graph_feature_with_normals_g(x, k1=20, k2=20, idx=None):
+    """Replaces ``get_graph_feature_with_normals_g`` (M4:164-205): [B, 6, N] -> [B, 7, N, k1] =
+    (clamp(n_i . n_j, -0.99, 0.99), n_j - n_i, n_i)."""
+    return _graph_feature(x, k1, k2, idx, METRIC_POINTS_NORMALS, EDGE_NORMAL_ANGLE)
+
+
+def splinenet_knn(x, k):
+    """``knn(x, k)`` of models/splinenet.py:9-22."""
+    return knn(x, k, k)
+
+
+def splinenet_get_graph_feature(x, k=20, idx=None):
+    """``get_graph_feature(x, k=20, idx=None)`` of models/splinenet.py:25-53."""
+    return get_graph_feature(x, k1=k, k2=k, idx=idx)
+
+
+# ----------------------------------------------------------------------------------
+# KNN_CUDA path
+# ----------------------------------------------------------------------------------
+def knn_cuda(ref: torch.Tensor, query: torch.Tensor, k: int, index_base: int = 0):
+    """Batched core of the KNN_CUDA replacement.  ref [B, dim, Nr], query [B, dim, Nq] ->
+    (dist [B, k, Nq] fp32 Euclidean, ind [B, k, Nq] int64)."""
+    require_cuda(ref, "ref", torch.float32)
+    require_cuda(query, "query", torch.float32)
+    if ref.dim() != 3 or query.dim() != 3 or ref.shape[0] != query.shape[0] or ref.shape[1] != query.shape[1]:
+        raise RuntimeError(f"ref.shape={tuple(ref.shape)} != query.shape={tuple(query.shape)}")
+    B, dim, nr = ref.shape
+    nq = query.shape[2]
+    L = _cabi.lib()
+    with torch.cuda.device(ref.device):
+        dist = torch.empty((B, k, nq), dtype=torch.float32, device=ref.device)
+        ind = torch.empty((B, k, nq), dtype=torch.int64, device=ref.device)
+        ws = workspace(L.gcanet_knn_cuda_workspace_bytes(B, dim, nr, nq, k), ref.device)
+        call("gcanet_knn_cuda", ptr(ref), nr, ptr(query), nq, dim, int(k), B, index_base, ptr(dist), ptr(ind),
+             ptr(ws), ws.numel(), stream())
+    return dist, ind
+
+
+def knn_cuda_pair(ref, query, k):
+    """Replaces ``knn(ref, query, k)`` of models/KNN_CUDA/knn_cuda/__init__.py:41-44:
+    ref [dim, Nr], query [dim, Nq] -> (dist [k, Nq], ind [k, Nq] int64, 0-based)."""
+    d, i = knn_cuda(ref.contiguous()[None], query.contiguous()[None], k, index_base=0)
+    return d[0], i[0]
+
+
+class KNN(torch.nn.Module):
+    """Replaces ``KNN(k, transpose_mode=False)`` (models/KNN_CUDA/knn_cuda/__init__.py:54-74).
+    transpose_mode=False: ref [B, dim, Nr], query [B, dim, Nq] -> D, I [B, k, Nq];
+    transpose_mode=True : ref [B, Nr, dim], query [B, Nq, dim] -> D, I [B, Nq, k].
+    The reference loops over the batch in Python; here the batch is one launch."""
+
+    def __init__(self, k, transpose_mode=False):
+        super().__init__()
+        self.k = k
+        self._t = transpose_mode
+
+    def forward(self, ref, query):
+        assert ref.size(0) == query.size(0), "ref.shape={} != query.shape={}".format(ref.shape, query.shape)
+        with torch.no_grad():
+            if self._t:
+                ref, query = ref.transpose(1, 2), query.transpose(1, 2)
+            D, I = knn_cuda(ref.float().contiguous(), query.float().contiguous(), self.k, index_base=0)
+            if self._t:
+                D, I = D.transpose(1, 2).contiguous(), I.transpose(1, 2).contiguous()
+        return D, I
+
+
+# ----------------------------------------------------------------------------------
+# PN2 grouping
+# ----------------------------------------------------------------------------------
+class GroupingOperation(torch.autograd.Function):
+    """Replaces ``GroupingOperation`` (PN2 pointnet2_utils.py:194-240): features [B, C, N] fp32
+    contiguous, idx [B, npoint, nsample] int32 contiguous -> [B, C, npoint, nsample].  Like the
+    reference's C++ checks (group_points.cpp:13-16) wrong dtype / layout / device raises."""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        require_cuda(features, "features", torch.float32)
+        require_cuda(idx, "idx", torch.int32)
+        B, C, N = features.shape
+        _, npnt, ns = idx.shape
+        with torch.cuda.device(features.device):
+            out = torch.empty((B, C, npnt, ns), dtype=torch.float32, device=features.device)
+            call("gcanet_group_points", B, C, N, npnt, ns, ptr(features), ptr(idx), ptr(out), stream())
+        ctx.save_for_backward(idx)
+        ctx.n = N
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        g = grad_out.contiguous()
+        B, C, npnt, ns = g.shape
+        with torch.cuda.device(g.device):
+            gp = torch.empty((B, C, ctx.n), dtype=torch.float32, device=g.device)
+            call("gcanet_group_points_grad", B, C, ctx.n, npnt, ns, ptr(g), ptr(idx), ptr(gp), stream())
+        return gp, None
+
+
+grouping_operation = GroupingOperation.apply
+
+
+def knn_point(group_size, point_cloud, query_cloud):
+    """Replaces ``knn_point`` (models/search_knn.py:11-14): (dist, idx), both [B, k, Nq]."""
+    return KNN(k=group_size, transpose_mode=False)(point_cloud, query_cloud)
+
+
+def group_points(group_size, point_cloud, query_cloud, point_features=None):
+    """Replaces ``group_points`` (models/search_knn.py:23-39): returns
+    (grouped_points [B, 3, Nq, k], grouped_features [B, F, Nq, k] or None, idx [B, Nq, k] int32)."""
+    _, idx = knn_point(group_size, point_cloud, query_cloud)
+    idx = idx.permute(0, 2, 1).type(torch.int32).contiguous()
+    grouped_points = grouping_operation(point_cloud.contiguous(), idx)
+    grouped_features = None if point_features is None else grouping_operation(point_features.contiguous(), idx)
+    return grouped_points, grouped_features, idx
+
+
+# ----------------------------------------------------------------------------------
+# fused EdgeConv block
+# ----------------------------------------------------------------------------------
+def to_point_major(x_cn: torch.Tensor, ld: int | None = None) -> torch.Tensor:
+    """[B, C, N] -> [B, N, ld] (ld = C rounded up to a multiple of 4 by default, zero padded)."""
+    require_cuda(x_cn, "x", torch.float32)
+    B, C, N = x_cn.shape
+    ld = ld or (C + 3) // 4 * 4
+    with torch.cuda.device(x_cn.device):
+        out = torch.empty((B, N, ld), dtype=torch.float32, device=x_cn.device)
+        call("gcanet_cn_to_nc", ptr(x_cn), ptr(out), B, C, N, ld, stream())
+    return out
+
+
+def to_channel_major(x_nc: torch.Tensor, C: int | None = None) -> torch.Tensor:
+    require_cuda(x_nc, "x", torch.float32)
+    B, N, ld = x_nc.shape
+    C = C or ld
+    with torch.cuda.device(x_nc.device):
+        out = torch.empty((B, C, N), dtype=torch.float32, device=x_nc.device)
+        call("gcanet_nc_to_cn", ptr(x_nc), ptr(out), B, C, N, ld, stream())
+    return out
+
+
+class _ToPointMajor(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_cn, ld):
+        ctx.C = x_cn.shape[1]
+        return to_point_major(x_cn, ld)
+
+    @staticmethod
+    def backward(ctx, g):
+        return to_channel_major(g.contiguous(), ctx.C), None
+
+
+class _EdgeConv(torch.autograd.Function):
+    """out_nc, out_cn = EdgeConv(x_nc, idx32, weight [Cout, 2C], gamma, beta)."""
+
+    @staticmethod
+    def forward(ctx, x_nc, idx32, weight, gamma, beta, C, groups, eps, slope, want_cn):
+        require_cuda(x_nc, "x_nc", torch.float32)
+        require_cuda(idx32, "idx", torch.int32)
+        weight = weight.contiguous()
+        gamma, beta = gamma.contiguous(), beta.contiguous()
+        for t, nme in ((weight, "weight"), (gamma, "gamma"), (beta, "beta")):
+            require_cuda(t, nme, torch.float32)
+        B, N, ldx = x_nc.shape
+        k = idx32.shape[2]
+        Cout = weight.shape[0]
+        if weight.shape[1] != 2 * C:
+            raise RuntimeError(f"weight must be [Cout, {2 * C}] (got {tuple(weight.shape)})")
+        if tuple(idx32.shape[:2]) != (B, N):
+            raise RuntimeError(f"idx must be [B, N, k] (got {tuple(idx32.shape)})")
+        desc = EdgeConvDesc(B, N, C, ldx, Cout, k, groups, eps, slope)
+        L = _cabi.lib()
+        with torch.cuda.device(x_nc.device):
+            saved_bytes = L.gcanet_edgeconv_saved_bytes(_ct.byref(desc))
+            ws_bytes = L.gcanet_edgeconv_workspace_bytes(_ct.byref(desc))
+            if saved_bytes == 0:
+                raise RuntimeError("gcanet_b200 edgeconv: " + L.gcanet_last_error().decode())
+            saved = workspace(saved_bytes, x_nc.device)
+            ws = workspace(ws_bytes, x_nc.device)
+            out_nc = torch.empty((B, N, Cout), dtype=torch.float32, device=x_nc.device)
+            out_cn = torch.empty((B, Cout, N), dtype=torch.float32, device=x_nc.device) if want_cn else None
+            with _timed(f"edgeconv_fwd[C={C},Cout={Cout}]"):
+                call("gcanet_edgeconv_forward", _ct.byref(desc), ptr(x_nc), ptr(idx32), ptr(weight), ptr(gamma),
+                     ptr(beta), ptr(out_nc), ptr(out_cn), ptr(saved), ptr(ws), ws.numel(), stream())
+        ctx.save_for_backward(x_nc, idx32, weight, gamma, beta, saved)
+        ctx.desc = desc
+        ctx.want_cn = want_cn
+        return out_nc, out_cn
+
+    @staticmethod
+    def backward(ctx, g_nc, g_cn):
+        x_nc, idx32, weight, gamma, beta, saved = ctx.saved_tensors
+        desc = ctx.desc
+        L = _cabi.lib()
+        with torch.cuda.device(x_nc.device):
+            g = None
+            if g_nc is not None:
+                g = g_nc.contiguous()
+            if g_cn is not None:
+                t = to_point_major(g_cn.contiguous(), desc.Cout)
+                g = t if g is None else g + t
+            if g is None:
+                g = torch.zeros((desc.B, desc.N, desc.Cout), dtype=torch.float32, device=x_nc.device)
+            need_x = ctx.needs_input_grad[0]
+            gx = torch.empty_like(x_nc) if need_x else None
+            gw = torch.empty_like(weight)
+            gg = torch.empty_like(gamma)
+            gb = torch.empty_like(beta)
+            ws = workspace(L.gcanet_edgeconv_workspace_bytes(_ct.byref(desc)), x_nc.device)
+            with _timed(f"edgeconv_bwd[C={desc.C},Cout={desc.Cout}]"):
+                call("gcanet_edgeconv_backward", _ct.byref(desc), ptr(x_nc), ptr(idx32), ptr(weight), ptr(gamma),
+                     ptr(beta), ptr(g), ptr(saved), ptr(gx), ptr(gw), ptr(gg), ptr(gb), ptr(ws), ws.numel(), stream())
+        return gx, None, gw, gg, gb, None, None, None, None, None
+
+
+def edgeconv(x_nc, idx32, weight, gamma, beta, C, groups=2, eps=1e-5, slope=0.2, want_cn=True):
+    """Fused replacement of ``get_graph_feature(x, idx=idx) -> Conv2d(2C, Cout, 1, bias=False) ->
+    GroupNorm(groups, Cout) -> LeakyReLU(slope) -> max over k`` (M4:469-481, M4:494-505).
+
+    x_nc [B, N, ld] point-major (``to_point_major``), idx32 [B, N, k] int32, weight [Cout, 2C]
+    (or the conv's [Cout, 2C, 1, 1]).  Returns (out_nc [B, N, Cout], out_cn [B, Cout, N] or None);
+    differentiable in x_nc, weight, gamma, beta."""
+    w2 = weight.reshape(weight.shape[0], -1)
+    return _EdgeConv.apply(x_nc, idx32, w2, gamma, beta, int(C), int(groups), float(eps), float(slope), bool(want_cn))

@@ -1,0 +1,136 @@
+"""nn.Module front end: the reference's DGCNN encoder with the three EdgeConv layers (and
+the kNN graphs feeding them) running on the fused B200 kernels.
+
+``DGCNNEncoderGn`` keeps the reference's constructor signature, attribute names and
+``state_dict`` keys (``conv{1,2,3}.0.weight`` [Cout, 2C, 1, 1], ``bn{1,2,3}.{weight,bias}``,
+``bn4``/``bn5`` declared and unused, ``mlp1``, ``bnmlp1``; M4:455-486) so reference
+checkpoints load unchanged (trainer_new.py:126-134).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as G
+
+LEAKY_SLOPE = 0.2
+
+
+class DGCNNEncoderGn(nn.Module):
+    """Drop-in for ``DGCNNEncoderGn`` (M4:455-534).
+
+    forward(x [B, 3 or 6, N]) -> [B, 1280, N].  The three EdgeConv blocks and their dynamic
+    kNN graphs (M4:493-505 / M4:514-527) run through ``gcanet_b200.functional.edgeconv``;
+    the tail (Conv1d 256->1024 + GroupNorm + ReLU + global max + concat, M4:507-511) is the
+    consumer of the hot path and stays on torch (cuBLAS), see SURVEY.md 8(a) a7.
+    """
+
+    def __init__(self, mode=0, nn_nb=80, input_channels=3):
+        super().__init__()
+        self.k = nn_nb
+        self.dilation_factor = 1
+        self.mode = mode
+        self.drop = 0.0
+        self.bn1 = nn.GroupNorm(2, 64)
+        self.bn2 = nn.GroupNorm(2, 64)
+        self.bn3 = nn.GroupNorm(2, 128)
+        self.bn4 = nn.GroupNorm(4, 256)
+        self.bn5 = nn.GroupNorm(8, 1024)
+        c_in = input_channels * 2 if mode == 5 else input_channels
+        act = nn.LeakyReLU(negative_slope=LEAKY_SLOPE)
+        self.conv1 = nn.Sequential(nn.Conv2d(c_in, 64, kernel_size=1, bias=False), self.bn1, act)
+        self.conv2 = nn.Sequential(nn.Conv2d(64 * 2, 64, kernel_size=1, bias=False), self.bn2, act)
+        self.conv3 = nn.Sequential(nn.Conv2d(64 * 2, 128, kernel_size=1, bias=False), self.bn3, act)
+        self.mlp1 = nn.Conv1d(256, 1024, 1)
+        self.bnmlp1 = nn.GroupNorm(8, 1024)
+
+    # -- hot path ------------------------------------------------------------------
+    def _block(self, x_nc, x_cn, conv, C, metric):
+        """One EdgeConv layer: graph on x_cn (no gradient, M4:33), fused conv/GN/act/max on x_nc."""
+        _, idx32 = G.knn_graph(x_cn, self.k, self.k, metric, want64=False, want32=True)
+        gn = conv[1]
+        return G.edgeconv(x_nc, idx32, conv[0].weight, gn.weight, gn.bias, C, groups=gn.num_groups, eps=gn.eps,
+                          slope=conv[2].negative_slope, want_cn=True)
+
+    def edge_stack(self, x):
+        """x [B, C, N] -> (x1 [B,64,N], x2 [B,64,N], x3 [B,128,N]) -- the path bench.py times."""
+        if not x.is_cuda:
+            raise RuntimeError("gcanet_b200.DGCNNEncoderGn has no CPU path")
+        x = x.float().contiguous()
+        C = x.shape[1]
+        if 2 * C != self.conv1[0].in_channels:
+            raise RuntimeError(f"conv1 expects {self.conv1[0].in_channels} edge channels, input has C={C}")
+        metric = G.METRIC_POINTS_NORMALS if self.mode == 5 else G.METRIC_L2
+        x_nc = G._ToPointMajor.apply(x, (C + 3) // 4 * 4)
+        x1_nc, x1 = self._block(x_nc, x, self.conv1, C, metric)
+        x2_nc, x2 = self._block(x1_nc, x1, self.conv2, 64, G.METRIC_L2)
+        _, x3 = self._block(x2_nc, x2, self.conv3, 64, G.METRIC_L2)
+        return x1, x2, x3
+
+    # -- consumer (torch) ------------------------------------------------------------
+    def tail(self, x1, x2, x3):
+        batch_size, num_points = x1.shape[0], x1.shape[2]
+        x_features = torch.cat((x1, x2, x3), dim=1)
+        x = F.relu(self.bnmlp1(self.mlp1(x_features)))
+        x4 = x.max(dim=2)[0]
+        x4 = x4.view(batch_size, 1024, 1).repeat(1, 1, num_points)
+        return torch.cat([x4, x_features], 1)
+
+    def forward(self, x):
+        return self.tail(*self.edge_stack(x))
+
+
+class SoftProjection(nn.Module):
+    """Drop-in for ``SoftProjection`` (models/search_knn.py:44-174): soft nearest-neighbour
+    projection / feature propagation on top of ``knn_point`` + ``grouping_operation``; same
+    constructor, ``forward(point_cloud, query_cloud, point_features=None, action=...)``,
+    ``project`` / ``propagate`` / ``project_and_propagate`` and ``sigma()``."""
+
+    def __init__(self, group_size, initial_temperature=1.0, is_temperature_trainable=True, min_sigma=1e-4):
+        super().__init__()
+        self._group_size = group_size
+        self._temperature = torch.nn.Parameter(
+            torch.tensor(initial_temperature, requires_grad=is_temperature_trainable, dtype=torch.float32))
+        self._min_sigma = torch.tensor(min_sigma, dtype=torch.float32)
+
+    def forward(self, point_cloud, query_cloud, point_features=None, action="project"):
+        point_cloud = point_cloud.contiguous()
+        query_cloud = query_cloud.contiguous()
+        if action == "project":
+            return self.project(point_cloud, query_cloud)
+        elif action == "propagate":
+            return self.propagate(point_cloud, point_features, query_cloud)
+        elif action == "project_and_propagate":
+            return self.project_and_propagate(point_cloud, point_features, query_cloud)
+        raise ValueError("action should be one of the following: 'project', 'propagate', 'project_and_propagate'")
+
+    def _group_points(self, point_cloud, query_cloud, point_features=None):
+        grouped_points, grouped_features, _ = G.group_points(self._group_size, point_cloud, query_cloud, point_features)
+        return grouped_points, grouped_features
+
+    def _get_distances(self, grouped_points, query_cloud):
+        deltas = grouped_points - query_cloud.unsqueeze(-1).expand_as(grouped_points)
+        return torch.sum(deltas ** 2, dim=1, keepdim=True) / self.sigma()
+
+    def sigma(self):
+        device = self._temperature.device
+        return torch.max(self._temperature ** 2, self._min_sigma.to(device))
+
+    def project_and_propagate(self, point_cloud, point_features, query_cloud):
+        grouped_points, grouped_features = self._group_points(point_cloud, query_cloud, point_features)
+        weights = torch.softmax(-self._get_distances(grouped_points, query_cloud), dim=3)
+        return torch.sum(grouped_points * weights, dim=3), torch.sum(grouped_features * weights, dim=3)
+
+    def propagate(self, point_cloud, point_features, query_cloud):
+        grouped_points, grouped_features = self._group_points(point_cloud, query_cloud, point_features)
+        weights = torch.softmax(-self._get_distances(grouped_points, query_cloud), dim=3)
+        return torch.sum(grouped_features * weights, dim=3)
+
+    def project(self, point_cloud, query_cloud, hard=False):
+        grouped_points, _ = self._group_points(point_cloud, query_cloud)
+        weights = torch.softmax(-self._get_distances(grouped_points, query_cloud), dim=3)
+        if hard:
+            raise NotImplementedError
+        weights = weights.repeat(1, 3, 1, 1)
+        return torch.sum(grouped_points * weights, dim=3)

@@ -1,0 +1,178 @@
+/* gcanet_b200 -- C-ABI of the B200-native DGCNN kNN-graph + EdgeConv path.
+ *
+ * One shared library (gcanet_b200/lib/libgcanet_b200.so, sm_100a only).  Every entry
+ * point takes plain device pointers, integer sizes and a CUDA stream; nothing in this
+ * header depends on PyTorch.  Rules that hold for every function:
+ *
+ *   - all data pointers are DEVICE pointers, fp32 unless the name says otherwise,
+ *     dense row-major in the shape written in the comment;
+ *   - the library never allocates, frees or synchronises: outputs and scratch
+ *     (`ws`, sized by the matching *_workspace_bytes) are passed in by the caller,
+ *     kernels are enqueued on `stream` and the call returns immediately, so every
+ *     function may be captured in a CUDA graph;
+ *   - re-entrant, no mutable global state, uses the calling thread's current device;
+ *   - returns GCANET_OK (0) or a negative gcanet_status; gcanet_last_error() gives
+ *     the message for the calling thread.  Nothing here ever exits the process (the
+ *     reference's PN2 wrapper does: _ext-src/include/cuda_utils.h:30-39);
+ *   - there is no CPU path: host pointers are a caller error.
+ *
+ * "Replaces" cites the reference interface each entry point stands in for; paths are
+ * relative to the reference root, M4 = models/dgcnn-hais-concat-direct-4.py,
+ * KNN = models/KNN_CUDA/knn_cuda, PN2 = models/Pointnet2_PyTorch-master/
+ * pointnet2_ops_lib/pointnet2_ops.
+ */
+#ifndef GCANET_B200_H_
+#define GCANET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCANET_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GCANET_API __attribute__((visibility("default")))
+#else
+#define GCANET_API
+#endif
+
+typedef void *gcanet_stream_t; /* cudaStream_t */
+
+typedef enum {
+    GCANET_OK = 0,
+    GCANET_ERR_INVALID_ARGUMENT = -1, /* bad size / null pointer / unsupported combination  */
+    GCANET_ERR_WORKSPACE = -2,        /* ws too small or misaligned (needs 256-byte alignment) */
+    GCANET_ERR_CUDA = -3,             /* a CUDA runtime call or launch failed                  */
+    GCANET_ERR_UNSUPPORTED_DEVICE = -4 /* not an sm_100 device                                 */
+} gcanet_status;
+
+/* Neighbour metric of gcanet_knn_graph. */
+typedef enum {
+    GCANET_METRIC_L2 = 0,            /* -|x_i - x_j|^2 in expansion form        (M4:36-38)   */
+    GCANET_METRIC_POINTS_NORMALS = 1 /* d_p * (1 + (2 - 2 n_i.n_j)), needs C = 6 (M4:61-73)   */
+} gcanet_metric;
+
+/* Edge-feature variant of gcanet_graph_feature*. */
+typedef enum {
+    GCANET_EDGE_DIFF_CENTER = 0, /* (x_j - x_i, x_i)                      F = 2C  (M4:120-123) */
+    GCANET_EDGE_NORMAL_ANGLE = 1 /* (clamp(n_i.n_j,+-.99), n_j-n_i, n_i)  F = 7, C = 6 (M4:189-204) */
+} gcanet_edge_variant;
+
+GCANET_API int gcanet_abi_version(void);
+GCANET_API const char *gcanet_last_error(void);
+GCANET_API const char *gcanet_status_string(int status);
+/* Number of kernels this process has launched through the library so far (statistics only). */
+GCANET_API unsigned long long gcanet_launch_count(void);
+/* 0 when the current device is sm_100 (B200), GCANET_ERR_UNSUPPORTED_DEVICE otherwise. */
+GCANET_API int gcanet_check_device(void);
+
+/* ------------------------------------------------------------------ layouts
+ * The reference keeps clouds channel-major, x[B][C][N] (train_new.py:25-26).  The fused
+ * EdgeConv kernels work point-major, x[B][N][ld] with ld >= C (padding columns are
+ * written as zero by cn_to_nc and ignored by nc_to_cn). */
+GCANET_API int gcanet_cn_to_nc(const float *x_cn, float *x_nc, int B, int C, int N, int ld, gcanet_stream_t stream);
+GCANET_API int gcanet_nc_to_cn(const float *x_nc, float *x_cn, int B, int C, int N, int ld, gcanet_stream_t stream);
+
+/* ------------------------------------------------------------------ kNN graph (torch path)
+ * Replaces knn(x,k1,k2) M4:30-47, knn_points_normals(x,k1,k2) M4:50-90 and
+ * splinenet.knn(x,k) models/splinenet.py:9-22: per cloud, the k2 nearest points of every
+ * point under `metric`, nearest first, the point itself included, then the reference's
+ * dilation sub-sampling columns 0, s, 2s, ... with s = k2 / k1 (integer division, M4:32).
+ *   x      [B][C][N]
+ *   idx64  [B][N][kout] int64 or NULL;  idx32 [B][N][kout] int32 or NULL  (at least one)
+ *   kout = gcanet_knn_graph_columns(k1, k2);  requires 1 <= k1 <= k2 <= min(N, 1024).
+ * Distances are fp32 with the reference's expansion arithmetic; no N x N matrix is
+ * ever written to memory. */
+GCANET_API int gcanet_knn_graph_columns(int k1, int k2);
+GCANET_API size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric);
+GCANET_API int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int k2, int metric,
+                     int64_t *idx64, int32_t *idx32, void *ws, size_t ws_bytes,
+                     gcanet_stream_t stream);
+
+/* ------------------------------------------------------------------ kNN (KNN_CUDA path)
+ * Replaces knn_device(ref,ref_nb,query,query_nb,dim,k,dist,ind,stream) KNN/csrc/cuda/knn.cpp:11-21
+ * (kernels knn.cu:29-183) and the Python batch loop around it (KNN/__init__.py:41-74):
+ * cross-set brute-force kNN with Euclidean (sqrt) distances, ascending, ties keep the
+ * lower reference index first.
+ *   ref [batch][dim][ref_nb], query [batch][dim][query_nb]
+ *   dist [batch][k][query_nb], ind [batch][k][query_nb] int64, values in
+ *   [index_base, ref_nb + index_base): index_base = 1 reproduces knn_device, 0 the
+ *   Python-level knn() (KNN/__init__.py:43).  Unlike the reference no [ref_nb][query_nb]
+ *   scratch matrix is needed (knn.cpp:36).  Requires 1 <= k <= min(ref_nb, 1024). */
+GCANET_API size_t gcanet_knn_cuda_workspace_bytes(int batch, int dim, int ref_nb, int query_nb, int k);
+GCANET_API int gcanet_knn_cuda(const float *ref, int ref_nb, const float *query, int query_nb, int dim, int k,
+                    int batch, int index_base, float *dist, int64_t *ind, void *ws, size_t ws_bytes,
+                    gcanet_stream_t stream);
+
+/* ------------------------------------------------------------------ materialised edge features
+ * Replaces the gather/repeat/cat part of get_graph_feature M4:103-123,
+ * get_graph_feature_with_normals M4:140-160 and get_graph_feature_with_normals_g M4:177-204.
+ *   x [B][C][N], idx [B][N][k] int64 (values in [0,N)), out [B][N][k][F]
+ * (the reference returns this buffer viewed as [B][F][N][k] via permute(0,3,1,2)).
+ * The gradient w.r.t. x (autograd of index/sub/cat/mul in the reference) is
+ * gcanet_graph_feature_grad: grad_out [B][N][k][F] -> grad_x [B][C][N] (overwritten).
+ * ws: a point-major staging copy, sized by the matching *_workspace_bytes.  An index
+ * outside [0,N) is undefined behaviour, as in the reference. */
+GCANET_API int gcanet_graph_feature_channels(int C, int variant);
+GCANET_API size_t gcanet_graph_feature_workspace_bytes(int B, int C, int N, int k, int variant);
+GCANET_API int gcanet_graph_feature(const float *x, const int64_t *idx, float *out, int B, int C, int N, int k,
+                         int variant, void *ws, size_t ws_bytes, gcanet_stream_t stream);
+GCANET_API size_t gcanet_graph_feature_grad_workspace_bytes(int B, int C, int N, int k, int variant);
+GCANET_API int gcanet_graph_feature_grad(const float *grad_out, const float *x, const int64_t *idx, float *grad_x,
+                              int B, int C, int N, int k, int variant, void *ws, size_t ws_bytes,
+                              gcanet_stream_t stream);
+
+/* ------------------------------------------------------------------ grouping (PN2 path)
+ * Replaces group_points_kernel_wrapper / group_points_grad_kernel_wrapper
+ * (PN2/_ext-src/src/group_points.cpp:4-10, kernels group_points_gpu.cu:8-28,43-64); same
+ * argument order plus the stream.  points [b][c][n], idx [b][npoints][nsample] int32,
+ * out [b][c][npoints][nsample]; grad_points [b][c][n] is overwritten (the reference
+ * accumulates into a zeroed tensor, group_points.cpp:48-50). */
+GCANET_API int gcanet_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                        const int32_t *idx, float *out, gcanet_stream_t stream);
+GCANET_API int gcanet_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                             const int32_t *idx, float *grad_points, gcanet_stream_t stream);
+
+/* ------------------------------------------------------------------ fused EdgeConv block
+ * Replaces, for one layer, get_graph_feature(x, idx=idx) -> Conv2d(2C,Cout,1,bias=False) ->
+ * GroupNorm(groups,Cout,eps) -> LeakyReLU(slope) -> max over k  (M4:469-481, M4:494-505) and
+ * its autograd backward, without ever forming the [B][2C][N][k] edge tensor or the
+ * [B][Cout][N][k] activation (see DESIGN.md for the identities used).
+ *
+ *   x_nc   [B][N][ldx]   point-major input, ldx >= C
+ *   idx    [B][N][k]     int32 neighbour lists (gcanet_knn_graph's idx32)
+ *   weight [Cout][2C]    conv weight, columns [0,C) multiply x_j - x_i, [C,2C) multiply x_i
+ *   gamma, beta [Cout]   GroupNorm affine
+ *   out_nc [B][N][Cout]  and, if not NULL, out_cn [B][Cout][N] (the reference layout)
+ *   saved  opaque, gcanet_edgeconv_saved_bytes(); must be kept untouched until backward
+ *   ws     scratch, gcanet_edgeconv_workspace_bytes()
+ * Constraints: Cout % 32 == 0, Cout <= 256, Cout % groups == 0, (Cout/groups) % (Cout/32) == 0,
+ * C <= 256, 1 <= k <= 255.
+ *
+ * backward: grad_out_nc [B][N][Cout] -> grad_x_nc [B][N][ldx] (or NULL to skip; padding
+ * columns are zeroed), grad_weight [Cout][2C], grad_gamma, grad_beta [Cout], all overwritten. */
+typedef struct {
+    int B, N, C, ldx, Cout, k, groups;
+    float eps;   /* GroupNorm epsilon, reference 1e-5 */
+    float slope; /* LeakyReLU negative slope, reference 0.2 */
+} gcanet_edgeconv_desc;
+
+GCANET_API size_t gcanet_edgeconv_saved_bytes(const gcanet_edgeconv_desc *d);
+GCANET_API size_t gcanet_edgeconv_workspace_bytes(const gcanet_edgeconv_desc *d);
+GCANET_API int gcanet_edgeconv_forward(const gcanet_edgeconv_desc *d, const float *x_nc, const int32_t *idx,
+                            const float *weight, const float *gamma, const float *beta,
+                            float *out_nc, float *out_cn, void *saved, void *ws, size_t ws_bytes,
+                            gcanet_stream_t stream);
+GCANET_API int gcanet_edgeconv_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const int32_t *idx,
+                             const float *weight, const float *gamma, const float *beta,
+                             const float *grad_out_nc, const void *saved, float *grad_x_nc,
+                             float *grad_weight, float *grad_gamma, float *grad_beta, void *ws,
+                             size_t ws_bytes, gcanet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCANET_B200_H_ */

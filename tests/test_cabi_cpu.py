@@ -1,0 +1,93 @@
+"""CPU suite, part 2: the C-ABI library and the host-side mirror, without any compute.
+
+* libgcanet_b200.so loads and exports every symbol include/gcanet_b200.h declares;
+* argument validation returns status codes + messages (never exits, never touches a device);
+* the Python front end refuses CPU tensors instead of falling back.
+"""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import gcanet_b200 as gb
+from gcanet_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gcanet_b200.h")).read()
+    return sorted(set(re.findall(r"GCANET_API[^;(]*?\b(gcanet_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 20
+    raw = ctypes.CDLL(_cabi.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} is declared in include/gcanet_b200.h but not exported"
+    # and the ctypes table covers the whole header (no entry point left unbound)
+    assert sorted(_cabi.SIGNATURES) == names
+
+
+def test_abi_version_and_status_strings():
+    L = _cabi.lib()
+    assert L.gcanet_abi_version() == 1
+    assert L.gcanet_status_string(0) == b"ok"
+    assert b"workspace" in L.gcanet_status_string(-2)
+
+
+def test_knn_columns_follow_reference_dilation():
+    L = _cabi.lib()
+    import numpy as np
+    for k1, k2 in [(20, 20), (10, 20), (50, 80), (7, 20), (1, 1), (3, 10)]:
+        assert L.gcanet_knn_graph_columns(k1, k2) == len(np.arange(0, k2, k2 // k1))   # M4:32
+    assert L.gcanet_knn_graph_columns(0, 5) == 0 and L.gcanet_knn_graph_columns(6, 5) == 0
+
+
+def test_argument_validation_without_device():
+    L = _cabi.lib()
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(256)     # never dereferenced: validation fails first
+    assert L.gcanet_knn_graph(null, 1, 3, 10, 2, 2, 0, null, null, null, 0, null) == -1
+    assert b"null pointer" in L.gcanet_last_error()
+    assert L.gcanet_knn_graph(one, 1, 3, 10, 20, 20, 0, one, null, one, 1 << 20, null) == -1
+    assert b"exceeds the number of points" in L.gcanet_last_error()
+    assert L.gcanet_knn_graph(one, 1, 3, 10, 2, 2, 1, one, null, one, 1 << 20, null) == -1
+    assert b"C = 6" in L.gcanet_last_error()
+    assert L.gcanet_knn_graph(one, 1, 3, 10, 2, 2, 0, one, null, null, 0, null) == -2     # workspace
+    assert L.gcanet_knn_cuda(one, 5, one, 5, 3, 6, 1, 0, one, one, null, 0, null) == -1
+    d = _cabi.EdgeConvDesc(2, 100, 64, 64, 48, 20, 2, 1e-5, 0.2)                             # Cout % 32 != 0
+    assert L.gcanet_edgeconv_saved_bytes(ctypes.byref(d)) == 0
+    assert b"Cout" in L.gcanet_last_error()
+    d = _cabi.EdgeConvDesc(16, 10000, 64, 64, 128, 50, 2, 1e-5, 0.2)
+    saved = L.gcanet_edgeconv_saved_bytes(ctypes.byref(d))
+    # [P|Q] + ysel + ysum (fp32) + arg (u8) per (point, channel): 4*(2+1+1)+1 = 17 bytes
+    assert abs(saved - 16 * 10000 * 128 * 17) < 1 << 16
+    assert L.gcanet_edgeconv_workspace_bytes(ctypes.byref(d)) > 0
+
+
+def test_cpu_tensors_are_refused():
+    x = torch.randn(1, 3, 32)
+    for fn in (lambda: gb.knn(x, 4, 4), lambda: gb.get_graph_feature(x, 4, 4),
+               lambda: gb.KNN(2)(x, x), lambda: gb.grouping_operation(x, torch.zeros(1, 2, 2, dtype=torch.int32)),
+               lambda: gb.DGCNNEncoderGn(mode=0, nn_nb=4, input_channels=6)(x)):
+        with pytest.raises(RuntimeError):
+            fn()
+
+
+def test_encoder_state_dict_keys_match_reference_layout():
+    enc = gb.DGCNNEncoderGn(mode=5, nn_nb=80, input_channels=6)
+    sd = enc.state_dict()
+    assert tuple(sd["conv1.0.weight"].shape) == (64, 12, 1, 1)
+    assert tuple(sd["conv2.0.weight"].shape) == (64, 128, 1, 1)
+    assert tuple(sd["conv3.0.weight"].shape) == (128, 128, 1, 1)
+    for key in ("bn1.weight", "bn2.bias", "bn3.weight", "bn4.weight", "bn5.bias", "conv1.1.weight",
+                "mlp1.weight", "mlp1.bias", "bnmlp1.weight"):
+        assert key in sd
+    from oracle import dgcnn_oracle as orc
+    ref = orc.DGCNNEncoderGn(mode=5, nn_nb=80, input_channels=6)
+    assert list(ref.state_dict()) == list(sd)
+    enc.load_state_dict(ref.state_dict())
