@@ -117,6 +117,7 @@ struct ScanArgs {
     int k_major;            // 0: out[b][q][col]   1: out[b][col][q]
     int index_base;
     int TR;                 // reference tile (multiple of 32)
+    const int *row_filter;  // optional [B][Nq]: only queries with a non-zero flag are computed / written
 };
 
 // CDIM > 0: compile-time dimension, queries in registers.  CDIM == 0: runtime C, queries in smem.
@@ -135,6 +136,16 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
     const int q0 = blockIdx.x * QPB + warp * R;
     const float *ref = a.ref + (size_t)b * C * a.Nr;
     const float *qry = a.qry + (size_t)b * C * a.Nq;
+
+    if (a.row_filter != nullptr) {
+        // fallback mode: leave unless one of this CTA's queries is flagged
+        int flagged = 0;
+        if (threadIdx.x < QPB) {
+            int q = blockIdx.x * QPB + threadIdx.x;
+            flagged = q < a.Nq ? a.row_filter[(size_t)b * a.Nq + q] : 0;
+        }
+        if (!__syncthreads_or(flagged)) return;
+    }
 
     // stage this CTA's queries (zero for out-of-range ones)
     for (int e = threadIdx.x; e < C * QPB; e += kThreads) {
@@ -263,6 +274,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
     for (int r = 0; r < R; ++r) {
         int q = q0 + r;
         if (q >= a.Nq) continue;
+        if (a.row_filter != nullptr && a.row_filter[(size_t)b * a.Nq + q] == 0) continue;
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             int p = s * 32 + lane - (32 * KS - a.k);   // rank among the k real entries
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_bigk_kernel(ScanArgs a) {
         }
     }
     __syncwarp();
-    if (q < a.Nq) {
+    if (q < a.Nq && (a.row_filter == nullptr || a.row_filter[(size_t)b * a.Nq + q] != 0)) {
         for (int p = lane; p < k; p += 32) {
             if (p % a.step) continue;
             int col = p / a.step;
@@ -439,11 +451,30 @@ static int launch_sqnorm(const float *x, float *out, int B, int C, int Cuse, int
     return GCANET_OK;
 }
 
+int launch_sqnorm_public(const float *x, float *out, int B, int C, int Cuse, int N, cudaStream_t st) {
+    return launch_sqnorm(x, out, B, C, Cuse, N, st);
+}
+
+static int scan_self(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
+                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st);
+
+// re-runs the CUDA-core scan for the queries flagged in row_filter (tensor-core path overflow)
+int knn_fallback_rows(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
+                      int64_t *idx64, int32_t *idx32, cudaStream_t st) {
+    return scan_self(x, norms, row_filter, B, C, N, k1, k2, GCANET_METRIC_L2, idx64, idx32, st);
+}
+
 int knn_graph_cuda_cores(const float *x, int B, int C, int N, int k1, int k2, int metric, int64_t *idx64,
                          int32_t *idx32, float *norms, cudaStream_t st) {
     int rc = launch_sqnorm(x, norms, B, C, metric == GCANET_METRIC_POINTS_NORMALS ? 3 : C, N, st);
     if (rc) return rc;
+    return scan_self(x, norms, nullptr, B, C, N, k1, k2, metric, idx64, idx32, st);
+}
+
+static int scan_self(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
+                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st) {
     ScanArgs a{};
+    a.row_filter = row_filter;
     a.ref = x; a.qry = x; a.ref_norm = norms; a.qry_norm = norms;
     a.C = C; a.Nr = N; a.Nq = N; a.k = k2;
     a.step = k2 / k1; a.kout = gcanet_knn_graph_columns(k1, k2);
@@ -458,6 +489,12 @@ int knn_graph_cuda_cores(const float *x, int B, int C, int N, int k1, int k2, in
     return launch_scan_k<0, METRIC_L2, 4>(a, B, st);
 }
 
+// knn_tc.cu
+size_t knn_tc_workspace_bytes(int B, int C, int N);
+bool knn_tc_supported(int C, int N, int k2);
+int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, int64_t *idx64, int32_t *idx32,
+                           void *ws, cudaStream_t st);
+
 }  // namespace gcanet
 
 using namespace gcanet;
@@ -468,8 +505,13 @@ extern "C" int gcanet_knn_graph_columns(int k1, int k2) {
     return (k2 + step - 1) / step;
 }
 
+static bool use_tensor_cores(int C, int N, int k2, int metric) {
+    return metric == GCANET_METRIC_L2 && knn_tc_supported(C, N, k2);   // any flag bit makes this false
+}
+
 extern "C" size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric) {
-    (void)C; (void)k2; (void)metric;
+    if (B < 1 || C < 1 || N < 1) return 0;
+    if (use_tensor_cores(C, N, k2, metric)) return knn_tc_workspace_bytes(B, C, N);
     return align_up((size_t)B * N * sizeof(float));
 }
 
@@ -481,15 +523,21 @@ extern "C" int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int
     GCANET_REQUIRE(k1 >= 1 && k2 >= k1, "knn_graph: need 1 <= k1 <= k2 (k1=%d k2=%d)", k1, k2);
     GCANET_REQUIRE(k2 <= N, "knn_graph: k2=%d exceeds the number of points N=%d (topk would raise, M4:43)", k2, N);
     GCANET_REQUIRE(k2 <= 1024, "knn_graph: k2=%d > 1024 unsupported", k2);
+    const int flags = metric & ~0xff;
+    GCANET_REQUIRE((flags & ~GCANET_KNN_FLAG_NO_TENSOR_CORES) == 0, "knn_graph: unknown flag bits in metric 0x%x", metric);
+    const int metric_in = metric;
+    metric &= 0xff;
     GCANET_REQUIRE(metric == GCANET_METRIC_L2 || metric == GCANET_METRIC_POINTS_NORMALS, "knn_graph: bad metric %d", metric);
     GCANET_REQUIRE(metric != GCANET_METRIC_POINTS_NORMALS || C == 6,
                    "knn_graph: the points x normals metric needs C = 6 (got %d)", C);
     GCANET_REQUIRE(C <= 1024, "knn_graph: C=%d > 1024 unsupported", C);
-    if (ws == nullptr || ws_bytes < gcanet_knn_graph_workspace_bytes(B, C, N, k2, metric) ||
+    if (ws == nullptr || ws_bytes < gcanet_knn_graph_workspace_bytes(B, C, N, k2, metric_in) ||
         (reinterpret_cast<uintptr_t>(ws) % kAlign) != 0) {
         set_error("knn_graph: workspace too small or misaligned (%zu bytes given)", ws_bytes);
         return GCANET_ERR_WORKSPACE;
     }
+    if (flags == 0 && use_tensor_cores(C, N, k2, metric))
+        return knn_graph_tensor_cores(x, B, C, N, k1, k2, idx64, idx32, ws, as_stream(stream));
     return knn_graph_cuda_cores(x, B, C, N, k1, k2, metric, idx64, idx32, static_cast<float *>(ws), as_stream(stream));
 }
 

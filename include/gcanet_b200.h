@@ -55,6 +55,11 @@ typedef enum {
     GCANET_METRIC_POINTS_NORMALS = 1 /* d_p * (1 + (2 - 2 n_i.n_j)), needs C = 6 (M4:61-73)   */
 } gcanet_metric;
 
+/* May be OR-ed into `metric`: run the CUDA-core scan even where the tensor-core path applies
+ * (C = 64 / 128 with the L2 metric).  Both paths return fp32-exact neighbour lists; the flag
+ * exists for A/B tests and benchmarks. */
+#define GCANET_KNN_FLAG_NO_TENSOR_CORES 0x100
+
 /* Edge-feature variant of gcanet_graph_feature*. */
 typedef enum {
     GCANET_EDGE_DIFF_CENTER = 0, /* (x_j - x_i, x_i)                      F = 2C  (M4:120-123) */
@@ -85,7 +90,9 @@ GCANET_API int gcanet_nc_to_cn(const float *x_nc, float *x_cn, int B, int C, int
  *   idx64  [B][N][kout] int64 or NULL;  idx32 [B][N][kout] int32 or NULL  (at least one)
  *   kout = gcanet_knn_graph_columns(k1, k2);  requires 1 <= k1 <= k2 <= min(N, 1024).
  * Distances are fp32 with the reference's expansion arithmetic; no N x N matrix is
- * ever written to memory. */
+ * ever written to memory.  For C = 64 / 128 (L2 metric, k2 <= 128, N >= 128) candidates are
+ * pruned on the tensor cores (tcgen05, bf16x3 split) and the survivors re-ranked in exact
+ * fp32; every other shape runs the CUDA-core scan. */
 GCANET_API int gcanet_knn_graph_columns(int k1, int k2);
 GCANET_API size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric);
 GCANET_API int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int k2, int metric,
