@@ -62,6 +62,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// same, for the single-thread producer / MMA roles: back off between probes so the spin does
+// not steal issue slots from the epilogue warps that share the scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(40);
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -159,12 +177,17 @@ __global__ void tc_prep_kernel(const float *__restrict__ x, __nv_bfloat16 *__res
     }
 }
 
-// nmax[b] = max_n norm[b][n]   (one CTA per cloud)
-__global__ void tc_normmax_kernel(const float *__restrict__ norm, float *__restrict__ nmax, int N) {
+// nmax[b] = max_n norm[b][n]; norm_pad[b][0:Npad] = norm[b] followed by +inf   (one CTA per cloud)
+__global__ void tc_normmax_kernel(const float *__restrict__ norm, float *__restrict__ nmax,
+                                  float *__restrict__ norm_pad, int N, int Npad) {
     __shared__ float red[32];
     const int b = blockIdx.x;
     float m = 0.f;
-    for (int n = threadIdx.x; n < N; n += blockDim.x) m = fmaxf(m, norm[(size_t)b * N + n]);
+    for (int n = threadIdx.x; n < Npad; n += blockDim.x) {
+        float v = n < N ? norm[(size_t)b * N + n] : CUDART_INF_F;
+        norm_pad[(size_t)b * Npad + n] = v;
+        if (n < N) m = fmaxf(m, v);
+    }
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULLW, m, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();
@@ -179,6 +202,8 @@ __global__ void tc_normmax_kernel(const float *__restrict__ norm, float *__restr
 // scan
 // ---------------------------------------------------------------------------------
 struct TcScanArgs {
+    const float *norm_pad;  // [B][Npad] key norms, Npad = tiles * TC_BN, +inf past N (masks the zero-filled keys)
+    int Npad;
     const float *norm;   // [B][N]
     const float *nmax;   // [B]
     uint2 *cand;         // [B][N][TC_CAP]  (approx distance bits, key index)
@@ -242,21 +267,20 @@ __device__ __forceinline__ void compact_row(uint2 *ptr, int n, int k, float marg
 }
 
 template <int C>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, C == 64 ? 2 : 1)
 knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
     constexpr int NBLK = 2 * C / TC_KB;                 // 128-byte K blocks per row: hi blocks then lo blocks
     constexpr int NH = C / TC_KB;                       // hi (= lo) blocks
     constexpr int BLK_BYTES = TC_BM * 128;              // one K block of a 128-row tile: 16 KB
     constexpr int TILE_BYTES = NBLK * BLK_BYTES;        // 32 KB (C=64) / 64 KB (C=128)
-    constexpr int STAGES = C == 64 ? 4 : 2;
+    constexpr int STAGES = 2;                           // C = 64: 96 KB per CTA -> two CTAs share an SM
     constexpr int ACC = 2;                              // TMEM accumulator stages
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                                  // query tile
     uint8_t *sB = smem + TILE_BYTES;                     // STAGES key tiles
-    float *s_rn = reinterpret_cast<float *>(sB + STAGES * TILE_BYTES);      // [2][TC_BN] key norms
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_rn + 2 * TC_BN);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * TILE_BYTES);
     uint64_t *full = bars;                 // [STAGES]  TMA -> MMA
     uint64_t *empty = bars + STAGES;       // [STAGES]  MMA -> TMA
     uint64_t *a_full = bars + 2 * STAGES;  // [1]
@@ -291,7 +315,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = 0; t < tiles; ++t) {
-                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_wait_backoff(&empty[stage], phase ^ 1);
                 mbar_expect_tx(&full[stage], TILE_BYTES);
                 uint8_t *dst = sB + stage * TILE_BYTES;
 #pragma unroll
@@ -308,8 +332,8 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, accphase = 0;
             for (int t = 0; t < tiles; ++t) {
-                mbar_wait(&t_empty[acc], accphase ^ 1);
-                mbar_wait(&full[stage], phase);
+                mbar_wait_backoff(&t_empty[acc], accphase ^ 1);
+                mbar_wait_backoff(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(sB + stage * TILE_BYTES);
                 const uint32_t d_tmem = tmem_base + acc * TC_BN;
@@ -339,7 +363,6 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
         // ===================== epilogue: one query row per thread =====================
         const int ew = warp & 3;                          // TMEM lane group this warp may access
         const int row = ew * 32 + lane;                   // accumulator row = TMEM lane
-        const int et = (warp - 2) * 32 + lane;            // 0..127: index among the epilogue threads
         const int q = q0 + row;
         const bool active = q < a.N;
         const size_t grow = (size_t)b * a.N + (active ? q : 0);
@@ -349,40 +372,29 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
         float thr = active ? CUDART_INF_F : -CUDART_INF_F;   // inactive rows never append
         int cnt = 0;
         bool ovf = false;
-
-        // key norms of tile 0
-        {
-            int j = et;
-            s_rn[et] = j < a.N ? a.norm[(size_t)b * a.N + j] : CUDART_INF_F;
-        }
-        named_bar_sync(1, 128);
+        const float4 *rn4 = reinterpret_cast<const float4 *>(a.norm_pad + (size_t)b * a.Npad);
 
         int acc = 0;
         uint32_t accphase = 0;
         for (int t = 0; t < tiles; ++t) {
-            // prefetch the next tile's key norm while this tile is processed
-            float next_rn = CUDART_INF_F;
-            {
-                int j = (t + 1) * TC_BN + et;
-                if (t + 1 < tiles && j < a.N) next_rn = a.norm[(size_t)b * a.N + j];
-            }
             mbar_wait(&t_full[acc], accphase);
             tc_fence_after();
-            const float *rn = s_rn + (t & 1) * TC_BN;
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN;
-#pragma unroll 1
+            uint32_t v[2][32];
+            tmem_ld32(taddr, v[0]);
+#pragma unroll
             for (int ch = 0; ch < TC_BN / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(taddr + ch * 32, v);
-                tmem_ld_wait();
+                tmem_ld_wait();                                     // chunk ch is in v[ch & 1]
+                if (ch + 1 < TC_BN / 32) tmem_ld32(taddr + (ch + 1) * 32, v[(ch + 1) & 1]);   // prefetch the next chunk
                 const int jbase = t * TC_BN + ch * 32;
+                const float4 *rn = rn4 + (jbase >> 2);               // same address in every lane: one broadcast load
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 n4 = *reinterpret_cast<const float4 *>(rn + ch * 32 + c4 * 4);
+                    const float4 n4 = __ldg(rn + c4);
                     const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float d = fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]);   // +inf for keys >= N
+                        const float d = fmaf(-2.f, __uint_as_float(v[ch & 1][c4 * 4 + e]), nn[e]);   // +inf for keys >= N
                         if (d < thr) {
                             buf[cnt] = make_uint2(__float_as_uint(d), (uint32_t)(jbase + c4 * 4 + e));
                             ++cnt;
@@ -412,9 +424,6 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[acc]);
             if (++acc == ACC) { acc = 0; accphase ^= 1; }
-            // publish the next tile's norms (all 128 epilogue threads are past tile t-1's reads)
-            s_rn[((t + 1) & 1) * TC_BN + et] = next_rn;
-            named_bar_sync(1, 128);
         }
 
         // final compaction of every row so the re-rank sees ~k + slack candidates
@@ -558,6 +567,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += align_up(bn * 2 * C * sizeof(__nv_bfloat16));   // xs
     t += align_up(bn * C * sizeof(float));               // x_nc
     t += align_up(bn * sizeof(float));                   // norm
+    t += align_up((size_t)B * (ceil_div(N, TC_BN) * TC_BN) * sizeof(float));   // norm_pad
     t += align_up((size_t)B * sizeof(float));            // nmax
     t += align_up(bn * TC_CAP * sizeof(uint2));          // cand
     t += align_up(bn * sizeof(int));                     // cand_cnt
@@ -578,8 +588,8 @@ template <int C>
 static int launch_tc(const CUtensorMap &tmap, TcScanArgs sa, RerankArgs ra, int B, cudaStream_t st) {
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int TILE_BYTES = NBLK * TC_BM * 128;
-    constexpr int STAGES = C == 64 ? 4 : 2;
-    const size_t smem = 1024 + (size_t)(1 + STAGES) * TILE_BYTES + 2 * TC_BN * sizeof(float) + 32 * sizeof(uint64_t);
+    constexpr int STAGES = 2;
+    const size_t smem = 1024 + (size_t)(1 + STAGES) * TILE_BYTES + 32 * sizeof(uint64_t);
     auto kern = knn_tc_scan_kernel<C>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(sa.N, TC_BM), B);
@@ -600,6 +610,8 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     __nv_bfloat16 *xs = cv.take<__nv_bfloat16>(bn * 2 * C);
     float *x_nc = cv.take<float>(bn * C);
     float *norm = cv.take<float>(bn);
+    const int Npad = ceil_div(N, TC_BN) * TC_BN;
+    float *norm_pad = cv.take<float>((size_t)B * Npad);
     float *nmax = cv.take<float>(B);
     uint2 *cand = cv.take<uint2>(bn * TC_CAP);
     int *cand_cnt = cv.take<int>(bn);
@@ -611,7 +623,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         dim3 grid(ceil_div(N, 32), ceil_div(C, 32), B), block(32, 8);
         tc_prep_kernel<<<grid, block, 0, st>>>(x, xs, x_nc, C, N);
         GCANET_LAUNCH_OK("tc_prep_kernel");
-        tc_normmax_kernel<<<B, 256, 0, st>>>(norm, nmax, N);
+        tc_normmax_kernel<<<B, 256, 0, st>>>(norm, nmax, norm_pad, N, Npad);
         GCANET_LAUNCH_OK("tc_normmax_kernel");
     }
 
@@ -627,7 +639,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("knn_graph: cuTensorMapEncodeTiled failed (%d)", (int)cr); return GCANET_ERR_CUDA; }
 
-    TcScanArgs sa{norm, nmax, cand, cand_cnt, overflow, N, k2, ceil_div(N, TC_BN)};
+    TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, ceil_div(N, TC_BN)};
     RerankArgs ra{x_nc, norm, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2)};
     rc = C == 64 ? launch_tc<64>(tmap, sa, ra, B, st) : launch_tc<128>(tmap, sa, ra, B, st);
     if (rc) return rc;
