@@ -259,6 +259,9 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     e2e_value = world * B_PER_GPU / (ms_e2e / 1e3)
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 
