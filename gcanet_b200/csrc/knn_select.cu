@@ -2,18 +2,20 @@
 //
 // One warp owns R queries; the 32 lanes each take one reference point of the current
 // group, so a group of 32 candidates costs C*R FMAs per lane plus one compare per query.
-// The running k-best of every query is an ascending list distributed over the warp's
-// registers (position p lives in slot p/32 of lane p%32); a candidate is inserted with
-// two ballots (rank) and a shuffle-up (shift).  Only candidates that beat the current
-// k-th distance reach the insertion, which after the first few hundred references is
-// rare, so the scan is FMA/compare bound.
+// Every query keeps a candidate list in shared memory and a threshold (an upper bound of
+// its current k-th distance): lanes whose candidate beats the threshold append it with one
+// ballot + prefix-popcount (no per-candidate serialisation).  A list that is about to
+// overflow is shrunk by its warp: bisection for a bound with count(d <= bound) >= k, keep
+// d <= bound, the bound becomes the new threshold.  After the scan the survivors are ranked
+// by (distance, index) and the k best written in order.  Only O(k log(N/k)) candidates per
+// query ever reach a list, so the scan is FMA/compare bound.
 //
 // Arithmetic follows the reference so that index sets agree up to fp32 ties:
 //   L2   (M4:36-38)  d = fl(fl(|x_j|^2 - 2 x_i.x_j) + |x_i|^2), norms summed without FMA
 //   PN   (M4:61-73)  d = d_p * (1 + (2 - 2 n_i.n_j)),  d_p as above on channels 0..2
 //   SSD  (KNN/csrc/cuda/knn.cu:73-76)  d = sum_c fma(t, t, d), t = ref_c - query_c
-// Ties: a candidate equal to the current k-th is rejected and an equal candidate is
-// placed after its equals, so the lower reference index wins (knn.cu:125,149).
+// Ties: ranking by (distance, index) keeps the lower reference index first and a later
+// candidate equal to the k-th never displaces it (knn.cu:125,149).
 #include "common.cuh"
 
 #include <math_constants.h>
@@ -44,42 +46,9 @@ __global__ void sqnorm_kernel(const float *__restrict__ x, float *__restrict__ o
 }
 
 // ---------------------------------------------------------------------------------
-// warp-distributed ascending list
+// per-query candidate list in shared memory, maintained by one warp
 // ---------------------------------------------------------------------------------
-template <int KS>
-struct WarpList {
-    float v[KS];
-    int id[KS];
-
-    // The list has 32*KS positions but only the last k are real: the first 32*KS - k hold
-    // -inf sentinels that never move, so the k-th best always sits in the last position
-    // and the threshold is one shuffle from a fixed register.
-    __device__ __forceinline__ void init(int k, int lane) {
-#pragma unroll
-        for (int s = 0; s < KS; ++s) { v[s] = (s * 32 + lane < 32 * KS - k) ? -CUDART_INF_F : CUDART_INF_F; id[s] = 0; }
-    }
-    // All lanes pass the same (d, j).
-    __device__ __forceinline__ void insert(float d, int j, int lane) {
-        int pos = 0;
-#pragma unroll
-        for (int s = 0; s < KS; ++s) pos += __popc(__ballot_sync(FULL, v[s] <= d));
-#pragma unroll
-        for (int t = 0; t < KS; ++t) {
-            const int s = KS - 1 - t;   // high slots first: slot s reads the old slot s-1
-            float uv = __shfl_up_sync(FULL, v[s], 1);
-            int ui = __shfl_up_sync(FULL, id[s], 1);
-            if (s > 0) {
-                float cv = __shfl_sync(FULL, v[s - 1], 31);
-                int ci = __shfl_sync(FULL, id[s - 1], 31);
-                if (lane == 0) { uv = cv; ui = ci; }
-            }
-            int p = s * 32 + lane;
-            if (p == pos) { v[s] = d; id[s] = j; }
-            else if (p > pos) { v[s] = uv; id[s] = ui; }
-        }
-    }
-    __device__ __forceinline__ float kth() const { return __shfl_sync(FULL, v[KS - 1], 31); }
-};
+constexpr int kSlack = 8;     // the bisection stops once the bound keeps <= k + kSlack entries
 
 // compile-time loop: keeps per-query state indexed by constants so it stays in registers
 template <int I, int N, typename F>
@@ -90,18 +59,89 @@ __device__ __forceinline__ void static_for(F &&f) {
     }
 }
 
-template <int KS>
-__device__ __forceinline__ void offer(WarpList<KS> &L, float &thr, float d, int j0, int lane) {
-    unsigned m = __ballot_sync(FULL, d < thr);
-    while (m) {
-        int src = __ffs(m) - 1;
-        m &= m - 1;
-        float dd = __shfl_sync(FULL, d, src);
-        if (dd < thr) {
-            L.insert(dd, j0 + src, lane);
-            thr = L.kth();
+// Ranks the n entries of a list by (distance, index), keeps the min(n, k) smallest IN ORDER
+// (entry of rank r moves to slot r) and returns the largest kept distance.
+template <int SL>
+__device__ __forceinline__ float rank_cut(float *ld, int *li, int n, int k, int lane) {
+    float dv[SL];
+    int di[SL], rank[SL];
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        const int e = s * 32 + lane;
+        dv[s] = e < n ? ld[e] : CUDART_INF_F;
+        di[s] = e < n ? li[e] : 0x7fffffff;
+        rank[s] = 0;
+    }
+    for (int e = 0; e < n; ++e) {
+        const float od = ld[e];
+        const int oi = li[e];
+#pragma unroll
+        for (int s = 0; s < SL; ++s) {
+            if (s * 32 >= n) break;
+            rank[s] += (od < dv[s] || (od == dv[s] && oi < di[s])) ? 1 : 0;
         }
     }
+    __syncwarp();
+    float kth = -CUDART_INF_F;
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        if (s * 32 + lane < n && rank[s] < k) { ld[rank[s]] = dv[s]; li[rank[s]] = di[s]; kth = fmaxf(kth, dv[s]); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(FULL, kth, o));
+    __syncwarp();
+    return kth;
+}
+
+// Shrinks a list of n > k entries to those with d <= bound, where count(d <= bound) >= k and,
+// ties permitting, <= k + kSlack (bisection on the values).  If ties would keep more than
+// `limit` entries the list is cut to exactly the k smallest by (distance, index) instead.
+// Returns the new count; `thr` becomes the bound: later candidates must be strictly below it
+// (they have larger indices, so an equal distance loses the tie anyway).
+template <int SL>
+__device__ __forceinline__ int shrink_list(float *ld, int *li, int n, int k, int limit, int lane, float &thr) {
+    float dv[SL];
+    int di[SL];
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        const int e = s * 32 + lane;
+        dv[s] = CUDART_INF_F;
+        di[s] = 0x7fffffff;
+        if (e < n) { dv[s] = ld[e]; di[s] = li[e]; mn = fminf(mn, dv[s]); mx = fmaxf(mx, dv[s]); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    }
+    float lo = mn, hi = mx;
+    int c_hi = n;
+    for (int it = 0; it < 32 && c_hi > k + kSlack; ++it) {
+        const float mid = 0.5f * lo + 0.5f * hi;
+        if (!(mid > lo && mid < hi)) break;            // interval exhausted: ties at hi
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < SL; ++s) c += (dv[s] <= mid) ? 1 : 0;
+        c = __reduce_add_sync(FULL, c);
+        if (c >= k) { hi = mid; c_hi = c; } else { lo = mid; }
+    }
+    __syncwarp();
+    if (c_hi > limit) {
+        thr = rank_cut<SL>(ld, li, n, k, lane);
+        return k;
+    }
+    int base = 0;
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        const bool keep = dv[s] <= hi && s * 32 + lane < n;
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) { const int p = base + __popc(m & ((1u << lane) - 1)); ld[p] = dv[s]; li[p] = di[s]; }
+        base += __popc(m);
+    }
+    __syncwarp();
+    thr = hi;
+    return base;
 }
 
 struct ScanArgs {
@@ -121,15 +161,19 @@ struct ScanArgs {
 };
 
 // CDIM > 0: compile-time dimension, queries in registers.  CDIM == 0: runtime C, queries in smem.
-template <int CDIM, int METRIC, int KS, int R>
+// SL: candidate-list capacity in units of 32 entries (needs k + kSlack + 32 <= 32 * SL).
+template <int CDIM, int METRIC, int SL, int R>
 __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int C = CDIM > 0 ? CDIM : a.C;
     const int TR = a.TR;
     constexpr int QPB = kWarps * R;
+    constexpr int CAP = 32 * SL;
     float *rs = smem;                 // [C][TR]
     float *rn = rs + (size_t)C * TR;  // [TR]
     float *qs = rn + TR;              // [C][QPB]
+    float *lds = qs + (size_t)C * QPB;                       // [QPB][CAP] candidate distances
+    int *lis = reinterpret_cast<int *>(lds + QPB * CAP);     // [QPB][CAP] candidate indices
 
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,10 +214,12 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
         }
     }
 
-    WarpList<KS> L[R];
     float thr[R];
+    int cnt[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { L[r].init(a.k, lane); thr[r] = CUDART_INF_F; }
+    for (int r = 0; r < R; ++r) { thr[r] = CUDART_INF_F; cnt[r] = 0; }
+    float *my_ld = lds + (size_t)(warp * R) * CAP;
+    int *my_li = lis + (size_t)(warp * R) * CAP;
 
     for (int t0 = 0; t0 < a.Nr; t0 += TR) {
         __syncthreads();   // previous tile fully consumed
@@ -263,30 +309,53 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
             const bool valid = j < a.Nr;
             static_for<0, R>([&](auto rc) {
                 constexpr int r = decltype(rc)::value;
-                float dr = valid ? d[r] : CUDART_INF_F;
-                offer<KS>(L[r], thr[r], dr, t0 + g * 32, lane);
+                const bool pass = valid && d[r] < thr[r];
+                const unsigned m = __ballot_sync(FULL, pass);
+                if (m) {
+                    if (pass) {
+                        const int p = cnt[r] + __popc(m & ((1u << lane) - 1));
+                        my_ld[r * CAP + p] = d[r];
+                        my_li[r * CAP + p] = j;
+                    }
+                    cnt[r] += __popc(m);
+                    if (cnt[r] > CAP - 32) {
+                        __syncwarp();
+                        cnt[r] = shrink_list<SL>(my_ld + r * CAP, my_li + r * CAP, cnt[r], a.k, CAP - 32, lane, thr[r]);
+                    }
+                }
             });
         }
     }
 
-    // write the lists
+    // rank the survivors and write the k best in order
+    __syncwarp();
+    static_for<0, R>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        const int q = q0 + r;
+        if (q >= a.Nq) return;
+        if (a.row_filter != nullptr && a.row_filter[(size_t)b * a.Nq + q] == 0) return;
+        float *ld = my_ld + r * CAP;
+        int *li = my_li + r * CAP;
+        float t = thr[r];
+        int n = cnt[r];
+        if (n > a.k + kSlack) n = shrink_list<SL>(ld, li, n, a.k, CAP, lane, t);   // cheap pre-shrink
+        rank_cut<SL>(ld, li, n, a.k, lane);                                         // k best, in order
+    });
+    __syncwarp();
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        int q = q0 + r;
+        const int q = q0 + r;
         if (q >= a.Nq) continue;
         if (a.row_filter != nullptr && a.row_filter[(size_t)b * a.Nq + q] == 0) continue;
-#pragma unroll
-        for (int s = 0; s < KS; ++s) {
-            int p = s * 32 + lane - (32 * KS - a.k);   // rank among the k real entries
-            if (p >= 0 && p % a.step == 0) {
-                int col = p / a.step;
-                size_t o = a.k_major ? ((size_t)b * a.kout + col) * a.Nq + q
-                                     : ((size_t)b * a.Nq + q) * a.kout + col;
-                int id = L[r].id[s] + a.index_base;
-                if (a.idx64) a.idx64[o] = id;
-                if (a.idx32) a.idx32[o] = id;
-                if (a.dist) a.dist[o] = sqrtf(L[r].v[s]);
-            }
+        for (int p = lane; p < a.k; p += 32) {
+            if (p % a.step) continue;
+            const int col = p / a.step;
+            const size_t o = a.k_major ? ((size_t)b * a.kout + col) * a.Nq + q
+                                       : ((size_t)b * a.Nq + q) * a.kout + col;
+            const int id = my_li[r * CAP + p] + a.index_base;
+            if (a.idx64) a.idx64[o] = id;
+            if (a.idx32) a.idx32[o] = id;
+            if (a.dist) a.dist[o] = sqrtf(my_ld[r * CAP + p]);
         }
     }
 }
@@ -408,11 +477,11 @@ static int pick_tile(int C, int Nr) {
     return tr < need ? tr : need;
 }
 
-template <int CDIM, int METRIC, int KS, int R>
+template <int CDIM, int METRIC, int SL, int R>
 static int launch_scan(ScanArgs a, int B, cudaStream_t st) {
     constexpr int QPB = kWarps * R;
-    size_t smem = ((size_t)a.C * a.TR + a.TR + (size_t)a.C * QPB) * sizeof(float);
-    auto kern = knn_scan_kernel<CDIM, METRIC, KS, R>;
+    size_t smem = ((size_t)a.C * a.TR + a.TR + (size_t)a.C * QPB + 2 * (size_t)QPB * 32 * SL) * sizeof(float);
+    auto kern = knn_scan_kernel<CDIM, METRIC, SL, R>;
     if (smem > 48 * 1024) GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(a.Nq, QPB), B);
     kern<<<grid, kThreads, smem, st>>>(a);
@@ -422,9 +491,10 @@ static int launch_scan(ScanArgs a, int B, cudaStream_t st) {
 
 template <int CDIM, int METRIC, int R>
 static int launch_scan_k(ScanArgs a, int B, cudaStream_t st) {
-    if (a.k <= 32) return launch_scan<CDIM, METRIC, 1, R>(a, B, st);
-    if (a.k <= 64) return launch_scan<CDIM, METRIC, 2, R>(a, B, st);
-    return launch_scan<CDIM, METRIC, 4, R>(a, B, st);
+    // list capacity 32*SL must hold k + kSlack survivors plus one 32-wide batch of new candidates
+    if (a.k + kSlack + 32 <= 96) return launch_scan<CDIM, METRIC, 3, R>(a, B, st);
+    if (a.k + kSlack + 32 <= 128) return launch_scan<CDIM, METRIC, 4, R>(a, B, st);
+    return launch_scan<CDIM, METRIC, 8, R>(a, B, st);
 }
 
 template <int METRIC>
@@ -481,10 +551,10 @@ static int scan_self(const float *x, const float *norms, const int *row_filter, 
     a.idx64 = idx64; a.idx32 = idx32; a.dist = nullptr; a.k_major = 0; a.index_base = 0;
     a.TR = pick_tile(C, N);
     if (metric == GCANET_METRIC_POINTS_NORMALS) {
-        if (k2 > 128) return launch_bigk<METRIC_PN>(a, B, st);
+        if (k2 > 200) return launch_bigk<METRIC_PN>(a, B, st);
         return launch_scan_k<6, METRIC_PN, 4>(a, B, st);
     }
-    if (k2 > 128) return launch_bigk<METRIC_L2>(a, B, st);
+    if (k2 > 200) return launch_bigk<METRIC_L2>(a, B, st);
     if (C == 3) return launch_scan_k<3, METRIC_L2, 4>(a, B, st);
     return launch_scan_k<0, METRIC_L2, 4>(a, B, st);
 }
@@ -561,7 +631,7 @@ extern "C" int gcanet_knn_cuda(const float *ref, int ref_nb, const float *query,
     a.idx64 = ind; a.idx32 = nullptr; a.dist = dist; a.k_major = 1; a.index_base = index_base;
     a.TR = pick_tile(dim, ref_nb);
     cudaStream_t st = as_stream(stream);
-    if (k > 128) return launch_bigk<METRIC_SSD>(a, batch, st);
+    if (k > 200) return launch_bigk<METRIC_SSD>(a, batch, st);
     if (dim == 3) return launch_scan_k<3, METRIC_SSD, 4>(a, batch, st);
     return launch_scan_k<0, METRIC_SSD, 4>(a, batch, st);
 }

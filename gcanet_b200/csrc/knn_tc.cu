@@ -66,19 +66,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // not steal issue slots from the epilogue warps that share the scheduler
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
     uint32_t done;
-    for (;;) {
+    do {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"   // hardware-suspended up to %3 ns
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
             : "memory");
-        if (done) break;
-        __nanosleep(40);
-    }
+    } while (!done);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -212,26 +210,15 @@ struct TcScanArgs {
     int N, k, tiles;     // tiles = ceil(N / TC_BN)
 };
 
-// Warp-cooperative compaction of one row's candidate list (entries [0, n) at `ptr`).
-// Finds hi with count(d <= hi) >= k by bisection, keeps d <= hi + margin, returns the new
-// count and threshold.  All 32 lanes participate; `ptr`, `n`, `margin` are warp-uniform.
-__device__ __forceinline__ void compact_row(uint2 *ptr, int n, int k, float margin, int lane, int &new_cnt, float &new_thr) {
-    constexpr int SL = TC_CAP / 32;
-    float dv[SL];
-    uint32_t di[SL];
+// Bisection over a warp-distributed list (entries e = s*32 + lane, +inf padding): returns hi with
+// count(d <= hi) >= k, stopping once <= k + TC_SLACK entries qualify or the interval is exhausted.
+template <int SL>
+__device__ __forceinline__ float select_bound(const float (&dv)[SL], int n, int k) {
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
 #pragma unroll
     for (int s = 0; s < SL; ++s) {
-        int e = s * 32 + lane;
-        dv[s] = CUDART_INF_F;
-        di[s] = 0;
-        if (e < n) {
-            uint2 t = ptr[e];
-            dv[s] = __uint_as_float(t.x);
-            di[s] = t.y;
-            mn = fminf(mn, dv[s]);
-            mx = fmaxf(mx, dv[s]);
-        }
+        mn = fminf(mn, dv[s]);
+        if (dv[s] < CUDART_INF_F) mx = fmaxf(mx, dv[s]);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -251,7 +238,27 @@ __device__ __forceinline__ void compact_row(uint2 *ptr, int n, int k, float marg
             if (c >= k) { hi = mid; c_hi = c; } else { lo = mid; }
         }
     }
-    const float keep_below = hi + margin;
+    return hi;
+}
+
+// Warp-cooperative compaction of one row's candidate list (entries [0, n) at `ptr`): keeps
+// d <= bound + margin, returns the new count and threshold.  `ptr`, `n`, `margin` are warp-uniform.
+__device__ __forceinline__ void compact_row(uint2 *ptr, int n, int k, float margin, int lane, int &new_cnt, float &new_thr) {
+    constexpr int SL = TC_CAP / 32;
+    float dv[SL];
+    uint32_t di[SL];
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        int e = s * 32 + lane;
+        dv[s] = CUDART_INF_F;
+        di[s] = 0;
+        if (e < n) {
+            uint2 t = ptr[e];
+            dv[s] = __uint_as_float(t.x);
+            di[s] = t.y;
+        }
+    }
+    const float keep_below = select_bound<SL>(dv, n, k) + margin;
     __syncwarp();
     int base = 0;
 #pragma unroll
@@ -426,18 +433,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
             if (++acc == ACC) { acc = 0; accphase ^= 1; }
         }
 
-        // final compaction of every row so the re-rank sees ~k + slack candidates
-        for (int r = 0; r < 32; ++r) {
-            const int n_r = __shfl_sync(FULLW, cnt, r);
-            const float m_r = __shfl_sync(FULLW, margin, r);
-            const unsigned long long p_r = __shfl_sync(FULLW, (unsigned long long)buf, r);
-            if (n_r > a.k + TC_SLACK) {
-                __syncwarp();
-                int nc; float nt;
-                compact_row(reinterpret_cast<uint2 *>(p_r), n_r, a.k, m_r, lane, nc, nt);
-                if (lane == r) cnt = nc;
-            }
-        }
+        // the last shrink of each list happens in the re-rank kernel (one warp per row, full occupancy)
         if (active) {
             a.cand_cnt[grow] = ovf ? 0 : cnt;
             a.overflow[grow] = (ovf || cnt < a.k) ? 1 : 0;
@@ -458,6 +454,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
 struct RerankArgs {
     const float *x_nc;     // [B][N][C]
     const float *norm;     // [B][N]
+    const float *nmax;     // [B]
     const uint2 *cand;     // [B][N][TC_CAP]
     const int *cand_cnt;   // [B][N]
     const int *overflow;   // [B][N]
@@ -466,10 +463,21 @@ struct RerankArgs {
     int N, k, step, kout;
 };
 
+template <int VEC>
+__device__ __forceinline__ void load_row(const float *p, float (&v)[VEC]) {
+    if constexpr (VEC == 2) {
+        float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y;
+    } else {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
     constexpr int VEC = C / 32;
     constexpr int SL = TC_CAP / 32;
+    __shared__ int s_idx[8][TC_CAP];
+    __shared__ float s_d[8][TC_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int q = blockIdx.x * 8 + warp;
@@ -479,62 +487,95 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
     const int n = a.cand_cnt[grow];
     const uint2 *cand = a.cand + grow * TC_CAP;
     const float *xb = a.x_nc + (size_t)b * a.N * C;
+    const float *nb = a.norm + (size_t)b * a.N;
+    int *sl = s_idx[warp];
+    float *sd = s_d[warp];
 
     float qv[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) qv[v] = xb[(size_t)q * C + lane * VEC + v];
-    const float qn = a.norm[grow];
+    load_row<VEC>(xb + (size_t)q * C + lane * VEC, qv);
+    const float qn = nb[q];
 
-    // my candidates: entries lane, lane+32, ...
-    float dv[SL];
-    int di[SL];
-#pragma unroll
-    for (int s = 0; s < SL; ++s) { dv[s] = CUDART_INF_F; di[s] = 0x7fffffff; }
+    // 1. last shrink of the list on the approximate distances (same bound + margin rule as the scan)
+    float ad[SL];
+    int aj[SL];
 #pragma unroll
     for (int s = 0; s < SL; ++s) {
-        if (s * 32 >= n) break;
         const int e = s * 32 + lane;
-        const int myj = e < n ? (int)cand[e].y : -1;
-        const int cntc = min(32, n - s * 32);
-        float mine = CUDART_INF_F;
-        for (int l = 0; l < cntc; ++l) {
-            const int j = __shfl_sync(FULLW, myj, l);
-            const float *xr = xb + (size_t)j * C + lane * VEC;
-            float part = 0.f;
+        ad[s] = CUDART_INF_F;
+        aj[s] = 0;
+        if (e < n) { uint2 t = cand[e]; ad[s] = __uint_as_float(t.x); aj[s] = (int)t.y; }
+    }
+    float keep_below = CUDART_INF_F;
+    if (n > a.k + TC_SLACK) keep_below = select_bound<SL>(ad, n, a.k) + TC_MARGIN * sqrtf(qn * a.nmax[b]);
+    int m = 0;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) part = fmaf(qv[v], __ldg(xr + v), part);
+    for (int s = 0; s < SL; ++s) {
+        const bool keep = ad[s] < CUDART_INF_F && ad[s] <= keep_below;
+        const unsigned msk = __ballot_sync(FULLW, keep);
+        if (keep) sl[m + __popc(msk & ((1u << lane) - 1))] = aj[s];
+        m += __popc(msk);
+    }
+    __syncwarp();
+
+    // 2. exact fp32 distances of the m survivors, four at a time (coalesced row loads, one
+    //    6-shuffle transposing reduction per four candidates)
+    for (int e0 = 0; e0 < m; e0 += 4) {
+        float part[4];
+        int jj[4];
 #pragma unroll
-            for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(FULLW, part, o);
+        for (int u = 0; u < 4; ++u) {
+            jj[u] = sl[min(e0 + u, m - 1)];
+            float xv[VEC];
+            load_row<VEC>(xb + (size_t)jj[u] * C + lane * VEC, xv);
+            float p = 0.f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) p = fmaf(qv[v], xv[v], p);
+            part[u] = p;
+        }
+        const bool h16 = lane & 16, h8 = lane & 8;
+        float k0 = h16 ? part[2] : part[0], k1 = h16 ? part[3] : part[1];
+        const float s0 = h16 ? part[0] : part[2], s1 = h16 ? part[1] : part[3];
+        k0 += __shfl_xor_sync(FULLW, s0, 16);
+        k1 += __shfl_xor_sync(FULLW, s1, 16);
+        float kk = h8 ? k1 : k0;
+        const float ss = h8 ? k0 : k1;
+        kk += __shfl_xor_sync(FULLW, ss, 8);
+        kk += __shfl_xor_sync(FULLW, kk, 4);
+        kk += __shfl_xor_sync(FULLW, kk, 2);
+        kk += __shfl_xor_sync(FULLW, kk, 1);
+        // lanes 8u .. 8u+7 now hold the dot product of candidate e0 + u
+        const int u = lane >> 3;
+        if ((lane & 7) == 0 && e0 + u < m) {
+            const int j = u == 0 ? jj[0] : (u == 1 ? jj[1] : (u == 2 ? jj[2] : jj[3]));
             // reference arithmetic: fl(fl(|x_j|^2 - 2 t) + |x_i|^2)
-            const float d = __fadd_rn(fmaf(-2.f, part, a.norm[(size_t)b * a.N + j]), qn);
-            if (l == lane) mine = d;
+            sd[e0 + u] = __fadd_rn(fmaf(-2.f, kk, nb[j]), qn);
         }
-        dv[s] = mine;
-        if (myj >= 0) di[s] = myj;
     }
+    __syncwarp();
 
-    // rank of each of my candidates among all n by (distance, index)
-    int rank[SL];
+    // 3. rank the survivors by (distance, index) and write the k best in order
+    float dv[SL];
+    int di[SL], rank[SL];
 #pragma unroll
-    for (int s = 0; s < SL; ++s) rank[s] = 0;
+    for (int s = 0; s < SL; ++s) {
+        const int e = s * 32 + lane;
+        dv[s] = e < m ? sd[e] : CUDART_INF_F;
+        di[s] = e < m ? sl[e] : 0x7fffffff;
+        rank[s] = 0;
+    }
+    for (int e = 0; e < m; ++e) {
+        const float od = sd[e];
+        const int oi = sl[e];
 #pragma unroll
-    for (int s2 = 0; s2 < SL; ++s2) {
-        if (s2 * 32 >= n) break;
-        const int cntc = min(32, n - s2 * 32);
-        for (int l = 0; l < cntc; ++l) {
-            const float od = __shfl_sync(FULLW, dv[s2], l);
-            const int oi = __shfl_sync(FULLW, di[s2], l);
-#pragma unroll
-            for (int s = 0; s < SL; ++s) {
-                if (s * 32 >= n) break;
-                rank[s] += (od < dv[s] || (od == dv[s] && oi < di[s])) ? 1 : 0;
-            }
+        for (int s = 0; s < SL; ++s) {
+            if (s * 32 >= m) break;
+            rank[s] += (od < dv[s] || (od == dv[s] && oi < di[s])) ? 1 : 0;
         }
     }
 #pragma unroll
     for (int s = 0; s < SL; ++s) {
         const int e = s * 32 + lane;
-        if (e < n && rank[s] < a.k && rank[s] % a.step == 0) {
+        if (e < m && rank[s] < a.k && rank[s] % a.step == 0) {
             const size_t o = grow * a.kout + rank[s] / a.step;
             if (a.idx64) a.idx64[o] = di[s];
             if (a.idx32) a.idx32[o] = di[s];
@@ -640,7 +681,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     if (cr != CUDA_SUCCESS) { set_error("knn_graph: cuTensorMapEncodeTiled failed (%d)", (int)cr); return GCANET_ERR_CUDA; }
 
     TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, ceil_div(N, TC_BN)};
-    RerankArgs ra{x_nc, norm, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2)};
+    RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2)};
     rc = C == 64 ? launch_tc<64>(tmap, sa, ra, B, st) : launch_tc<128>(tmap, sa, ra, B, st);
     if (rc) return rc;
     return knn_fallback_rows(x, norm, overflow, B, C, N, k1, k2, idx64, idx32, st);
