@@ -27,11 +27,12 @@ namespace gcanet {
 
 constexpr unsigned FULLW = 0xffffffffu;
 constexpr int TC_BM = 128;            // queries per CTA  (UMMA M)
-constexpr int TC_BN = 128;            // keys per tile    (UMMA N)
+constexpr int TC_BN = 64;             // keys per tile    (UMMA N); 64 keeps a CTA at ~66 KB so three share an SM
 constexpr int TC_KB = 64;             // bf16 elements per 128-byte swizzle row
 constexpr int TC_CAP = 256;           // candidate list capacity per query
 constexpr int TC_SLACK = 8;           // bisection stops once the bound keeps <= k + slack entries
 constexpr int TC_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int TC_NRING = 8;           // key-norm ring slots (producer is never more than 4 tiles ahead of the epilogue)
 constexpr float TC_MARGIN = 7.0e-4f;  // ~2^-10.5 : margin = TC_MARGIN * |q| * max|k|  
 
 // ---------------------------------------------------------------------------------
@@ -86,6 +87,12 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted on the same mbarrier as the tensor loads
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -274,20 +281,23 @@ __device__ __forceinline__ void compact_row(uint2 *ptr, int n, int k, float marg
 }
 
 template <int C>
-__global__ void __launch_bounds__(TC_THREADS, C == 64 ? 2 : 1)
-knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, C == 64 ? 3 : 1)
+knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, TcScanArgs a) {
     constexpr int NBLK = 2 * C / TC_KB;                 // 128-byte K blocks per row: hi blocks then lo blocks
     constexpr int NH = C / TC_KB;                       // hi (= lo) blocks
-    constexpr int BLK_BYTES = TC_BM * 128;              // one K block of a 128-row tile: 16 KB
-    constexpr int TILE_BYTES = NBLK * BLK_BYTES;        // 32 KB (C=64) / 64 KB (C=128)
-    constexpr int STAGES = 2;                           // C = 64: 96 KB per CTA -> two CTAs share an SM
+    constexpr int ABLK_BYTES = TC_BM * 128;             // one K block of the 128-query tile: 16 KB
+    constexpr int A_BYTES = NBLK * ABLK_BYTES;          // 32 KB (C=64) / 64 KB (C=128)
+    constexpr int BLK_BYTES = TC_BN * 128;              // one K block of a 64-key tile: 8 KB
+    constexpr int TILE_BYTES = NBLK * BLK_BYTES;        // 16 KB (C=64) / 32 KB (C=128)
+    constexpr int STAGES = 2;                           // C = 64: 32 + 2*16 KB per CTA -> three CTAs share an SM
     constexpr int ACC = 2;                              // TMEM accumulator stages
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                                  // query tile
-    uint8_t *sB = smem + TILE_BYTES;                     // STAGES key tiles
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * TILE_BYTES);
+    uint8_t *sB = smem + A_BYTES;                        // STAGES key tiles
+    float *s_rn = reinterpret_cast<float *>(sB + STAGES * TILE_BYTES);      // [TC_NRING][TC_BN] key norms
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_rn + TC_NRING * TC_BN);
     uint64_t *full = bars;                 // [STAGES]  TMA -> MMA
     uint64_t *empty = bars + STAGES;       // [STAGES]  MMA -> TMA
     uint64_t *a_full = bars + 2 * STAGES;  // [1]
@@ -301,7 +311,8 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
     const int tiles = a.tiles;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap);
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(a_full, 1);
         for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
@@ -316,17 +327,21 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(a_full, TILE_BYTES);
+            mbar_expect_tx(a_full, A_BYTES);
 #pragma unroll
-            for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(sA + kb * BLK_BYTES, &tmap, a_full, kb * TC_KB, q0, b);
+            for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(sA + kb * ABLK_BYTES, &tmap_q, a_full, kb * TC_KB, q0, b);
+            const float *rn_g = a.norm_pad + (size_t)b * a.Npad;
             int stage = 0;
             uint32_t phase = 0;
             for (int t = 0; t < tiles; ++t) {
                 mbar_wait_backoff(&empty[stage], phase ^ 1);
-                mbar_expect_tx(&full[stage], TILE_BYTES);
+                mbar_expect_tx(&full[stage], TILE_BYTES + TC_BN * sizeof(float));
                 uint8_t *dst = sB + stage * TILE_BYTES;
 #pragma unroll
-                for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(dst + kb * BLK_BYTES, &tmap, &full[stage], kb * TC_KB, t * TC_BN, b);
+                for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(dst + kb * BLK_BYTES, &tmap_k, &full[stage], kb * TC_KB, t * TC_BN, b);
+                // this tile's key norms ride on the same barrier; by the time the MMA that consumed the
+                // stage has committed to t_full, the epilogue may read them
+                bulk_load_1d(s_rn + (t % TC_NRING) * TC_BN, rn_g + (size_t)t * TC_BN, TC_BN * sizeof(float), &full[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -350,8 +365,8 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
 #pragma unroll
                     for (int ks = 0; ks < TC_KB / 16; ++ks) {
                         const uint32_t koff = ks * 32;        // 16 bf16 = 32 bytes inside the swizzled row
-                        const uint64_t a_hi = make_kmajor_sw128_desc(a_addr + hb * BLK_BYTES + koff);
-                        const uint64_t a_lo = make_kmajor_sw128_desc(a_addr + (NH + hb) * BLK_BYTES + koff);
+                        const uint64_t a_hi = make_kmajor_sw128_desc(a_addr + hb * ABLK_BYTES + koff);
+                        const uint64_t a_lo = make_kmajor_sw128_desc(a_addr + (NH + hb) * ABLK_BYTES + koff);
                         const uint64_t b_hi = make_kmajor_sw128_desc(b_addr + hb * BLK_BYTES + koff);
                         const uint64_t b_lo = make_kmajor_sw128_desc(b_addr + (NH + hb) * BLK_BYTES + koff);
                         umma_bf16(d_tmem, a_hi, b_hi, kIdesc, accum);
@@ -379,7 +394,6 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
         float thr = active ? CUDART_INF_F : -CUDART_INF_F;   // inactive rows never append
         int cnt = 0;
         bool ovf = false;
-        const float4 *rn4 = reinterpret_cast<const float4 *>(a.norm_pad + (size_t)b * a.Npad);
 
         int acc = 0;
         uint32_t accphase = 0;
@@ -394,10 +408,10 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap, TcScanArgs a) {
                 tmem_ld_wait();                                     // chunk ch is in v[ch & 1]
                 if (ch + 1 < TC_BN / 32) tmem_ld32(taddr + (ch + 1) * 32, v[(ch + 1) & 1]);   // prefetch the next chunk
                 const int jbase = t * TC_BN + ch * 32;
-                const float4 *rn = rn4 + (jbase >> 2);               // same address in every lane: one broadcast load
+                const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (t % TC_NRING) * TC_BN + ch * 32);   // broadcast reads
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 n4 = __ldg(rn + c4);
+                    const float4 n4 = rn[c4];
                     const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -617,7 +631,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
 }
 
 bool knn_tc_supported(int C, int N, int k2) {
-    return (C == 64 || C == 128) && k2 <= 128 && N >= TC_BN && k2 + TC_SLACK + 64 <= TC_CAP;
+    return (C == 64 || C == 128) && k2 <= 128 && N >= TC_BM && k2 + TC_SLACK + 64 <= TC_CAP;
 }
 
 // declared in knn_select.cu
@@ -626,15 +640,15 @@ int knn_fallback_rows(const float *x, const float *norms, const int *row_filter,
                       int64_t *idx64, int32_t *idx32, cudaStream_t st);
 
 template <int C>
-static int launch_tc(const CUtensorMap &tmap, TcScanArgs sa, RerankArgs ra, int B, cudaStream_t st) {
+static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcScanArgs sa, RerankArgs ra, int B, cudaStream_t st) {
     constexpr int NBLK = 2 * C / TC_KB;
-    constexpr int TILE_BYTES = NBLK * TC_BM * 128;
     constexpr int STAGES = 2;
-    const size_t smem = 1024 + (size_t)(1 + STAGES) * TILE_BYTES + 32 * sizeof(uint64_t);
+    const size_t smem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)STAGES * NBLK * TC_BN * 128 +
+                        TC_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t);
     auto kern = knn_tc_scan_kernel<C>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(sa.N, TC_BM), B);
-    kern<<<grid, TC_THREADS, smem, st>>>(tmap, sa);
+    kern<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
     GCANET_LAUNCH_OK("knn_tc_scan_kernel");
     dim3 rgrid(ceil_div(sa.N, 8), B);
     knn_tc_rerank_kernel<C><<<rgrid, 256, 0, st>>>(ra);
@@ -670,19 +684,24 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
 
     // 3-D tensor map over xs: (K = 2C bf16, N rows, B clouds), box = (64, 128, 1), 128-byte swizzle;
     // rows past N are zero-filled, so a partial last tile never reads the next cloud.
-    CUtensorMap tmap;
+    CUtensorMap tmap_q, tmap_k;
     cuuint64_t gdim[3] = {(cuuint64_t)(2 * C), (cuuint64_t)N, (cuuint64_t)B};
     cuuint64_t gstride[2] = {(cuuint64_t)(2 * C) * sizeof(__nv_bfloat16), (cuuint64_t)N * 2 * C * sizeof(__nv_bfloat16)};
-    cuuint32_t box[3] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_BM, 1};
     cuuint32_t estride[3] = {1, 1, 1};
-    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, xs, gdim, gstride, box, estride,
+    cuuint32_t box_q[3] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_BM, 1};
+    cuuint32_t box_k[3] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_BN, 1};
+    CUresult cr = encode(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, xs, gdim, gstride, box_q, estride,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr == CUDA_SUCCESS)
+        cr = encode(&tmap_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, xs, gdim, gstride, box_k, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("knn_graph: cuTensorMapEncodeTiled failed (%d)", (int)cr); return GCANET_ERR_CUDA; }
 
     TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, ceil_div(N, TC_BN)};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2)};
-    rc = C == 64 ? launch_tc<64>(tmap, sa, ra, B, st) : launch_tc<128>(tmap, sa, ra, B, st);
+    rc = C == 64 ? launch_tc<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<128>(tmap_q, tmap_k, sa, ra, B, st);
     if (rc) return rc;
     return knn_fallback_rows(x, norm, overflow, B, C, N, k1, k2, idx64, idx32, st);
 }
