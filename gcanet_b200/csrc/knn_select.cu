@@ -16,16 +16,12 @@
 //   SSD  (KNN/csrc/cuda/knn.cu:73-76)  d = sum_c fma(t, t, d), t = ref_c - query_c
 // Ties: ranking by (distance, index) keeps the lower reference index first and a later
 // candidate equal to the k-th never displaces it (knn.cu:125,149).
-#include "common.cuh"
-
-#include <math_constants.h>
-#include <type_traits>
+#include "knn_lists.cuh"
 
 namespace gcanet {
 
 enum { METRIC_L2 = 0, METRIC_PN = 1, METRIC_SSD = 2 };
 
-constexpr unsigned FULL = 0xffffffffu;
 constexpr int kWarps = 8;               // warps per CTA
 constexpr int kThreads = kWarps * 32;
 
@@ -45,105 +41,6 @@ __global__ void sqnorm_kernel(const float *__restrict__ x, float *__restrict__ o
     out[(size_t)b * N + n] = s;
 }
 
-// ---------------------------------------------------------------------------------
-// per-query candidate list in shared memory, maintained by one warp
-// ---------------------------------------------------------------------------------
-constexpr int kSlack = 8;     // the bisection stops once the bound keeps <= k + kSlack entries
-
-// compile-time loop: keeps per-query state indexed by constants so it stays in registers
-template <int I, int N, typename F>
-__device__ __forceinline__ void static_for(F &&f) {
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
-
-// Ranks the n entries of a list by (distance, index), keeps the min(n, k) smallest IN ORDER
-// (entry of rank r moves to slot r) and returns the largest kept distance.
-template <int SL>
-__device__ __forceinline__ float rank_cut(float *ld, int *li, int n, int k, int lane) {
-    float dv[SL];
-    int di[SL], rank[SL];
-#pragma unroll
-    for (int s = 0; s < SL; ++s) {
-        const int e = s * 32 + lane;
-        dv[s] = e < n ? ld[e] : CUDART_INF_F;
-        di[s] = e < n ? li[e] : 0x7fffffff;
-        rank[s] = 0;
-    }
-    for (int e = 0; e < n; ++e) {
-        const float od = ld[e];
-        const int oi = li[e];
-#pragma unroll
-        for (int s = 0; s < SL; ++s) {
-            if (s * 32 >= n) break;
-            rank[s] += (od < dv[s] || (od == dv[s] && oi < di[s])) ? 1 : 0;
-        }
-    }
-    __syncwarp();
-    float kth = -CUDART_INF_F;
-#pragma unroll
-    for (int s = 0; s < SL; ++s) {
-        if (s * 32 + lane < n && rank[s] < k) { ld[rank[s]] = dv[s]; li[rank[s]] = di[s]; kth = fmaxf(kth, dv[s]); }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(FULL, kth, o));
-    __syncwarp();
-    return kth;
-}
-
-// Shrinks a list of n > k entries to those with d <= bound, where count(d <= bound) >= k and,
-// ties permitting, <= k + kSlack (bisection on the values).  If ties would keep more than
-// `limit` entries the list is cut to exactly the k smallest by (distance, index) instead.
-// Returns the new count; `thr` becomes the bound: later candidates must be strictly below it
-// (they have larger indices, so an equal distance loses the tie anyway).
-template <int SL>
-__device__ __forceinline__ int shrink_list(float *ld, int *li, int n, int k, int limit, int lane, float &thr) {
-    float dv[SL];
-    int di[SL];
-    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-#pragma unroll
-    for (int s = 0; s < SL; ++s) {
-        const int e = s * 32 + lane;
-        dv[s] = CUDART_INF_F;
-        di[s] = 0x7fffffff;
-        if (e < n) { dv[s] = ld[e]; di[s] = li[e]; mn = fminf(mn, dv[s]); mx = fmaxf(mx, dv[s]); }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
-    }
-    float lo = mn, hi = mx;
-    int c_hi = n;
-    for (int it = 0; it < 32 && c_hi > k + kSlack; ++it) {
-        const float mid = 0.5f * lo + 0.5f * hi;
-        if (!(mid > lo && mid < hi)) break;            // interval exhausted: ties at hi
-        int c = 0;
-#pragma unroll
-        for (int s = 0; s < SL; ++s) c += (dv[s] <= mid) ? 1 : 0;
-        c = __reduce_add_sync(FULL, c);
-        if (c >= k) { hi = mid; c_hi = c; } else { lo = mid; }
-    }
-    __syncwarp();
-    if (c_hi > limit) {
-        thr = rank_cut<SL>(ld, li, n, k, lane);
-        return k;
-    }
-    int base = 0;
-#pragma unroll
-    for (int s = 0; s < SL; ++s) {
-        const bool keep = dv[s] <= hi && s * 32 + lane < n;
-        const unsigned m = __ballot_sync(FULL, keep);
-        if (keep) { const int p = base + __popc(m & ((1u << lane) - 1)); ld[p] = dv[s]; li[p] = di[s]; }
-        base += __popc(m);
-    }
-    __syncwarp();
-    thr = hi;
-    return base;
-}
-
 struct ScanArgs {
     const float *ref;       // [B][C][Nr]
     const float *qry;       // [B][C][Nq]
@@ -158,6 +55,7 @@ struct ScanArgs {
     int index_base;
     int TR;                 // reference tile (multiple of 32)
     const int *row_filter;  // optional [B][Nq]: only queries with a non-zero flag are computed / written
+    const int *cloud_filter;  // optional [B]: only clouds with a non-zero flag are computed
 };
 
 // CDIM > 0: compile-time dimension, queries in registers.  CDIM == 0: runtime C, queries in smem.
@@ -181,6 +79,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
     const float *ref = a.ref + (size_t)b * C * a.Nr;
     const float *qry = a.qry + (size_t)b * C * a.Nq;
 
+    if (a.cloud_filter != nullptr && a.cloud_filter[b] == 0) return;
     if (a.row_filter != nullptr) {
         // fallback mode: leave unless one of this CTA's queries is flagged
         int flagged = 0;
@@ -375,6 +274,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_bigk_kernel(ScanArgs a) {
     int *li = reinterpret_cast<int *>(lv + (size_t)kWarps * k);
 
     const int b = blockIdx.y;
+    if (a.cloud_filter != nullptr && a.cloud_filter[b] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * kWarps + warp;
     const float *ref = a.ref + (size_t)b * C * a.Nr;
@@ -526,7 +426,7 @@ int launch_sqnorm_public(const float *x, float *out, int B, int C, int Cuse, int
 }
 
 static int scan_self(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
-                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st);
+                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st, const int *cloud_filter = nullptr);
 
 // re-runs the CUDA-core scan for the queries flagged in row_filter (tensor-core path overflow)
 int knn_fallback_rows(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
@@ -542,9 +442,10 @@ int knn_graph_cuda_cores(const float *x, int B, int C, int N, int k1, int k2, in
 }
 
 static int scan_self(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
-                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st) {
+                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st, const int *cloud_filter) {
     ScanArgs a{};
     a.row_filter = row_filter;
+    a.cloud_filter = cloud_filter;
     a.ref = x; a.qry = x; a.ref_norm = norms; a.qry_norm = norms;
     a.C = C; a.Nr = N; a.Nq = N; a.k = k2;
     a.step = k2 / k1; a.kout = gcanet_knn_graph_columns(k1, k2);
@@ -558,6 +459,12 @@ static int scan_self(const float *x, const float *norms, const int *row_filter, 
     if (C == 3) return launch_scan_k<3, METRIC_L2, 4>(a, B, st);
     return launch_scan_k<0, METRIC_L2, 4>(a, B, st);
 }
+
+// knn_xyz.cu
+bool knn_xyz_supported(int C, int N, int k2, int metric);
+size_t knn_xyz_workspace_bytes(int B, int C, int N);
+int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metric, int64_t *idx64, int32_t *idx32,
+                  void *ws, float **norm_out, int **fallback_out, cudaStream_t st);
 
 // knn_tc.cu
 size_t knn_tc_workspace_bytes(int B, int C, int N);
@@ -582,6 +489,7 @@ static bool use_tensor_cores(int C, int N, int k2, int metric) {
 extern "C" size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric) {
     if (B < 1 || C < 1 || N < 1) return 0;
     if (use_tensor_cores(C, N, k2, metric)) return knn_tc_workspace_bytes(B, C, N);
+    if (knn_xyz_supported(C, N, k2, metric)) return knn_xyz_workspace_bytes(B, C, N);   // false when a flag bit is set
     return align_up((size_t)B * N * sizeof(float));
 }
 
@@ -594,7 +502,7 @@ extern "C" int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int
     GCANET_REQUIRE(k2 <= N, "knn_graph: k2=%d exceeds the number of points N=%d (topk would raise, M4:43)", k2, N);
     GCANET_REQUIRE(k2 <= 1024, "knn_graph: k2=%d > 1024 unsupported", k2);
     const int flags = metric & ~0xff;
-    GCANET_REQUIRE((flags & ~GCANET_KNN_FLAG_NO_TENSOR_CORES) == 0, "knn_graph: unknown flag bits in metric 0x%x", metric);
+    GCANET_REQUIRE((flags & ~GCANET_KNN_FLAG_BRUTE_FORCE) == 0, "knn_graph: unknown flag bits in metric 0x%x", metric);
     const int metric_in = metric;
     metric &= 0xff;
     GCANET_REQUIRE(metric == GCANET_METRIC_L2 || metric == GCANET_METRIC_POINTS_NORMALS, "knn_graph: bad metric %d", metric);
@@ -608,6 +516,14 @@ extern "C" int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int
     }
     if (flags == 0 && use_tensor_cores(C, N, k2, metric))
         return knn_graph_tensor_cores(x, B, C, N, k1, k2, idx64, idx32, ws, as_stream(stream));
+    if (flags == 0 && knn_xyz_supported(C, N, k2, metric)) {
+        float *norms = nullptr;
+        int *cloud_fallback = nullptr;
+        int rc = knn_graph_xyz(x, B, C, N, k1, k2, metric, idx64, idx32, ws, &norms, &cloud_fallback, as_stream(stream));
+        if (rc) return rc;
+        // clouds the pruned scan declined (points x normals with non-unit normals): brute force, filtered per cloud
+        return scan_self(x, norms, nullptr, B, C, N, k1, k2, metric, idx64, idx32, as_stream(stream), cloud_fallback);
+    }
     return knn_graph_cuda_cores(x, B, C, N, k1, k2, metric, idx64, idx32, static_cast<float *>(ws), as_stream(stream));
 }
 

@@ -68,15 +68,16 @@ def _as_f32_contig(x: torch.Tensor, name: str) -> torch.Tensor:
 # ----------------------------------------------------------------------------------
 # kNN graph (torch path)
 # ----------------------------------------------------------------------------------
-KNN_FLAG_NO_TENSOR_CORES = 0x100
+KNN_FLAG_BRUTE_FORCE = 0x100
 
 
 def knn_graph(x: torch.Tensor, k1: int, k2: int, metric: int = METRIC_L2, want64: bool = True,
-              want32: bool = False, tensor_cores: bool = True):
-    """x [B, C, N] -> (idx64 or None, idx32 or None), each [B, N, kout].  ``tensor_cores=False``
-    forces the CUDA-core scan where the tcgen05 path would apply (A/B tests)."""
-    if not tensor_cores:
-        metric = metric | KNN_FLAG_NO_TENSOR_CORES
+              want32: bool = False, tensor_cores: bool = True, brute_force: bool = False):
+    """x [B, C, N] -> (idx64 or None, idx32 or None), each [B, N, kout].  ``brute_force=True`` (or
+    the older ``tensor_cores=False``) forces the plain CUDA-core scan where an accelerated path
+    (tcgen05 pruning for C = 64/128, spatial pruning for xyz clouds) would apply -- for A/B tests."""
+    if brute_force or not tensor_cores:
+        metric = metric | KNN_FLAG_BRUTE_FORCE
     x = _as_f32_contig(x.detach(), "x")
     if x.dim() != 3:
         raise RuntimeError(f"x must be [B, C, N] (got {tuple(x.shape)})")

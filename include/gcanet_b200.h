@@ -55,10 +55,11 @@ typedef enum {
     GCANET_METRIC_POINTS_NORMALS = 1 /* d_p * (1 + (2 - 2 n_i.n_j)), needs C = 6 (M4:61-73)   */
 } gcanet_metric;
 
-/* May be OR-ed into `metric`: run the CUDA-core scan even where the tensor-core path applies
- * (C = 64 / 128 with the L2 metric).  Both paths return fp32-exact neighbour lists; the flag
- * exists for A/B tests and benchmarks. */
-#define GCANET_KNN_FLAG_NO_TENSOR_CORES 0x100
+/* May be OR-ed into `metric`: run the plain brute-force CUDA-core scan even where an accelerated
+ * path applies (tensor-core pruning for C = 64 / 128, spatial pruning for xyz clouds).  All
+ * paths return the same fp32-exact neighbour lists; the flag exists for A/B tests and benchmarks. */
+#define GCANET_KNN_FLAG_BRUTE_FORCE 0x100
+#define GCANET_KNN_FLAG_NO_TENSOR_CORES GCANET_KNN_FLAG_BRUTE_FORCE
 
 /* Edge-feature variant of gcanet_graph_feature*. */
 typedef enum {
@@ -92,7 +93,9 @@ GCANET_API int gcanet_nc_to_cn(const float *x_nc, float *x_cn, int B, int C, int
  * Distances are fp32 with the reference's expansion arithmetic; no N x N matrix is
  * ever written to memory.  For C = 64 / 128 (L2 metric, k2 <= 128, N >= 128) candidates are
  * pruned on the tensor cores (tcgen05, bf16x3 split) and the survivors re-ranked in exact
- * fp32; every other shape runs the CUDA-core scan. */
+ * fp32; xyz clouds (C = 3 L2, C = 6 points x normals, N >= 256) are Morton-sorted and scanned
+ * with AABB pruning; every other shape runs the brute-force CUDA-core scan.  The result does not
+ * depend on the path. */
 GCANET_API int gcanet_knn_graph_columns(int k1, int k2);
 GCANET_API size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric);
 GCANET_API int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int k2, int metric,

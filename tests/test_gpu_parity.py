@@ -131,6 +131,36 @@ def test_knn_tensor_core_path_on_activations_and_ties():
     check_knn_rows(i_h, orc.knn(xh, 50, 50), orc.knn_scores(xh), knn_tau(xh), check_order=True)
 
 
+# ------------------------------------------------------------------------------ spatially pruned xyz kNN
+@pytest.mark.parametrize("C,N,k,B,k1", [(3, 257, 20, 2, 20), (3, 10000, 50, 3, 50), (3, 10000, 80, 1, 80), (3, 5000, 20, 2, 10),
+                                        (6, 10000, 50, 2, 50), (6, 3001, 80, 2, 80), (3, 100000, 50, 1, 50), (3, 4000, 150, 1, 150)])
+def test_knn_xyz_pruned_path_equals_brute_force(C, N, k, B, k1):
+    """Morton sort + AABB pruning evaluates a fraction of the pairs but uses the same fp32 distance
+    arithmetic and the same (distance, index) ranking: the lists must be IDENTICAL to the brute-force scan."""
+    x = _t(abc_like_batch(B, N, seed=N + k, with_normals=(C == 6)))
+    x[:, :, 11] = x[:, :, 5]                                   # coincident points: index tie-break
+    xd = x.to(DEV)
+    metric = G.METRIC_POINTS_NORMALS if C == 6 else G.METRIC_L2
+    fast = G.knn_graph(xd, k1, k, metric)[0]
+    slow = G.knn_graph(xd, k1, k, metric, brute_force=True)[0]
+    assert torch.equal(fast, slow)
+
+
+def test_knn_xyz_pruned_path_degenerate_inputs():
+    # non-unit normals: no usable lower bound -> per-cloud brute-force fallback inside the same call
+    x = _t(abc_like_batch(2, 2000, seed=3, with_normals=True))
+    x[1, 3:6] *= 1.7
+    a = G.knn_graph(x.to(DEV), 30, 30, G.METRIC_POINTS_NORMALS)[0]
+    b = G.knn_graph(x.to(DEV), 30, 30, G.METRIC_POINTS_NORMALS, brute_force=True)[0]
+    assert torch.equal(a, b)
+    # all points identical / points on a line / a tiny cluster plus far outliers
+    for xx in (torch.ones(1, 3, 700), torch.linspace(0, 1, 900).view(1, 1, 900).repeat(1, 3, 1),
+               torch.cat([torch.randn(1, 3, 600) * 1e-3, torch.randn(1, 3, 40) * 50], dim=2)):
+        a = G.knn_graph(xx.to(DEV), 40, 40)[0]
+        b = G.knn_graph(xx.to(DEV), 40, 40, brute_force=True)[0]
+        assert torch.equal(a, b)
+
+
 def test_knn_errors():
     x = torch.randn(1, 3, 10)
     with pytest.raises(RuntimeError, match="no CPU path"):
