@@ -391,9 +391,10 @@ static int launch_scan(ScanArgs a, int B, cudaStream_t st) {
 
 template <int CDIM, int METRIC, int R>
 static int launch_scan_k(ScanArgs a, int B, cudaStream_t st) {
-    // list capacity 32*SL must hold k + kSlack survivors plus one 32-wide batch of new candidates
-    if (a.k + kSlack + 32 <= 96) return launch_scan<CDIM, METRIC, 3, R>(a, B, st);
-    if (a.k + kSlack + 32 <= 128) return launch_scan<CDIM, METRIC, 4, R>(a, B, st);
+    // list capacity 32*SL holds the k + kSlack survivors of a shrink, one 32-wide batch of new
+    // candidates, and >= 48 free slots so that shrinks stay rare
+    if (a.k <= 40) return launch_scan<CDIM, METRIC, 4, R>(a, B, st);
+    if (a.k <= 104) return launch_scan<CDIM, METRIC, 6, R>(a, B, st);
     return launch_scan<CDIM, METRIC, 8, R>(a, B, st);
 }
 
@@ -452,10 +453,10 @@ static int scan_self(const float *x, const float *norms, const int *row_filter, 
     a.idx64 = idx64; a.idx32 = idx32; a.dist = nullptr; a.k_major = 0; a.index_base = 0;
     a.TR = pick_tile(C, N);
     if (metric == GCANET_METRIC_POINTS_NORMALS) {
-        if (k2 > 200) return launch_bigk<METRIC_PN>(a, B, st);
+        if (k2 > 168) return launch_bigk<METRIC_PN>(a, B, st);
         return launch_scan_k<6, METRIC_PN, 4>(a, B, st);
     }
-    if (k2 > 200) return launch_bigk<METRIC_L2>(a, B, st);
+    if (k2 > 168) return launch_bigk<METRIC_L2>(a, B, st);
     if (C == 3) return launch_scan_k<3, METRIC_L2, 4>(a, B, st);
     return launch_scan_k<0, METRIC_L2, 4>(a, B, st);
 }
@@ -547,7 +548,7 @@ extern "C" int gcanet_knn_cuda(const float *ref, int ref_nb, const float *query,
     a.idx64 = ind; a.idx32 = nullptr; a.dist = dist; a.k_major = 1; a.index_base = index_base;
     a.TR = pick_tile(dim, ref_nb);
     cudaStream_t st = as_stream(stream);
-    if (k > 200) return launch_bigk<METRIC_SSD>(a, batch, st);
+    if (k > 168) return launch_bigk<METRIC_SSD>(a, batch, st);
     if (dim == 3) return launch_scan_k<3, METRIC_SSD, 4>(a, batch, st);
     return launch_scan_k<0, METRIC_SSD, 4>(a, batch, st);
 }

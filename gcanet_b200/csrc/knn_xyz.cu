@@ -255,8 +255,9 @@ __global__ void __launch_bounds__(XW * 32) knn_xyz_kernel(XyzArgs a) {
     // phase 2: every other tile, pruned by its AABB lower bound
     for (int base = 0; base < tiles; base += 32) {
         const int t = base + lane;
-        float lb = CUDART_INF_F;
-        if (t < tiles && (t < lo_t || t > hi_t)) {
+        const bool mine = t < tiles && (t < lo_t || t > hi_t);     // tiles of phase 1 are never rescanned
+        float lb = 0.f;
+        if (mine) {
             const float *bx = s_aabb + t * 6;
             float acc = 0.f;
 #pragma unroll
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(XW * 32) knn_xyz_kernel(XyzArgs a) {
             lb = cmin * acc * (1.f - 1e-5f) - abs_slack;
         }
         float tmax = fmaxf(fmaxf(thr[0], thr[1]), fmaxf(thr[2], thr[3]));
-        unsigned todo = __ballot_sync(FULL, lb <= tmax);
+        unsigned todo = __ballot_sync(FULL, mine && lb <= tmax);
         while (todo) {
             const int l = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -322,7 +323,7 @@ static int key_bits(int B) {
 
 bool knn_xyz_supported(int C, int N, int k2, int metric) {
     if (!((metric == GCANET_METRIC_L2 && C == 3) || (metric == GCANET_METRIC_POINTS_NORMALS && C == 6))) return false;
-    return N >= 256 && k2 + kSlack + 32 <= 256 && (size_t)((N + XT - 1) / XT) * 24 <= 96 * 1024;
+    return N >= 256 && k2 <= 168 && (size_t)((N + XT - 1) / XT) * 24 <= 96 * 1024;
 }
 
 size_t knn_xyz_workspace_bytes(int B, int C, int N) {
@@ -357,8 +358,8 @@ static int launch_xyz(XyzArgs a, cudaStream_t st) {
         GCANET_LAUNCH_OK("knn_xyz_kernel");
         return GCANET_OK;
     };
-    if (a.k + kSlack + 32 <= 96) return go(std::integral_constant<int, 3>{});
-    if (a.k + kSlack + 32 <= 128) return go(std::integral_constant<int, 4>{});
+    if (a.k <= 40) return go(std::integral_constant<int, 4>{});
+    if (a.k <= 104) return go(std::integral_constant<int, 6>{});
     return go(std::integral_constant<int, 8>{});
 }
 

@@ -463,3 +463,12 @@ def test_large_cloud_stress_100k():
     assert bool((st >= (kth - tau).unsqueeze(-1)).all())
     same = (idx[0, rows].sort(dim=1)[0] == io.sort(dim=1)[0]).all(dim=1)
     assert float(same.float().mean()) > 0.95
+
+
+def test_knn_xyz_pruned_path_cloud_edges():
+    """First / last Morton tiles see fewer neighbours in phase 1 (threshold may still be +inf when the
+    pruned phase starts): their tiles must not be scanned twice."""
+    for N, k in [(1001, 50), (2000, 41), (300, 100), (257, 150)]:
+        x = _t(abc_like_batch(2, N, seed=100 + N)).to(DEV)
+        a = G.knn_graph(x, k, k)[0]
+        assert torch.equal(a, G.knn_graph(x, k, k, brute_force=True)[0])
