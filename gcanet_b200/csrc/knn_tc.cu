@@ -220,7 +220,7 @@ struct TcScanArgs {
 // Bisection over a warp-distributed list (entries e = s*32 + lane, +inf padding): returns hi with
 // count(d <= hi) >= k, stopping once <= k + TC_SLACK entries qualify or the interval is exhausted.
 template <int SL>
-__device__ __forceinline__ float select_bound(const float (&dv)[SL], int n, int k) {
+__device__ __forceinline__ float select_bound(const float (&dv)[SL], int n, int k, float *lo_strict = nullptr) {
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
 #pragma unroll
     for (int s = 0; s < SL; ++s) {
@@ -232,7 +232,7 @@ __device__ __forceinline__ float select_bound(const float (&dv)[SL], int n, int 
         mn = fminf(mn, __shfl_xor_sync(FULLW, mn, o));
         mx = fmaxf(mx, __shfl_xor_sync(FULLW, mx, o));
     }
-    float lo = mn, hi = mx;
+    float lo = mn, hi = mx, lo_s = -CUDART_INF_F;     // lo_s: count(d <= lo_s) < k is PROVEN
     if (n > k) {
         int c_hi = n;
         for (int it = 0; it < 24 && c_hi > k + TC_SLACK; ++it) {
@@ -242,9 +242,10 @@ __device__ __forceinline__ float select_bound(const float (&dv)[SL], int n, int 
 #pragma unroll
             for (int s = 0; s < SL; ++s) c += (dv[s] <= mid) ? 1 : 0;
             c = __reduce_add_sync(FULLW, c);
-            if (c >= k) { hi = mid; c_hi = c; } else { lo = mid; }
+            if (c >= k) { hi = mid; c_hi = c; } else { lo = mid; lo_s = mid; }
         }
     }
+    if (lo_strict) *lo_strict = lo_s;
     return hi;
 }
 
@@ -475,6 +476,7 @@ struct RerankArgs {
     int64_t *idx64;
     int32_t *idx32;
     int N, k, step, kout;
+    int unordered;         // 1: the caller only needs the neighbour SET (EdgeConv is order-invariant)
 };
 
 template <int VEC>
@@ -509,7 +511,10 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
     load_row<VEC>(xb + (size_t)q * C + lane * VEC, qv);
     const float qn = nb[q];
 
-    // 1. last shrink of the list on the approximate distances (same bound + margin rule as the scan)
+    // 1. last shrink of the list on the approximate distances (same bound + margin rule as the scan).
+    //    In set-only mode entries with d~ <= lo - margin, where fewer than k entries have d~ <= lo, are
+    //    certainly among the exact k nearest (anything that could beat them also lies below lo): they are
+    //    written straight away and only the ambiguous band (lo - margin, hi + margin] is re-ranked.
     float ad[SL];
     int aj[SL];
 #pragma unroll
@@ -519,16 +524,31 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
         aj[s] = 0;
         if (e < n) { uint2 t = cand[e]; ad[s] = __uint_as_float(t.x); aj[s] = (int)t.y; }
     }
-    float keep_below = CUDART_INF_F;
-    if (n > a.k + TC_SLACK) keep_below = select_bound<SL>(ad, n, a.k) + TC_MARGIN * sqrtf(qn * a.nmax[b]);
-    int m = 0;
+    const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
+    float keep_below = CUDART_INF_F, sure_below = -CUDART_INF_F;
+    if (n > a.k + TC_SLACK) {
+        float lo_s;
+        keep_below = select_bound<SL>(ad, n, a.k, &lo_s) + margin;
+        if (a.unordered) sure_below = lo_s - margin;
+    }
+    int m = 0, n_sure = 0;
 #pragma unroll
     for (int s = 0; s < SL; ++s) {
-        const bool keep = ad[s] < CUDART_INF_F && ad[s] <= keep_below;
+        const bool valid = ad[s] < CUDART_INF_F;
+        const bool sure = valid && ad[s] <= sure_below;
+        const bool keep = valid && !sure && ad[s] <= keep_below;
         const unsigned msk = __ballot_sync(FULLW, keep);
+        const unsigned ssk = __ballot_sync(FULLW, sure);
         if (keep) sl[m + __popc(msk & ((1u << lane) - 1))] = aj[s];
+        if (sure) {
+            const size_t o = grow * a.kout + n_sure + __popc(ssk & ((1u << lane) - 1));
+            if (a.idx64) a.idx64[o] = aj[s];
+            if (a.idx32) a.idx32[o] = aj[s];
+        }
         m += __popc(msk);
+        n_sure += __popc(ssk);
     }
+    const int k_left = a.k - n_sure;                    // >= 1: fewer than k entries lie below lo
     __syncwarp();
 
     // 2. exact fp32 distances of the m survivors, four at a time (coalesced row loads, one
@@ -589,8 +609,8 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
 #pragma unroll
     for (int s = 0; s < SL; ++s) {
         const int e = s * 32 + lane;
-        if (e < m && rank[s] < a.k && rank[s] % a.step == 0) {
-            const size_t o = grow * a.kout + rank[s] / a.step;
+        if (e < m && rank[s] < k_left && rank[s] % a.step == 0) {
+            const size_t o = grow * a.kout + n_sure + rank[s] / a.step;
             if (a.idx64) a.idx64[o] = di[s];
             if (a.idx32) a.idx32[o] = di[s];
         }
@@ -657,7 +677,7 @@ static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcSca
 }
 
 int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, int64_t *idx64, int32_t *idx32,
-                           void *ws, cudaStream_t st) {
+                           void *ws, int unordered, cudaStream_t st) {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { set_error("knn_graph: cuTensorMapEncodeTiled is not available from the driver"); return GCANET_ERR_CUDA; }
     const size_t bn = (size_t)B * N;
@@ -700,7 +720,8 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     if (cr != CUDA_SUCCESS) { set_error("knn_graph: cuTensorMapEncodeTiled failed (%d)", (int)cr); return GCANET_ERR_CUDA; }
 
     TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, ceil_div(N, TC_BN)};
-    RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2)};
+    RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
+                  (unordered && k1 == k2) ? 1 : 0};
     rc = C == 64 ? launch_tc<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<128>(tmap_q, tmap_k, sa, ra, B, st);
     if (rc) return rc;
     return knn_fallback_rows(x, norm, overflow, B, C, N, k1, k2, idx64, idx32, st);

@@ -69,15 +69,18 @@ def _as_f32_contig(x: torch.Tensor, name: str) -> torch.Tensor:
 # kNN graph (torch path)
 # ----------------------------------------------------------------------------------
 KNN_FLAG_BRUTE_FORCE = 0x100
+KNN_FLAG_UNORDERED = 0x200
 
 
 def knn_graph(x: torch.Tensor, k1: int, k2: int, metric: int = METRIC_L2, want64: bool = True,
-              want32: bool = False, tensor_cores: bool = True, brute_force: bool = False):
+              want32: bool = False, tensor_cores: bool = True, brute_force: bool = False, ordered: bool = True):
     """x [B, C, N] -> (idx64 or None, idx32 or None), each [B, N, kout].  ``brute_force=True`` (or
     the older ``tensor_cores=False``) forces the plain CUDA-core scan where an accelerated path
     (tcgen05 pruning for C = 64/128, spatial pruning for xyz clouds) would apply -- for A/B tests."""
     if brute_force or not tensor_cores:
         metric = metric | KNN_FLAG_BRUTE_FORCE
+    if not ordered and int(k1) == int(k2):
+        metric = metric | KNN_FLAG_UNORDERED      # same exact neighbour set, order unspecified
     x = _as_f32_contig(x.detach(), "x")
     if x.dim() != 3:
         raise RuntimeError(f"x must be [B, C, N] (got {tuple(x.shape)})")
@@ -92,7 +95,7 @@ def knn_graph(x: torch.Tensor, k1: int, k2: int, metric: int = METRIC_L2, want64
         i32 = torch.empty((B, N, kout), dtype=torch.int32, device=x.device) if want32 else None
         ws_bytes = L.gcanet_knn_graph_workspace_bytes(B, C, N, k2, metric)
         ws = workspace(ws_bytes, x.device)
-        with _timed(f"knn_graph[C={C},metric={metric}]"):
+        with _timed(f"knn_graph[C={C},metric={metric & 0xff}]"):
             call("gcanet_knn_graph", ptr(x), B, C, N, k1, k2, metric, ptr(i64), ptr(i32), ptr(ws), ws.numel(), stream())
     return i64, i32
 

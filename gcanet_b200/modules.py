@@ -48,7 +48,7 @@ class DGCNNEncoderGn(nn.Module):
     # -- hot path ------------------------------------------------------------------
     def _block(self, x_nc, x_cn, conv, C, metric):
         """One EdgeConv layer: graph on x_cn (no gradient, M4:33), fused conv/GN/act/max on x_nc."""
-        _, idx32 = G.knn_graph(x_cn, self.k, self.k, metric, want64=False, want32=True)
+        _, idx32 = G.knn_graph(x_cn, self.k, self.k, metric, want64=False, want32=True, ordered=False)   # max over k is order-invariant
         gn = conv[1]
         return G.edgeconv(x_nc, idx32, conv[0].weight, gn.weight, gn.bias, C, groups=gn.num_groups, eps=gn.eps,
                           slope=conv[2].negative_slope, want_cn=True)

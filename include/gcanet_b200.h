@@ -60,6 +60,11 @@ typedef enum {
  * paths return the same fp32-exact neighbour lists; the flag exists for A/B tests and benchmarks. */
 #define GCANET_KNN_FLAG_BRUTE_FORCE 0x100
 #define GCANET_KNN_FLAG_NO_TENSOR_CORES GCANET_KNN_FLAG_BRUTE_FORCE
+/* May be OR-ed into `metric` when k1 == k2: the caller only needs each point's neighbour SET, not
+ * the nearest-first order (EdgeConv's max / sum over k is order-invariant).  The set is the same
+ * exact set; paths that can save work by not ordering it (the tensor-core path re-ranks only the
+ * candidates whose membership is in doubt) do so, the others ignore the flag. */
+#define GCANET_KNN_FLAG_UNORDERED 0x200
 
 /* Edge-feature variant of gcanet_graph_feature*. */
 typedef enum {

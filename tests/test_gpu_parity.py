@@ -472,3 +472,24 @@ def test_knn_xyz_pruned_path_cloud_edges():
         x = _t(abc_like_batch(2, N, seed=100 + N)).to(DEV)
         a = G.knn_graph(x, k, k)[0]
         assert torch.equal(a, G.knn_graph(x, k, k, brute_force=True)[0])
+
+
+@pytest.mark.parametrize("C,N,k", [(64, 10000, 50), (128, 3000, 20), (64, 700, 80), (3, 5000, 50)])
+def test_knn_unordered_mode_returns_the_same_sets(C, N, k):
+    """ordered=False (what the fused encoder asks for) may skip the final ordering but must return
+    exactly the same neighbour set per point."""
+    g = torch.Generator().manual_seed(C + N)
+    x = (torch.randn(2, C, N, generator=g) if C > 3 else _t(abc_like_batch(2, N, seed=1))).to(DEV)
+    a = G.knn_graph(x, k, k, want64=False, want32=True, ordered=True)[1]
+    b = G.knn_graph(x, k, k, want64=False, want32=True, ordered=False)[1]
+    assert torch.equal(a.sort(dim=2)[0], b.sort(dim=2)[0])
+    # real activations (clustered features)
+    if C == 64:
+        torch.manual_seed(0)
+        enc = orc.DGCNNEncoderGn(mode=0, nn_nb=20, input_channels=6)
+        xa = _t(abc_like_batch(2, 3000, seed=5))
+        with torch.no_grad():
+            x1 = enc.conv1(orc.get_graph_feature(xa, 20, 20)).max(dim=-1)[0].to(DEV)
+        a = G.knn_graph(x1, k, k, want64=False, want32=True, ordered=True)[1]
+        b = G.knn_graph(x1, k, k, want64=False, want32=True, ordered=False)[1]
+        assert torch.equal(a.sort(dim=2)[0], b.sort(dim=2)[0])
