@@ -215,6 +215,8 @@ struct TcScanArgs {
     int *cand_cnt;       // [B][N]
     int *overflow;       // [B][N]   1 = list overflowed, row must be redone by the fallback
     int N, k, tiles;     // tiles = ceil(N / TC_BN)
+    int tile_stride;     // key tiles are visited as (t * tile_stride) % tiles, stride coprime to tiles:
+                         // a spatially sorted cloud then looks like a random stream to the thresholds
 };
 
 // Bisection over a warp-distributed list (entries e = s*32 + lane, +inf padding): returns hi with
@@ -233,6 +235,7 @@ __device__ __forceinline__ float select_bound(const float (&dv)[SL], int n, int 
         mx = fmaxf(mx, __shfl_xor_sync(FULLW, mx, o));
     }
     float lo = mn, hi = mx, lo_s = -CUDART_INF_F;     // lo_s: count(d <= lo_s) < k is PROVEN
+    int c_lo = 0;
     if (n > k) {
         int c_hi = n;
         for (int it = 0; it < 24 && c_hi > k + TC_SLACK; ++it) {
@@ -242,7 +245,20 @@ __device__ __forceinline__ float select_bound(const float (&dv)[SL], int n, int 
 #pragma unroll
             for (int s = 0; s < SL; ++s) c += (dv[s] <= mid) ? 1 : 0;
             c = __reduce_add_sync(FULLW, c);
-            if (c >= k) { hi = mid; c_hi = c; } else { lo = mid; lo_s = mid; }
+            if (c >= k) { hi = mid; c_hi = c; } else { lo = mid; lo_s = mid; c_lo = c; }
+        }
+        if (lo_strict) {
+            // tighten the proven lower side too, so the ambiguous band (lo_s, hi] holds ~2*slack entries
+            float h2 = hi;
+            for (int it = 0; it < 12 && c_lo < k - TC_SLACK; ++it) {
+                float mid = 0.5f * lo + 0.5f * h2;
+                if (!(mid > lo && mid < h2)) break;
+                int c = 0;
+#pragma unroll
+                for (int s = 0; s < SL; ++s) c += (dv[s] <= mid) ? 1 : 0;
+                c = __reduce_add_sync(FULLW, c);
+                if (c < k) { lo = mid; lo_s = mid; c_lo = c; } else { h2 = mid; }
+            }
         }
     }
     if (lo_strict) *lo_strict = lo_s;
@@ -338,11 +354,12 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 mbar_wait_backoff(&empty[stage], phase ^ 1);
                 mbar_expect_tx(&full[stage], TILE_BYTES + TC_BN * sizeof(float));
                 uint8_t *dst = sB + stage * TILE_BYTES;
+                const int kt = (int)(((long long)t * a.tile_stride) % tiles);
 #pragma unroll
-                for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(dst + kb * BLK_BYTES, &tmap_k, &full[stage], kb * TC_KB, t * TC_BN, b);
+                for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(dst + kb * BLK_BYTES, &tmap_k, &full[stage], kb * TC_KB, kt * TC_BN, b);
                 // this tile's key norms ride on the same barrier; by the time the MMA that consumed the
                 // stage has committed to t_full, the epilogue may read them
-                bulk_load_1d(s_rn + (t % TC_NRING) * TC_BN, rn_g + (size_t)t * TC_BN, TC_BN * sizeof(float), &full[stage]);
+                bulk_load_1d(s_rn + (t % TC_NRING) * TC_BN, rn_g + (size_t)kt * TC_BN, TC_BN * sizeof(float), &full[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -399,6 +416,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         int acc = 0;
         uint32_t accphase = 0;
         for (int t = 0; t < tiles; ++t) {
+            const int kt = (int)(((long long)t * a.tile_stride) % tiles);
             mbar_wait(&t_full[acc], accphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN;
@@ -408,7 +426,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             for (int ch = 0; ch < TC_BN / 32; ++ch) {
                 tmem_ld_wait();                                     // chunk ch is in v[ch & 1]
                 if (ch + 1 < TC_BN / 32) tmem_ld32(taddr + (ch + 1) * 32, v[(ch + 1) & 1]);   // prefetch the next chunk
-                const int jbase = t * TC_BN + ch * 32;
+                const int jbase = kt * TC_BN + ch * 32;
                 const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (t % TC_NRING) * TC_BN + ch * 32);   // broadcast reads
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
@@ -597,13 +615,21 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
         di[s] = e < m ? sl[e] : 0x7fffffff;
         rank[s] = 0;
     }
-    for (int e = 0; e < m; ++e) {
-        const float od = sd[e];
-        const int oi = sl[e];
+    if (m <= 32) {
+        for (int e = 0; e < m; ++e) {
+            const float od = sd[e];
+            const int oi = sl[e];
+            rank[0] += (od < dv[0] || (od == dv[0] && oi < di[0])) ? 1 : 0;
+        }
+    } else {
+        for (int e = 0; e < m; ++e) {
+            const float od = sd[e];
+            const int oi = sl[e];
 #pragma unroll
-        for (int s = 0; s < SL; ++s) {
-            if (s * 32 >= m) break;
-            rank[s] += (od < dv[s] || (od == dv[s] && oi < di[s])) ? 1 : 0;
+            for (int s = 0; s < SL; ++s) {
+                if (s * 32 >= m) break;
+                rank[s] += (od < dv[s] || (od == dv[s] && oi < di[s])) ? 1 : 0;
+            }
         }
     }
 #pragma unroll
@@ -719,7 +745,12 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("knn_graph: cuTensorMapEncodeTiled failed (%d)", (int)cr); return GCANET_ERR_CUDA; }
 
-    TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, ceil_div(N, TC_BN)};
+    const int tiles = ceil_div(N, TC_BN);
+    int stride = (int)(tiles * 0.381966f);
+    if (stride < 1) stride = 1;
+    auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+    while (gcd(stride, tiles) != 1) ++stride;
+    TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, stride};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                   (unordered && k1 == k2) ? 1 : 0};
     rc = C == 64 ? launch_tc<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<128>(tmap_q, tmap_k, sa, ra, B, st);

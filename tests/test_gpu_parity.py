@@ -493,3 +493,15 @@ def test_knn_unordered_mode_returns_the_same_sets(C, N, k):
         a = G.knn_graph(x1, k, k, want64=False, want32=True, ordered=True)[1]
         b = G.knn_graph(x1, k, k, want64=False, want32=True, ordered=False)[1]
         assert torch.equal(a.sort(dim=2)[0], b.sort(dim=2)[0])
+
+
+def test_knn_tensor_core_path_on_spatially_sorted_features():
+    """Keys arriving in a spatially coherent order (sorted clouds) are the adversarial case for a
+    streaming threshold; the strided tile order must keep the result exact."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 64, 5000, generator=g)
+    order = torch.argsort(x[0, 0])                    # sort the cloud along one feature axis
+    xs = x[:, :, order].contiguous()
+    i_tc = G.knn_graph(xs.to(DEV), 50, 50)[0]
+    n = check_knn_rows(i_tc, orc.knn(xs, 50, 50), orc.knn_scores(xs), knn_tau(xs))
+    assert n <= 3
