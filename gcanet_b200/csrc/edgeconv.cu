@@ -220,8 +220,9 @@ struct VecIO<8> {
 struct FwdArgs {
     const float *pq;       // [B][N][2*Cout]
     const int32_t *idx;    // [B][N][k]
-    float *ymax, *ymin, *ysum;           // [B][N][Cout]
-    unsigned char *amax, *amin;          // [B][N][Cout]
+    const float *gamma;    // [Cout]  only its sign is used: the extreme that survives max_k(LReLU(GN(.)))
+    float *ysel, *ysum;    // [B][N][Cout]  selected pre-norm value (max_k y if gamma >= 0 else min_k y), sum_k y
+    unsigned char *arg;    // [B][N][Cout]  the k that attains ysel
     double *part;          // [B][nblk][G][2]
     int N, Cout, k, G;
 };
@@ -235,34 +236,39 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
     const int c0 = lane * VEC;
     const float *pq = a.pq + (size_t)b * a.N * 2 * Cout;
     double s1 = 0.0, s2 = 0.0;
+    float sg[VEC];
+    VecIO<VEC>::ld(a.gamma + c0, sg);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) sg[v] = sg[v] < 0.f ? -1.f : 1.f;
 
     for (int pi = 0; pi < kPtsPerWarp; ++pi) {
         const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
         if (i >= a.N) break;
-        float q[VEC], vmax[VEC], vmin[VEC], vsum[VEC], vsq[VEC];
-        int kmax[VEC], kmin[VEC];
+        // z = sign(gamma) * y: one running max covers both signs (y itself is exact: only a sign flip)
+        float q[VEC], zmax[VEC], vsum[VEC], vsq[VEC];
+        int kbest[VEC];
         VecIO<VEC>::ld(pq + (size_t)i * 2 * Cout + Cout + c0, q);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { vmax[v] = -CUDART_INF_F; vmin[v] = CUDART_INF_F; vsum[v] = 0.f; vsq[v] = 0.f; kmax[v] = 0; kmin[v] = 0; }
+        for (int v = 0; v < VEC; ++v) { zmax[v] = -CUDART_INF_F; vsum[v] = 0.f; vsq[v] = 0.f; kbest[v] = 0; }
         const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
         for (int base = 0; base < k; base += 32) {
             const int cnt = min(32, k - base);
             const int myj = lane < cnt ? ip[base + lane] : 0;
             int t = 0;
-            for (; t + 4 <= cnt; t += 4) {
-                float p[4][VEC];
+            for (; t + 8 <= cnt; t += 8) {
+                float p[8][VEC];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     int j = __shfl_sync(FULLM, myj, t + u);
                     VecIO<VEC>::ld(pq + (size_t)j * 2 * Cout + c0, p[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 8; ++u)
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
-                        float y = p[u][v] + q[v];
-                        if (y > vmax[v]) { vmax[v] = y; kmax[v] = base + t + u; }
-                        if (y < vmin[v]) { vmin[v] = y; kmin[v] = base + t + u; }
+                        const float y = p[u][v] + q[v];
+                        const float z = sg[v] * y;
+                        if (z > zmax[v]) { zmax[v] = z; kbest[v] = base + t + u; }
                         vsum[v] += y;
                         vsq[v] = fmaf(y, y, vsq[v]);
                     }
@@ -273,22 +279,23 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
                 VecIO<VEC>::ld(pq + (size_t)j * 2 * Cout + c0, p);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    float y = p[v] + q[v];
-                    if (y > vmax[v]) { vmax[v] = y; kmax[v] = base + t; }
-                    if (y < vmin[v]) { vmin[v] = y; kmin[v] = base + t; }
+                    const float y = p[v] + q[v];
+                    const float z = sg[v] * y;
+                    if (z > zmax[v]) { zmax[v] = z; kbest[v] = base + t; }
                     vsum[v] += y;
                     vsq[v] = fmaf(y, y, vsq[v]);
                 }
             }
         }
         const size_t o = ((size_t)b * a.N + i) * Cout + c0;
-        VecIO<VEC>::st(a.ymax + o, vmax);
-        VecIO<VEC>::st(a.ymin + o, vmin);
+        float ys[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) ys[v] = sg[v] * zmax[v];
+        VecIO<VEC>::st(a.ysel + o, ys);
         VecIO<VEC>::st(a.ysum + o, vsum);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            a.amax[o + v] = (unsigned char)kmax[v];
-            a.amin[o + v] = (unsigned char)kmin[v];
+            a.arg[o + v] = (unsigned char)kbest[v];
             s1 += (double)vsum[v];
             s2 += (double)vsq[v];
         }
@@ -306,29 +313,34 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
     }
 }
 
-// stats[b][g] = (mean, rstd)
+// stats[b][g] = (mean, rstd); one warp per (b, g) sums the per-CTA fp64 partials in a fixed order
 __global__ void gn_stats_kernel(const double *__restrict__ part, float *__restrict__ stats, int nblk, int G,
                                 double count, float eps) {
-    const int b = blockIdx.x, g = threadIdx.x;
+    const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (g >= G) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < nblk; ++i) {
+    for (int i = lane; i < nblk; i += 32) {
         s1 += part[(((size_t)b * nblk + i) * G + g) * 2 + 0];
         s2 += part[(((size_t)b * nblk + i) * G + g) * 2 + 1];
     }
-    double mean = s1 / count;
-    double var = s2 / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[((size_t)b * G + g) * 2 + 0] = (float)mean;
-    stats[((size_t)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    for (int o = 16; o; o >>= 1) {
+        s1 += __shfl_xor_sync(FULLM, s1, o);
+        s2 += __shfl_xor_sync(FULLM, s2, o);
+    }
+    if (lane == 0) {
+        double mean = s1 / count;
+        double var = s2 / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stats[((size_t)b * G + g) * 2 + 0] = (float)mean;
+        stats[((size_t)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
 }
 
-// picks max or min by the sign of gamma, applies GroupNorm + LeakyReLU; ymax/amax become ysel/arg
-__global__ void edge_finish_kernel(float *__restrict__ ymax, const float *__restrict__ ymin,
-                                   unsigned char *__restrict__ amax, const unsigned char *__restrict__ amin,
-                                   const float *__restrict__ stats, const float *__restrict__ gamma,
-                                   const float *__restrict__ beta, float *__restrict__ out_nc,
-                                   float *__restrict__ out_cn, int N, int Cout, int G, float slope) {
+// GroupNorm + LeakyReLU of the selected extreme: out = LReLU((ysel - mean) * rstd * gamma + beta)
+__global__ void edge_finish_kernel(const float *__restrict__ ysel, const float *__restrict__ stats,
+                                   const float *__restrict__ gamma, const float *__restrict__ beta,
+                                   float *__restrict__ out_nc, float *__restrict__ out_cn, int N, int Cout, int G,
+                                   float slope) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -342,9 +354,7 @@ __global__ void edge_finish_kernel(float *__restrict__ ymax, const float *__rest
             float o = 0.f;
             if (n < N) {
                 const size_t e = ((size_t)b * N + n) * Cout + c;
-                float ys = ymax[e];
-                if (gm < 0.f) { ys = ymin[e]; ymax[e] = ys; amax[e] = amin[e]; }
-                o = lrelu((ys - mean) * rstd * gm + bt, slope);
+                o = lrelu((ysel[e] - mean) * rstd * gm + bt, slope);
                 out_nc[e] = o;
             }
             tile[r][threadIdx.x] = o;
@@ -415,22 +425,30 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_reduce_kernel(BwdArgs a
 }
 
 // per cloud: S1[c] = sum_i du, S2[c] = sum_i du*yhat  ->  sbc[b][c][2] (double) and coef[b][g] = (A_g, K_g)
+// One CTA per cloud; each warp reduces a channel at a time over the per-CTA partials (fixed order).
 __global__ void edge_bwd_coef_kernel(const float *__restrict__ part, const float *__restrict__ stats,
                                      const float *__restrict__ gamma, double *__restrict__ sbc,
                                      float *__restrict__ coef, int nblk, int Cout, int G, double count) {
     extern __shared__ double sh[];      // [Cout][2] weighted by gamma
     const int b = blockIdx.x;
     const int cpg = Cout / G;
-    for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int c = warp; c < Cout; c += nwarp) {
         double s1 = 0.0, s2 = 0.0;
-        for (int i = 0; i < nblk; ++i) {
+        for (int i = lane; i < nblk; i += 32) {
             s1 += (double)part[(((size_t)b * nblk + i) * Cout + c) * 2 + 0];
             s2 += (double)part[(((size_t)b * nblk + i) * Cout + c) * 2 + 1];
         }
-        sbc[((size_t)b * Cout + c) * 2 + 0] = s1;
-        sbc[((size_t)b * Cout + c) * 2 + 1] = s2;
-        sh[c * 2 + 0] = s1 * (double)gamma[c];
-        sh[c * 2 + 1] = s2 * (double)gamma[c];
+        for (int o = 16; o; o >>= 1) {
+            s1 += __shfl_xor_sync(FULLM, s1, o);
+            s2 += __shfl_xor_sync(FULLM, s2, o);
+        }
+        if (lane == 0) {
+            sbc[((size_t)b * Cout + c) * 2 + 0] = s1;
+            sbc[((size_t)b * Cout + c) * 2 + 1] = s2;
+            sh[c * 2 + 0] = s1 * (double)gamma[c];
+            sh[c * 2 + 1] = s2 * (double)gamma[c];
+        }
     }
     __syncthreads();
     if (threadIdx.x < G) {
@@ -545,20 +563,16 @@ static size_t plan_saved(const gcanet_edgeconv_desc *d, void *base, Saved *s) {
 }
 
 struct FwdWs {
-    float *wcat, *ymin;
-    unsigned char *amin;
+    float *wcat;
     double *part;
 };
 
 static size_t plan_fwd(const gcanet_edgeconv_desc *d, void *base, FwdWs *w) {
     Carver cv(base);
-    size_t bn = (size_t)d->B * d->N;
     int nblk = ceil_div(d->N, kPtsPerCta);
     float *wcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
-    float *ymin = cv.take<float>(bn * d->Cout);
-    unsigned char *amin = cv.take<unsigned char>(bn * d->Cout);
     double *part = cv.take<double>((size_t)d->B * nblk * d->groups * 2);
-    if (w) { w->wcat = wcat; w->ymin = ymin; w->amin = amin; w->part = part; }
+    if (w) { w->wcat = wcat; w->part = part; }
     return cv.off;
 }
 
@@ -610,16 +624,15 @@ static int run_forward(const gcanet_edgeconv_desc *d, const float *x_nc, const i
     GCANET_LAUNCH_OK("prep_wcat_kernel");
     int rc = launch_sgemm_nn(x_nc, w.wcat, sv.pq, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, 2 * Cout, st);
     if (rc) return rc;
-    FwdArgs fa{sv.pq, idx, sv.ysel, w.ymin, sv.ysum, sv.arg, w.amin, w.part, d->N, Cout, d->k, d->groups};
+    FwdArgs fa{sv.pq, idx, gamma, sv.ysel, sv.ysum, sv.arg, w.part, d->N, Cout, d->k, d->groups};
     const int nblk = ceil_div(d->N, kPtsPerCta);
     edge_gather_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(fa);
     GCANET_LAUNCH_OK("edge_gather_reduce_kernel");
     double count = (double)(Cout / d->groups) * d->N * d->k;
-    gn_stats_kernel<<<d->B, 32, 0, st>>>(w.part, sv.stats, nblk, d->groups, count, d->eps);
+    gn_stats_kernel<<<d->B, 32 * d->groups, 0, st>>>(w.part, sv.stats, nblk, d->groups, count, d->eps);
     GCANET_LAUNCH_OK("gn_stats_kernel");
     dim3 fg(ceil_div(d->N, 32), Cout / 32, d->B), fb(32, 8);
-    edge_finish_kernel<<<fg, fb, 0, st>>>(sv.ysel, w.ymin, sv.arg, w.amin, sv.stats, gamma, beta, out_nc, out_cn, d->N,
-                                          Cout, d->groups, d->slope);
+    edge_finish_kernel<<<fg, fb, 0, st>>>(sv.ysel, sv.stats, gamma, beta, out_nc, out_cn, d->N, Cout, d->groups, d->slope);
     GCANET_LAUNCH_OK("edge_finish_kernel");
     return GCANET_OK;
 }
@@ -642,7 +655,7 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     edge_bwd_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
     GCANET_LAUNCH_OK("edge_bwd_reduce_kernel");
     double count = (double)(Cout / d->groups) * d->N * d->k;
-    edge_bwd_coef_kernel<<<d->B, 128, Cout * 2 * sizeof(double), st>>>(w.part, sv.stats, gamma, w.sbc, w.coef, nblk, Cout,
+    edge_bwd_coef_kernel<<<d->B, 512, Cout * 2 * sizeof(double), st>>>(w.part, sv.stats, gamma, w.sbc, w.coef, nblk, Cout,
                                                                       d->groups, count);
     GCANET_LAUNCH_OK("edge_bwd_coef_kernel");
     edge_bwd_affine_kernel<<<ceil_div(Cout, 128), 128, 0, st>>>(w.sbc, grad_gamma, grad_beta, d->B, Cout);
