@@ -160,10 +160,97 @@ static int launch_sgemm_nn(const float *A, const float *Bm, float *Cm, int M, in
     return GCANET_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// out[K][N] = A[M][K]^T B[M][N]  (weight gradient: reduction over the B*N points).
+// Split over M; every split writes its own [K][N] partial, reduced afterwards in a fixed order.
+//   K <= 8 : each thread owns one output column and K accumulators, rows are streamed
+//   else   : 64 x 64 output tiles, 16 rows of M per step, 4 x 4 outputs per thread
+// ---------------------------------------------------------------------------------
+constexpr int TN_T = 64, TN_BK = 16;
+
+__global__ void __launch_bounds__(256) sgemm_tn64_kernel(const float *__restrict__ A, const float *__restrict__ Bm,
+                                                         float *__restrict__ part, int M, int N, int K, int lda,
+                                                         int ldb, int rows_per_split) {
+    __shared__ __align__(16) float As[TN_BK][TN_T];
+    __shared__ __align__(16) float Bs[TN_BK][TN_T];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.x * TN_T, c0 = blockIdx.y * TN_T;
+    const int lo = blockIdx.z * rows_per_split, hi = min(M, lo + rows_per_split);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int kr = tid >> 4, q4 = (tid & 15) * 4;       // one float4 of A and one of B per thread per step
+    for (int m0 = lo; m0 < hi; m0 += TN_BK) {
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+        if (m0 + kr < hi) {
+            if (c0 + q4 < K) va = *reinterpret_cast<const float4 *>(A + (size_t)(m0 + kr) * lda + c0 + q4);
+            if (n0 + q4 < N) vb = *reinterpret_cast<const float4 *>(Bm + (size_t)(m0 + kr) * ldb + n0 + q4);
+        }
+        *reinterpret_cast<float4 *>(&As[kr][q4]) = va;
+        *reinterpret_cast<float4 *>(&Bs[kr][q4]) = vb;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TN_BK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *out = part + (size_t)blockIdx.z * K * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = c0 + ty * 4 + i, c = n0 + tx * 4;
+        if (r < K && c < N) *reinterpret_cast<float4 *>(out + (size_t)r * N + c) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+// K <= 8.  blockDim = 256; thread t owns column n = t % N2 of row group t / N2 (N2 = N rounded to the block).
+__global__ void __launch_bounds__(256) sgemm_tn_smallk_kernel(const float *__restrict__ A, const float *__restrict__ Bm,
+                                                              float *__restrict__ part, int M, int N, int K, int lda,
+                                                              int ldb, int rows_per_split) {
+    __shared__ float red[8][256];
+    const int groups = 256 / N > 0 ? 256 / N : 1;       // row groups working on interleaved rows
+    const int col = threadIdx.x % N, grp = threadIdx.x / N;
+    const bool live = grp < groups && (N <= 256);
+    const int lo = blockIdx.x * rows_per_split, hi = min(M, lo + rows_per_split);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    if (live) {
+        for (int m = lo + grp; m < hi; m += groups) {
+            const float bv = Bm[(size_t)m * ldb + col];
+            const float *ar = A + (size_t)m * lda;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < K) acc[c] = fmaf(ar[c], bv, acc[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) red[c][threadIdx.x] = live ? acc[c] : 0.f;
+    __syncthreads();
+    for (int e = threadIdx.x; e < K * N; e += 256) {
+        const int c = e / N, n = e % N;
+        float s = 0.f;
+        for (int g = 0; g < groups; ++g) s += red[c][g * N + n];
+        part[(size_t)blockIdx.x * K * N + e] = s;
+    }
+}
+
 static int tn_splits(int M, int N, int K) {
-    int tiles = ceil_div(N, BN) * ceil_div(K, BM);
-    int splits = (2 * kNumSMs + tiles - 1) / tiles;
-    int max_splits = ceil_div(M, 4 * BK);
+    int splits;
+    if (K <= 8 && N <= 256) splits = 4 * kNumSMs;
+    else {
+        int tiles = ceil_div(N, TN_T) * ceil_div(K, TN_T);
+        splits = (4 * kNumSMs + tiles - 1) / tiles;
+    }
+    int max_splits = ceil_div(M, 4 * TN_BK);
     if (splits > max_splits) splits = max_splits;
     return splits < 1 ? 1 : splits;
 }
@@ -172,11 +259,16 @@ static int tn_splits(int M, int N, int K) {
 static int launch_sgemm_tn(const float *A, const float *Bm, float *out, float *part, int M, int N, int K, int lda,
                            int ldb, cudaStream_t st) {
     int splits = tn_splits(M, N, K);
-    int rows = ceil_div(ceil_div(M, splits), BK) * BK;
+    int rows = ceil_div(ceil_div(M, splits), TN_BK) * TN_BK;
     splits = ceil_div(M, rows);
-    dim3 grid(ceil_div(N, BN), ceil_div(K, BM), splits);
-    sgemm_kernel<true><<<grid, 256, 0, st>>>(A, Bm, part, M, N, K, lda, ldb, N, rows);
-    GCANET_LAUNCH_OK("sgemm_kernel<TN>");
+    if (K <= 8 && N <= 256) {
+        sgemm_tn_smallk_kernel<<<splits, 256, 0, st>>>(A, Bm, part, M, N, K, lda, ldb, rows);
+        GCANET_LAUNCH_OK("sgemm_tn_smallk_kernel");
+    } else {
+        dim3 grid(ceil_div(N, TN_T), ceil_div(K, TN_T), splits);
+        sgemm_tn64_kernel<<<grid, 256, 0, st>>>(A, Bm, part, M, N, K, lda, ldb, rows);
+        GCANET_LAUNCH_OK("sgemm_tn64_kernel");
+    }
     int count = K * N;
     reduce_splits_kernel<<<ceil_div(count, 256), 256, 0, st>>>(part, out, count, splits);
     GCANET_LAUNCH_OK("reduce_splits_kernel");
