@@ -27,8 +27,10 @@ __device__ __forceinline__ void static_for(F &&f) {
 
 // Ranks the n entries of a list by (distance, index), keeps the min(n, k) smallest IN ORDER
 // (entry of rank r moves to slot r) and returns the largest kept distance.
+// (not inlined: called from rare paths of kernels that are otherwise unrolled over several queries;
+// inlining every copy blows the instruction cache)
 template <int SL>
-__device__ __forceinline__ float rank_cut(float *ld, int *li, int n, int k, int lane) {
+__device__ __noinline__ float rank_cut(float *ld, int *li, int n, int k, int lane) {
     float dv[SL];
     int di[SL], rank[SL];
 #pragma unroll
@@ -59,13 +61,40 @@ __device__ __forceinline__ float rank_cut(float *ld, int *li, int n, int k, int 
     return kth;
 }
 
+// Set-only finish: removes the n - k largest entries by (distance, index) -- n - k <= kSlack after a
+// shrink -- leaving the k smallest in slots [0, k) in arbitrary order.
+template <int SL>
+__device__ __noinline__ void drop_largest(float *ld, int *li, int n, int k, int lane) {
+    while (n > k) {
+        // lexicographic max of (d, idx) over the list
+        float bd = -CUDART_INF_F;
+        int bi = -1, bp = -1;
+        for (int e = lane; e < n; e += 32) {
+            const float d = ld[e];
+            const int i = li[e];
+            if (d > bd || (d == bd && i > bi)) { bd = d; bi = i; bp = e; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float od = __shfl_xor_sync(FULL, bd, o);
+            const int oi = __shfl_xor_sync(FULL, bi, o);
+            const int op = __shfl_xor_sync(FULL, bp, o);
+            if (od > bd || (od == bd && oi > bi)) { bd = od; bi = oi; bp = op; }
+        }
+        // move the last entry into the hole
+        if (lane == 0 && bp != n - 1) { ld[bp] = ld[n - 1]; li[bp] = li[n - 1]; }
+        --n;
+        __syncwarp();
+    }
+}
+
 // Shrinks a list of n > k entries to those with d <= bound, where count(d <= bound) >= k and,
 // ties permitting, <= k + kSlack (bisection on the values).  If ties would keep more than
 // `limit` entries the list is cut to exactly the k smallest by (distance, index) instead.
 // Returns the new count; `thr` becomes the bound: later candidates must be strictly below it
 // (they have larger indices, so an equal distance loses the tie anyway).
 template <int SL>
-__device__ __forceinline__ int shrink_list(float *ld, int *li, int n, int k, int limit, int lane, float &thr) {
+__device__ __noinline__ int shrink_list(float *ld, int *li, int n, int k, int limit, int lane, float &thr) {
     float dv[SL];
     int di[SL];
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;

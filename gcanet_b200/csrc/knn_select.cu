@@ -465,7 +465,7 @@ static int scan_self(const float *x, const float *norms, const int *row_filter, 
 bool knn_xyz_supported(int C, int N, int k2, int metric);
 size_t knn_xyz_workspace_bytes(int B, int C, int N);
 int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metric, int64_t *idx64, int32_t *idx32,
-                  void *ws, float **norm_out, int **fallback_out, cudaStream_t st);
+                  void *ws, float **norm_out, int **fallback_out, int unordered, cudaStream_t st);
 
 // knn_tc.cu
 size_t knn_tc_workspace_bytes(int B, int C, int N);
@@ -524,7 +524,8 @@ extern "C" int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int
     if (flags == 0 && knn_xyz_supported(C, N, k2, metric)) {
         float *norms = nullptr;
         int *cloud_fallback = nullptr;
-        int rc = knn_graph_xyz(x, B, C, N, k1, k2, metric, idx64, idx32, ws, &norms, &cloud_fallback, as_stream(stream));
+        int rc = knn_graph_xyz(x, B, C, N, k1, k2, metric, idx64, idx32, ws, &norms, &cloud_fallback, unordered,
+                               as_stream(stream));
         if (rc) return rc;
         // clouds the pruned scan declined (points x normals with non-unit normals): brute force, filtered per cloud
         return scan_self(x, norms, nullptr, B, C, N, k1, k2, metric, idx64, idx32, as_stream(stream), cloud_fallback);

@@ -147,6 +147,7 @@ struct XyzArgs {
     int64_t *idx64;
     int32_t *idx32;
     int *fallback;        // [B] set to 1 when the cloud must take the brute-force path (PN, c <= 0)
+    int unordered;        // 1: only the neighbour set is needed, skip the final ordering
 };
 
 template <int CDIM, bool PN, int SL>
@@ -239,42 +240,48 @@ __global__ void __launch_bounds__(XW * 32) knn_xyz_kernel(XyzArgs a) {
         });
     };
 
-    // phase 1: own tile and Morton neighbours -- tightens the thresholds before any pruning decision;
-    // widened until every query has seen at least k references
-    int lo_t = tile0, hi_t = tile0;
-    scan_tile(tile0);
+    // Two passes over the tile list with ONE copy of the scan code:
+    //   pass 0: own tile and its Morton neighbours, unconditionally -- brings the thresholds close to
+    //           the final k-th distances before any pruning decision (the window is wide enough for
+    //           every query to see at least k + 32 references);
+    //   pass 1: every other tile, only if its AABB lower bound is within the largest threshold.
+    int lo_t, hi_t;
     {
-        const int need_tiles = (a.k + XT - 1) / XT + 2;
-        for (int s = 1; s <= need_tiles || (hi_t - lo_t + 1) * XT < a.k + XT; ++s) {
-            if (tile0 - s < 0 && tile0 + s >= tiles) break;
-            if (tile0 - s >= 0) { scan_tile(tile0 - s); lo_t = tile0 - s; }
-            if (tile0 + s < tiles) { scan_tile(tile0 + s); hi_t = tile0 + s; }
+        int half = (a.k + XT - 1) / XT + 2;
+        lo_t = max(0, tile0 - half);
+        hi_t = min(tiles - 1, tile0 + half);
+        while ((hi_t - lo_t + 1) * XT < a.k + 2 * XT && (lo_t > 0 || hi_t < tiles - 1)) {
+            if (lo_t > 0) --lo_t;
+            if (hi_t < tiles - 1) ++hi_t;
         }
     }
-
-    // phase 2: every other tile, pruned by its AABB lower bound
-    for (int base = 0; base < tiles; base += 32) {
-        const int t = base + lane;
-        const bool mine = t < tiles && (t < lo_t || t > hi_t);     // tiles of phase 1 are never rescanned
-        float lb = 0.f;
-        if (mine) {
-            const float *bx = s_aabb + t * 6;
-            float acc = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int b0 = pass == 0 ? (lo_t / 32) * 32 : 0;
+        const int b1 = pass == 0 ? hi_t + 1 : tiles;
+        for (int base = b0; base < b1; base += 32) {
+            const int t = base + lane;
+            const bool in_window = t >= lo_t && t <= hi_t;
+            const bool mine = t < tiles && (pass == 0 ? in_window : !in_window);
+            float lb = -CUDART_INF_F;                                  // pass 0: always scanned
+            if (mine && pass == 1) {
+                const float *bx = s_aabb + t * 6;
+                float acc = 0.f;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float g = fmaxf(fmaxf(bx[c] - qmax[c], qmin[c] - bx[3 + c]), 0.f);
-                acc = fmaf(g, g, acc);
+                for (int c = 0; c < 3; ++c) {
+                    const float g = fmaxf(fmaxf(bx[c] - qmax[c], qmin[c] - bx[3 + c]), 0.f);
+                    acc = fmaf(g, g, acc);
+                }
+                lb = cmin * acc * (1.f - 1e-5f) - abs_slack;
             }
-            lb = cmin * acc * (1.f - 1e-5f) - abs_slack;
-        }
-        float tmax = fmaxf(fmaxf(thr[0], thr[1]), fmaxf(thr[2], thr[3]));
-        unsigned todo = __ballot_sync(FULL, mine && lb <= tmax);
-        while (todo) {
-            const int l = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const float lbt = __shfl_sync(FULL, lb, l);
-            tmax = fmaxf(fmaxf(thr[0], thr[1]), fmaxf(thr[2], thr[3]));
-            if (lbt <= tmax) scan_tile(base + l);
+            float tmax = fmaxf(fmaxf(thr[0], thr[1]), fmaxf(thr[2], thr[3]));
+            unsigned todo = __ballot_sync(FULL, mine && lb <= tmax);
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float lbt = __shfl_sync(FULL, lb, l);
+                tmax = fmaxf(fmaxf(thr[0], thr[1]), fmaxf(thr[2], thr[3]));
+                if (lbt <= tmax) scan_tile(base + l);
+            }
         }
     }
 
@@ -288,7 +295,8 @@ __global__ void __launch_bounds__(XW * 32) knn_xyz_kernel(XyzArgs a) {
         float *ld = my_ld + r * CAP;
         int *li = my_li + r * CAP;
         if (n > a.k + kSlack) n = shrink_list<SL>(ld, li, n, a.k, CAP, lane, t);
-        rank_cut<SL>(ld, li, n, a.k, lane);
+        if (a.unordered && n <= a.k + kSlack) drop_largest<SL>(ld, li, n, a.k, lane);   // k best, any order
+        else rank_cut<SL>(ld, li, n, a.k, lane);                                          // k best, in order
     });
     __syncwarp();
 #pragma unroll
@@ -359,13 +367,14 @@ static int launch_xyz(XyzArgs a, cudaStream_t st) {
         return GCANET_OK;
     };
     if (a.k <= 40) return go(std::integral_constant<int, 4>{});
+    if (a.k <= 72) return go(std::integral_constant<int, 5>{});
     if (a.k <= 104) return go(std::integral_constant<int, 6>{});
     return go(std::integral_constant<int, 8>{});
 }
 
 // Returns GCANET_OK; *fallback_flags (device, [B]) tells the caller which clouds need the brute-force scan.
 int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metric, int64_t *idx64, int32_t *idx32,
-                  void *ws, float **norm_out, int **fallback_out, cudaStream_t st) {
+                  void *ws, float **norm_out, int **fallback_out, int unordered, cudaStream_t st) {
     const size_t bn = (size_t)B * N;
     const int tiles = ceil_div(N, XT);
     const int end_bit = key_bits(B);
@@ -396,7 +405,8 @@ int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metri
     xyz_gather_kernel<<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(x, norm, vals_out, sc, sn, perm, aabb, B, C, N, tiles);
     GCANET_LAUNCH_OK("xyz_gather_kernel");
 
-    XyzArgs a{sc, sn, perm, aabb, bbox, B, N, tiles, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2), idx64, idx32, fallback};
+    XyzArgs a{sc, sn, perm, aabb, bbox, B, N, tiles, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2), idx64, idx32, fallback,
+              (unordered && k1 == k2) ? 1 : 0};
     rc = metric == GCANET_METRIC_L2 ? launch_xyz<3, false>(a, st) : launch_xyz<6, true>(a, st);
     if (rc) return rc;
     *norm_out = norm;
