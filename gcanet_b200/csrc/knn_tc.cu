@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace gcanet {
 
@@ -215,6 +216,7 @@ struct TcScanArgs {
     int *cand_cnt;       // [B][N]
     int *overflow;       // [B][N]   1 = list overflowed, row must be redone by the fallback
     int N, k, tiles;     // tiles = ceil(N / TC_BN)
+    int debug_no_append; // measurement aid (GCANET_TC_DEBUG=1): thresholds start at -inf, nothing is ever appended
     int tile_stride;     // key tiles are visited as (t * tile_stride) % tiles, stride coprime to tiles:
                          // a spatially sorted cloud then looks like a random stream to the thresholds
 };
@@ -409,7 +411,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         uint2 *buf = a.cand + grow * TC_CAP;
         const float qn = active ? a.norm[grow] : 0.f;
         const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
-        float thr = active ? CUDART_INF_F : -CUDART_INF_F;   // inactive rows never append
+        float thr = (active && !a.debug_no_append) ? CUDART_INF_F : -CUDART_INF_F;   // inactive rows never append
         int cnt = 0;
         bool ovf = false;
 
@@ -696,6 +698,7 @@ static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcSca
     dim3 grid(ceil_div(sa.N, TC_BM), B);
     kern<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
     GCANET_LAUNCH_OK("knn_tc_scan_kernel");
+    if (sa.debug_no_append) return GCANET_OK;      // measurement aid: scan pipeline only
     dim3 rgrid(ceil_div(sa.N, 8), B);
     knn_tc_rerank_kernel<C><<<rgrid, 256, 0, st>>>(ra);
     GCANET_LAUNCH_OK("knn_tc_rerank_kernel");
@@ -750,11 +753,15 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     if (stride < 1) stride = 1;
     auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
     while (gcd(stride, tiles) != 1) ++stride;
-    TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, stride};
+    // GCANET_TC_DEBUG=1 (measurement aid, tools/time_knn.py): run the scan pipeline with appends disabled
+    // and stop after it -- gives the TMA + MMA + TMEM-read + compare floor of the kernel.
+    const char *dbg = getenv("GCANET_TC_DEBUG");
+    TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, (dbg && dbg[0] == '1') ? 1 : 0, stride};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                   (unordered && k1 == k2) ? 1 : 0};
     rc = C == 64 ? launch_tc<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<128>(tmap_q, tmap_k, sa, ra, B, st);
     if (rc) return rc;
+    if (sa.debug_no_append) return GCANET_OK;
     return knn_fallback_rows(x, norm, overflow, B, C, N, k1, k2, idx64, idx32, st);
 }
 
