@@ -23,6 +23,6 @@ from .functional import (  # noqa: F401
     to_channel_major,
     to_point_major,
 )
-from .modules import DGCNNEncoderGn, SoftProjection  # noqa: F401
+from .modules import DGCNNEncoderGn, NormalEdgeHead, SoftProjection  # noqa: F401
 
 __version__ = "0.1.0"

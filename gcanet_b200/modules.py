@@ -134,3 +134,26 @@ class SoftProjection(nn.Module):
             raise NotImplementedError
         weights = weights.repeat(1, 3, 1, 1)
         return torch.sum(grouped_points * weights, dim=3)
+
+
+class NormalEdgeHead(nn.Module):
+    """The 4th EdgeConv of the reference, on normals: ``conv_normal`` (M4:584-587) applied to
+    ``get_graph_feature_with_normals_g(points, k, k)`` and reduced with max over k (M4:691-693).
+
+    Same parameter names as in ``PrimitivesEmbeddingDGCNGn`` (``bn_normal``, ``conv_normal.0.weight``
+    [64, 7, 1, 1]).  The neighbour graph (points x normals metric) and the 7-channel edge feature
+    come from the CUDA path; the 7 -> 64 conv + GroupNorm + LeakyReLU + max run on torch -- with
+    F = 7 the materialised feature is small ([B, 7, N, k] = 224 MB at B = 16, N = 10k, k = 50).  In mode 5
+    this graph is identical to the encoder's layer-1 graph (M4:493 vs M4:691): pass ``idx`` to reuse it.
+    """
+
+    def __init__(self, nn_nb=80):
+        super().__init__()
+        self.k = nn_nb
+        self.bn_normal = nn.GroupNorm(2, 64)
+        self.conv_normal = nn.Sequential(nn.Conv2d(7, 64, kernel_size=1, bias=False), self.bn_normal,
+                                         nn.LeakyReLU(negative_slope=LEAKY_SLOPE))
+
+    def forward(self, points, idx=None):
+        feat = G.get_graph_feature_with_normals_g(points, k1=self.k, k2=self.k, idx=idx)
+        return self.conv_normal(feat).max(dim=-1, keepdim=False)[0]

@@ -505,3 +505,25 @@ def test_knn_tensor_core_path_on_spatially_sorted_features():
     i_tc = G.knn_graph(xs.to(DEV), 50, 50)[0]
     n = check_knn_rows(i_tc, orc.knn(xs, 50, 50), orc.knn_scores(xs), knn_tau(xs))
     assert n <= 3
+
+
+def test_normal_edge_head_golden(golden_dir):
+    """conv_normal head (M4:584-587, 691-693) against the fixture made from the reference's
+    get_graph_feature_with_normals_g; forward 1e-4, weight gradients 2e-3 relative."""
+    fx = np.load(os.path.join(golden_dir, "normal_head_small.npz"))
+    head = gb.NormalEdgeHead(nn_nb=int(fx["k"]))
+    with torch.no_grad():
+        for name, p in head.named_parameters():
+            p.copy_(_t(fx[f"param.{name}"]))
+    head.to(DEV)
+    x6 = _t(fx["x6"]).to(DEV)
+    out = head(x6)
+    want = _t(fx["out"])
+    d = (out.cpu() - want).abs()
+    assert float((d > 1e-4 * float(want.abs().max())).float().mean()) < 2e-3      # a tie-flipped neighbour moves a max
+    (out * _t(fx["cot"]).to(DEV)).sum().backward()
+    for name, p in head.named_parameters():
+        assert rel_err(p.grad, _t(fx[f"grad.{name}"])) < 5e-3, name
+    # reusing the encoder's layer-1 graph (mode 5) gives the same result
+    idx = gb.knn_points_normals(x6, int(fx["k"]), int(fx["k"]))
+    assert torch.equal(head(x6, idx=idx), out.detach()) or float((head(x6, idx=idx) - out).abs().max()) < 1e-6
