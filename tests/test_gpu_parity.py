@@ -511,6 +511,7 @@ def test_normal_edge_head_golden(golden_dir):
     """conv_normal head (M4:584-587, 691-693) against the fixture made from the reference's
     get_graph_feature_with_normals_g; forward 1e-4, weight gradients 2e-3 relative."""
     fx = np.load(os.path.join(golden_dir, "normal_head_small.npz"))
+    torch.backends.cudnn.allow_tf32 = False          # the 7 -> 64 conv is torch's (cuDNN defaults to TF32)
     head = gb.NormalEdgeHead(nn_nb=int(fx["k"]))
     with torch.no_grad():
         for name, p in head.named_parameters():
