@@ -312,7 +312,9 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     constexpr int ACC = 2;                              // TMEM accumulator stages
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // align inside the shared window with plain pointer arithmetic: casting through an integer would
+    // make every later access a generic load/store instead of LDS/STS
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = smem;                                  // query tile
     uint8_t *sB = smem + A_BYTES;                        // STAGES key tiles
     float *s_rn = reinterpret_cast<float *>(sB + STAGES * TILE_BYTES);      // [TC_NRING][TC_BN] key norms

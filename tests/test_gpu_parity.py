@@ -528,3 +528,26 @@ def test_normal_edge_head_golden(golden_dir):
     # reusing the encoder's layer-1 graph (mode 5) gives the same result
     idx = gb.knn_points_normals(x6, int(fx["k"]), int(fx["k"]))
     assert torch.equal(head(x6, idx=idx), out.detach()) or float((head(x6, idx=idx) - out).abs().max()) < 1e-6
+
+
+def test_large_cloud_feature_space_100k():
+    """Config 5, feature-space half: one 100 000-point cloud with C = 64 through the tensor-core path
+    (the reference needs a 40 GB distance matrix per cloud, M4:36-41); sampled rows against a chunked
+    fp32 oracle in the reference's expansion arithmetic."""
+    N, k, C = 100000, 50, 64
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, C, N, generator=g)
+    idx = gb.knn(x.to(DEV), k, k).cpu()
+    rows = torch.arange(0, N, 2503)
+    xb = x[0]
+    sq = torch.sum(xb ** 2, dim=0, keepdim=True)
+    score = -sq - (-2 * torch.matmul(xb[:, rows].t(), xb)) - sq[:, rows].t()        # [R, N]
+    io = score.topk(k, dim=-1)[1]
+    tau = knn_tau(x)[0, rows]
+    st = torch.gather(score, 1, idx[0, rows]).double()
+    kth = torch.gather(score, 1, io).double().min(dim=1)[0]
+    assert bool((st >= (kth - tau).unsqueeze(-1)).all())
+    same = (idx[0, rows].sort(dim=1)[0] == io.sort(dim=1)[0]).all(dim=1)
+    assert float(same.float().mean()) > 0.95
+    srt = idx.sort(dim=2)[0]
+    assert bool((srt[:, :, 1:] != srt[:, :, :-1]).all())
