@@ -18,6 +18,7 @@ from .functional import (  # noqa: F401
     knn_graph,
     knn_point,
     knn_points_normals,
+    normal_edgeconv,
     splinenet_get_graph_feature,
     splinenet_knn,
     to_channel_major,

@@ -25,6 +25,14 @@ class EdgeConvDesc(ctypes.Structure):
 
 _DESC_P = ctypes.POINTER(EdgeConvDesc)
 
+
+class NormalEdgeDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("N", c_int), ("ldx", c_int), ("Cout", c_int), ("k", c_int), ("groups", c_int),
+                ("eps", c_float), ("slope", c_float)]
+
+
+_NDESC_P = ctypes.POINTER(NormalEdgeDesc)
+
 # name -> (restype, argtypes); mirrors include/gcanet_b200.h one to one
 SIGNATURES = {
     "gcanet_abi_version": (c_int, []),
@@ -54,6 +62,10 @@ SIGNATURES = {
     "gcanet_edgeconv_workspace_bytes": (c_size_t, [_DESC_P]),
     "gcanet_edgeconv_forward": (c_int, [_DESC_P] + [c_void_p] * 9 + [c_size_t, c_void_p]),
     "gcanet_edgeconv_backward": (c_int, [_DESC_P] + [c_void_p] * 12 + [c_size_t, c_void_p]),
+    "gcanet_normal_edgeconv_saved_bytes": (c_size_t, [_NDESC_P]),
+    "gcanet_normal_edgeconv_workspace_bytes": (c_size_t, [_NDESC_P]),
+    "gcanet_normal_edgeconv_forward": (c_int, [_NDESC_P] + [c_void_p] * 9 + [c_size_t, c_void_p]),
+    "gcanet_normal_edgeconv_backward": (c_int, [_NDESC_P] + [c_void_p] * 11 + [c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -770,6 +770,330 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     return GCANET_OK;
 }
 
+// =================================================================================
+// EdgeConv on normals (conv_normal, M4:584-587 / M4:691-693): 7-channel edge feature
+//   e_ik = (clamp(n_i.n_j, -.99, .99), n_j - n_i, n_i),  y_ik = W e_ik,  then GroupNorm, LeakyReLU, max over k.
+// The feature is rebuilt per edge from the 12-byte normal of the neighbour, so neither
+// [B][7][N][k] nor [B][64][N][k] exists.  Only parameter gradients are produced: the inputs of this
+// head are data (points and normals), never activations.  With dy_ik = [k=k*] s + A_g + K_g y_ik:
+//   dW[c][f] = sum_i s_ic e_{i,k*(i,c),f}  +  sum_b ( A_g E1_b[f] + K_g sum_f' W[c][f'] E2_b[f'][f] ),
+// E1_b = sum_ik e_ik, E2_b = sum_ik e_ik e_ik^T (35 numbers per cloud, accumulated in the forward pass).
+// =================================================================================
+constexpr int kNF = 7;                 // edge-feature channels
+constexpr int kNMom = 35;              // 7 first moments + 28 unique second moments
+
+__device__ __forceinline__ float normal_angle(float a0, float a1, float a2, float b0, float b1, float b2) {
+    // reference: elementwise product summed over the 3 channels, then clamp (M4:194)
+    float d = __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+    return fminf(fmaxf(d, -0.99f), 0.99f);
+}
+
+struct NFwdArgs {
+    const float *x_nc;     // [B][N][ldx], normals in columns 3..5
+    const int32_t *idx;    // [B][N][k]
+    const float *weight;   // [Cout][7]
+    const float *gamma;
+    float *ysel;           // [B][N][Cout]
+    unsigned char *arg;    // [B][N][Cout]
+    double *part;          // [B][nblk][G][2]   group moments of y
+    double *mom_part;      // [B][nblk][kNMom]  feature moments
+    int N, ldx, Cout, k, G;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kGWarps * 32) normal_edge_forward_kernel(NFwdArgs a) {
+    __shared__ double red[kGWarps * 32][2];
+    __shared__ float s_e[kGWarps][8];
+    __shared__ double s_mom[kGWarps][kNMom];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cout = a.Cout, k = a.k, c0 = lane * VEC;
+    const float *xb = a.x_nc + (size_t)b * a.N * a.ldx;
+    float w[VEC][kNF], sg[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+        for (int f = 0; f < kNF; ++f) w[v][f] = a.weight[(size_t)(c0 + v) * kNF + f];
+        sg[v] = a.gamma[c0 + v] < 0.f ? -1.f : 1.f;
+    }
+    // moment slots of this lane: item `lane` and, for lanes 0..2, item 32 + lane
+    // items 0..6 = E1[f]; items 7.. = E2 pairs (f <= g) in row-major order
+    int f1[2], g1[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        int item = lane + 32 * t;
+        f1[t] = -1; g1[t] = -1;
+        if (item < kNF) { f1[t] = item; }
+        else if (item < kNMom) {
+            int r = item - kNF, f = 0;
+            while (r >= kNF - f) { r -= kNF - f; ++f; }
+            f1[t] = f; g1[t] = f + r;
+        }
+    }
+    float macc[2] = {0.f, 0.f};
+    double s1 = 0.0, s2 = 0.0;
+
+    for (int pi = 0; pi < kPtsPerWarp; ++pi) {
+        const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
+        if (i >= a.N) break;
+        const float a0 = xb[(size_t)i * a.ldx + 3], a1 = xb[(size_t)i * a.ldx + 4], a2 = xb[(size_t)i * a.ldx + 5];
+        float base[VEC], zmax[VEC], vsum[VEC], vsq[VEC];
+        int kbest[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            // n_i enters through (n_j - n_i) and through the last three channels
+            base[v] = (w[v][4] - w[v][1]) * a0 + (w[v][5] - w[v][2]) * a1 + (w[v][6] - w[v][3]) * a2;
+            zmax[v] = -CUDART_INF_F; vsum[v] = 0.f; vsq[v] = 0.f; kbest[v] = 0;
+        }
+        const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
+        for (int kk = 0; kk < k; ++kk) {
+            const int j = ip[kk];                                   // same address in every lane
+            const float b0 = xb[(size_t)j * a.ldx + 3], b1 = xb[(size_t)j * a.ldx + 4], b2 = xb[(size_t)j * a.ldx + 5];
+            const float ang = normal_angle(a0, a1, a2, b0, b1, b2);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float y = fmaf(w[v][0], ang, base[v]);
+                y = fmaf(w[v][1], b0, y);
+                y = fmaf(w[v][2], b1, y);
+                y = fmaf(w[v][3], b2, y);
+                const float z = sg[v] * y;
+                if (z > zmax[v]) { zmax[v] = z; kbest[v] = kk; }
+                vsum[v] += y;
+                vsq[v] = fmaf(y, y, vsq[v]);
+            }
+            // feature moments: every lane owns up to two of the 35 sums
+            const float e[kNF] = {ang, b0 - a0, b1 - a1, b2 - a2, a0, a1, a2};
+            if (lane < kNF) s_e[warp][lane] = lane == 0 ? e[0] : (lane == 1 ? e[1] : (lane == 2 ? e[2] : (lane == 3 ? e[3] : (lane == 4 ? e[4] : (lane == 5 ? e[5] : e[6])))));
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (f1[t] >= 0) macc[t] += g1[t] >= 0 ? s_e[warp][f1[t]] * s_e[warp][g1[t]] : s_e[warp][f1[t]];
+            __syncwarp();
+        }
+        const size_t o = ((size_t)b * a.N + i) * Cout + c0;
+        float ys[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            ys[v] = sg[v] * zmax[v];
+            a.arg[o + v] = (unsigned char)kbest[v];
+            s1 += (double)vsum[v];
+            s2 += (double)vsq[v];
+        }
+        VecIO<VEC>::st(a.ysel + o, ys);
+    }
+    red[threadIdx.x][0] = s1;
+    red[threadIdx.x][1] = s2;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        int item = lane + 32 * t;
+        if (item < kNMom) s_mom[warp][item] = (double)macc[t];
+    }
+    __syncthreads();
+    if (threadIdx.x < a.G * 2) {
+        const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const int lanes_per_group = 32 / a.G;
+        double s = 0.0;
+        for (int wv = 0; wv < kGWarps; ++wv)
+            for (int l = g * lanes_per_group; l < (g + 1) * lanes_per_group; ++l) s += red[wv * 32 + l][which];
+        a.part[(((size_t)b * gridDim.x + blockIdx.x) * a.G + g) * 2 + which] = s;
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + kNMom) {
+        const int item = threadIdx.x - 64;
+        double s = 0.0;
+        for (int wv = 0; wv < kGWarps; ++wv) s += s_mom[wv][item];
+        a.mom_part[((size_t)b * gridDim.x + blockIdx.x) * kNMom + item] = s;
+    }
+}
+
+// mom[b][0:7] = E1, mom[b][7:56] = E2 as a full symmetric 7x7
+__global__ void normal_edge_moments_kernel(const double *__restrict__ mom_part, float *__restrict__ mom, int nblk) {
+    __shared__ double tot[kNMom];
+    const int b = blockIdx.x;
+    if (threadIdx.x < kNMom) {
+        double s = 0.0;
+        for (int i = 0; i < nblk; ++i) s += mom_part[((size_t)b * nblk + i) * kNMom + threadIdx.x];
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNF) mom[b * 56 + threadIdx.x] = (float)tot[threadIdx.x];
+    if (threadIdx.x < kNF * kNF) {
+        int f = threadIdx.x / kNF, g = threadIdx.x % kNF;
+        int lo = f < g ? f : g, hi = f < g ? g : f;
+        int item = kNF;
+        for (int r = 0; r < lo; ++r) item += kNF - r;
+        item += hi - lo;
+        mom[b * 56 + kNF + threadIdx.x] = (float)tot[item];
+    }
+}
+
+struct NBwdArgs {
+    const float *x_nc;
+    const int32_t *idx;
+    const float *ysel, *stats, *gamma, *beta, *gout;
+    const unsigned char *arg;
+    float *dw_part;        // [B][nblk][Cout][7]
+    int N, ldx, Cout, k, G;
+    float slope;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kGWarps * 32) normal_edge_bwd_kernel(NBwdArgs a) {
+    __shared__ float red[kGWarps][32 * VEC][kNF];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cout = a.Cout, c0 = lane * VEC;
+    const int cpg = Cout / a.G;
+    const float mean = a.stats[((size_t)b * a.G + c0 / cpg) * 2 + 0], rstd = a.stats[((size_t)b * a.G + c0 / cpg) * 2 + 1];
+    const float *xb = a.x_nc + (size_t)b * a.N * a.ldx;
+    float gm[VEC], bt[VEC], acc[VEC][kNF];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        gm[v] = a.gamma[c0 + v];
+        bt[v] = a.beta[c0 + v];
+#pragma unroll
+        for (int f = 0; f < kNF; ++f) acc[v][f] = 0.f;
+    }
+    for (int pi = 0; pi < kPtsPerWarp; ++pi) {
+        const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
+        if (i >= a.N) break;
+        const float a0 = xb[(size_t)i * a.ldx + 3], a1 = xb[(size_t)i * a.ldx + 4], a2 = xb[(size_t)i * a.ldx + 5];
+        const size_t o = ((size_t)b * a.N + i) * Cout + c0;
+        const int32_t *ip = a.idx + ((size_t)b * a.N + i) * a.k;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float yh = (a.ysel[o + v] - mean) * rstd;
+            const float u = yh * gm[v] + bt[v];
+            const float g = a.gout[o + v];
+            const float s = rstd * gm[v] * (u > 0.f ? g : g * a.slope);
+            const int j = ip[a.arg[o + v]];
+            const float b0 = xb[(size_t)j * a.ldx + 3], b1 = xb[(size_t)j * a.ldx + 4], b2 = xb[(size_t)j * a.ldx + 5];
+            const float e[kNF] = {normal_angle(a0, a1, a2, b0, b1, b2), b0 - a0, b1 - a1, b2 - a2, a0, a1, a2};
+#pragma unroll
+            for (int f = 0; f < kNF; ++f) acc[v][f] = fmaf(s, e[f], acc[v][f]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+        for (int f = 0; f < kNF; ++f) red[warp][c0 + v][f] = acc[v][f];
+    __syncthreads();
+    for (int e = threadIdx.x; e < Cout * kNF; e += blockDim.x) {
+        const int c = e / kNF, f = e % kNF;
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < kGWarps; ++wv) s += red[wv][c][f];
+        a.dw_part[((size_t)b * gridDim.x + blockIdx.x) * Cout * kNF + e] = s;
+    }
+}
+
+// dW[c][f] = sum_{b,blk} dw_part + sum_b (A_g E1_b[f] + K_g sum_f' W[c][f'] E2_b[f'][f])
+__global__ void normal_edge_dw_kernel(const float *__restrict__ dw_part, const float *__restrict__ coef,
+                                      const float *__restrict__ mom, const float *__restrict__ weight,
+                                      float *__restrict__ dW, int B, int nblk, int Cout, int G) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Cout * kNF) return;
+    const int c = e / kNF, f = e % kNF;
+    const int g = c / (Cout / G);
+    double s = 0.0;
+    for (int b = 0; b < B; ++b) {
+        for (int i = 0; i < nblk; ++i) s += (double)dw_part[((size_t)b * nblk + i) * Cout * kNF + e];
+        const float Ag = coef[((size_t)b * G + g) * 2 + 0], Kg = coef[((size_t)b * G + g) * 2 + 1];
+        const float *m = mom + b * 56;
+        double we2 = 0.0;
+        for (int fp = 0; fp < kNF; ++fp) we2 += (double)weight[(size_t)c * kNF + fp] * (double)m[kNF + fp * kNF + f];
+        s += (double)Ag * (double)m[f] + (double)Kg * we2;
+    }
+    dW[e] = (float)s;
+}
+
+struct NSaved {
+    float *ysel, *stats, *mom;
+    unsigned char *arg;
+};
+
+static size_t plan_nsaved(const gcanet_normal_edge_desc *d, void *base, NSaved *s) {
+    Carver cv(base);
+    size_t bn = (size_t)d->B * d->N;
+    float *ysel = cv.take<float>(bn * d->Cout);
+    unsigned char *arg = cv.take<unsigned char>(bn * d->Cout);
+    float *stats = cv.take<float>((size_t)d->B * d->groups * 2);
+    float *mom = cv.take<float>((size_t)d->B * 56);
+    if (s) { s->ysel = ysel; s->arg = arg; s->stats = stats; s->mom = mom; }
+    return cv.off;
+}
+
+struct NWs {
+    double *part, *mom_part, *sbc;
+    float *rpart, *coef, *dw_part;
+};
+
+static size_t plan_nws(const gcanet_normal_edge_desc *d, void *base, NWs *w) {
+    Carver cv(base);
+    int nblk = ceil_div(d->N, kPtsPerCta);
+    double *part = cv.take<double>((size_t)d->B * nblk * d->groups * 2);
+    double *mom_part = cv.take<double>((size_t)d->B * nblk * kNMom);
+    double *sbc = cv.take<double>((size_t)d->B * d->Cout * 2);
+    float *rpart = cv.take<float>((size_t)d->B * nblk * d->Cout * 2);
+    float *coef = cv.take<float>((size_t)d->B * d->groups * 2);
+    float *dw_part = cv.take<float>((size_t)d->B * nblk * d->Cout * kNF);
+    if (w) { w->part = part; w->mom_part = mom_part; w->sbc = sbc; w->rpart = rpart; w->coef = coef; w->dw_part = dw_part; }
+    return cv.off;
+}
+
+static int check_ndesc(const gcanet_normal_edge_desc *d) {
+    GCANET_REQUIRE(d != nullptr, "normal_edgeconv: null descriptor");
+    GCANET_REQUIRE(d->B >= 1 && d->B <= 65535 && d->N >= 1 && d->k >= 1 && d->k <= 255, "normal_edgeconv: bad shape B=%d N=%d k=%d", d->B, d->N, d->k);
+    GCANET_REQUIRE(d->ldx >= 6, "normal_edgeconv: x_nc needs xyz + normals (ldx=%d < 6)", d->ldx);
+    GCANET_REQUIRE(d->Cout == 32 || d->Cout == 64 || d->Cout == 128, "normal_edgeconv: Cout=%d must be 32, 64 or 128", d->Cout);
+    GCANET_REQUIRE(d->groups >= 1 && d->Cout % d->groups == 0 && 32 % d->groups == 0, "normal_edgeconv: groups=%d must divide 32 and Cout", d->groups);
+    GCANET_REQUIRE(d->eps > 0.f, "normal_edgeconv: eps must be positive");
+    return GCANET_OK;
+}
+
+template <int VEC>
+static int run_nforward(const gcanet_normal_edge_desc *d, const float *x_nc, const int32_t *idx, const float *weight,
+                        const float *gamma, const float *beta, float *out_nc, float *out_cn, const NSaved &sv,
+                        const NWs &w, cudaStream_t st) {
+    const int nblk = ceil_div(d->N, kPtsPerCta);
+    NFwdArgs fa{x_nc, idx, weight, gamma, sv.ysel, sv.arg, w.part, w.mom_part, d->N, d->ldx, d->Cout, d->k, d->groups};
+    normal_edge_forward_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(fa);
+    GCANET_LAUNCH_OK("normal_edge_forward_kernel");
+    double count = (double)(d->Cout / d->groups) * d->N * d->k;
+    gn_stats_kernel<<<d->B, 32 * d->groups, 0, st>>>(w.part, sv.stats, nblk, d->groups, count, d->eps);
+    GCANET_LAUNCH_OK("gn_stats_kernel");
+    normal_edge_moments_kernel<<<d->B, 64, 0, st>>>(w.mom_part, sv.mom, nblk);
+    GCANET_LAUNCH_OK("normal_edge_moments_kernel");
+    dim3 fg(ceil_div(d->N, 32), d->Cout / 32, d->B), fb(32, 8);
+    edge_finish_kernel<<<fg, fb, 0, st>>>(sv.ysel, sv.stats, gamma, beta, out_nc, out_cn, d->N, d->Cout, d->groups, d->slope);
+    GCANET_LAUNCH_OK("edge_finish_kernel");
+    return GCANET_OK;
+}
+
+template <int VEC>
+static int run_nbackward(const gcanet_normal_edge_desc *d, const float *x_nc, const int32_t *idx, const float *weight,
+                         const float *gamma, const float *beta, const float *gout, const NSaved &sv, float *grad_weight,
+                         float *grad_gamma, float *grad_beta, const NWs &w, cudaStream_t st) {
+    const int nblk = ceil_div(d->N, kPtsPerCta);
+    const int Cout = d->Cout;
+    BwdArgs ba{nullptr, sv.ysel, nullptr, sv.stats, gamma, beta, gout, sv.arg, idx, w.rpart, w.coef, nullptr, nullptr,
+               d->N, Cout, d->k, d->groups, d->slope};
+    edge_bwd_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
+    GCANET_LAUNCH_OK("edge_bwd_reduce_kernel");
+    double count = (double)(Cout / d->groups) * d->N * d->k;
+    edge_bwd_coef_kernel<<<d->B, 512, Cout * 2 * sizeof(double), st>>>(w.rpart, sv.stats, gamma, w.sbc, w.coef, nblk, Cout,
+                                                                      d->groups, count);
+    GCANET_LAUNCH_OK("edge_bwd_coef_kernel");
+    edge_bwd_affine_kernel<<<ceil_div(Cout, 128), 128, 0, st>>>(w.sbc, grad_gamma, grad_beta, d->B, Cout);
+    GCANET_LAUNCH_OK("edge_bwd_affine_kernel");
+    NBwdArgs na{x_nc, idx, sv.ysel, sv.stats, gamma, beta, gout, sv.arg, w.dw_part, d->N, d->ldx, Cout, d->k, d->groups, d->slope};
+    normal_edge_bwd_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(na);
+    GCANET_LAUNCH_OK("normal_edge_bwd_kernel");
+    normal_edge_dw_kernel<<<ceil_div(Cout * kNF, 128), 128, 0, st>>>(w.dw_part, w.coef, sv.mom, weight, grad_weight, d->B,
+                                                                     nblk, Cout, d->groups);
+    GCANET_LAUNCH_OK("normal_edge_dw_kernel");
+    return GCANET_OK;
+}
+
 }  // namespace gcanet
 
 using namespace gcanet;
@@ -834,5 +1158,58 @@ extern "C" int gcanet_edgeconv_backward(const gcanet_edgeconv_desc *d, const flo
         case 2: return run_backward<2>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_x_nc, grad_weight, grad_gamma, grad_beta, w, st);
         case 4: return run_backward<4>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_x_nc, grad_weight, grad_gamma, grad_beta, w, st);
         default: return run_backward<8>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_x_nc, grad_weight, grad_gamma, grad_beta, w, st);
+    }
+}
+
+extern "C" size_t gcanet_normal_edgeconv_saved_bytes(const gcanet_normal_edge_desc *d) {
+    if (check_ndesc(d) != GCANET_OK) return 0;
+    return plan_nsaved(d, nullptr, nullptr);
+}
+
+extern "C" size_t gcanet_normal_edgeconv_workspace_bytes(const gcanet_normal_edge_desc *d) {
+    if (check_ndesc(d) != GCANET_OK) return 0;
+    return plan_nws(d, nullptr, nullptr);
+}
+
+extern "C" int gcanet_normal_edgeconv_forward(const gcanet_normal_edge_desc *d, const float *x_nc, const int32_t *idx,
+                                              const float *weight, const float *gamma, const float *beta,
+                                              float *out_nc, float *out_cn, void *saved, void *ws, size_t ws_bytes,
+                                              gcanet_stream_t stream) {
+    int rc = check_ndesc(d);
+    if (rc) return rc;
+    GCANET_REQUIRE(x_nc && idx && weight && gamma && beta && out_nc && saved, "normal_edgeconv_forward: null pointer");
+    GCANET_REQUIRE(reinterpret_cast<uintptr_t>(saved) % kAlign == 0, "normal_edgeconv_forward: saved buffer must be 256-byte aligned");
+    rc = check_ws("normal_edgeconv_forward", ws, ws_bytes, plan_nws(d, nullptr, nullptr));
+    if (rc) return rc;
+    NSaved sv; NWs w;
+    plan_nsaved(d, saved, &sv);
+    plan_nws(d, ws, &w);
+    cudaStream_t st = as_stream(stream);
+    switch (d->Cout / 32) {
+        case 1: return run_nforward<1>(d, x_nc, idx, weight, gamma, beta, out_nc, out_cn, sv, w, st);
+        case 2: return run_nforward<2>(d, x_nc, idx, weight, gamma, beta, out_nc, out_cn, sv, w, st);
+        default: return run_nforward<4>(d, x_nc, idx, weight, gamma, beta, out_nc, out_cn, sv, w, st);
+    }
+}
+
+extern "C" int gcanet_normal_edgeconv_backward(const gcanet_normal_edge_desc *d, const float *x_nc, const int32_t *idx,
+                                               const float *weight, const float *gamma, const float *beta,
+                                               const float *grad_out_nc, const void *saved, float *grad_weight,
+                                               float *grad_gamma, float *grad_beta, void *ws, size_t ws_bytes,
+                                               gcanet_stream_t stream) {
+    int rc = check_ndesc(d);
+    if (rc) return rc;
+    GCANET_REQUIRE(x_nc && idx && weight && gamma && beta && grad_out_nc && saved && grad_weight && grad_gamma && grad_beta,
+                   "normal_edgeconv_backward: null pointer");
+    rc = check_ws("normal_edgeconv_backward", ws, ws_bytes, plan_nws(d, nullptr, nullptr));
+    if (rc) return rc;
+    NSaved sv; NWs w;
+    plan_nsaved(d, const_cast<void *>(saved), &sv);
+    plan_nws(d, ws, &w);
+    cudaStream_t st = as_stream(stream);
+    switch (d->Cout / 32) {
+        case 1: return run_nbackward<1>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_weight, grad_gamma, grad_beta, w, st);
+        case 2: return run_nbackward<2>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_weight, grad_gamma, grad_beta, w, st);
+        default: return run_nbackward<4>(d, x_nc, idx, weight, gamma, beta, grad_out_nc, sv, grad_weight, grad_gamma, grad_beta, w, st);
     }
 }

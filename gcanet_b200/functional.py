@@ -13,7 +13,7 @@ import ctypes as _ct
 import torch
 
 from . import _cabi
-from ._cabi import EdgeConvDesc, call, ptr, require_cuda, stream, workspace
+from ._cabi import EdgeConvDesc, NormalEdgeDesc, call, ptr, require_cuda, stream, workspace
 
 METRIC_L2 = 0
 METRIC_POINTS_NORMALS = 1
@@ -400,3 +400,58 @@ def edgeconv(x_nc, idx32, weight, gamma, beta, C, groups=2, eps=1e-5, slope=0.2,
     differentiable in x_nc, weight, gamma, beta."""
     w2 = weight.reshape(weight.shape[0], -1)
     return _EdgeConv.apply(x_nc, idx32, w2, gamma, beta, int(C), int(groups), float(eps), float(slope), bool(want_cn))
+
+
+class _NormalEdgeConv(torch.autograd.Function):
+    """out_cn = max_k LReLU(GN(conv_normal(edge feature of normals)))  -- parameter gradients only."""
+
+    @staticmethod
+    def forward(ctx, x_nc, idx32, weight, gamma, beta, groups, eps, slope):
+        require_cuda(x_nc, "x_nc", torch.float32)
+        require_cuda(idx32, "idx", torch.int32)
+        weight, gamma, beta = weight.contiguous(), gamma.contiguous(), beta.contiguous()
+        B, N, ldx = x_nc.shape
+        k = idx32.shape[2]
+        Cout = weight.shape[0]
+        if weight.shape[1] != 7:
+            raise RuntimeError(f"conv_normal weight must be [Cout, 7] (got {tuple(weight.shape)})")
+        desc = NormalEdgeDesc(B, N, ldx, Cout, k, groups, eps, slope)
+        L = _cabi.lib()
+        with torch.cuda.device(x_nc.device):
+            saved_bytes = L.gcanet_normal_edgeconv_saved_bytes(_ct.byref(desc))
+            if saved_bytes == 0:
+                raise RuntimeError("gcanet_b200 normal_edgeconv: " + L.gcanet_last_error().decode())
+            saved = workspace(saved_bytes, x_nc.device)
+            ws = workspace(L.gcanet_normal_edgeconv_workspace_bytes(_ct.byref(desc)), x_nc.device)
+            out_nc = torch.empty((B, N, Cout), dtype=torch.float32, device=x_nc.device)
+            out_cn = torch.empty((B, Cout, N), dtype=torch.float32, device=x_nc.device)
+            with _timed(f"normal_edgeconv_fwd[Cout={Cout}]"):
+                call("gcanet_normal_edgeconv_forward", _ct.byref(desc), ptr(x_nc), ptr(idx32), ptr(weight), ptr(gamma),
+                     ptr(beta), ptr(out_nc), ptr(out_cn), ptr(saved), ptr(ws), ws.numel(), stream())
+        ctx.save_for_backward(x_nc, idx32, weight, gamma, beta, saved)
+        ctx.desc = desc
+        return out_cn
+
+    @staticmethod
+    def backward(ctx, g_cn):
+        x_nc, idx32, weight, gamma, beta, saved = ctx.saved_tensors
+        desc = ctx.desc
+        L = _cabi.lib()
+        with torch.cuda.device(x_nc.device):
+            g = to_point_major(g_cn.contiguous(), desc.Cout)
+            gw, gg, gb = torch.empty_like(weight), torch.empty_like(gamma), torch.empty_like(beta)
+            ws = workspace(L.gcanet_normal_edgeconv_workspace_bytes(_ct.byref(desc)), x_nc.device)
+            with _timed(f"normal_edgeconv_bwd[Cout={desc.Cout}]"):
+                call("gcanet_normal_edgeconv_backward", _ct.byref(desc), ptr(x_nc), ptr(idx32), ptr(weight), ptr(gamma),
+                     ptr(beta), ptr(g), ptr(saved), ptr(gw), ptr(gg), ptr(gb), ptr(ws), ws.numel(), stream())
+        return None, None, gw, gg, gb, None, None, None
+
+
+def normal_edgeconv(points, idx32, weight, gamma, beta, groups=2, eps=1e-5, slope=0.2):
+    """Fused replacement of ``conv_normal(get_graph_feature_with_normals_g(points, idx=idx)).max(-1)[0]``
+    (M4:584-587, M4:691-693).  points [B, 6, N] (xyz + normals, data -- no gradient flows to it),
+    idx32 [B, N, k] int32, weight [64, 7] or [64, 7, 1, 1].  Returns [B, Cout, N]; differentiable in
+    weight, gamma, beta."""
+    x_nc = to_point_major(points.detach().float().contiguous(), 8)
+    return _NormalEdgeConv.apply(x_nc, idx32, weight.reshape(weight.shape[0], -1), gamma, beta, int(groups),
+                                 float(eps), float(slope))

@@ -141,10 +141,12 @@ class NormalEdgeHead(nn.Module):
     ``get_graph_feature_with_normals_g(points, k, k)`` and reduced with max over k (M4:691-693).
 
     Same parameter names as in ``PrimitivesEmbeddingDGCNGn`` (``bn_normal``, ``conv_normal.0.weight``
-    [64, 7, 1, 1]).  The neighbour graph (points x normals metric) and the 7-channel edge feature
-    come from the CUDA path; the 7 -> 64 conv + GroupNorm + LeakyReLU + max run on torch -- with
-    F = 7 the materialised feature is small ([B, 7, N, k] = 224 MB at B = 16, N = 10k, k = 50).  In mode 5
-    this graph is identical to the encoder's layer-1 graph (M4:493 vs M4:691): pass ``idx`` to reuse it.
+    [64, 7, 1, 1]).  The neighbour graph (points x normals metric) comes from ``knn_graph`` and the whole
+    block runs in the fused kernel ``normal_edgeconv`` (the 7-channel feature is rebuilt per edge, nothing
+    of size N*k is stored).  ``points`` is data in the reference (xyz + normals of the input cloud); if it
+    does require a gradient the block falls back to the materialised feature + torch conv, which is
+    differentiable in ``points``.  In mode 5 this graph is identical to the encoder's layer-1 graph
+    (M4:493 vs M4:691): pass ``idx`` to reuse it.
     """
 
     def __init__(self, nn_nb=80):
@@ -155,5 +157,16 @@ class NormalEdgeHead(nn.Module):
                                          nn.LeakyReLU(negative_slope=LEAKY_SLOPE))
 
     def forward(self, points, idx=None):
-        feat = G.get_graph_feature_with_normals_g(points, k1=self.k, k2=self.k, idx=idx)
-        return self.conv_normal(feat).max(dim=-1, keepdim=False)[0]
+        if points.requires_grad:
+            feat = G.get_graph_feature_with_normals_g(points, k1=self.k, k2=self.k, idx=idx)
+            return self.conv_normal(feat).max(dim=-1, keepdim=False)[0]
+        if not points.is_cuda:
+            raise RuntimeError("gcanet_b200.NormalEdgeHead has no CPU path")
+        if idx is None:
+            _, idx32 = G.knn_graph(points, self.k, self.k, G.METRIC_POINTS_NORMALS, want64=False, want32=True,
+                                   ordered=False)
+        else:
+            idx32 = idx.to(torch.int32).contiguous()
+        gn = self.bn_normal
+        return G.normal_edgeconv(points, idx32, self.conv_normal[0].weight, gn.weight, gn.bias, groups=gn.num_groups,
+                                 eps=gn.eps, slope=self.conv_normal[2].negative_slope)

@@ -187,6 +187,33 @@ GCANET_API int gcanet_edgeconv_backward(const gcanet_edgeconv_desc *d, const flo
                              float *grad_weight, float *grad_gamma, float *grad_beta, void *ws,
                              size_t ws_bytes, gcanet_stream_t stream);
 
+/* ------------------------------------------------------------------ fused EdgeConv on normals
+ * Replaces get_graph_feature_with_normals_g(points, idx=idx) -> conv_normal = Conv2d(7,Cout,1,bias=False)
+ * -> GroupNorm -> LeakyReLU -> max over k (M4:584-587, M4:691-693) and the parameter gradients of its
+ * backward.  The 7-channel edge feature (clamp(n_i.n_j, +-.99), n_j - n_i, n_i) is rebuilt per edge
+ * from the neighbour's normal; neither [B][7][N][k] nor [B][Cout][N][k] is formed.
+ *   x_nc   [B][N][ldx], ldx >= 6, normals in columns 3..5 (gcanet_cn_to_nc of the reference's [B][6][N])
+ *   idx    [B][N][k] int32;  weight [Cout][7];  gamma, beta [Cout];  Cout in {32, 64, 128}
+ *   out_nc [B][N][Cout], out_cn [B][Cout][N] or NULL
+ * backward produces grad_weight [Cout][7], grad_gamma, grad_beta (all overwritten).  There is no
+ * gradient w.r.t. x: in the reference this head is fed the input points and normals (data). */
+typedef struct {
+    int B, N, ldx, Cout, k, groups;
+    float eps, slope;
+} gcanet_normal_edge_desc;
+
+GCANET_API size_t gcanet_normal_edgeconv_saved_bytes(const gcanet_normal_edge_desc *d);
+GCANET_API size_t gcanet_normal_edgeconv_workspace_bytes(const gcanet_normal_edge_desc *d);
+GCANET_API int gcanet_normal_edgeconv_forward(const gcanet_normal_edge_desc *d, const float *x_nc, const int32_t *idx,
+                                              const float *weight, const float *gamma, const float *beta,
+                                              float *out_nc, float *out_cn, void *saved, void *ws, size_t ws_bytes,
+                                              gcanet_stream_t stream);
+GCANET_API int gcanet_normal_edgeconv_backward(const gcanet_normal_edge_desc *d, const float *x_nc, const int32_t *idx,
+                                               const float *weight, const float *gamma, const float *beta,
+                                               const float *grad_out_nc, const void *saved, float *grad_weight,
+                                               float *grad_gamma, float *grad_beta, void *ws, size_t ws_bytes,
+                                               gcanet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
