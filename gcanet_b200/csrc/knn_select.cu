@@ -471,7 +471,7 @@ int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metri
 size_t knn_tc_workspace_bytes(int B, int C, int N);
 bool knn_tc_supported(int C, int N, int k2);
 int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, int64_t *idx64, int32_t *idx32,
-                           void *ws, int unordered, cudaStream_t st);
+                           void *ws, int unordered, int no_prune, cudaStream_t st);
 
 }  // namespace gcanet
 
@@ -484,14 +484,14 @@ extern "C" int gcanet_knn_graph_columns(int k1, int k2) {
 }
 
 static bool use_tensor_cores(int C, int N, int k2, int metric) {
-    metric &= ~GCANET_KNN_FLAG_UNORDERED;
+    metric &= ~(GCANET_KNN_FLAG_UNORDERED | GCANET_KNN_FLAG_NO_PRUNE);
     return metric == GCANET_METRIC_L2 && knn_tc_supported(C, N, k2);   // the brute-force flag makes this false
 }
 
 extern "C" size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric) {
     if (B < 1 || C < 1 || N < 1) return 0;
     if (use_tensor_cores(C, N, k2, metric)) return knn_tc_workspace_bytes(B, C, N);
-    if (knn_xyz_supported(C, N, k2, metric & ~GCANET_KNN_FLAG_UNORDERED)) return knn_xyz_workspace_bytes(B, C, N);
+    if (knn_xyz_supported(C, N, k2, metric & ~(GCANET_KNN_FLAG_UNORDERED | GCANET_KNN_FLAG_NO_PRUNE))) return knn_xyz_workspace_bytes(B, C, N);
     return align_up((size_t)B * N * sizeof(float));
 }
 
@@ -504,10 +504,11 @@ extern "C" int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int
     GCANET_REQUIRE(k2 <= N, "knn_graph: k2=%d exceeds the number of points N=%d (topk would raise, M4:43)", k2, N);
     GCANET_REQUIRE(k2 <= 1024, "knn_graph: k2=%d > 1024 unsupported", k2);
     int flags = metric & ~0xff;
-    GCANET_REQUIRE((flags & ~(GCANET_KNN_FLAG_BRUTE_FORCE | GCANET_KNN_FLAG_UNORDERED)) == 0,
+    GCANET_REQUIRE((flags & ~(GCANET_KNN_FLAG_BRUTE_FORCE | GCANET_KNN_FLAG_UNORDERED | GCANET_KNN_FLAG_NO_PRUNE)) == 0,
                    "knn_graph: unknown flag bits in metric 0x%x", metric);
     const int unordered = (flags & GCANET_KNN_FLAG_UNORDERED) ? 1 : 0;
-    flags &= ~GCANET_KNN_FLAG_UNORDERED;
+    const int no_prune = (flags & GCANET_KNN_FLAG_NO_PRUNE) ? 1 : 0;
+    flags &= ~(GCANET_KNN_FLAG_UNORDERED | GCANET_KNN_FLAG_NO_PRUNE);
     const int metric_in = metric;
     metric &= 0xff;
     GCANET_REQUIRE(metric == GCANET_METRIC_L2 || metric == GCANET_METRIC_POINTS_NORMALS, "knn_graph: bad metric %d", metric);
@@ -520,7 +521,7 @@ extern "C" int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int
         return GCANET_ERR_WORKSPACE;
     }
     if (flags == 0 && use_tensor_cores(C, N, k2, metric))
-        return knn_graph_tensor_cores(x, B, C, N, k1, k2, idx64, idx32, ws, unordered, as_stream(stream));
+        return knn_graph_tensor_cores(x, B, C, N, k1, k2, idx64, idx32, ws, unordered, no_prune, as_stream(stream));
     if (flags == 0 && knn_xyz_supported(C, N, k2, metric)) {
         float *norms = nullptr;
         int *cloud_fallback = nullptr;

@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <cuda_bf16.h>
 #include <math_constants.h>
 #include <stdlib.h>
@@ -159,8 +160,10 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_
 // prep
 // ---------------------------------------------------------------------------------
 // xs[b][n][0:C] = hi, xs[b][n][C:2C] = lo ; x_nc[b][n][c] = x ; transposes through smem
+// `inv` (may be null): xs row of point n is written at sorted position inv[b][n] (pruned path); x_nc keeps
+// the original order either way
 __global__ void tc_prep_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ xs, float *__restrict__ x_nc,
-                               int C, int N) {
+                               const int *__restrict__ inv, int C, int N) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const float *s = x + (size_t)b * C * N;
@@ -175,9 +178,10 @@ __global__ void tc_prep_kernel(const float *__restrict__ x, __nv_bfloat16 *__res
             float v = tile[threadIdx.x][r];
             __nv_bfloat16 hi = __float2bfloat16_rn(v);
             __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-            size_t row = (size_t)b * N + n;
-            xs[row * 2 * C + c] = hi;
-            xs[row * 2 * C + C + c] = lo;
+            const size_t row = (size_t)b * N + n;
+            const size_t srow = inv ? (size_t)b * N + inv[row] : row;
+            xs[srow * 2 * C + c] = hi;
+            xs[srow * 2 * C + C + c] = lo;
             x_nc[row * C + c] = v;
         }
     }
@@ -191,7 +195,7 @@ __global__ void tc_normmax_kernel(const float *__restrict__ norm, float *__restr
     float m = 0.f;
     for (int n = threadIdx.x; n < Npad; n += blockDim.x) {
         float v = n < N ? norm[(size_t)b * N + n] : CUDART_INF_F;
-        norm_pad[(size_t)b * Npad + n] = v;
+        if (norm_pad) norm_pad[(size_t)b * Npad + n] = v;
         if (n < N) m = fmaxf(m, v);
     }
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULLW, m, o));
@@ -299,7 +303,10 @@ __device__ __forceinline__ void compact_row(uint2 *ptr, int n, int k, float marg
     new_thr = keep_below;
 }
 
-template <int C>
+// MODE 0 = product.  Measurement aids (GCANET_TC_DEBUG=1/2/3, tools/time_knn.py), separate instantiations so the
+// product kernel's code is untouched: 1 = appends off (thresholds at -inf), 2 = TMEM loads + a trivial
+// consumer (no distance, no compare), 3 = no TMEM loads at all (TMA + MMA + barrier hand-offs only).
+template <int C, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, C == 64 ? 3 : 1)
 knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, TcScanArgs a) {
     constexpr int NBLK = 2 * C / TC_KB;                 // 128-byte K blocks per row: hi blocks then lo blocks
@@ -424,6 +431,26 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             mbar_wait(&t_full[acc], accphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN;
+            if constexpr (MODE >= 2) {
+                if constexpr (MODE == 2) {
+                    uint32_t w[2][32];
+                    tmem_ld32(taddr, w[0]);
+#pragma unroll
+                    for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                        tmem_ld_wait();
+                        if (ch + 1 < TC_BN / 32) tmem_ld32(taddr + (ch + 1) * 32, w[(ch + 1) & 1]);
+                        uint32_t o = 0;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) o |= w[ch & 1][e];
+                        if (o == 0x7fc12345u) cnt++;          // keeps the loads alive
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[acc]);
+                if (++acc == ACC) { acc = 0; accphase ^= 1; }
+                continue;
+            }
             uint32_t v[2][32];
             tmem_ld32(taddr, v[0]);
 #pragma unroll
@@ -499,6 +526,7 @@ struct RerankArgs {
     int32_t *idx32;
     int N, k, step, kout;
     int unordered;         // 1: the caller only needs the neighbour SET (EdgeConv is order-invariant)
+    const int *perm;       // pruned path: rows and candidates are sorted positions, perm[b][s] = original index; else null
 };
 
 template <int VEC>
@@ -518,12 +546,15 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
     __shared__ float s_d[8][TC_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    const int q = blockIdx.x * 8 + warp;
-    if (q >= a.N) return;
+    const int qs = blockIdx.x * 8 + warp;                 // row in the scan's order
+    if (qs >= a.N) return;
+    const size_t srow = (size_t)b * a.N + qs;
+    const int *perm = a.perm ? a.perm + (size_t)b * a.N : nullptr;
+    const int q = perm ? perm[qs] : qs;                   // original point index
     const size_t grow = (size_t)b * a.N + q;
     if (a.overflow[grow]) return;                         // the fallback kernel writes this row
-    const int n = a.cand_cnt[grow];
-    const uint2 *cand = a.cand + grow * TC_CAP;
+    const int n = a.cand_cnt[srow];
+    const uint2 *cand = a.cand + srow * TC_CAP;
     const float *xb = a.x_nc + (size_t)b * a.N * C;
     const float *nb = a.norm + (size_t)b * a.N;
     int *sl = s_idx[warp];
@@ -544,7 +575,11 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
         const int e = s * 32 + lane;
         ad[s] = CUDART_INF_F;
         aj[s] = 0;
-        if (e < n) { uint2 t = cand[e]; ad[s] = __uint_as_float(t.x); aj[s] = (int)t.y; }
+        if (e < n) {
+            uint2 t = cand[e];
+            ad[s] = __uint_as_float(t.x);
+            aj[s] = perm ? perm[t.y] : (int)t.y;
+        }
     }
     const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
     float keep_below = CUDART_INF_F, sure_below = -CUDART_INF_F;
@@ -648,6 +683,660 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
 }
 
 // ---------------------------------------------------------------------------------
+// pruned scan (default for N >= TCP_MIN_N, k <= 64): the cloud is sorted along a Morton curve in the
+// space of its three leading principal directions, 64-key tiles get an AABB in that space, and a
+// query tile only visits key tiles whose lower bound can still beat its largest threshold.
+//
+// Bound: for orthonormal directions v_1..v_3, |V^T(q - x)|^2 <= |q - x|^2, hence
+//   |q - x|^2 >= dist^2(AABB(V^T q : q in query tile), AABB(V^T x : x in key tile)) =: LB.
+// The directions only have to be orthonormal (checked in the PCA kernel, else they are zeroed =
+// no pruning); how well they capture the variance only decides how much is skipped.
+// ---------------------------------------------------------------------------------
+constexpr int TCP_MIN_N = 1024;
+constexpr int TCP_SPLIT = 20;         // partial Gram matrices per cloud
+constexpr int TCP_PRE = 8;            // tiles of the threshold pre-pass
+constexpr int TCP_ITERS = 16;         // subspace iterations
+constexpr uint32_t TCP_END = 0xffffffffu;
+constexpr int TCP_ACC = 4;            // TMEM accumulator stages (4 x 64 columns)
+constexpr int TCP_NRING = 16;         // key-norm ring: the producer runs at most STAGES + ACC + 1 tiles ahead of the epilogue
+__host__ __device__ constexpr int tcp_stages(int C) { return C == 64 ? 4 : 3; }
+
+// part[b][sp][C*C + C] = (sum_n x x^T | sum_n x) over the sp-th slice of the cloud's points
+template <int C>
+__global__ void __launch_bounds__(256) tcp_moments_kernel(const float *__restrict__ x, float *__restrict__ part, int N) {
+    constexpr int R = C / 16;
+    __shared__ float t[C][33];
+    const int b = blockIdx.y, sp = blockIdx.x, tid = threadIdx.x;
+    const int chunk = (N + TCP_SPLIT - 1) / TCP_SPLIT;
+    const int n_lo = sp * chunk, n_hi = min(N, n_lo + chunk);
+    const float *xb = x + (size_t)b * C * N;
+    const int ti = tid >> 4, tj = tid & 15;
+    float acc[R][R];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
+    float sum = 0.f;
+    for (int n0 = n_lo; n0 < n_hi; n0 += 32) {
+        for (int c = tid >> 5; c < C; c += 8) {
+            const int n = n0 + (tid & 31);
+            t[c][tid & 31] = n < n_hi ? xb[(size_t)c * N + n] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int p = 0; p < 32; ++p) {
+            float av[R], bv[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) { av[i] = t[ti * R + i][p]; bv[i] = t[tj * R + i][p]; }
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+#pragma unroll
+                for (int j = 0; j < R; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (tid < C) {
+#pragma unroll 8
+            for (int p = 0; p < 32; ++p) sum += t[tid][p];
+        }
+        __syncthreads();
+    }
+    float *o = part + ((size_t)b * TCP_SPLIT + sp) * (C * C + C);
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) o[(ti * R + i) * C + tj * R + j] = acc[i][j];
+    if (tid < C) o[C * C + tid] = sum;
+}
+
+// pca[b] = { V[3][C], m[3] = V mu, sigma_1 }  (3*C + 4 floats): three orthonormal directions spanning (approximately)
+// the leading principal subspace of the cloud, by subspace iteration on its covariance.  One CTA per cloud.
+template <int C>
+__global__ void __launch_bounds__(256) tcp_pca_kernel(const float *__restrict__ part, float *__restrict__ pca, int N) {
+    extern __shared__ float sm[];
+    float *cov = sm;                  // [C][C+1]
+    float *mu = cov + C * (C + 1);    // [C]
+    float *V = mu + C;                // [3][C]
+    float *W = V + 3 * C;             // [3][C]
+    __shared__ float s_lambda[3];
+    __shared__ int s_ok;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const float *pb = part + (size_t)b * TCP_SPLIT * (C * C + C);
+    const float invN = 1.f / (float)N;
+    if (tid < C) {
+        float s = 0.f;
+        for (int sp = 0; sp < TCP_SPLIT; ++sp) s += pb[(size_t)sp * (C * C + C) + C * C + tid];
+        mu[tid] = s * invN;
+    }
+    __syncthreads();
+    for (int e = tid; e < C * C; e += 256) {
+        float s = 0.f;
+        for (int sp = 0; sp < TCP_SPLIT; ++sp) s += pb[(size_t)sp * (C * C + C) + e];
+        const int r = e / C, c = e % C;
+        cov[r * (C + 1) + c] = s * invN - mu[r] * mu[c];
+    }
+    for (int e = tid; e < 3 * C; e += 256) {
+        unsigned h = (unsigned)e * 2654435761u + 12345u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        W[e] = (float)(h & 0xffff) * (2.f / 65535.f) - 1.f;
+    }
+    __syncthreads();
+
+    // Gram-Schmidt of W into V by warp 0 (lane holds C/32 entries of each vector)
+    auto orthonormalize = [&]() {
+        if (tid < 32) {
+            constexpr int E = C / 32;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                float w[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = W[i * C + lane + 32 * e];
+                for (int pass = 0; pass < 2; ++pass) {        // twice: re-orthogonalisation keeps |V^T V - I| at fp32 level
+                    for (int j = 0; j < i; ++j) {
+                        float d = 0.f;
+#pragma unroll
+                        for (int e = 0; e < E; ++e) d = fmaf(w[e], V[j * C + lane + 32 * e], d);
+                        for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(FULLW, d, o);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) w[e] = fmaf(-d, V[j * C + lane + 32 * e], w[e]);
+                    }
+                }
+                float nn = 0.f;
+#pragma unroll
+                for (int e = 0; e < E; ++e) nn = fmaf(w[e], w[e], nn);
+                for (int o = 16; o; o >>= 1) nn += __shfl_xor_sync(FULLW, nn, o);
+                const float inv = nn > 1e-30f ? rsqrtf(nn) : 0.f;
+                if (lane == 0) s_lambda[i] = sqrtf(nn);
+#pragma unroll
+                for (int e = 0; e < E; ++e) V[i * C + lane + 32 * e] = w[e] * inv;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    };
+    orthonormalize();
+    for (int it = 0; it < TCP_ITERS; ++it) {
+        for (int e = tid; e < 3 * C; e += 256) {
+            const int i = e / C, r = e % C;
+            float s = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < C; ++c) s = fmaf(cov[r * (C + 1) + c], V[i * C + c], s);
+            W[e] = s;
+        }
+        __syncthreads();
+        orthonormalize();
+    }
+    // validity: V must be orthonormal for the bound to hold; anything else (degenerate cloud, NaN input) -> no pruning
+    if (tid == 0) {
+        bool ok = true;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j <= i; ++j) {
+                float d = 0.f;
+                for (int c = 0; c < C; ++c) d = fmaf(V[i * C + c], V[j * C + c], d);
+                const float want = i == j ? 1.f : 0.f;
+                if (!(fabsf(d - want) <= 1e-4f)) ok = false;
+            }
+        s_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    float *o = pca + (size_t)b * (3 * C + 4);
+    for (int e = tid; e < 3 * C; e += 256) o[e] = s_ok ? V[e] : 0.f;
+    if (tid < 3) {
+        float m = 0.f;
+        for (int c = 0; c < C; ++c) m = fmaf(V[tid * C + c], mu[c], m);
+        o[3 * C + tid] = s_ok ? m : 0.f;
+    }
+    if (tid == 3) o[3 * C + 3] = s_ok ? fmaxf(s_lambda[0], fmaxf(s_lambda[1], s_lambda[2])) : 0.f;   // = sigma_1^2 (largest |cov v|)
+}
+
+__device__ __forceinline__ unsigned tcp_spread10(unsigned v) {   // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// proj[i][b][n] = v_i . x_n ; sort key = (cloud, 30-bit Morton code of the projections in a +-4 sigma_1 cube)
+template <int C>
+__global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restrict__ x, const float *__restrict__ pca,
+                                                          float *__restrict__ proj, unsigned long long *__restrict__ keys,
+                                                          int *__restrict__ vals, int B, int N) {
+    __shared__ float V[3 * C + 4];
+    const int b = blockIdx.y;
+    for (int e = threadIdx.x; e < 3 * C + 4; e += 128) V[e] = pca[(size_t)b * (3 * C + 4) + e];
+    __syncthreads();
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    if (n >= N) return;
+    const float *xb = x + (size_t)b * C * N + n;
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) {
+        const float v = xb[(size_t)c * N];
+        p0 = fmaf(V[c], v, p0);
+        p1 = fmaf(V[C + c], v, p1);
+        p2 = fmaf(V[2 * C + c], v, p2);
+    }
+    const size_t o = (size_t)b * N + n;
+    proj[o] = p0;
+    proj[(size_t)B * N + o] = p1;
+    proj[2 * (size_t)B * N + o] = p2;
+    const float sig = sqrtf(fmaxf(V[3 * C + 3], 0.f));
+    const float sc = sig > 0.f ? 1024.f / (8.f * sig) : 0.f;
+    const float pv[3] = {p0, p1, p2};
+    unsigned code = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float t = (pv[i] - V[3 * C + i]) * sc + 512.f;
+        t = t == t ? t : 0.f;                                   // NaN -> 0
+        code |= tcp_spread10((unsigned)fminf(fmaxf(t, 0.f), 1023.f)) << i;
+    }
+    keys[o] = ((unsigned long long)b << 32) | code;
+    vals[o] = n;
+}
+
+// one warp per 64-key tile of the sorted order: perm / inverse permutation, sorted key norms (+inf padding),
+// tile AABB in the projected space
+__global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ sorted_vals, const float *__restrict__ norm,
+                                                        const float *__restrict__ proj, int *__restrict__ perm,
+                                                        int *__restrict__ inv, float *__restrict__ norm_pad,
+                                                        float *__restrict__ boxes, int B, int N, int Npad, int tiles) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= tiles) return;
+    float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+    for (int h = 0; h < TC_BN / 32; ++h) {
+        const int s = t * TC_BN + h * 32 + lane;
+        if (s < N) {
+            const int o = sorted_vals[(size_t)b * N + s];
+            perm[(size_t)b * N + s] = o;
+            inv[(size_t)b * N + o] = s;
+            norm_pad[(size_t)b * Npad + s] = norm[(size_t)b * N + o];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float p = proj[(size_t)i * B * N + (size_t)b * N + o];
+                mn[i] = fminf(mn[i], p);
+                mx[i] = fmaxf(mx[i], p);
+            }
+        } else if (s < Npad) {
+            norm_pad[(size_t)b * Npad + s] = CUDART_INF_F;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        for (int o = 16; o; o >>= 1) {
+            mn[i] = fminf(mn[i], __shfl_xor_sync(FULLW, mn[i], o));
+            mx[i] = fmaxf(mx[i], __shfl_xor_sync(FULLW, mx[i], o));
+        }
+    if (lane == 0) {
+        float *bx = boxes + ((size_t)b * tiles + t) * 6;
+        bx[0] = mn[0]; bx[1] = mn[1]; bx[2] = mn[2]; bx[3] = mx[0]; bx[4] = mx[1]; bx[5] = mx[2];
+    }
+}
+
+struct TcpScanArgs {
+    const float *norm_pad;  // [B][Npad] key norms in sorted order, +inf past N
+    int Npad;
+    const float *nmax;      // [B]
+    const float *boxes;     // [B][tiles][6]
+    const int *perm;        // [B][N] sorted position -> original index
+    uint2 *cand;            // [B][N][TC_CAP]  rows in sorted order, key ids are sorted positions
+    int *cand_cnt;          // [B][N]          rows in sorted order
+    int *overflow;          // [B][N]          rows in ORIGINAL order (consumed by the fallback scan)
+    int *visited;           // [B][query tiles] statistics: key tiles scanned in the main pass (may be null)
+    int N, k, tiles, pre, P;  // P = tiles rounded up to a power of two (sort width)
+};
+
+// thread-local selection over the 64 slot minima: smallest bound with count(m <= bound) >= k found by bisection
+__device__ __forceinline__ float slot_bound(const float (&m)[TC_BN], int k, int iters) {
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    int nf = 0;
+#pragma unroll
+    for (int s = 0; s < TC_BN; ++s) {
+        mn = fminf(mn, m[s]);
+        if (m[s] < CUDART_INF_F) { mx = fmaxf(mx, m[s]); ++nf; }
+    }
+    if (nf < k) return CUDART_INF_F;
+    float lo = mn, hi = mx;
+    for (int it = 0; it < iters; ++it) {
+        const float mid = 0.5f * lo + 0.5f * hi;
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < TC_BN; ++s) c += (m[s] <= mid) ? 1 : 0;
+        if (c >= k) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+
+template <int C>
+__global__ void __launch_bounds__(TC_THREADS, C == 64 ? 2 : 1)
+knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
+    constexpr int NBLK = 2 * C / TC_KB;
+    constexpr int NH = C / TC_KB;
+    constexpr int ABLK_BYTES = TC_BM * 128;
+    constexpr int A_BYTES = NBLK * ABLK_BYTES;
+    constexpr int BLK_BYTES = TC_BN * 128;
+    constexpr int TILE_BYTES = NBLK * BLK_BYTES;
+    // The hand-offs (TMA -> MMA -> epilogue -> MMA -> TMA) each cost a barrier round trip of ~1 us under load, so the
+    // rings are deep: the epilogue should never wait for an accumulator.  C = 64: 32 + 4*16 KB -> two CTAs per SM.
+    constexpr int STAGES = tcp_stages(C);
+    constexpr int ACC = TCP_ACC;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + A_BYTES;
+    float *s_rn = reinterpret_cast<float *>(sB + STAGES * TILE_BYTES);      // [TCP_NRING][TC_BN] key norms
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_rn + TCP_NRING * TC_BN);
+    uint64_t *full = bars;
+    uint64_t *empty = bars + STAGES;
+    uint64_t *a_full = bars + 2 * STAGES;
+    uint64_t *t_full = a_full + 1;
+    uint64_t *t_empty = t_full + ACC;
+    uint64_t *thr_ready = t_empty + ACC;                    // [1] epilogue -> producer: final thresholds of pass A are published
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(thr_ready + 1);
+    uint32_t *s_kt = tmem_slot + 1;                         // [STAGES] key tile in the stage, TCP_END = end-of-pass marker
+    volatile int *s_end = reinterpret_cast<volatile int *>(s_kt + STAGES);   // [2] stream position of the pass A / pass B end marker
+    volatile float *s_wthr = reinterpret_cast<volatile float *>(const_cast<int *>(s_end) + 2);   // [4] max true-distance threshold per epilogue warp
+    // [P] (bf16-truncated lower bound << 16) | tile, ascending; 8 bytes per entry while it is being sorted
+    uint32_t *s_ord = reinterpret_cast<uint32_t *>(smem + ((reinterpret_cast<uint8_t *>(const_cast<float *>(s_wthr) + 4) - smem + 7) & ~(size_t)7));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * TC_BM;
+    const int tiles = a.tiles;
+    const int pre = a.pre;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(a_full, 1);
+        for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        mbar_init(thr_ready, 4);
+        s_end[0] = 0x7fffffff;
+        s_end[1] = 0x7fffffff;
+        for (int s = 0; s < 4; ++s) s_wthr[s] = CUDART_INF_F;
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, ACC * TC_BN);
+
+    // ---- tile order: lower bound of every key tile against this CTA's query box, ascending
+    {
+        const float *bx = a.boxes + (size_t)b * tiles * 6;
+        const int t0 = 2 * blockIdx.x, t1 = min(t0 + 1, tiles - 1);
+        float qlo[3], qhi[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            qlo[i] = fminf(bx[t0 * 6 + i], bx[t1 * 6 + i]);
+            qhi[i] = fmaxf(bx[t0 * 6 + 3 + i], bx[t1 * 6 + 3 + i]);
+        }
+        const float slack = 2e-5f * sqrtf(a.nmax[b]);          // covers fp32 rounding of the projections
+        // 64-bit keys: lower bound (exact bits) | centre distance (16 bits, orders the tiles whose boxes overlap) | tile
+        unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_ord);
+        for (int t = threadIdx.x; t < a.P; t += TC_THREADS) {
+            unsigned long long key = ~0ull;
+            if (t < tiles) {
+                float lb = 0.f, cd = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float tlo = bx[t * 6 + i], thi = bx[t * 6 + 3 + i];
+                    float g = fmaxf(qlo[i] - thi, tlo - qhi[i]);
+                    g = fmaxf(g - slack, 0.f);
+                    lb = fmaf(g, g, lb);
+                    const float dc = 0.5f * ((qlo[i] + qhi[i]) - (tlo + thi));
+                    cd = fmaf(dc, dc, cd);
+                }
+                lb *= 0.999f;
+                if (!(lb >= 0.f)) lb = 0.f;                      // NaN boxes never prune
+                lb = fminf(lb, 3.0e38f);
+                if (!(cd >= 0.f)) cd = 0.f;
+                cd = fminf(cd, 3.0e38f);
+                key = ((unsigned long long)__float_as_uint(lb) << 32) | (__float_as_uint(cd) & 0xffff0000u) | (uint32_t)t;
+            }
+            s_key[t] = key;
+        }
+        __syncthreads();
+        if (a.P <= 512) {
+            // few tiles: every thread ranks its own keys against all others (keys are unique), no barrier ladder
+            uint32_t packed[3];
+            int rank[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int t = threadIdx.x + u * TC_THREADS;
+                rank[u] = -1;
+                if (t < tiles) {
+                    const unsigned long long kx = s_key[t];
+                    int r = 0;
+                    for (int j = 0; j < tiles; ++j) r += (s_key[j] < kx) ? 1 : 0;
+                    rank[u] = r;
+                    packed[u] = ((uint32_t)(kx >> 32) & 0xffff0000u) | ((uint32_t)kx & 0xffffu);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (rank[u] >= 0) s_ord[rank[u]] = packed[u];
+            __syncthreads();
+        } else {
+        for (int kk = 2; kk <= a.P; kk <<= 1)
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < a.P; i += TC_THREADS) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const unsigned long long x0 = s_key[i], x1 = s_key[l];
+                        const bool up = (i & kk) == 0;
+                        if ((x0 > x1) == up) { s_key[i] = x1; s_key[l] = x0; }
+                    }
+                }
+                __syncthreads();
+            }
+        // compact in place to 32 bits per tile: (lower bound truncated to bf16 = rounded DOWN) | tile
+        // (32-bit slot i overlays 64-bit slots <= i, all of which earlier rounds or this round's reads have consumed)
+        for (int base = 0; base < a.P; base += TC_THREADS) {
+            const int i = base + threadIdx.x;
+            uint32_t packed = 0;
+            if (i < a.P) {
+                const unsigned long long kx = s_key[i];
+                packed = ((uint32_t)(kx >> 32) & 0xffff0000u) | ((uint32_t)kx & 0xffffu);
+            }
+            __syncthreads();
+            if (i < a.P) s_ord[i] = packed;
+            __syncthreads();
+        }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(a_full, A_BYTES);
+#pragma unroll
+            for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(sA + kb * ABLK_BYTES, &tmap_q, a_full, kb * TC_KB, q0, b);
+            const float *rn_g = a.norm_pad + (size_t)b * a.Npad;
+            int stage = 0, seq = 0, nvis = 0;
+            uint32_t phase = 0;
+            // pass A feeds the threshold search (slot minima), pass B the candidate collection; both walk the tiles
+            // nearest first and stop at the first tile whose lower bound exceeds every row's threshold
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int i = 0; i < tiles; ++i) {
+                    const uint32_t e = s_ord[i];
+                    if (pass == 1 || i >= pre) {
+                        // thresholds only ever decrease: a stale (larger) value is safe
+                        const float thr = fmaxf(fmaxf(s_wthr[0], s_wthr[1]), fmaxf(s_wthr[2], s_wthr[3]));
+                        if (__uint_as_float(e & 0xffff0000u) > thr) break;     // every later tile has a larger bound
+                    }
+                    const int kt = (int)(e & 0xffffu);
+                    mbar_wait_backoff(&empty[stage], phase ^ 1);
+                    s_kt[stage] = (uint32_t)kt;
+                    mbar_expect_tx(&full[stage], TILE_BYTES + TC_BN * sizeof(float));
+                    uint8_t *dst = sB + stage * TILE_BYTES;
+#pragma unroll
+                    for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(dst + kb * BLK_BYTES, &tmap_k, &full[stage], kb * TC_KB, kt * TC_BN, b);
+                    bulk_load_1d(s_rn + (seq % TCP_NRING) * TC_BN, rn_g + (size_t)kt * TC_BN, TC_BN * sizeof(float), &full[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    ++seq;
+                    if (pass == 1) ++nvis;
+                }
+                // end-of-pass marker travels through the same barriers
+                mbar_wait_backoff(&empty[stage], phase ^ 1);
+                s_kt[stage] = TCP_END;
+                mbar_arrive(&full[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                ++seq;
+                if (pass == 0) mbar_wait_backoff(thr_ready, 0);      // pass B prunes with the final thresholds
+            }
+            if (a.visited) a.visited[(size_t)b * gridDim.x + blockIdx.x] = nvis;
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            mbar_wait(a_full, 0);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA);
+            int stage = 0, acc = 0, seq = 0, markers = 0;
+            uint32_t phase = 0, accphase = 0;
+            for (;; ++seq) {
+                mbar_wait_backoff(&t_empty[acc], accphase ^ 1);
+                mbar_wait_backoff(&full[stage], phase);
+                if (s_kt[stage] == TCP_END) {
+                    s_end[markers] = seq;                    // visible to the epilogue through the arrive below
+                    mbar_arrive(&empty[stage]);
+                    mbar_arrive(&t_full[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++acc == ACC) { acc = 0; accphase ^= 1; }
+                    if (++markers == 2) break;
+                    continue;
+                }
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(sB + stage * TILE_BYTES);
+                const uint32_t d_tmem = tmem_base + acc * TC_BN;
+                uint32_t accum = 0;
+#pragma unroll
+                for (int hb = 0; hb < NH; ++hb) {
+#pragma unroll
+                    for (int ks = 0; ks < TC_KB / 16; ++ks) {
+                        const uint32_t koff = ks * 32;
+                        const uint64_t a_hi = make_kmajor_sw128_desc(a_addr + hb * ABLK_BYTES + koff);
+                        const uint64_t a_lo = make_kmajor_sw128_desc(a_addr + (NH + hb) * ABLK_BYTES + koff);
+                        const uint64_t b_hi = make_kmajor_sw128_desc(b_addr + hb * BLK_BYTES + koff);
+                        const uint64_t b_lo = make_kmajor_sw128_desc(b_addr + (NH + hb) * BLK_BYTES + koff);
+                        umma_bf16(d_tmem, a_hi, b_hi, kIdesc, accum);
+                        accum = 1;
+                        umma_bf16(d_tmem, a_hi, b_lo, kIdesc, 1);
+                        umma_bf16(d_tmem, a_lo, b_hi, kIdesc, 1);
+                    }
+                }
+                umma_commit(&empty[stage]);
+                umma_commit(&t_full[acc]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == ACC) { acc = 0; accphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: one query row per thread =====================
+        const int ew = warp & 3;
+        const int row = ew * 32 + lane;
+        const int q = q0 + row;                               // sorted position
+        const bool active = q < a.N;
+        const size_t srow = (size_t)b * a.N + (active ? q : 0);
+        uint2 *buf = a.cand + srow * TC_CAP;
+        const float qn = active ? a.norm_pad[(size_t)b * a.Npad + q] : 0.f;
+        const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
+        float thr = active ? CUDART_INF_F : -CUDART_INF_F;
+        int cnt = 0, seq = 0;
+        bool ovf = false;
+        int acc = 0;
+        uint32_t accphase = 0;
+
+        // ---- pass A: per-column-slot minima over the visited tiles.  The 64 slot minima belong to 64 different
+        // keys, so the k-th smallest of them bounds the row's k-th distance from above; nothing is stored.
+        {
+            float m[TC_BN];
+#pragma unroll
+            for (int s = 0; s < TC_BN; ++s) m[s] = CUDART_INF_F;
+            int done = 0, refresh_at = pre > 0 ? pre : 8;
+            for (;; ++seq) {
+                mbar_wait(&t_full[acc], accphase);
+                if (seq == s_end[0]) break;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN;
+#pragma unroll
+                for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + ch * 32, v);
+                    tmem_ld_wait();
+                    const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + ch * 32);
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 n4 = rn[c4];
+                        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            m[ch * 32 + c4 * 4 + e] = fminf(m[ch * 32 + c4 * 4 + e], fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[acc]);
+                if (++acc == ACC) { acc = 0; accphase ^= 1; }
+                if (++done == refresh_at) {
+                    // let the producer start skipping: publish the bound reached so far
+                    refresh_at *= 2;
+                    float wt = active ? slot_bound(m, a.k, 8) + margin + qn : -CUDART_INF_F;
+                    for (int o = 16; o; o >>= 1) wt = fmaxf(wt, __shfl_xor_sync(FULLW, wt, o));
+                    if (lane == 0) s_wthr[ew] = wt;
+                }
+            }
+            // end marker of pass A: final thresholds
+            if (active) thr = slot_bound(m, a.k, 12) + margin;
+            float wt = active ? thr + qn : -CUDART_INF_F;
+            for (int o = 16; o; o >>= 1) wt = fmaxf(wt, __shfl_xor_sync(FULLW, wt, o));
+            __syncwarp();
+            if (lane == 0) {
+                s_wthr[ew] = wt;
+                mbar_arrive(thr_ready);
+                mbar_arrive(&t_empty[acc]);
+            }
+            if (++acc == ACC) { acc = 0; accphase ^= 1; }
+            ++seq;
+        }
+
+        // ---- pass B: same order again, every key below the row's threshold becomes a candidate
+        for (int i = 0;; ++i, ++seq) {
+            mbar_wait(&t_full[acc], accphase);
+            if (seq == s_end[1]) break;
+            tc_fence_after();
+            const int kt = (int)(s_ord[i] & 0xffffu);
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN;
+            uint32_t v[2][32];
+            tmem_ld32(taddr, v[0]);
+#pragma unroll
+            for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                tmem_ld_wait();
+                if (ch + 1 < TC_BN / 32) tmem_ld32(taddr + (ch + 1) * 32, v[(ch + 1) & 1]);
+                const int jbase = kt * TC_BN + ch * 32;
+                const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + ch * 32);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 n4 = rn[c4];
+                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float d = fmaf(-2.f, __uint_as_float(v[ch & 1][c4 * 4 + e]), nn[e]);
+                        if (d < thr) {
+                            buf[cnt] = make_uint2(__float_as_uint(d), (uint32_t)(jbase + c4 * 4 + e));
+                            ++cnt;
+                        }
+                    }
+                }
+                unsigned need = __ballot_sync(FULLW, cnt > TC_CAP - 32);
+                if (need) {
+                    while (need) {
+                        const int r = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int n_r = __shfl_sync(FULLW, cnt, r);
+                        const float m_r = __shfl_sync(FULLW, margin, r);
+                        const unsigned long long p_r = __shfl_sync(FULLW, (unsigned long long)buf, r);
+                        __syncwarp();
+                        int nc; float nt;
+                        compact_row(reinterpret_cast<uint2 *>(p_r), n_r, a.k, m_r, lane, nc, nt);
+                        if (lane == r) {
+                            cnt = nc;
+                            thr = fminf(thr, nt);
+                            if (nc > TC_CAP - 32) { ovf = true; cnt = 0; thr = -CUDART_INF_F; }
+                        }
+                    }
+                    float wt = (active && !ovf) ? thr + qn : -CUDART_INF_F;
+                    for (int o = 16; o; o >>= 1) wt = fmaxf(wt, __shfl_xor_sync(FULLW, wt, o));
+                    if (lane == 0) s_wthr[ew] = wt;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[acc]);
+            if (++acc == ACC) { acc = 0; accphase ^= 1; }
+        }
+
+        if (active) {
+            a.cand_cnt[srow] = ovf ? 0 : cnt;
+            a.overflow[(size_t)b * a.N + a.perm[srow]] = (ovf || cnt < a.k) ? 1 : 0;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, ACC * TC_BN);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -666,9 +1355,34 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+static size_t tcp_cub_temp_bytes(size_t n, int end_bit) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const int *)nullptr, (int *)nullptr, (int)n, 0, end_bit);
+    return bytes;
+}
+static int tcp_key_bits(int B) {
+    int bits = 32;
+    while ((1 << (bits - 32)) < B) ++bits;
+    return bits;
+}
+static bool tcp_supported(int N, int k2) {
+    return N >= TCP_MIN_N && k2 <= TC_BN && ceil_div(N, TC_BN) <= 2048;
+}
+
 size_t knn_tc_workspace_bytes(int B, int C, int N) {
     size_t bn = (size_t)B * N;
     size_t t = 0;
+    // pruned path
+    t += align_up((size_t)B * TCP_SPLIT * (C * C + C) * sizeof(float));   // partial moments
+    t += align_up((size_t)B * (3 * C + 4) * sizeof(float));               // pca
+    t += align_up(3 * bn * sizeof(float));                                // projections
+    t += 2 * align_up(bn * sizeof(unsigned long long));                   // keys in/out
+    t += 2 * align_up(bn * sizeof(int));                                  // vals in/out
+    t += align_up(tcp_cub_temp_bytes(bn, tcp_key_bits(B)));               // cub temp
+    t += 2 * align_up(bn * sizeof(int));                                  // perm, inv
+    t += align_up((size_t)B * ceil_div(N, TC_BN) * 6 * sizeof(float));    // tile boxes
+    t += align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));          // visited-tile statistics
     t += align_up(bn * 2 * C * sizeof(__nv_bfloat16));   // xs
     t += align_up(bn * C * sizeof(float));               // x_nc
     t += align_up(bn * sizeof(float));                   // norm
@@ -689,13 +1403,13 @@ int launch_sqnorm_public(const float *x, float *out, int B, int C, int Cuse, int
 int knn_fallback_rows(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
                       int64_t *idx64, int32_t *idx32, cudaStream_t st);
 
-template <int C>
+template <int C, int MODE = 0>
 static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcScanArgs sa, RerankArgs ra, int B, cudaStream_t st) {
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int STAGES = 2;
     const size_t smem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)STAGES * NBLK * TC_BN * 128 +
                         TC_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t);
-    auto kern = knn_tc_scan_kernel<C>;
+    auto kern = knn_tc_scan_kernel<C, MODE>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(sa.N, TC_BM), B);
     kern<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
@@ -707,12 +1421,60 @@ static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcSca
     return GCANET_OK;
 }
 
+template <int C>
+static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpScanArgs sa, RerankArgs ra, int B, cudaStream_t st) {
+    constexpr int NBLK = 2 * C / TC_KB;
+    constexpr int STAGES = tcp_stages(C);
+    const size_t smem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)STAGES * NBLK * TC_BN * 128 +
+                        TCP_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t) + (size_t)sa.P * 8;
+    auto kern = knn_tcp_scan_kernel<C>;
+    GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(sa.N, TC_BM), B);
+    kern<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
+    GCANET_LAUNCH_OK("knn_tcp_scan_kernel");
+    dim3 rgrid(ceil_div(sa.N, 8), B);
+    knn_tc_rerank_kernel<C><<<rgrid, 256, 0, st>>>(ra);
+    GCANET_LAUNCH_OK("knn_tc_rerank_kernel");
+    return GCANET_OK;
+}
+
+template <int C>
+static int launch_tcp_prep(const float *x, float *part, float *pca, float *proj, unsigned long long *keys, int *vals,
+                           int B, int N, cudaStream_t st) {
+    tcp_moments_kernel<C><<<dim3(TCP_SPLIT, B), 256, 0, st>>>(x, part, N);
+    GCANET_LAUNCH_OK("tcp_moments_kernel");
+    const size_t smem = ((size_t)C * (C + 1) + 7 * C) * sizeof(float);
+    auto kern = tcp_pca_kernel<C>;
+    if (smem > 48 * 1024) GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, 256, smem, st>>>(part, pca, N);
+    GCANET_LAUNCH_OK("tcp_pca_kernel");
+    tcp_project_kernel<C><<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(x, pca, proj, keys, vals, B, N);
+    GCANET_LAUNCH_OK("tcp_project_kernel");
+    return GCANET_OK;
+}
+
 int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, int64_t *idx64, int32_t *idx32,
-                           void *ws, int unordered, cudaStream_t st) {
+                           void *ws, int unordered, int no_prune, cudaStream_t st) {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { set_error("knn_graph: cuTensorMapEncodeTiled is not available from the driver"); return GCANET_ERR_CUDA; }
     const size_t bn = (size_t)B * N;
     Carver cv(ws);
+    float *part = cv.take<float>((size_t)B * TCP_SPLIT * (C * C + C));
+    float *pca = cv.take<float>((size_t)B * (3 * C + 4));
+    float *proj = cv.take<float>(3 * bn);
+    unsigned long long *keys_in = cv.take<unsigned long long>(bn);
+    unsigned long long *keys_out = cv.take<unsigned long long>(bn);
+    int *vals_in = cv.take<int>(bn);
+    int *vals_out = cv.take<int>(bn);
+    const int end_bit = tcp_key_bits(B);
+    size_t temp_bytes = tcp_cub_temp_bytes(bn, end_bit);
+    void *temp = cv.take<char>(temp_bytes);
+    int *perm = cv.take<int>(bn);
+    int *inv = cv.take<int>(bn);
+    float *boxes = cv.take<float>((size_t)B * ceil_div(N, TC_BN) * 6);
+    int *visited = cv.take<int>((size_t)B * ceil_div(N, TC_BM));
+    const char *env_np = getenv("GCANET_TC_NO_PRUNE");
+    const bool prune = !no_prune && tcp_supported(N, k2) && !(env_np && env_np[0] == '1') && !getenv("GCANET_TC_DEBUG");
     __nv_bfloat16 *xs = cv.take<__nv_bfloat16>(bn * 2 * C);
     float *x_nc = cv.take<float>(bn * C);
     float *norm = cv.take<float>(bn);
@@ -725,11 +1487,21 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
 
     int rc = launch_sqnorm_public(x, norm, B, C, C, N, st);
     if (rc) return rc;
+    const int tiles = ceil_div(N, TC_BN);
+    if (prune) {
+        rc = C == 64 ? launch_tcp_prep<64>(x, part, pca, proj, keys_in, vals_in, B, N, st)
+                     : launch_tcp_prep<128>(x, part, pca, proj, keys_in, vals_in, B, N, st);
+        if (rc) return rc;
+        GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
+        count_launch();
+        tcp_tiles_kernel<<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes, B, N, Npad, tiles);
+        GCANET_LAUNCH_OK("tcp_tiles_kernel");
+    }
     {
         dim3 grid(ceil_div(N, 32), ceil_div(C, 32), B), block(32, 8);
-        tc_prep_kernel<<<grid, block, 0, st>>>(x, xs, x_nc, C, N);
+        tc_prep_kernel<<<grid, block, 0, st>>>(x, xs, x_nc, prune ? inv : nullptr, C, N);
         GCANET_LAUNCH_OK("tc_prep_kernel");
-        tc_normmax_kernel<<<B, 256, 0, st>>>(norm, nmax, norm_pad, N, Npad);
+        tc_normmax_kernel<<<B, 256, 0, st>>>(norm, nmax, prune ? nullptr : norm_pad, N, Npad);
         GCANET_LAUNCH_OK("tc_normmax_kernel");
     }
 
@@ -750,7 +1522,33 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("knn_graph: cuTensorMapEncodeTiled failed (%d)", (int)cr); return GCANET_ERR_CUDA; }
 
-    const int tiles = ceil_div(N, TC_BN);
+    if (prune) {
+        int P = 16;
+        while (P < tiles) P <<= 1;
+        int pre = TCP_PRE;
+        if (const char *e = getenv("GCANET_TC_PRE")) pre = atoi(e);          // measurement aid
+        if (pre > tiles) pre = tiles;
+        if (pre < 0) pre = 0;
+        TcpScanArgs sa{norm_pad, Npad, nmax, boxes, perm, cand, cand_cnt, overflow, visited, N, k2, tiles, pre, P};
+        RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
+                      (unordered && k1 == k2) ? 1 : 0, perm};
+        rc = C == 64 ? launch_tcp<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128>(tmap_q, tmap_k, sa, ra, B, st);
+        if (rc) return rc;
+        const char *stats = getenv("GCANET_TC_STATS");
+        if (stats && stats[0] == '1') {            // measurement aid: synchronises
+            const int nq = B * ceil_div(N, TC_BM);
+            int *h = (int *)malloc(nq * sizeof(int));
+            GCANET_CUDA_OK(cudaStreamSynchronize(st));
+            GCANET_CUDA_OK(cudaMemcpy(h, visited, nq * sizeof(int), cudaMemcpyDeviceToHost));
+            double s = 0;
+            for (int i = 0; i < nq; ++i) s += h[i];
+            qsort(h, nq, sizeof(int), [](const void *u, const void *v) { return *(const int *)u - *(const int *)v; });
+            fprintf(stderr, "[gcanet] pruned kNN C=%d: %.1f of %d key tiles visited per query tile (min %d, median %d, p90 %d, p99 %d, max %d)\n",
+                    C, s / nq, tiles, h[0], h[nq / 2], h[nq * 9 / 10], h[nq * 99 / 100], h[nq - 1]);
+            free(h);
+        }
+        return knn_fallback_rows(x, norm, overflow, B, C, N, k1, k2, idx64, idx32, st);
+    }
     int stride = (int)(tiles * 0.381966f);
     if (stride < 1) stride = 1;
     auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
@@ -758,10 +1556,14 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     // GCANET_TC_DEBUG=1 (measurement aid, tools/time_knn.py): run the scan pipeline with appends disabled
     // and stop after it -- gives the TMA + MMA + TMEM-read + compare floor of the kernel.
     const char *dbg = getenv("GCANET_TC_DEBUG");
-    TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, (dbg && dbg[0] == '1') ? 1 : 0, stride};
+    const int dbg_mode = (dbg && dbg[0] >= '1' && dbg[0] <= '3') ? dbg[0] - '0' : 0;
+    TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, dbg_mode, stride};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                   (unordered && k1 == k2) ? 1 : 0};
-    rc = C == 64 ? launch_tc<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<128>(tmap_q, tmap_k, sa, ra, B, st);
+    if (dbg_mode >= 2 && C == 64)
+        rc = dbg_mode == 2 ? launch_tc<64, 2>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<64, 3>(tmap_q, tmap_k, sa, ra, B, st);
+    else
+        rc = C == 64 ? launch_tc<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<128>(tmap_q, tmap_k, sa, ra, B, st);
     if (rc) return rc;
     if (sa.debug_no_append) return GCANET_OK;
     return knn_fallback_rows(x, norm, overflow, B, C, N, k1, k2, idx64, idx32, st);

@@ -70,15 +70,20 @@ def _as_f32_contig(x: torch.Tensor, name: str) -> torch.Tensor:
 # ----------------------------------------------------------------------------------
 KNN_FLAG_BRUTE_FORCE = 0x100
 KNN_FLAG_UNORDERED = 0x200
+KNN_FLAG_NO_PRUNE = 0x400
 
 
 def knn_graph(x: torch.Tensor, k1: int, k2: int, metric: int = METRIC_L2, want64: bool = True,
-              want32: bool = False, tensor_cores: bool = True, brute_force: bool = False, ordered: bool = True):
+              want32: bool = False, tensor_cores: bool = True, brute_force: bool = False, ordered: bool = True,
+              prune: bool = True):
     """x [B, C, N] -> (idx64 or None, idx32 or None), each [B, N, kout].  ``brute_force=True`` (or
     the older ``tensor_cores=False``) forces the plain CUDA-core scan where an accelerated path
-    (tcgen05 pruning for C = 64/128, spatial pruning for xyz clouds) would apply -- for A/B tests."""
+    (tcgen05 pruning for C = 64/128, spatial pruning for xyz clouds) would apply; ``prune=False`` makes
+    the tensor-core path scan every key tile instead of skipping by bounding box -- for A/B tests."""
     if brute_force or not tensor_cores:
         metric = metric | KNN_FLAG_BRUTE_FORCE
+    if not prune:
+        metric = metric | KNN_FLAG_NO_PRUNE
     if not ordered and int(k1) == int(k2):
         metric = metric | KNN_FLAG_UNORDERED      # same exact neighbour set, order unspecified
     x = _as_f32_contig(x.detach(), "x")

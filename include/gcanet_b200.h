@@ -65,6 +65,10 @@ typedef enum {
  * exact set; paths that can save work by not ordering it (the tensor-core path re-ranks only the
  * candidates whose membership is in doubt) do so, the others ignore the flag. */
 #define GCANET_KNN_FLAG_UNORDERED 0x200
+/* May be OR-ed into `metric`: the tensor-core path scans every key tile instead of sorting the cloud
+ * along its principal directions and skipping tiles whose bounding box cannot hold a neighbour.
+ * Same result either way; for A/B tests and benchmarks. */
+#define GCANET_KNN_FLAG_NO_PRUNE 0x400
 
 /* Edge-feature variant of gcanet_graph_feature*. */
 typedef enum {

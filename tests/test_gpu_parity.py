@@ -507,6 +507,53 @@ def test_knn_tensor_core_path_on_spatially_sorted_features():
     assert n <= 3
 
 
+def _layer_activations(B, N, seed, k=20):
+    """x1, x2 of the oracle encoder on synthetic clouds: the clustered, low-intrinsic-dimension features
+    the bounding-box pruning of the tensor-core path is built for."""
+    torch.manual_seed(0)
+    enc = orc.DGCNNEncoderGn(mode=0, nn_nb=k, input_channels=6)
+    x = _t(abc_like_batch(B, N, seed=seed))
+    with torch.no_grad():
+        x1 = enc.conv1(orc.get_graph_feature(x, k, k)).max(dim=-1)[0]
+        x2 = enc.conv2(orc.get_graph_feature(x1, k, k)).max(dim=-1)[0]
+    return x1, x2
+
+
+@pytest.mark.parametrize("N,k,B", [(10000, 50, 2), (4097, 20, 2), (1025, 64, 1), (3000, 50, 3)])
+def test_knn_pruned_tensor_core_path_equals_full_scan(N, k, B):
+    """Sorting the cloud along its principal directions and skipping key tiles by bounding box must not
+    change a single index: same lists as the full tensor-core scan, ordered and unordered, on real
+    activations (where most tiles are skipped) and on Gaussians (where none are)."""
+    x1, x2 = _layer_activations(B, N, seed=21)
+    g = torch.Generator().manual_seed(N + k)
+    for x in (x1, x2, torch.randn(B, 64, N, generator=g)):
+        xd = x.to(DEV)
+        a = G.knn_graph(xd, k, k, prune=True)[0]
+        b = G.knn_graph(xd, k, k, prune=False)[0]
+        assert torch.equal(a, b)
+        c = G.knn_graph(xd, k, k, want64=False, want32=True, ordered=False, prune=True)[1]
+        assert torch.equal(c.sort(dim=2)[0].long(), a.sort(dim=2)[0])
+    n = check_knn_rows(a, orc.knn(x, k, k), orc.knn_scores(x), knn_tau(x))
+    assert n <= max(3, B * N // 2000)
+
+
+def test_knn_pruned_path_c128_and_degenerate_clouds():
+    x1, x2 = _layer_activations(1, 3000, seed=8)
+    x = torch.cat([x1, x2], dim=1)                     # [1, 128, 3000]
+    xd = x.to(DEV)
+    assert torch.equal(G.knn_graph(xd, 50, 50)[0], G.knn_graph(xd, 50, 50, prune=False)[0])
+    # rank-deficient clouds: constant, one-dimensional, and a cloud with a NaN-free huge outlier
+    z = torch.ones(1, 64, 1500, device=DEV)
+    assert torch.equal(G.knn_graph(z, 20, 20)[0], G.knn_graph(z, 20, 20, prune=False)[0])
+    line = torch.zeros(1, 64, 2000)
+    line[0, 5] = torch.linspace(-1, 1, 2000)
+    assert torch.equal(G.knn_graph(line.to(DEV), 20, 20)[0], G.knn_graph(line.to(DEV), 20, 20, prune=False)[0])
+    out = x1.clone()
+    out[0, :, 17] += 1000.0
+    od = out.to(DEV)
+    assert torch.equal(G.knn_graph(od, 50, 50)[0], G.knn_graph(od, 50, 50, prune=False)[0])
+
+
 def test_normal_edge_head_golden(golden_dir):
     """conv_normal head (M4:584-587, 691-693) against the fixture made from the reference's
     get_graph_feature_with_normals_g; forward 1e-4, weight gradients 2e-3 relative."""
