@@ -54,7 +54,8 @@ struct ScanArgs {
     int k_major;            // 0: out[b][q][col]   1: out[b][col][q]
     int index_base;
     int TR;                 // reference tile (multiple of 32)
-    const int *row_filter;  // optional [B][Nq]: only queries with a non-zero flag are computed / written
+    const int *qlist;       // optional [B][Nq] + qcount [B]: only the listed queries are computed / written (the
+    const int *qcount;      //   tensor-core path's overflow rows); CTAs then stride over the list
     const int *cloud_filter;  // optional [B]: only clouds with a non-zero flag are computed
 };
 
@@ -75,26 +76,22 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
 
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * QPB + warp * R;
     const float *ref = a.ref + (size_t)b * C * a.Nr;
     const float *qry = a.qry + (size_t)b * C * a.Nq;
 
     if (a.cloud_filter != nullptr && a.cloud_filter[b] == 0) return;
-    if (a.row_filter != nullptr) {
-        // fallback mode: leave unless one of this CTA's queries is flagged
-        int flagged = 0;
-        if (threadIdx.x < QPB) {
-            int q = blockIdx.x * QPB + threadIdx.x;
-            flagged = q < a.Nq ? a.row_filter[(size_t)b * a.Nq + q] : 0;
-        }
-        if (!__syncthreads_or(flagged)) return;
-    }
+    // list mode: slot s of this cloud's work is query qlist[b][s]; otherwise slot = query
+    const int *ql = a.qlist ? a.qlist + (size_t)b * a.Nq : nullptr;
+    const int nq = ql ? a.qcount[b] : a.Nq;
+    for (int vbx = blockIdx.x; vbx * QPB < nq; vbx += gridDim.x) {
+    const int q0 = vbx * QPB + warp * R;
+    __syncthreads();   // shared memory of the previous round is free
 
     // stage this CTA's queries (zero for out-of-range ones)
     for (int e = threadIdx.x; e < C * QPB; e += kThreads) {
         int c = e / QPB, qq = e % QPB;
-        int q = blockIdx.x * QPB + qq;
-        qs[e] = q < a.Nq ? qry[(size_t)c * a.Nq + q] : 0.f;
+        int sl = vbx * QPB + qq;
+        qs[e] = sl < nq ? qry[(size_t)c * a.Nq + (ql ? ql[sl] : sl)] : 0.f;
     }
     __syncthreads();
 
@@ -108,8 +105,8 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
         }
         qn[r] = 0.f;
         if (METRIC != METRIC_SSD) {
-            int q = q0 + r;
-            qn[r] = q < a.Nq ? a.qry_norm[(size_t)b * a.Nq + q] : 0.f;
+            int sl = q0 + r;
+            qn[r] = sl < nq ? a.qry_norm[(size_t)b * a.Nq + (ql ? ql[sl] : sl)] : 0.f;
         }
     }
 
@@ -230,9 +227,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
     __syncwarp();
     static_for<0, R>([&](auto rc) {
         constexpr int r = decltype(rc)::value;
-        const int q = q0 + r;
-        if (q >= a.Nq) return;
-        if (a.row_filter != nullptr && a.row_filter[(size_t)b * a.Nq + q] == 0) return;
+        if (q0 + r >= nq) return;
         float *ld = my_ld + r * CAP;
         int *li = my_li + r * CAP;
         float t = thr[r];
@@ -243,9 +238,8 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int q = q0 + r;
-        if (q >= a.Nq) continue;
-        if (a.row_filter != nullptr && a.row_filter[(size_t)b * a.Nq + q] == 0) continue;
+        if (q0 + r >= nq) continue;
+        const int q = ql ? ql[q0 + r] : q0 + r;
         for (int p = lane; p < a.k; p += 32) {
             if (p % a.step) continue;
             const int col = p / a.step;
@@ -257,6 +251,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
             if (a.dist) a.dist[o] = sqrtf(my_ld[r * CAP + p]);
         }
     }
+    }   // slots of this CTA
 }
 
 // ---------------------------------------------------------------------------------
@@ -352,7 +347,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_bigk_kernel(ScanArgs a) {
         }
     }
     __syncwarp();
-    if (q < a.Nq && (a.row_filter == nullptr || a.row_filter[(size_t)b * a.Nq + q] != 0)) {
+    if (q < a.Nq) {
         for (int p = lane; p < k; p += 32) {
             if (p % a.step) continue;
             int col = p / a.step;
@@ -383,7 +378,9 @@ static int launch_scan(ScanArgs a, int B, cudaStream_t st) {
     size_t smem = ((size_t)a.C * a.TR + a.TR + (size_t)a.C * QPB + 2 * (size_t)QPB * 32 * SL) * sizeof(float);
     auto kern = knn_scan_kernel<CDIM, METRIC, SL, R>;
     if (smem > 48 * 1024) GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ceil_div(a.Nq, QPB), B);
+    int gx = ceil_div(a.Nq, QPB);
+    if (a.qlist != nullptr && gx > 48) gx = 48;      // list mode: a few CTAs per cloud stride over the (usually empty) list
+    dim3 grid(gx, B);
     kern<<<grid, kThreads, smem, st>>>(a);
     GCANET_LAUNCH_OK("knn_scan_kernel");
     return GCANET_OK;
@@ -426,26 +423,27 @@ int launch_sqnorm_public(const float *x, float *out, int B, int C, int Cuse, int
     return launch_sqnorm(x, out, B, C, Cuse, N, st);
 }
 
-static int scan_self(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
+static int scan_self(const float *x, const float *norms, const int *qlist, const int *qcount, int B, int C, int N, int k1, int k2,
                      int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st, const int *cloud_filter = nullptr);
 
-// re-runs the CUDA-core scan for the queries flagged in row_filter (tensor-core path overflow)
-int knn_fallback_rows(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
+// re-runs the CUDA-core scan for the queries listed in qlist[b][0 .. qcount[b]) (tensor-core path overflow)
+int knn_fallback_rows(const float *x, const float *norms, const int *qlist, const int *qcount, int B, int C, int N, int k1, int k2,
                       int64_t *idx64, int32_t *idx32, cudaStream_t st) {
-    return scan_self(x, norms, row_filter, B, C, N, k1, k2, GCANET_METRIC_L2, idx64, idx32, st);
+    return scan_self(x, norms, qlist, qcount, B, C, N, k1, k2, GCANET_METRIC_L2, idx64, idx32, st);
 }
 
 int knn_graph_cuda_cores(const float *x, int B, int C, int N, int k1, int k2, int metric, int64_t *idx64,
                          int32_t *idx32, float *norms, cudaStream_t st) {
     int rc = launch_sqnorm(x, norms, B, C, metric == GCANET_METRIC_POINTS_NORMALS ? 3 : C, N, st);
     if (rc) return rc;
-    return scan_self(x, norms, nullptr, B, C, N, k1, k2, metric, idx64, idx32, st);
+    return scan_self(x, norms, nullptr, nullptr, B, C, N, k1, k2, metric, idx64, idx32, st);
 }
 
-static int scan_self(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
+static int scan_self(const float *x, const float *norms, const int *qlist, const int *qcount, int B, int C, int N, int k1, int k2,
                      int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st, const int *cloud_filter) {
     ScanArgs a{};
-    a.row_filter = row_filter;
+    a.qlist = qlist;
+    a.qcount = qcount;
     a.cloud_filter = cloud_filter;
     a.ref = x; a.qry = x; a.ref_norm = norms; a.qry_norm = norms;
     a.C = C; a.Nr = N; a.Nq = N; a.k = k2;
@@ -529,7 +527,7 @@ extern "C" int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int
                                as_stream(stream));
         if (rc) return rc;
         // clouds the pruned scan declined (points x normals with non-unit normals): brute force, filtered per cloud
-        return scan_self(x, norms, nullptr, B, C, N, k1, k2, metric, idx64, idx32, as_stream(stream), cloud_fallback);
+        return scan_self(x, norms, nullptr, nullptr, B, C, N, k1, k2, metric, idx64, idx32, as_stream(stream), cloud_fallback);
     }
     return knn_graph_cuda_cores(x, B, C, N, k1, k2, metric, idx64, idx32, static_cast<float *>(ws), as_stream(stream));
 }

@@ -527,6 +527,8 @@ struct RerankArgs {
     int N, k, step, kout;
     int unordered;         // 1: the caller only needs the neighbour SET (EdgeConv is order-invariant)
     const int *perm;       // pruned path: rows and candidates are sorted positions, perm[b][s] = original index; else null
+    int *fb_list;          // [B][N] rows left to the CUDA-core fallback (overflowed lists), fb_count [B] (zeroed by the host)
+    int *fb_count;
 };
 
 template <int VEC>
@@ -538,32 +540,42 @@ __device__ __forceinline__ void load_row(const float *p, float (&v)[VEC]) {
     }
 }
 
-template <int C>
-__global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
+// Two-sided bisection over a warp-distributed list (entries e = s*32 + lane, +inf padding, n > k of them finite):
+// returns hi with count(d <= hi) >= k and lo with count(d <= lo) < k, as close to the k-th smallest as the
+// values allow (stops when the two counts differ by one, or the interval cannot be split: ties).
+template <int SL>
+__device__ __forceinline__ void kth_bracket(const float (&dv)[SL], int k, float &lo_out, float &hi_out) {
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        mn = fminf(mn, dv[s]);
+        if (dv[s] < CUDART_INF_F) mx = fmaxf(mx, dv[s]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(FULLW, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(FULLW, mx, o));
+    }
+    float lo = mn, hi = mx, lo_s = -CUDART_INF_F;     // lo_s: count(d <= lo_s) < k is PROVEN (lo = mn itself is not)
+    int c_lo = 0, c_hi = 0x7fffffff;
+    for (int it = 0; it < 40 && c_hi - c_lo > 1; ++it) {
+        const float mid = 0.5f * lo + 0.5f * hi;
+        if (!(mid > lo && mid < hi)) break;           // interval exhausted (ties)
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < SL; ++s) c += (dv[s] <= mid) ? 1 : 0;
+        c = __reduce_add_sync(FULLW, c);
+        if (c >= k) { hi = mid; c_hi = c; } else { lo = mid; lo_s = mid; c_lo = c; }
+    }
+    lo_out = lo_s;
+    hi_out = hi;
+}
+
+template <int C, int SL>
+__device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *cand, int n, const int *perm, const float *xb,
+                                           const float *nb, int q, float qn, const float (&qv)[C / 32], float margin,
+                                           size_t grow, int *sl, float *sd, int lane) {
     constexpr int VEC = C / 32;
-    constexpr int SL = TC_CAP / 32;
-    __shared__ int s_idx[8][TC_CAP];
-    __shared__ float s_d[8][TC_CAP];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y;
-    const int qs = blockIdx.x * 8 + warp;                 // row in the scan's order
-    if (qs >= a.N) return;
-    const size_t srow = (size_t)b * a.N + qs;
-    const int *perm = a.perm ? a.perm + (size_t)b * a.N : nullptr;
-    const int q = perm ? perm[qs] : qs;                   // original point index
-    const size_t grow = (size_t)b * a.N + q;
-    if (a.overflow[grow]) return;                         // the fallback kernel writes this row
-    const int n = a.cand_cnt[srow];
-    const uint2 *cand = a.cand + srow * TC_CAP;
-    const float *xb = a.x_nc + (size_t)b * a.N * C;
-    const float *nb = a.norm + (size_t)b * a.N;
-    int *sl = s_idx[warp];
-    float *sd = s_d[warp];
-
-    float qv[VEC];
-    load_row<VEC>(xb + (size_t)q * C + lane * VEC, qv);
-    const float qn = nb[q];
-
     // 1. last shrink of the list on the approximate distances (same bound + margin rule as the scan).
     //    In set-only mode entries with d~ <= lo - margin, where fewer than k entries have d~ <= lo, are
     //    certainly among the exact k nearest (anything that could beat them also lies below lo): they are
@@ -581,11 +593,11 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
             aj[s] = perm ? perm[t.y] : (int)t.y;
         }
     }
-    const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
     float keep_below = CUDART_INF_F, sure_below = -CUDART_INF_F;
-    if (n > a.k + TC_SLACK) {
-        float lo_s;
-        keep_below = select_bound<SL>(ad, n, a.k, &lo_s) + margin;
+    if (n > a.k) {
+        float lo_s, hi;
+        kth_bracket<SL>(ad, a.k, lo_s, hi);
+        keep_below = hi + margin;
         if (a.unordered) sure_below = lo_s - margin;
     }
     int m = 0, n_sure = 0;
@@ -680,6 +692,37 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
             if (a.idx32) a.idx32[o] = di[s];
         }
     }
+    (void)q;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
+    constexpr int VEC = C / 32;
+    __shared__ int s_idx[8][TC_CAP];
+    __shared__ float s_d[8][TC_CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int qs = blockIdx.x * 8 + warp;                 // row in the scan's order
+    if (qs >= a.N) return;
+    const size_t srow = (size_t)b * a.N + qs;
+    const int *perm = a.perm ? a.perm + (size_t)b * a.N : nullptr;
+    const int q = perm ? perm[qs] : qs;                   // original point index
+    const size_t grow = (size_t)b * a.N + q;
+    if (a.overflow[grow]) {                               // the fallback kernel writes this row
+        if (lane == 0) a.fb_list[(size_t)b * a.N + atomicAdd(&a.fb_count[b], 1)] = q;
+        return;
+    }
+    const int n = a.cand_cnt[srow];
+    const uint2 *cand = a.cand + srow * TC_CAP;
+    const float *xb = a.x_nc + (size_t)b * a.N * C;
+    const float *nb = a.norm + (size_t)b * a.N;
+    float qv[VEC];
+    load_row<VEC>(xb + (size_t)q * C + lane * VEC, qv);
+    const float qn = nb[q];
+    const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
+    // short lists (the pruned scan's fixed thresholds leave ~2k entries) take the narrow instantiation
+    if (n <= 128) rerank_row<C, 4>(a, cand, n, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+    else rerank_row<C, TC_CAP / 32>(a, cand, n, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
 }
 
 // ---------------------------------------------------------------------------------
@@ -695,20 +738,22 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
 constexpr int TCP_MIN_N = 1024;
 constexpr int TCP_SPLIT = 20;         // partial Gram matrices per cloud
 constexpr int TCP_PRE = 8;            // tiles of the threshold pre-pass
-constexpr int TCP_ITERS = 16;         // subspace iterations
+constexpr int TCP_ITERS = 8;          // subspace iterations
 constexpr uint32_t TCP_END = 0xffffffffu;
 constexpr int TCP_ACC = 4;            // TMEM accumulator stages (4 x 64 columns)
 constexpr int TCP_NRING = 16;         // key-norm ring: the producer runs at most STAGES + ACC + 1 tiles ahead of the epilogue
 __host__ __device__ constexpr int tcp_stages(int C) { return C == 64 ? 4 : 3; }
 
-// part[b][sp][C*C + C] = (sum_n x x^T | sum_n x) over the sp-th slice of the cloud's points
+// part[b][sp][C*C + C] = (sum_n x x^T | sum_n x) over the sp-th slice of a strided subsample of the cloud's points
+// (every `stride`-th point, Ns of them: the directions only steer the pruning, a sample is enough)
 template <int C>
-__global__ void __launch_bounds__(256) tcp_moments_kernel(const float *__restrict__ x, float *__restrict__ part, int N) {
+__global__ void __launch_bounds__(256) tcp_moments_kernel(const float *__restrict__ x, float *__restrict__ part, int N,
+                                                          int Ns, int stride) {
     constexpr int R = C / 16;
     __shared__ float t[C][33];
     const int b = blockIdx.y, sp = blockIdx.x, tid = threadIdx.x;
-    const int chunk = (N + TCP_SPLIT - 1) / TCP_SPLIT;
-    const int n_lo = sp * chunk, n_hi = min(N, n_lo + chunk);
+    const int chunk = (Ns + TCP_SPLIT - 1) / TCP_SPLIT;
+    const int n_lo = sp * chunk, n_hi = min(Ns, n_lo + chunk);
     const float *xb = x + (size_t)b * C * N;
     const int ti = tid >> 4, tj = tid & 15;
     float acc[R][R];
@@ -720,7 +765,7 @@ __global__ void __launch_bounds__(256) tcp_moments_kernel(const float *__restric
     for (int n0 = n_lo; n0 < n_hi; n0 += 32) {
         for (int c = tid >> 5; c < C; c += 8) {
             const int n = n0 + (tid & 31);
-            t[c][tid & 31] = n < n_hi ? xb[(size_t)c * N + n] : 0.f;
+            t[c][tid & 31] = n < n_hi ? xb[(size_t)c * N + (size_t)n * stride] : 0.f;
         }
         __syncthreads();
 #pragma unroll 4
@@ -816,10 +861,15 @@ __global__ void __launch_bounds__(256) tcp_pca_kernel(const float *__restrict__ 
     for (int it = 0; it < TCP_ITERS; ++it) {
         for (int e = tid; e < 3 * C; e += 256) {
             const int i = e / C, r = e % C;
-            float s = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < C; ++c) s = fmaf(cov[r * (C + 1) + c], V[i * C + c], s);
-            W[e] = s;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+            for (int c = 0; c < C; c += 4) {
+                s0 = fmaf(cov[r * (C + 1) + c], V[i * C + c], s0);
+                s1 = fmaf(cov[r * (C + 1) + c + 1], V[i * C + c + 1], s1);
+                s2 = fmaf(cov[r * (C + 1) + c + 2], V[i * C + c + 2], s2);
+                s3 = fmaf(cov[r * (C + 1) + c + 3], V[i * C + c + 3], s3);
+            }
+            W[e] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
         orthonormalize();
@@ -859,8 +909,8 @@ __device__ __forceinline__ unsigned tcp_spread10(unsigned v) {   // 10 bits -> e
 // proj[i][b][n] = v_i . x_n ; sort key = (cloud, 30-bit Morton code of the projections in a +-4 sigma_1 cube)
 template <int C>
 __global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restrict__ x, const float *__restrict__ pca,
-                                                          float *__restrict__ proj, unsigned long long *__restrict__ keys,
-                                                          int *__restrict__ vals, int B, int N) {
+                                                          float *__restrict__ proj, unsigned *__restrict__ keys,
+                                                          int *__restrict__ vals, int B, int N, int bits) {
     __shared__ float V[3 * C + 4];
     const int b = blockIdx.y;
     for (int e = threadIdx.x; e < 3 * C + 4; e += 128) V[e] = pca[(size_t)b * (3 * C + 4) + e];
@@ -888,9 +938,9 @@ __global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restric
     for (int i = 0; i < 3; ++i) {
         float t = (pv[i] - V[3 * C + i]) * sc + 512.f;
         t = t == t ? t : 0.f;                                   // NaN -> 0
-        code |= tcp_spread10((unsigned)fminf(fmaxf(t, 0.f), 1023.f)) << i;
+        code |= tcp_spread10(((unsigned)fminf(fmaxf(t, 0.f), 1023.f)) >> (10 - bits)) << i;
     }
-    keys[o] = ((unsigned long long)b << 32) | code;
+    keys[o] = ((unsigned)b << (3 * bits)) | code;              // cloud | Morton code with `bits` bits per axis
     vals[o] = n;
 }
 
@@ -899,11 +949,13 @@ __global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restric
 __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ sorted_vals, const float *__restrict__ norm,
                                                         const float *__restrict__ proj, int *__restrict__ perm,
                                                         int *__restrict__ inv, float *__restrict__ norm_pad,
-                                                        float *__restrict__ boxes, int B, int N, int Npad, int tiles) {
+                                                        float *__restrict__ boxes, unsigned *__restrict__ nmax_bits,
+                                                        int B, int N, int Npad, int tiles) {
     const int b = blockIdx.y;
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (t >= tiles) return;
     float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    float nm = 0.f;
 #pragma unroll
     for (int h = 0; h < TC_BN / 32; ++h) {
         const int s = t * TC_BN + h * 32 + lane;
@@ -911,7 +963,9 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
             const int o = sorted_vals[(size_t)b * N + s];
             perm[(size_t)b * N + s] = o;
             inv[(size_t)b * N + o] = s;
-            norm_pad[(size_t)b * Npad + s] = norm[(size_t)b * N + o];
+            const float nv = norm[(size_t)b * N + o];
+            norm_pad[(size_t)b * Npad + s] = nv;
+            nm = fmaxf(nm, nv);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const float p = proj[(size_t)i * B * N + (size_t)b * N + o];
@@ -928,7 +982,9 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
             mn[i] = fminf(mn[i], __shfl_xor_sync(FULLW, mn[i], o));
             mx[i] = fmaxf(mx[i], __shfl_xor_sync(FULLW, mx[i], o));
         }
+    for (int o = 16; o; o >>= 1) nm = fmaxf(nm, __shfl_xor_sync(FULLW, nm, o));
     if (lane == 0) {
+        atomicMax(nmax_bits + b, __float_as_uint(nm));       // norms are >= 0: the bit patterns order like the values
         float *bx = boxes + ((size_t)b * tiles + t) * 6;
         bx[0] = mn[0]; bx[1] = mn[1]; bx[2] = mn[2]; bx[3] = mx[0]; bx[4] = mx[1]; bx[5] = mx[2];
     }
@@ -1357,17 +1413,22 @@ static EncodeTiledFn get_encode_fn() {
 
 static size_t tcp_cub_temp_bytes(size_t n, int end_bit) {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned *)nullptr, (unsigned *)nullptr,
                                     (const int *)nullptr, (int *)nullptr, (int)n, 0, end_bit);
     return bytes;
 }
-static int tcp_key_bits(int B) {
-    int bits = 32;
-    while ((1 << (bits - 32)) < B) ++bits;
+static int tcp_cloud_bits(int B) {
+    int bits = 0;
+    while ((1 << bits) < B) ++bits;
     return bits;
 }
-static bool tcp_supported(int N, int k2) {
-    return N >= TCP_MIN_N && k2 <= TC_BN && ceil_div(N, TC_BN) <= 2048;
+// Morton bits per axis so that (cloud | code) fits a 32-bit radix key
+static int tcp_axis_bits(int B) {
+    int bits = (32 - tcp_cloud_bits(B)) / 3;
+    return bits > 10 ? 10 : bits;
+}
+static bool tcp_supported(int B, int N, int k2) {
+    return N >= TCP_MIN_N && k2 <= TC_BN && ceil_div(N, TC_BN) <= 2048 && tcp_axis_bits(B) >= 5;
 }
 
 size_t knn_tc_workspace_bytes(int B, int C, int N) {
@@ -1377,12 +1438,13 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += align_up((size_t)B * TCP_SPLIT * (C * C + C) * sizeof(float));   // partial moments
     t += align_up((size_t)B * (3 * C + 4) * sizeof(float));               // pca
     t += align_up(3 * bn * sizeof(float));                                // projections
-    t += 2 * align_up(bn * sizeof(unsigned long long));                   // keys in/out
+    t += 2 * align_up(bn * sizeof(unsigned));                             // keys in/out
     t += 2 * align_up(bn * sizeof(int));                                  // vals in/out
-    t += align_up(tcp_cub_temp_bytes(bn, tcp_key_bits(B)));               // cub temp
+    t += align_up(tcp_cub_temp_bytes(bn, 32));                            // cub temp
     t += 2 * align_up(bn * sizeof(int));                                  // perm, inv
     t += align_up((size_t)B * ceil_div(N, TC_BN) * 6 * sizeof(float));    // tile boxes
     t += align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));          // visited-tile statistics
+    t += align_up(bn * sizeof(int)) + align_up((size_t)B * sizeof(int));  // fallback row list + counts
     t += align_up(bn * 2 * C * sizeof(__nv_bfloat16));   // xs
     t += align_up(bn * C * sizeof(float));               // x_nc
     t += align_up(bn * sizeof(float));                   // norm
@@ -1400,7 +1462,7 @@ bool knn_tc_supported(int C, int N, int k2) {
 
 // declared in knn_select.cu
 int launch_sqnorm_public(const float *x, float *out, int B, int C, int Cuse, int N, cudaStream_t st);
-int knn_fallback_rows(const float *x, const float *norms, const int *row_filter, int B, int C, int N, int k1, int k2,
+int knn_fallback_rows(const float *x, const float *norms, const int *qlist, const int *qcount, int B, int C, int N, int k1, int k2,
                       int64_t *idx64, int32_t *idx32, cudaStream_t st);
 
 template <int C, int MODE = 0>
@@ -1439,16 +1501,19 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
 }
 
 template <int C>
-static int launch_tcp_prep(const float *x, float *part, float *pca, float *proj, unsigned long long *keys, int *vals,
+static int launch_tcp_prep(const float *x, float *part, float *pca, float *proj, unsigned *keys, int *vals,
                            int B, int N, cudaStream_t st) {
-    tcp_moments_kernel<C><<<dim3(TCP_SPLIT, B), 256, 0, st>>>(x, part, N);
+    int stride = N / 1024;
+    stride = stride < 1 ? 1 : (stride > 8 ? 8 : stride);
+    const int Ns = (N + stride - 1) / stride;
+    tcp_moments_kernel<C><<<dim3(TCP_SPLIT, B), 256, 0, st>>>(x, part, N, Ns, stride);
     GCANET_LAUNCH_OK("tcp_moments_kernel");
     const size_t smem = ((size_t)C * (C + 1) + 7 * C) * sizeof(float);
     auto kern = tcp_pca_kernel<C>;
     if (smem > 48 * 1024) GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, 256, smem, st>>>(part, pca, N);
+    kern<<<B, 256, smem, st>>>(part, pca, Ns);
     GCANET_LAUNCH_OK("tcp_pca_kernel");
-    tcp_project_kernel<C><<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(x, pca, proj, keys, vals, B, N);
+    tcp_project_kernel<C><<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(x, pca, proj, keys, vals, B, N, tcp_axis_bits(B));
     GCANET_LAUNCH_OK("tcp_project_kernel");
     return GCANET_OK;
 }
@@ -1462,19 +1527,22 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     float *part = cv.take<float>((size_t)B * TCP_SPLIT * (C * C + C));
     float *pca = cv.take<float>((size_t)B * (3 * C + 4));
     float *proj = cv.take<float>(3 * bn);
-    unsigned long long *keys_in = cv.take<unsigned long long>(bn);
-    unsigned long long *keys_out = cv.take<unsigned long long>(bn);
+    unsigned *keys_in = cv.take<unsigned>(bn);
+    unsigned *keys_out = cv.take<unsigned>(bn);
     int *vals_in = cv.take<int>(bn);
     int *vals_out = cv.take<int>(bn);
-    const int end_bit = tcp_key_bits(B);
-    size_t temp_bytes = tcp_cub_temp_bytes(bn, end_bit);
+    const int end_bit = tcp_cloud_bits(B) + 3 * tcp_axis_bits(B);
+    size_t temp_bytes = tcp_cub_temp_bytes(bn, 32);
     void *temp = cv.take<char>(temp_bytes);
     int *perm = cv.take<int>(bn);
     int *inv = cv.take<int>(bn);
     float *boxes = cv.take<float>((size_t)B * ceil_div(N, TC_BN) * 6);
     int *visited = cv.take<int>((size_t)B * ceil_div(N, TC_BM));
+    int *fb_list = cv.take<int>(bn);
+    int *fb_count = cv.take<int>(B);
+    GCANET_CUDA_OK(cudaMemsetAsync(fb_count, 0, B * sizeof(int), st));
     const char *env_np = getenv("GCANET_TC_NO_PRUNE");
-    const bool prune = !no_prune && tcp_supported(N, k2) && !(env_np && env_np[0] == '1') && !getenv("GCANET_TC_DEBUG");
+    const bool prune = !no_prune && tcp_supported(B, N, k2) && !(env_np && env_np[0] == '1') && !getenv("GCANET_TC_DEBUG");
     __nv_bfloat16 *xs = cv.take<__nv_bfloat16>(bn * 2 * C);
     float *x_nc = cv.take<float>(bn * C);
     float *norm = cv.take<float>(bn);
@@ -1494,15 +1562,19 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         if (rc) return rc;
         GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
         count_launch();
-        tcp_tiles_kernel<<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes, B, N, Npad, tiles);
+        GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
+        tcp_tiles_kernel<<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes,
+                                                                      reinterpret_cast<unsigned *>(nmax), B, N, Npad, tiles);
         GCANET_LAUNCH_OK("tcp_tiles_kernel");
     }
     {
         dim3 grid(ceil_div(N, 32), ceil_div(C, 32), B), block(32, 8);
         tc_prep_kernel<<<grid, block, 0, st>>>(x, xs, x_nc, prune ? inv : nullptr, C, N);
         GCANET_LAUNCH_OK("tc_prep_kernel");
-        tc_normmax_kernel<<<B, 256, 0, st>>>(norm, nmax, prune ? nullptr : norm_pad, N, Npad);
-        GCANET_LAUNCH_OK("tc_normmax_kernel");
+        if (!prune) {
+            tc_normmax_kernel<<<B, 256, 0, st>>>(norm, nmax, norm_pad, N, Npad);
+            GCANET_LAUNCH_OK("tc_normmax_kernel");
+        }
     }
 
     // 3-D tensor map over xs: (K = 2C bf16, N rows, B clouds), box = (64, 128, 1), 128-byte swizzle;
@@ -1531,7 +1603,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         if (pre < 0) pre = 0;
         TcpScanArgs sa{norm_pad, Npad, nmax, boxes, perm, cand, cand_cnt, overflow, visited, N, k2, tiles, pre, P};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
-                      (unordered && k1 == k2) ? 1 : 0, perm};
+                      (unordered && k1 == k2) ? 1 : 0, perm, fb_list, fb_count};
         rc = C == 64 ? launch_tcp<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128>(tmap_q, tmap_k, sa, ra, B, st);
         if (rc) return rc;
         const char *stats = getenv("GCANET_TC_STATS");
@@ -1547,7 +1619,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
                     C, s / nq, tiles, h[0], h[nq / 2], h[nq * 9 / 10], h[nq * 99 / 100], h[nq - 1]);
             free(h);
         }
-        return knn_fallback_rows(x, norm, overflow, B, C, N, k1, k2, idx64, idx32, st);
+        return knn_fallback_rows(x, norm, fb_list, fb_count, B, C, N, k1, k2, idx64, idx32, st);
     }
     int stride = (int)(tiles * 0.381966f);
     if (stride < 1) stride = 1;
@@ -1559,14 +1631,14 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     const int dbg_mode = (dbg && dbg[0] >= '1' && dbg[0] <= '3') ? dbg[0] - '0' : 0;
     TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, dbg_mode, stride};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
-                  (unordered && k1 == k2) ? 1 : 0};
+                  (unordered && k1 == k2) ? 1 : 0, nullptr, fb_list, fb_count};
     if (dbg_mode >= 2 && C == 64)
         rc = dbg_mode == 2 ? launch_tc<64, 2>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<64, 3>(tmap_q, tmap_k, sa, ra, B, st);
     else
         rc = C == 64 ? launch_tc<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<128>(tmap_q, tmap_k, sa, ra, B, st);
     if (rc) return rc;
     if (sa.debug_no_append) return GCANET_OK;
-    return knn_fallback_rows(x, norm, overflow, B, C, N, k1, k2, idx64, idx32, st);
+    return knn_fallback_rows(x, norm, fb_list, fb_count, B, C, N, k1, k2, idx64, idx32, st);
 }
 
 }  // namespace gcanet
