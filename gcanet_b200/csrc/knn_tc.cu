@@ -273,8 +273,9 @@ __device__ __forceinline__ float select_bound(const float (&dv)[SL], int n, int 
 
 // Warp-cooperative compaction of one row's candidate list (entries [0, n) at `ptr`): keeps
 // d <= bound + margin, returns the new count and threshold.  `ptr`, `n`, `margin` are warp-uniform.
+template <int CAPACITY = TC_CAP>
 __device__ __forceinline__ void compact_row(uint2 *ptr, int n, int k, float margin, int lane, int &new_cnt, float &new_thr) {
-    constexpr int SL = TC_CAP / 32;
+    constexpr int SL = CAPACITY / 32;
     float dv[SL];
     uint32_t di[SL];
 #pragma unroll
@@ -527,6 +528,7 @@ struct RerankArgs {
     int N, k, step, kout;
     int unordered;         // 1: the caller only needs the neighbour SET (EdgeConv is order-invariant)
     const int *perm;       // pruned path: rows and candidates are sorted positions, perm[b][s] = original index; else null
+    int split;             // 1: a row's list is two halves of TC_CAP / 2 entries with counts cand_cnt[2 row], cand_cnt[2 row + 1]
     int *fb_list;          // [B][N] rows left to the CUDA-core fallback (overflowed lists), fb_count [B] (zeroed by the host)
     int *fb_count;
 };
@@ -572,7 +574,7 @@ __device__ __forceinline__ void kth_bracket(const float (&dv)[SL], int k, float 
 }
 
 template <int C, int SL>
-__device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *cand, int n, const int *perm, const float *xb,
+__device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *cand, int n, int n0, const int *perm, const float *xb,
                                            const float *nb, int q, float qn, const float (&qv)[C / 32], float margin,
                                            size_t grow, int *sl, float *sd, int lane) {
     constexpr int VEC = C / 32;
@@ -588,7 +590,7 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
         ad[s] = CUDART_INF_F;
         aj[s] = 0;
         if (e < n) {
-            uint2 t = cand[e];
+            uint2 t = cand[e < n0 ? e : e - n0 + TC_CAP / 2];      // second half-list starts at TC_CAP / 2 (n0 = n: one list)
             ad[s] = __uint_as_float(t.x);
             aj[s] = perm ? perm[t.y] : (int)t.y;
         }
@@ -712,7 +714,8 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
         if (lane == 0) a.fb_list[(size_t)b * a.N + atomicAdd(&a.fb_count[b], 1)] = q;
         return;
     }
-    const int n = a.cand_cnt[srow];
+    const int n0 = a.split ? a.cand_cnt[2 * srow] : a.cand_cnt[srow];
+    const int n = a.split ? n0 + a.cand_cnt[2 * srow + 1] : n0;
     const uint2 *cand = a.cand + srow * TC_CAP;
     const float *xb = a.x_nc + (size_t)b * a.N * C;
     const float *nb = a.norm + (size_t)b * a.N;
@@ -721,8 +724,8 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
     const float qn = nb[q];
     const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
     // short lists (the pruned scan's fixed thresholds leave ~2k entries) take the narrow instantiation
-    if (n <= 128) rerank_row<C, 4>(a, cand, n, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
-    else rerank_row<C, TC_CAP / 32>(a, cand, n, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+    if (n <= 128) rerank_row<C, 4>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+    else rerank_row<C, TC_CAP / 32>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
 }
 
 // ---------------------------------------------------------------------------------
@@ -740,6 +743,8 @@ constexpr int TCP_SPLIT = 20;         // partial Gram matrices per cloud
 constexpr int TCP_PRE = 8;            // tiles of the threshold pre-pass
 constexpr int TCP_ITERS = 8;          // subspace iterations
 constexpr uint32_t TCP_END = 0xffffffffu;
+constexpr int TCP_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int TCP_HCAP = TC_CAP / 2;  // each of a row's two epilogue threads owns half of its candidate list
 constexpr int TCP_ACC = 4;            // TMEM accumulator stages (4 x 64 columns)
 constexpr int TCP_NRING = 16;         // key-norm ring: the producer runs at most STAGES + ACC + 1 tiles ahead of the epilogue
 __host__ __device__ constexpr int tcp_stages(int C) { return C == 64 ? 4 : 3; }
@@ -950,12 +955,14 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
                                                         const float *__restrict__ proj, int *__restrict__ perm,
                                                         int *__restrict__ inv, float *__restrict__ norm_pad,
                                                         float *__restrict__ boxes, unsigned *__restrict__ nmax_bits,
-                                                        int B, int N, int Npad, int tiles) {
+                                                        unsigned *__restrict__ wkey, int B, int N, int Npad, int tiles) {
+    __shared__ float s_box[8][6];
     const int b = blockIdx.y;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (t >= tiles) return;
+    const int wl = threadIdx.x >> 5;
+    const int t = blockIdx.x * 8 + wl, lane = threadIdx.x & 31;
     float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     float nm = 0.f;
+    if (t < tiles) {
 #pragma unroll
     for (int h = 0; h < TC_BN / 32; ++h) {
         const int s = t * TC_BN + h * 32 + lane;
@@ -988,6 +995,39 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
         float *bx = boxes + ((size_t)b * tiles + t) * 6;
         bx[0] = mn[0]; bx[1] = mn[1]; bx[2] = mn[2]; bx[3] = mx[0]; bx[4] = mx[1]; bx[5] = mx[2];
     }
+    }
+    // scheduling key of the query tile (two key tiles = warps 2i, 2i+1): squared diagonal of its box
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { s_box[wl][i] = mn[i]; s_box[wl][3 + i] = mx[i]; }
+    }
+    __syncthreads();
+    if (lane == 0 && (wl & 1) == 0 && t < tiles) {
+        float d2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float e = fmaxf(s_box[wl][3 + i], s_box[wl + 1][3 + i]) - fminf(s_box[wl][i], s_box[wl + 1][i]);   // an empty partner box is (+inf, -inf)
+            d2 = fmaf(e, e, d2);
+        }
+        if (!(d2 >= 0.f)) d2 = 0.f;
+        wkey[(size_t)b * ((tiles + 1) / 2) + (t >> 1)] = __float_as_uint(d2);
+    }
+}
+
+// work[rank] = i for query tile i = b * qtiles + qt, ranked by the squared diagonal of its bounding box in the
+// projected space (wkey, written by tcp_tiles_kernel), largest first.  Every thread ranks one tile against all.
+constexpr int TCP_MAX_WORK = 65536;
+__global__ void __launch_bounds__(256) tcp_work_order_kernel(const unsigned *__restrict__ wkey, int *__restrict__ work, int n) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;    // one warp per tile
+    if (i >= n) return;
+    const unsigned mine = wkey[i];
+    int rank = 0;
+    for (int j = lane; j < n; j += 32) {
+        const unsigned o = __ldg(wkey + j);
+        rank += (o > mine || (o == mine && j < i)) ? 1 : 0;
+    }
+    rank = __reduce_add_sync(FULLW, rank);
+    if (lane == 0) work[rank] = i;
 }
 
 struct TcpScanArgs {
@@ -1000,7 +1040,9 @@ struct TcpScanArgs {
     int *cand_cnt;          // [B][N]          rows in sorted order
     int *overflow;          // [B][N]          rows in ORIGINAL order (consumed by the fallback scan)
     int *visited;           // [B][query tiles] statistics: key tiles scanned in the main pass (may be null)
+    const int *work;        // [B * qtiles] query tiles (b * qtiles + qt) in launch order, or null = natural order
     int N, k, tiles, pre, P;  // P = tiles rounded up to a power of two (sort width)
+    int qtiles;
 };
 
 // thread-local selection over the 64 slot minima: smallest bound with count(m <= bound) >= k found by bisection
@@ -1025,7 +1067,7 @@ __device__ __forceinline__ float slot_bound(const float (&m)[TC_BN], int k, int 
 }
 
 template <int C>
-__global__ void __launch_bounds__(TC_THREADS, C == 64 ? 2 : 1)
+__global__ void __launch_bounds__(TCP_THREADS, C == 64 ? 2 : 1)
 knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int NH = C / TC_KB;
@@ -1053,13 +1095,20 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(thr_ready + 1);
     uint32_t *s_kt = tmem_slot + 1;                         // [STAGES] key tile in the stage, TCP_END = end-of-pass marker
     volatile int *s_end = reinterpret_cast<volatile int *>(s_kt + STAGES);   // [2] stream position of the pass A / pass B end marker
-    volatile float *s_wthr = reinterpret_cast<volatile float *>(const_cast<int *>(s_end) + 2);   // [4] max true-distance threshold per epilogue warp
+    volatile float *s_wthr = reinterpret_cast<volatile float *>(const_cast<int *>(s_end) + 2);   // [8] max true-distance threshold per epilogue warp
+    int *s_cnt = reinterpret_cast<int *>(const_cast<float *>(s_wthr) + 8);      // [2][128] final half-list counts (-1 = overflowed)
+    int *s_ovf = s_cnt + TC_BM;                                                   //   (second half of s_cnt)
+    volatile float *s_xf = reinterpret_cast<volatile float *>(s_ovf + TC_BM);     // [2][2][128] pair exchange (double-buffered)
     // [P] (bf16-truncated lower bound << 16) | tile, ascending; 8 bytes per entry while it is being sorted
-    uint32_t *s_ord = reinterpret_cast<uint32_t *>(smem + ((reinterpret_cast<uint8_t *>(const_cast<float *>(s_wthr) + 4) - smem + 7) & ~(size_t)7));
+    uint32_t *s_ord = reinterpret_cast<uint32_t *>(smem + ((reinterpret_cast<uint8_t *>(const_cast<float *>(s_xf) + 4 * TC_BM) - smem + 7) & ~(size_t)7));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y;
-    const int q0 = blockIdx.x * TC_BM;
+    // CTAs take the query tiles in the order of a.work (largest bounding box first: those scan the most key tiles,
+    // and starting them last would leave the tail of the grid to a few long-running CTAs)
+    const int item = a.work ? a.work[blockIdx.x] : (int)blockIdx.x;
+    const int b = item / a.qtiles;
+    const int qt = item - b * a.qtiles;
+    const int q0 = qt * TC_BM;
     const int tiles = a.tiles;
     const int pre = a.pre;
 
@@ -1068,11 +1117,11 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tma_prefetch_desc(&tmap_k);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(a_full, 1);
-        for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
-        mbar_init(thr_ready, 4);
+        for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
+        mbar_init(thr_ready, 8);
         s_end[0] = 0x7fffffff;
         s_end[1] = 0x7fffffff;
-        for (int s = 0; s < 4; ++s) s_wthr[s] = CUDART_INF_F;
+        for (int s = 0; s < 8; ++s) s_wthr[s] = CUDART_INF_F;
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, ACC * TC_BN);
@@ -1080,7 +1129,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // ---- tile order: lower bound of every key tile against this CTA's query box, ascending
     {
         const float *bx = a.boxes + (size_t)b * tiles * 6;
-        const int t0 = 2 * blockIdx.x, t1 = min(t0 + 1, tiles - 1);
+        const int t0 = 2 * qt, t1 = min(t0 + 1, tiles - 1);
         float qlo[3], qhi[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -1090,7 +1139,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const float slack = 2e-5f * sqrtf(a.nmax[b]);          // covers fp32 rounding of the projections
         // 64-bit keys: lower bound (exact bits) | centre distance (16 bits, orders the tiles whose boxes overlap) | tile
         unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_ord);
-        for (int t = threadIdx.x; t < a.P; t += TC_THREADS) {
+        for (int t = threadIdx.x; t < a.P; t += TCP_THREADS) {
             unsigned long long key = ~0ull;
             if (t < tiles) {
                 float lb = 0.f, cd = 0.f;
@@ -1119,7 +1168,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             int rank[3];
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
-                const int t = threadIdx.x + u * TC_THREADS;
+                const int t = threadIdx.x + u * TCP_THREADS;
                 rank[u] = -1;
                 if (t < tiles) {
                     const unsigned long long kx = s_key[t];
@@ -1137,7 +1186,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         } else {
         for (int kk = 2; kk <= a.P; kk <<= 1)
             for (int j = kk >> 1; j > 0; j >>= 1) {
-                for (int i = threadIdx.x; i < a.P; i += TC_THREADS) {
+                for (int i = threadIdx.x; i < a.P; i += TCP_THREADS) {
                     const int l = i ^ j;
                     if (l > i) {
                         const unsigned long long x0 = s_key[i], x1 = s_key[l];
@@ -1149,7 +1198,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
         // compact in place to 32 bits per tile: (lower bound truncated to bf16 = rounded DOWN) | tile
         // (32-bit slot i overlays 64-bit slots <= i, all of which earlier rounds or this round's reads have consumed)
-        for (int base = 0; base < a.P; base += TC_THREADS) {
+        for (int base = 0; base < a.P; base += TCP_THREADS) {
             const int i = base + threadIdx.x;
             uint32_t packed = 0;
             if (i < a.P) {
@@ -1183,7 +1232,8 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     const uint32_t e = s_ord[i];
                     if (pass == 1 || i >= pre) {
                         // thresholds only ever decrease: a stale (larger) value is safe
-                        const float thr = fmaxf(fmaxf(s_wthr[0], s_wthr[1]), fmaxf(s_wthr[2], s_wthr[3]));
+                        const float thr = fmaxf(fmaxf(fmaxf(s_wthr[0], s_wthr[1]), fmaxf(s_wthr[2], s_wthr[3])),
+                                                fmaxf(fmaxf(s_wthr[4], s_wthr[5]), fmaxf(s_wthr[6], s_wthr[7])));
                         if (__uint_as_float(e & 0xffff0000u) > thr) break;     // every later tile has a larger bound
                     }
                     const int kt = (int)(e & 0xffffu);
@@ -1206,7 +1256,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 ++seq;
                 if (pass == 0) mbar_wait_backoff(thr_ready, 0);      // pass B prunes with the final thresholds
             }
-            if (a.visited) a.visited[(size_t)b * gridDim.x + blockIdx.x] = nvis;
+            if (a.visited) a.visited[(size_t)b * a.qtiles + qt] = nvis;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -1254,9 +1304,13 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
         }
     } else {
-        // ===================== epilogue: one query row per thread =====================
-        const int ew = warp & 3;
-        const int row = ew * 32 + lane;
+        // ===================== epilogue: two threads per query row, 32 key columns each =====================
+        // warps 2..5 take columns 0..31 of every tile, warps 6..9 columns 32..63; a warp may only touch the TMEM
+        // lane quarter warp % 4, which also fixes its 32 rows
+        const int ewi = warp - 2;                             // 0..7
+        const int lg = warp & 3;                              // TMEM lane quarter
+        const int hf = ewi >> 2;                              // column half
+        const int row = lg * 32 + lane;
         const int q = q0 + row;                               // sorted position
         const bool active = q < a.N;
         const size_t srow = (size_t)b * a.N + (active ? q : 0);
@@ -1264,57 +1318,93 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const float qn = active ? a.norm_pad[(size_t)b * a.Npad + q] : 0.f;
         const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
         float thr = active ? CUDART_INF_F : -CUDART_INF_F;
-        int cnt = 0, seq = 0;
-        bool ovf = false;
-        int acc = 0;
+        int seq = 0, acc = 0;
         uint32_t accphase = 0;
+        int xbuf = 0;                                         // exchange buffer parity (same sequence in both threads of a row)
+        const int pair_bar = 1 + lg;                          // named barrier shared by the two warps of a lane quarter
 
-        // ---- pass A: per-column-slot minima over the visited tiles.  The 64 slot minima belong to 64 different
-        // keys, so the k-th smallest of them bounds the row's k-th distance from above; nothing is stored.
-        {
-            float m[TC_BN];
+        // the two threads of a row combine a value (sum for counts, min / max for ranges) through shared memory
+        auto pair_exchange = [&](float mine) -> float {
+            s_xf[(xbuf * 2 + hf) * TC_BM + row] = mine;
+            named_bar_sync(pair_bar, 64);
+            const float other = s_xf[(xbuf * 2 + (hf ^ 1)) * TC_BM + row];
+            xbuf ^= 1;
+            return other;
+        };
+        // smallest bound with count(slot minima of the row <= bound) >= k, by bisection over both threads' 32 slots
+        auto row_bound = [&](const float (&m)[32], int iters) -> float {
+            float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+            int nf = 0;
 #pragma unroll
-            for (int s = 0; s < TC_BN; ++s) m[s] = CUDART_INF_F;
+            for (int s = 0; s < 32; ++s) {
+                mn = fminf(mn, m[s]);
+                if (m[s] < CUDART_INF_F) { mx = fmaxf(mx, m[s]); ++nf; }
+            }
+            mn = fminf(mn, pair_exchange(mn));
+            mx = fmaxf(mx, pair_exchange(mx));
+            nf += (int)pair_exchange((float)nf);
+            float lo = mn, hi = mx;
+            int c_hi = nf;
+            // The two warps of a lane quarter hold the same 32 rows and see the same totals, so they leave the loop in
+            // the same iteration (the exchanges stay aligned): when every row has exactly k slots below its bound
+            // (nothing left to gain) or after `iters` halvings.
+            for (int it = 0; it < iters; ++it) {
+                if (__all_sync(FULLW, c_hi <= a.k)) break;
+                const float mid = 0.5f * lo + 0.5f * hi;
+                int c = 0;
+#pragma unroll
+                for (int s = 0; s < 32; ++s) c += (m[s] <= mid) ? 1 : 0;
+                c += (int)pair_exchange((float)c);
+                if (c >= a.k) { hi = mid; c_hi = c; } else lo = mid;
+            }
+            return nf >= a.k ? hi : CUDART_INF_F;
+        };
+
+        // ---- pass A: per-column-slot minima over the visited tiles.  The 64 slot minima of a row belong to 64
+        // different keys, so the k-th smallest of them bounds the row's k-th distance from above; nothing is stored.
+        {
+            float m[32];
+#pragma unroll
+            for (int s = 0; s < 32; ++s) m[s] = CUDART_INF_F;
             int done = 0, refresh_at = pre > 0 ? pre : 8;
             for (;; ++seq) {
                 mbar_wait(&t_full[acc], accphase);
                 if (seq == s_end[0]) break;
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN;
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_BN + hf * 32;
+                uint32_t v[32];
+                tmem_ld32(taddr, v);
+                tmem_ld_wait();
+                const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + hf * 32);
 #pragma unroll
-                for (int ch = 0; ch < TC_BN / 32; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + ch * 32, v);
-                    tmem_ld_wait();
-                    const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + ch * 32);
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 n4 = rn[c4];
+                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4) {
-                        const float4 n4 = rn[c4];
-                        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            m[ch * 32 + c4 * 4 + e] = fminf(m[ch * 32 + c4 * 4 + e], fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]));
-                    }
+                    for (int e = 0; e < 4; ++e)
+                        m[c4 * 4 + e] = fminf(m[c4 * 4 + e], fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]));
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&t_empty[acc]);
                 if (++acc == ACC) { acc = 0; accphase ^= 1; }
                 if (++done == refresh_at) {
-                    // let the producer start skipping: publish the bound reached so far
-                    refresh_at *= 2;
-                    float wt = active ? slot_bound(m, a.k, 8) + margin + qn : -CUDART_INF_F;
+                    // let the producer start skipping: publish the bound reached so far (after pre, 2 pre, 4 pre tiles)
+                    refresh_at = refresh_at < 4 * (pre > 0 ? pre : 8) ? refresh_at * 2 : 0x7fffffff;
+                    const float bd = row_bound(m, 6);
+                    float wt = active ? bd + margin + qn : -CUDART_INF_F;
                     for (int o = 16; o; o >>= 1) wt = fmaxf(wt, __shfl_xor_sync(FULLW, wt, o));
-                    if (lane == 0) s_wthr[ew] = wt;
+                    if (lane == 0) s_wthr[ewi] = wt;
                 }
             }
-            // end marker of pass A: final thresholds
-            if (active) thr = slot_bound(m, a.k, 12) + margin;
+            // end marker of pass A: final thresholds (bit-identical in the two threads of a row)
+            const float bd = row_bound(m, 11);
+            if (active) thr = bd + margin;
             float wt = active ? thr + qn : -CUDART_INF_F;
             for (int o = 16; o; o >>= 1) wt = fmaxf(wt, __shfl_xor_sync(FULLW, wt, o));
             __syncwarp();
             if (lane == 0) {
-                s_wthr[ew] = wt;
+                s_wthr[ewi] = wt;
                 mbar_arrive(thr_ready);
                 mbar_arrive(&t_empty[acc]);
             }
@@ -1322,65 +1412,87 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             ++seq;
         }
 
-        // ---- pass B: same order again, every key below the row's threshold becomes a candidate
+        // ---- pass B: same order again, every key below the row's threshold becomes a candidate.  Each thread owns
+        // half of the row's list (capacity TCP_HCAP): no shared counter, and a half that fills up is compacted by
+        // its warp exactly like in the full scan (its k-th smallest entry is a valid bound for the whole row).
+        uint2 *hbuf = buf + hf * TCP_HCAP;
+        // The half-list is 1 KB and 1 KB-aligned, so appending only ever changes the low 32 address bits: the write
+        // pointer is kept as a (running low word, constant high word) pair -- one predicated add per append instead
+        // of a 64-bit index computation.
+        const uint32_t hb_lo0 = (uint32_t)reinterpret_cast<uintptr_t>(hbuf);
+        unsigned long long wp = reinterpret_cast<unsigned long long>(hbuf);
+        int cnt = 0;
+        bool ovf = false;
         for (int i = 0;; ++i, ++seq) {
             mbar_wait(&t_full[acc], accphase);
             if (seq == s_end[1]) break;
             tc_fence_after();
             const int kt = (int)(s_ord[i] & 0xffffu);
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_BN;
-            uint32_t v[2][32];
-            tmem_ld32(taddr, v[0]);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_BN + hf * 32;
+            uint32_t v[32];
+            tmem_ld32(taddr, v);
+            tmem_ld_wait();
+            const int jbase = kt * TC_BN + hf * 32;
+            const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + hf * 32);
 #pragma unroll
-            for (int ch = 0; ch < TC_BN / 32; ++ch) {
-                tmem_ld_wait();
-                if (ch + 1 < TC_BN / 32) tmem_ld32(taddr + (ch + 1) * 32, v[(ch + 1) & 1]);
-                const int jbase = kt * TC_BN + ch * 32;
-                const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + ch * 32);
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 n4 = rn[c4];
+                const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 n4 = rn[c4];
-                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float d = fmaf(-2.f, __uint_as_float(v[ch & 1][c4 * 4 + e]), nn[e]);
-                        if (d < thr) {
-                            buf[cnt] = make_uint2(__float_as_uint(d), (uint32_t)(jbase + c4 * 4 + e));
-                            ++cnt;
-                        }
-                    }
-                }
-                unsigned need = __ballot_sync(FULLW, cnt > TC_CAP - 32);
-                if (need) {
-                    while (need) {
-                        const int r = __ffs(need) - 1;
-                        need &= need - 1;
-                        const int n_r = __shfl_sync(FULLW, cnt, r);
-                        const float m_r = __shfl_sync(FULLW, margin, r);
-                        const unsigned long long p_r = __shfl_sync(FULLW, (unsigned long long)buf, r);
-                        __syncwarp();
-                        int nc; float nt;
-                        compact_row(reinterpret_cast<uint2 *>(p_r), n_r, a.k, m_r, lane, nc, nt);
-                        if (lane == r) {
-                            cnt = nc;
-                            thr = fminf(thr, nt);
-                            if (nc > TC_CAP - 32) { ovf = true; cnt = 0; thr = -CUDART_INF_F; }
-                        }
-                    }
-                    float wt = (active && !ovf) ? thr + qn : -CUDART_INF_F;
-                    for (int o = 16; o; o >>= 1) wt = fmaxf(wt, __shfl_xor_sync(FULLW, wt, o));
-                    if (lane == 0) s_wthr[ew] = wt;
+                for (int e = 0; e < 4; ++e) {
+                    const float d = fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]);   // +inf for keys >= N
+                    // if (d < thr) { *wp = (d, index); ++wp; } as two predicated instructions: only the low address
+                    // word ever changes (see above)
+                    asm volatile(
+                        "{\n"
+                        ".reg .pred p;\n"
+                        ".reg .u32 lo, hi;\n"
+                        "setp.lt.f32 p, %1, %2;\n"
+                        "@p st.global.v2.b32 [%0], {%3, %4};\n"
+                        "mov.b64 {lo, hi}, %0;\n"
+                        "@p add.u32 lo, lo, 8;\n"
+                        "mov.b64 %0, {lo, hi};\n"
+                        "}\n"
+                        : "+l"(wp)
+                        : "f"(d), "f"(thr), "r"(__float_as_uint(d)), "r"(jbase + c4 * 4 + e)
+                        : "memory");
                 }
             }
+            cnt = (int)(((uint32_t)wp - hb_lo0) >> 3);
+            // accumulator drained: hand it back before any list maintenance
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[acc]);
             if (++acc == ACC) { acc = 0; accphase ^= 1; }
+            // half-lists that could overflow during the next 32 columns are compacted now (rare)
+            unsigned need = __ballot_sync(FULLW, cnt > TCP_HCAP - 32);
+            while (need) {
+                const int r = __ffs(need) - 1;
+                need &= need - 1;
+                const int n_r = __shfl_sync(FULLW, cnt, r);
+                const float m_r = __shfl_sync(FULLW, margin, r);
+                const unsigned long long p_r = __shfl_sync(FULLW, (unsigned long long)hbuf, r);
+                __syncwarp();
+                int nc; float nt;
+                compact_row<TCP_HCAP>(reinterpret_cast<uint2 *>(p_r), n_r, a.k, m_r, lane, nc, nt);
+                if (lane == r) {
+                    cnt = nc;
+                    thr = fminf(thr, nt);
+                    if (nc > TCP_HCAP - 32) { ovf = true; cnt = 0; thr = -CUDART_INF_F; }
+                    wp = reinterpret_cast<unsigned long long>(hbuf + cnt);
+                }
+            }
         }
 
-        if (active) {
-            a.cand_cnt[srow] = ovf ? 0 : cnt;
-            a.overflow[(size_t)b * a.N + a.perm[srow]] = (ovf || cnt < a.k) ? 1 : 0;
+        // the row's two halves meet through shared memory: both must be done before the totals are written
+        s_cnt[hf * TC_BM + row] = ovf ? -1 : cnt;
+        named_bar_sync(5, 256);
+        if (active && hf == 0) {
+            const int c0 = s_cnt[row], c1 = s_cnt[TC_BM + row];
+            const bool bad = c0 < 0 || c1 < 0 || c0 + c1 < a.k;
+            a.cand_cnt[2 * srow] = bad ? 0 : c0;
+            a.cand_cnt[2 * srow + 1] = bad ? 0 : c1;
+            a.overflow[(size_t)b * a.N + a.perm[srow]] = bad ? 1 : 0;
         }
     }
 
@@ -1444,6 +1556,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += 2 * align_up(bn * sizeof(int));                                  // perm, inv
     t += align_up((size_t)B * ceil_div(N, TC_BN) * 6 * sizeof(float));    // tile boxes
     t += align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));          // visited-tile statistics
+    t += 2 * align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));      // launch order of the query tiles + its sort keys
     t += align_up(bn * sizeof(int)) + align_up((size_t)B * sizeof(int));  // fallback row list + counts
     t += align_up(bn * 2 * C * sizeof(__nv_bfloat16));   // xs
     t += align_up(bn * C * sizeof(float));               // x_nc
@@ -1451,7 +1564,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += align_up((size_t)B * (ceil_div(N, TC_BN) * TC_BN) * sizeof(float));   // norm_pad
     t += align_up((size_t)B * sizeof(float));            // nmax
     t += align_up(bn * TC_CAP * sizeof(uint2));          // cand
-    t += align_up(bn * sizeof(int));                     // cand_cnt
+    t += align_up(2 * bn * sizeof(int));                 // cand_cnt (two halves per row on the pruned path)
     t += align_up(bn * sizeof(int));                     // overflow
     return t;
 }
@@ -1488,11 +1601,11 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int STAGES = tcp_stages(C);
     const size_t smem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)STAGES * NBLK * TC_BN * 128 +
-                        TCP_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t) + (size_t)sa.P * 8;
+                        TCP_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t) + 6 * TC_BM * sizeof(float) + (size_t)sa.P * 8;
     auto kern = knn_tcp_scan_kernel<C>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ceil_div(sa.N, TC_BM), B);
-    kern<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
+    dim3 grid(ceil_div(sa.N, TC_BM) * B);
+    kern<<<grid, TCP_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
     GCANET_LAUNCH_OK("knn_tcp_scan_kernel");
     dim3 rgrid(ceil_div(sa.N, 8), B);
     knn_tc_rerank_kernel<C><<<rgrid, 256, 0, st>>>(ra);
@@ -1538,6 +1651,8 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     int *inv = cv.take<int>(bn);
     float *boxes = cv.take<float>((size_t)B * ceil_div(N, TC_BN) * 6);
     int *visited = cv.take<int>((size_t)B * ceil_div(N, TC_BM));
+    int *work_buf = cv.take<int>((size_t)B * ceil_div(N, TC_BM));
+    unsigned *wkey = cv.take<unsigned>((size_t)B * ceil_div(N, TC_BM));
     int *fb_list = cv.take<int>(bn);
     int *fb_count = cv.take<int>(B);
     GCANET_CUDA_OK(cudaMemsetAsync(fb_count, 0, B * sizeof(int), st));
@@ -1550,7 +1665,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     float *norm_pad = cv.take<float>((size_t)B * Npad);
     float *nmax = cv.take<float>(B);
     uint2 *cand = cv.take<uint2>(bn * TC_CAP);
-    int *cand_cnt = cv.take<int>(bn);
+    int *cand_cnt = cv.take<int>(2 * bn);
     int *overflow = cv.take<int>(bn);
 
     int rc = launch_sqnorm_public(x, norm, B, C, C, N, st);
@@ -1564,7 +1679,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         count_launch();
         GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
         tcp_tiles_kernel<<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes,
-                                                                      reinterpret_cast<unsigned *>(nmax), B, N, Npad, tiles);
+                                                                      reinterpret_cast<unsigned *>(nmax), wkey, B, N, Npad, tiles);
         GCANET_LAUNCH_OK("tcp_tiles_kernel");
     }
     {
@@ -1601,9 +1716,16 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         if (const char *e = getenv("GCANET_TC_PRE")) pre = atoi(e);          // measurement aid
         if (pre > tiles) pre = tiles;
         if (pre < 0) pre = 0;
-        TcpScanArgs sa{norm_pad, Npad, nmax, boxes, perm, cand, cand_cnt, overflow, visited, N, k2, tiles, pre, P};
+        const int qtiles = ceil_div(N, TC_BM);
+        const int *work = nullptr;
+        if (B * qtiles <= TCP_MAX_WORK && !getenv("GCANET_TC_NO_ORDER")) {
+            tcp_work_order_kernel<<<ceil_div(B * qtiles, 8), 256, 0, st>>>(wkey, work_buf, B * qtiles);
+            GCANET_LAUNCH_OK("tcp_work_order_kernel");
+            work = work_buf;
+        }
+        TcpScanArgs sa{norm_pad, Npad, nmax, boxes, perm, cand, cand_cnt, overflow, visited, work, N, k2, tiles, pre, P, qtiles};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
-                      (unordered && k1 == k2) ? 1 : 0, perm, fb_list, fb_count};
+                      (unordered && k1 == k2) ? 1 : 0, perm, 1, fb_list, fb_count};
         rc = C == 64 ? launch_tcp<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128>(tmap_q, tmap_k, sa, ra, B, st);
         if (rc) return rc;
         const char *stats = getenv("GCANET_TC_STATS");
@@ -1618,6 +1740,18 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
             fprintf(stderr, "[gcanet] pruned kNN C=%d: %.1f of %d key tiles visited per query tile (min %d, median %d, p90 %d, p99 %d, max %d)\n",
                     C, s / nq, tiles, h[0], h[nq / 2], h[nq * 9 / 10], h[nq * 99 / 100], h[nq - 1]);
             free(h);
+            int *hc2 = (int *)malloc(2 * bn * sizeof(int)), *hc = (int *)malloc(bn * sizeof(int)), *ho = (int *)malloc(bn * sizeof(int));
+            GCANET_CUDA_OK(cudaMemcpy(hc2, cand_cnt, 2 * bn * sizeof(int), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < bn; ++i) hc[i] = hc2[2 * i] + hc2[2 * i + 1];
+            free(hc2);
+            GCANET_CUDA_OK(cudaMemcpy(ho, overflow, bn * sizeof(int), cudaMemcpyDeviceToHost));
+            double sc = 0;
+            long no = 0, nz = 0, big = 0;
+            int mxc = 0;
+            for (size_t i = 0; i < bn; ++i) { sc += hc[i]; no += ho[i]; nz += hc[i] == 0; big += hc[i] > 160; if (hc[i] > mxc) mxc = hc[i]; }
+            fprintf(stderr, "[gcanet]   candidates per row: mean %.1f, max %d, rows > 160: %ld, rows with 0: %ld, overflow rows: %ld of %zu\n",
+                    sc / bn, mxc, big, nz, no, bn);
+            free(hc); free(ho);
         }
         return knn_fallback_rows(x, norm, fb_list, fb_count, B, C, N, k1, k2, idx64, idx32, st);
     }
@@ -1631,7 +1765,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     const int dbg_mode = (dbg && dbg[0] >= '1' && dbg[0] <= '3') ? dbg[0] - '0' : 0;
     TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, dbg_mode, stride};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
-                  (unordered && k1 == k2) ? 1 : 0, nullptr, fb_list, fb_count};
+                  (unordered && k1 == k2) ? 1 : 0, nullptr, 0, fb_list, fb_count};
     if (dbg_mode >= 2 && C == 64)
         rc = dbg_mode == 2 ? launch_tc<64, 2>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<64, 3>(tmap_q, tmap_k, sa, ra, B, st);
     else
