@@ -473,6 +473,8 @@ struct BwdArgs {
     int *deg;          // [B][N]
     int N, Cout, k, G;
     float slope;
+    const float *x_nc; // [B][N][LDX]  small-C variant only
+    float *xt;         // [B][N][LDX]  small-C variant only: sum of x_i over the in-edges (i -> j)
 };
 
 template <int VEC>
@@ -616,6 +618,96 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_kernel(BwdArgs 
     }
 }
 
+// Small-C variant (LDX = 4 / 8: layer 1, xyz or xyz + normals) of the scatter pass.  The dense term of dP_j, the sum
+// over in-edges of A_g + K_g Q_i, is linear in x_i (Q_i = Wq x_i): only X~_j = sum_{i->j} x_i (LDX floats per edge
+// instead of Cout) and deg_j are scattered, and  deg_j A_g + K_g Wq X~_j  is added per point by
+// edge_bwd_degfix_small_kernel.  The sparse term [k = k*] s_i is one scalar atomic per (point, channel).
+// (The forward gather does not get the analogous treatment: rebuilding P_j = W1 x_j per edge costs more issue
+// slots than the L2 traffic it saves -- measured 0.34 ms against 0.28 ms.)
+template <int VEC, int LDX>
+__global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_small_kernel(BwdArgs a) {
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cout = a.Cout, k = a.k, c0 = lane * VEC;
+    const int cpg = Cout / a.G;
+    const int g = c0 / cpg;
+    const float mean = a.stats[((size_t)b * a.G + g) * 2 + 0], rstd = a.stats[((size_t)b * a.G + g) * 2 + 1];
+    const float Ag = a.coef[((size_t)b * a.G + g) * 2 + 0], Kg = a.coef[((size_t)b * a.G + g) * 2 + 1];
+    float gm[VEC], bt[VEC];
+    VecIO<VEC>::ld(a.gamma + c0, gm);
+    VecIO<VEC>::ld(a.beta + c0, bt);
+    float *dpq = a.dpq + (size_t)b * a.N * 2 * Cout;
+    const float *xb = a.x_nc + (size_t)b * a.N * LDX;
+    float *xt = a.xt + (size_t)b * a.N * LDX;
+    for (int pi = 0; pi < kPtsPerWarp; ++pi) {
+        const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
+        if (i >= a.N) break;
+        const size_t o = ((size_t)b * a.N + i) * Cout + c0;
+        float ys[VEC], gg[VEC], ysum[VEC], s[VEC], dq[VEC];
+        VecIO<VEC>::ld(a.ysel + o, ys);
+        VecIO<VEC>::ld(a.gout + o, gg);
+        VecIO<VEC>::ld(a.ysum + o, ysum);
+        const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int ak = a.arg[o + v];
+            float yh = (ys[v] - mean) * rstd;
+            float u = yh * gm[v] + bt[v];
+            float du = u > 0.f ? gg[v] : gg[v] * a.slope;
+            s[v] = rstd * gm[v] * du;
+            dq[v] = s[v] + (float)k * Ag + Kg * ysum[v];
+            atomicAdd(dpq + (size_t)ip[ak] * 2 * Cout + c0 + v, s[v]);
+        }
+        VecIO<VEC>::st(dpq + (size_t)i * 2 * Cout + Cout + c0, dq);
+        float xi[LDX];
+#pragma unroll
+        for (int c4 = 0; c4 < LDX / 4; ++c4) VecIO<4>::ld(xb + (size_t)i * LDX + c4 * 4, xi + c4 * 4);
+        for (int base = 0; base < k; base += 32) {
+            if (base + lane < k) {
+                const int j = ip[base + lane];
+                atomicAdd(a.deg + (size_t)b * a.N + j, 1);
+#pragma unroll
+                for (int c4 = 0; c4 < LDX / 4; ++c4) VecIO<4>::red(xt + (size_t)j * LDX + c4 * 4, xi + c4 * 4);
+            }
+        }
+    }
+}
+
+// dP[j][c] += deg_j (A_g + K_g P[j][c]) + K_g sum_c' Wq[c'][c] X~_j[c'],  Wq[c'][c] = wcatT[Cout + c][c']
+template <int LDX>
+__global__ void edge_bwd_degfix_small_kernel(float *__restrict__ dpq, const float *__restrict__ pq, const int *__restrict__ deg,
+                                             const float *__restrict__ coef, const float *__restrict__ xt,
+                                             const float *__restrict__ wcatT, int N, int Cout, int G, long long total4) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total4) return;
+    const int c4 = Cout / 4;
+    long long bn = t / c4;
+    int c = (int)(t % c4) * 4;
+    int b = (int)(bn / N);
+    const float Ag = coef[((size_t)b * G + c / (Cout / G)) * 2 + 0], Kg = coef[((size_t)b * G + c / (Cout / G)) * 2 + 1];
+    const float dg = (float)deg[bn];
+    float x[LDX];
+#pragma unroll
+    for (int q4 = 0; q4 < LDX / 4; ++q4) {
+        float4 v = *reinterpret_cast<const float4 *>(xt + bn * LDX + q4 * 4);
+        x[q4 * 4] = v.x; x[q4 * 4 + 1] = v.y; x[q4 * 4 + 2] = v.z; x[q4 * 4 + 3] = v.w;
+    }
+    float4 p = *reinterpret_cast<const float4 *>(pq + bn * 2 * Cout + c);
+    float4 *o = reinterpret_cast<float4 *>(dpq + bn * 2 * Cout + c);
+    float4 v = *o;
+    const float pv[4] = {p.x, p.y, p.z, p.w};
+    float out[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float *wq = wcatT + (size_t)(Cout + c + e) * LDX;
+        float qs = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < LDX; ++cc) qs = fmaf(wq[cc], x[cc], qs);
+        out[e] += dg * fmaf(Kg, pv[e], Ag) + Kg * qs;
+    }
+    *o = make_float4(out[0], out[1], out[2], out[3]);
+}
+
 // dP[j][c] += deg_j * K_g * P[j][c]
 __global__ void edge_bwd_degfix_kernel(float *__restrict__ dpq, const float *__restrict__ pq, const int *__restrict__ deg,
                                        const float *__restrict__ coef, int N, int Cout, int G, long long total4) {
@@ -669,7 +761,7 @@ static size_t plan_fwd(const gcanet_edgeconv_desc *d, void *base, FwdWs *w) {
 }
 
 struct BwdWs {
-    float *wcatT, *dpq, *part, *coef, *dwcat, *dwpart;
+    float *wcatT, *dpq, *part, *coef, *dwcat, *dwpart, *xt;
     int *deg;
     double *sbc;
 };
@@ -687,7 +779,8 @@ static size_t plan_bwd(const gcanet_edgeconv_desc *d, void *base, BwdWs *w) {
     float *coef = cv.take<float>((size_t)d->B * d->groups * 2);
     float *dwcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
     float *dwpart = cv.take<float>((size_t)tn_splits(M, 2 * d->Cout, d->ldx) * d->ldx * 2 * d->Cout);
-    if (w) { w->wcatT = wcatT; w->dpq = dpq; w->deg = deg; w->part = part; w->sbc = sbc; w->coef = coef; w->dwcat = dwcat; w->dwpart = dwpart; }
+    float *xt = cv.take<float>(d->ldx <= 8 ? bn * d->ldx : 0);
+    if (w) { w->xt = xt; w->wcatT = wcatT; w->dpq = dpq; w->deg = deg; w->part = part; w->sbc = sbc; w->coef = coef; w->dwcat = dwcat; w->dwpart = dwpart; }
     return cv.off;
 }
 
@@ -742,8 +835,10 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     GCANET_CUDA_OK(cudaMemsetAsync(w.dpq, 0, bn * 2 * Cout * sizeof(float), st));
     GCANET_CUDA_OK(cudaMemsetAsync(w.deg, 0, bn * sizeof(int), st));
 
+    const bool small = d->ldx == 4 || d->ldx == 8;
+    if (small) GCANET_CUDA_OK(cudaMemsetAsync(w.xt, 0, bn * d->ldx * sizeof(float), st));
     BwdArgs ba{sv.pq, sv.ysel, sv.ysum, sv.stats, gamma, beta, gout, sv.arg, idx, w.part, w.coef, w.dpq, w.deg,
-               d->N, Cout, d->k, d->groups, d->slope};
+               d->N, Cout, d->k, d->groups, d->slope, x_nc, w.xt};
     edge_bwd_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
     GCANET_LAUNCH_OK("edge_bwd_reduce_kernel");
     double count = (double)(Cout / d->groups) * d->N * d->k;
@@ -752,12 +847,25 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     GCANET_LAUNCH_OK("edge_bwd_coef_kernel");
     edge_bwd_affine_kernel<<<ceil_div(Cout, 128), 128, 0, st>>>(w.sbc, grad_gamma, grad_beta, d->B, Cout);
     GCANET_LAUNCH_OK("edge_bwd_affine_kernel");
-    edge_bwd_scatter_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
-    GCANET_LAUNCH_OK("edge_bwd_scatter_kernel");
     long long total4 = (long long)bn * (Cout / 4);
-    edge_bwd_degfix_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, d->N, Cout,
-                                                                            d->groups, total4);
-    GCANET_LAUNCH_OK("edge_bwd_degfix_kernel");
+    if (small) {
+        if (d->ldx == 4) edge_bwd_scatter_small_kernel<VEC, 4><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
+        else edge_bwd_scatter_small_kernel<VEC, 8><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
+        GCANET_LAUNCH_OK("edge_bwd_scatter_small_kernel");
+        if (d->ldx == 4)
+            edge_bwd_degfix_small_kernel<4><<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, w.xt, w.wcatT,
+                                                                                           d->N, Cout, d->groups, total4);
+        else
+            edge_bwd_degfix_small_kernel<8><<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, w.xt, w.wcatT,
+                                                                                           d->N, Cout, d->groups, total4);
+        GCANET_LAUNCH_OK("edge_bwd_degfix_small_kernel");
+    } else {
+        edge_bwd_scatter_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
+        GCANET_LAUNCH_OK("edge_bwd_scatter_kernel");
+        edge_bwd_degfix_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, d->N, Cout,
+                                                                                d->groups, total4);
+        GCANET_LAUNCH_OK("edge_bwd_degfix_kernel");
+    }
     // dWcat[ldx][2Cout] = X^T dPQ ; dW from it
     int rc = launch_sgemm_tn(x_nc, w.dpq, w.dwcat, w.dwpart, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, st);
     if (rc) return rc;
