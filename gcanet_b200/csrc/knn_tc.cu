@@ -592,7 +592,7 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
         if (e < n) {
             uint2 t = cand[e < n0 ? e : e - n0 + TC_CAP / 2];      // second half-list starts at TC_CAP / 2 (n0 = n: one list)
             ad[s] = __uint_as_float(t.x);
-            aj[s] = perm ? perm[t.y] : (int)t.y;
+            aj[s] = (int)t.y;                                       // scan-order id; mapped through perm only if it survives
         }
     }
     float keep_below = CUDART_INF_F, sure_below = -CUDART_INF_F;
@@ -610,11 +610,14 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
         const bool keep = valid && !sure && ad[s] <= keep_below;
         const unsigned msk = __ballot_sync(FULLW, keep);
         const unsigned ssk = __ballot_sync(FULLW, sure);
-        if (keep) sl[m + __popc(msk & ((1u << lane) - 1))] = aj[s];
-        if (sure) {
-            const size_t o = grow * a.kout + n_sure + __popc(ssk & ((1u << lane) - 1));
-            if (a.idx64) a.idx64[o] = aj[s];
-            if (a.idx32) a.idx32[o] = aj[s];
+        if (keep || sure) {
+            const int jo = perm ? perm[aj[s]] : aj[s];              // original point index
+            if (keep) sl[m + __popc(msk & ((1u << lane) - 1))] = jo;
+            else {
+                const size_t o = grow * a.kout + n_sure + __popc(ssk & ((1u << lane) - 1));
+                if (a.idx64) a.idx64[o] = jo;
+                if (a.idx32) a.idx32[o] = jo;
+            }
         }
         m += __popc(msk);
         n_sure += __popc(ssk);
@@ -739,9 +742,9 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
 // no pruning); how well they capture the variance only decides how much is skipped.
 // ---------------------------------------------------------------------------------
 constexpr int TCP_MIN_N = 1024;
-constexpr int TCP_SPLIT = 20;         // partial Gram matrices per cloud
+constexpr int TCP_SPLIT = 8;          // partial Gram matrices per cloud
 constexpr int TCP_PRE = 8;            // tiles of the threshold pre-pass
-constexpr int TCP_ITERS = 8;          // subspace iterations
+constexpr int TCP_ITERS = 5;          // subspace iterations (lambda_3 / lambda_4 is ~4 on layer activations: 4^5 = 1000x)
 constexpr uint32_t TCP_END = 0xffffffffu;
 constexpr int TCP_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int TCP_HCAP = TC_CAP / 2;  // each of a row's two epilogue threads owns half of its candidate list
@@ -880,16 +883,17 @@ __global__ void __launch_bounds__(256) tcp_pca_kernel(const float *__restrict__ 
         orthonormalize();
     }
     // validity: V must be orthonormal for the bound to hold; anything else (degenerate cloud, NaN input) -> no pruning
-    if (tid == 0) {
+    if (tid < 32) {
         bool ok = true;
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j <= i; ++j) {
                 float d = 0.f;
-                for (int c = 0; c < C; ++c) d = fmaf(V[i * C + c], V[j * C + c], d);
+                for (int c = lane; c < C; c += 32) d = fmaf(V[i * C + c], V[j * C + c], d);
+                for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(FULLW, d, o);
                 const float want = i == j ? 1.f : 0.f;
                 if (!(fabsf(d - want) <= 1e-4f)) ok = false;
             }
-        s_ok = ok ? 1 : 0;
+        if (lane == 0) s_ok = ok ? 1 : 0;
     }
     __syncthreads();
     float *o = pca + (size_t)b * (3 * C + 4);
@@ -1536,7 +1540,9 @@ static int tcp_cloud_bits(int B) {
 }
 // Morton bits per axis so that (cloud | code) fits a 32-bit radix key
 static int tcp_axis_bits(int B) {
-    int bits = (32 - tcp_cloud_bits(B)) / 3;
+    // 24 key bits = three 8-bit radix passes; 6 bits per axis (262 144 cells) at B = 16 is far finer than a 64-point tile
+    int bits = (24 - tcp_cloud_bits(B)) / 3;
+    if (bits < 5) bits = (32 - tcp_cloud_bits(B)) / 3;      // many clouds: spend a fourth pass rather than coarsen the cells
     return bits > 10 ? 10 : bits;
 }
 static bool tcp_supported(int B, int N, int k2) {
