@@ -88,6 +88,50 @@ __device__ __noinline__ void drop_largest(float *ld, int *li, int n, int k, int 
     }
 }
 
+// Set-only finish for n > k entries: bisection on the distance until exactly k entries lie at or below the bound
+// (the usual case: one pass of compaction and no ranking at all); if ties at the k-th distance make that impossible
+// the tie group is trimmed by (distance, index) with drop_largest.  Leaves the k smallest in slots [0, k).
+template <int SL>
+__device__ __noinline__ void select_k_unordered(float *ld, int *li, int n, int k, int lane) {
+    float dv[SL];
+    int di[SL];
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        const int e = s * 32 + lane;
+        dv[s] = CUDART_INF_F;
+        di[s] = 0x7fffffff;
+        if (e < n) { dv[s] = ld[e]; di[s] = li[e]; mn = fminf(mn, dv[s]); mx = fmaxf(mx, dv[s]); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    }
+    float lo = mn, hi = mx;
+    int c_hi = n;
+    for (int it = 0; it < 48 && c_hi > k; ++it) {
+        const float mid = 0.5f * lo + 0.5f * hi;
+        if (!(mid > lo && mid < hi)) break;            // interval exhausted: ties at hi
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < SL; ++s) c += (dv[s] <= mid) ? 1 : 0;
+        c = __reduce_add_sync(FULL, c);
+        if (c >= k) { hi = mid; c_hi = c; } else { lo = mid; }
+    }
+    __syncwarp();
+    int base = 0;
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        const bool keep = dv[s] <= hi && s * 32 + lane < n;
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) { const int p = base + __popc(m & ((1u << lane) - 1)); ld[p] = dv[s]; li[p] = di[s]; }
+        base += __popc(m);
+    }
+    __syncwarp();
+    if (base > k) drop_largest<SL>(ld, li, base, k, lane);
+}
+
 // Shrinks a list of n > k entries to those with d <= bound, where count(d <= bound) >= k and,
 // ties permitting, <= k + kSlack (bisection on the values).  If ties would keep more than
 // `limit` entries the list is cut to exactly the k smallest by (distance, index) instead.

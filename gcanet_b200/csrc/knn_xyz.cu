@@ -294,9 +294,12 @@ __global__ void __launch_bounds__(XW * 32) knn_xyz_kernel(XyzArgs a) {
         int n = cnt[r];
         float *ld = my_ld + r * CAP;
         int *li = my_li + r * CAP;
-        if (n > a.k + kSlack) n = shrink_list<SL>(ld, li, n, a.k, CAP, lane, t);
-        if (a.unordered && n <= a.k + kSlack) drop_largest<SL>(ld, li, n, a.k, lane);   // k best, any order
-        else rank_cut<SL>(ld, li, n, a.k, lane);                                          // k best, in order
+        if (a.unordered) {
+            if (n > a.k) select_k_unordered<SL>(ld, li, n, a.k, lane);                    // k best, any order
+        } else {
+            if (n > a.k + kSlack) n = shrink_list<SL>(ld, li, n, a.k, CAP, lane, t);
+            rank_cut<SL>(ld, li, n, a.k, lane);                                           // k best, in order
+        }
     });
     __syncwarp();
 #pragma unroll
