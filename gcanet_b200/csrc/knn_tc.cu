@@ -958,7 +958,8 @@ __global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restric
 __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ sorted_vals, const float *__restrict__ norm,
                                                         const float *__restrict__ proj, int *__restrict__ perm,
                                                         int *__restrict__ inv, float *__restrict__ norm_pad,
-                                                        float *__restrict__ boxes, unsigned *__restrict__ nmax_bits,
+                                                        float *__restrict__ boxes, float *__restrict__ boxes32,
+                                                        unsigned *__restrict__ nmax_bits,
                                                         unsigned *__restrict__ wkey, int B, int N, int Npad, int tiles) {
     __shared__ float s_box[8][6];
     const int b = blockIdx.y;
@@ -970,6 +971,7 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
 #pragma unroll
     for (int h = 0; h < TC_BN / 32; ++h) {
         const int s = t * TC_BN + h * 32 + lane;
+        float hmn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hmx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
         if (s < N) {
             const int o = sorted_vals[(size_t)b * N + s];
             perm[(size_t)b * N + s] = o;
@@ -980,19 +982,27 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const float p = proj[(size_t)i * B * N + (size_t)b * N + o];
-                mn[i] = fminf(mn[i], p);
-                mx[i] = fmaxf(mx[i], p);
+                hmn[i] = p;
+                hmx[i] = p;
             }
         } else if (s < Npad) {
             norm_pad[(size_t)b * Npad + s] = CUDART_INF_F;
         }
-    }
+        // box of this 32-point half (the rows one epilogue warp of the scan owns), then merged into the tile's box
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-        for (int o = 16; o; o >>= 1) {
-            mn[i] = fminf(mn[i], __shfl_xor_sync(FULLW, mn[i], o));
-            mx[i] = fmaxf(mx[i], __shfl_xor_sync(FULLW, mx[i], o));
+        for (int i = 0; i < 3; ++i) {
+            for (int o = 16; o; o >>= 1) {
+                hmn[i] = fminf(hmn[i], __shfl_xor_sync(FULLW, hmn[i], o));
+                hmx[i] = fmaxf(hmx[i], __shfl_xor_sync(FULLW, hmx[i], o));
+            }
+            mn[i] = fminf(mn[i], hmn[i]);
+            mx[i] = fmaxf(mx[i], hmx[i]);
         }
+        if (lane == 0) {
+            float *hb = boxes32 + ((size_t)b * tiles * 2 + t * 2 + h) * 6;
+            hb[0] = hmn[0]; hb[1] = hmn[1]; hb[2] = hmn[2]; hb[3] = hmx[0]; hb[4] = hmx[1]; hb[5] = hmx[2];
+        }
+    }
     for (int o = 16; o; o >>= 1) nm = fmaxf(nm, __shfl_xor_sync(FULLW, nm, o));
     if (lane == 0) {
         atomicMax(nmax_bits + b, __float_as_uint(nm));       // norms are >= 0: the bit patterns order like the values
@@ -1039,6 +1049,7 @@ struct TcpScanArgs {
     int Npad;
     const float *nmax;      // [B]
     const float *boxes;     // [B][tiles][6]
+    const float *boxes32;   // [B][2 * tiles][6] boxes of the 32-point halves (= the rows of one epilogue warp)
     const int *perm;        // [B][N] sorted position -> original index
     uint2 *cand;            // [B][N][TC_CAP]  rows in sorted order, key ids are sorted positions
     int *cand_cnt;          // [B][N]          rows in sorted order
@@ -1103,7 +1114,8 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     int *s_cnt = reinterpret_cast<int *>(const_cast<float *>(s_wthr) + 8);      // [2][128] final half-list counts (-1 = overflowed)
     int *s_ovf = s_cnt + TC_BM;                                                   //   (second half of s_cnt)
     volatile float *s_xf = reinterpret_cast<volatile float *>(s_ovf + TC_BM);     // [2][2][128] pair exchange (double-buffered)
-    // [P] (bf16-truncated lower bound << 16) | tile, ascending; 8 bytes per entry while it is being sorted
+    // [P] (bf16-truncated lower bound << 16) | tile, ascending; 8 bytes per entry while it is being sorted;
+    // followed by [4][P] bf16-truncated lower bounds of the same tiles against each 32-row group of the query tile
     uint32_t *s_ord = reinterpret_cast<uint32_t *>(smem + ((reinterpret_cast<uint8_t *>(const_cast<float *>(s_xf) + 4 * TC_BM) - smem + 7) & ~(size_t)7));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1215,6 +1227,30 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         }
     }
+    // ---- the same bound per 32-row group: an epilogue warp skips the tiles none of ITS rows can use
+    uint16_t *s_lbw = reinterpret_cast<uint16_t *>(s_ord + 2 * a.P);
+    {
+        const float *bx = a.boxes + (size_t)b * tiles * 6;
+        const float slack = 2e-5f * sqrtf(a.nmax[b]);
+        for (int e = threadIdx.x; e < 4 * tiles; e += TCP_THREADS) {
+            const int g = e / tiles, i = e - g * tiles;
+            const int t = (int)(s_ord[i] & 0xffffu);
+            float lb = 0.f;
+            if (q0 + g * 32 < a.N) {
+                const float *qb = a.boxes32 + ((size_t)b * tiles * 2 + (q0 >> 5) + g) * 6;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float gp = fmaxf(qb[c] - bx[t * 6 + 3 + c], bx[t * 6 + c] - qb[3 + c]);
+                    gp = fmaxf(gp - slack, 0.f);
+                    lb = fmaf(gp, gp, lb);
+                }
+                lb *= 0.999f;
+                if (!(lb >= 0.f)) lb = 0.f;
+                lb = fminf(lb, 3.0e38f);
+            }
+            s_lbw[g * a.P + i] = (uint16_t)(__float_as_uint(lb) >> 16);      // truncation rounds the bound DOWN
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1234,7 +1270,10 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             for (int pass = 0; pass < 2; ++pass) {
                 for (int i = 0; i < tiles; ++i) {
                     const uint32_t e = s_ord[i];
-                    if (pass == 1 || i >= pre) {
+                    // pass B re-reads the `pre` nearest tiles whatever the bounds turn out to be, so they are
+                    // requested while the epilogue is still finishing pass A; only then wait for its final bounds
+                    if (pass == 1 && i == pre) mbar_wait_backoff(thr_ready, 0);
+                    if (i >= pre) {
                         // thresholds only ever decrease: a stale (larger) value is safe
                         const float thr = fmaxf(fmaxf(fmaxf(s_wthr[0], s_wthr[1]), fmaxf(s_wthr[2], s_wthr[3])),
                                                 fmaxf(fmaxf(s_wthr[4], s_wthr[5]), fmaxf(s_wthr[6], s_wthr[7])));
@@ -1258,7 +1297,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 mbar_arrive(&full[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 ++seq;
-                if (pass == 0) mbar_wait_backoff(thr_ready, 0);      // pass B prunes with the final thresholds
+                if (pass == 1 && tiles <= pre) mbar_wait_backoff(thr_ready, 0);   // (not yet waited for above)
             }
             if (a.visited) a.visited[(size_t)b * a.qtiles + qt] = nvis;
         }
@@ -1325,6 +1364,8 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         int seq = 0, acc = 0;
         uint32_t accphase = 0;
         int xbuf = 0;                                         // exchange buffer parity (same sequence in both threads of a row)
+        const uint16_t *lbw = s_lbw + lg * a.P;               // this warp's lower bound of the i-th tile of the order
+        float wbound = CUDART_INF_F;                          // largest true-distance bound among this warp's rows
         const int pair_bar = 1 + lg;                          // named barrier shared by the two warps of a lane quarter
 
         // the two threads of a row combine a value (sum for counts, min / max for ranges) through shared memory
@@ -1375,18 +1416,22 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 mbar_wait(&t_full[acc], accphase);
                 if (seq == s_end[0]) break;
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_BN + hf * 32;
-                uint32_t v[32];
-                tmem_ld32(taddr, v);
-                tmem_ld_wait();
-                const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + hf * 32);
+                // a tile whose bound against this warp's 32 rows exceeds all their current bounds holds no key that
+                // could lower any of them: its slot minima are not needed (the final bound is the same without them)
+                if (__uint_as_float((uint32_t)lbw[seq] << 16) <= wbound) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_BN + hf * 32;
+                    uint32_t v[32];
+                    tmem_ld32(taddr, v);
+                    tmem_ld_wait();
+                    const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + hf * 32);
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 n4 = rn[c4];
-                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 n4 = rn[c4];
+                        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        m[c4 * 4 + e] = fminf(m[c4 * 4 + e], fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]));
+                        for (int e = 0; e < 4; ++e)
+                            m[c4 * 4 + e] = fminf(m[c4 * 4 + e], fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1399,6 +1444,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     float wt = active ? bd + margin + qn : -CUDART_INF_F;
                     for (int o = 16; o; o >>= 1) wt = fmaxf(wt, __shfl_xor_sync(FULLW, wt, o));
                     if (lane == 0) s_wthr[ewi] = wt;
+                    wbound = wt;
                 }
             }
             // end marker of pass A: final thresholds (bit-identical in the two threads of a row)
@@ -1414,6 +1460,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
             if (++acc == ACC) { acc = 0; accphase ^= 1; }
             ++seq;
+            wbound = wt;
         }
 
         // ---- pass B: same order again, every key below the row's threshold becomes a candidate.  Each thread owns
@@ -1431,6 +1478,14 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_wait(&t_full[acc], accphase);
             if (seq == s_end[1]) break;
             tc_fence_after();
+            if (__uint_as_float((uint32_t)lbw[i] << 16) > wbound) {
+                // no row of this warp can have a candidate in the tile: only keep the pipeline moving
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[acc]);
+                if (++acc == ACC) { acc = 0; accphase ^= 1; }
+                continue;
+            }
             const int kt = (int)(s_ord[i] & 0xffffu);
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_BN + hf * 32;
             uint32_t v[32];
@@ -1560,7 +1615,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += 2 * align_up(bn * sizeof(int));                                  // vals in/out
     t += align_up(tcp_cub_temp_bytes(bn, 32));                            // cub temp
     t += 2 * align_up(bn * sizeof(int));                                  // perm, inv
-    t += align_up((size_t)B * ceil_div(N, TC_BN) * 6 * sizeof(float));    // tile boxes
+    t += 3 * align_up((size_t)B * ceil_div(N, TC_BN) * 6 * sizeof(float));   // tile boxes + boxes of their 32-point halves
     t += align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));          // visited-tile statistics
     t += 2 * align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));      // launch order of the query tiles + its sort keys
     t += align_up(bn * sizeof(int)) + align_up((size_t)B * sizeof(int));  // fallback row list + counts
@@ -1607,7 +1662,7 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int STAGES = tcp_stages(C);
     const size_t smem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)STAGES * NBLK * TC_BN * 128 +
-                        TCP_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t) + 6 * TC_BM * sizeof(float) + (size_t)sa.P * 8;
+                        TCP_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t) + 6 * TC_BM * sizeof(float) + (size_t)sa.P * 16;
     auto kern = knn_tcp_scan_kernel<C>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(sa.N, TC_BM) * B);
@@ -1656,6 +1711,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     int *perm = cv.take<int>(bn);
     int *inv = cv.take<int>(bn);
     float *boxes = cv.take<float>((size_t)B * ceil_div(N, TC_BN) * 6);
+    float *boxes32 = cv.take<float>((size_t)B * ceil_div(N, TC_BN) * 12);
     int *visited = cv.take<int>((size_t)B * ceil_div(N, TC_BM));
     int *work_buf = cv.take<int>((size_t)B * ceil_div(N, TC_BM));
     unsigned *wkey = cv.take<unsigned>((size_t)B * ceil_div(N, TC_BM));
@@ -1684,7 +1740,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
         count_launch();
         GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
-        tcp_tiles_kernel<<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes,
+        tcp_tiles_kernel<<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes, boxes32,
                                                                       reinterpret_cast<unsigned *>(nmax), wkey, B, N, Npad, tiles);
         GCANET_LAUNCH_OK("tcp_tiles_kernel");
     }
@@ -1729,7 +1785,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
             GCANET_LAUNCH_OK("tcp_work_order_kernel");
             work = work_buf;
         }
-        TcpScanArgs sa{norm_pad, Npad, nmax, boxes, perm, cand, cand_cnt, overflow, visited, work, N, k2, tiles, pre, P, qtiles};
+        TcpScanArgs sa{norm_pad, Npad, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, N, k2, tiles, pre, P, qtiles};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                       (unordered && k1 == k2) ? 1 : 0, perm, 1, fb_list, fb_count};
         rc = C == 64 ? launch_tcp<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128>(tmap_q, tmap_k, sa, ra, B, st);
