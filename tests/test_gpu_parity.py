@@ -554,6 +554,28 @@ def test_knn_pruned_path_c128_and_degenerate_clouds():
     assert torch.equal(G.knn_graph(od, 50, 50)[0], G.knn_graph(od, 50, 50, prune=False)[0])
 
 
+@pytest.mark.parametrize("B,N,k", [(1, 1024, 1), (33, 1087, 7), (5, 2048, 64), (2, 6000, 50)])
+def test_knn_pruned_path_shapes_and_ties(B, N, k):
+    """Cloud counts that change the sort-key layout, sizes around the tile boundaries, k = 1 and k = 64 (every
+    column slot needed), and clouds where a third of the points coincide (candidate lists overflow, rows go to
+    the CUDA-core fallback list): always the same lists as the full scan."""
+    x1, _ = _layer_activations(min(B, 3), N, seed=40 + B)
+    x = x1.repeat((B + x1.shape[0] - 1) // x1.shape[0], 1, 1)[:B].clone()
+    x += 0.01 * torch.randn(x.shape, generator=torch.Generator().manual_seed(B))      # clouds differ
+    xd = x.to(DEV)
+    assert torch.equal(G.knn_graph(xd, k, k)[0], G.knn_graph(xd, k, k, prune=False)[0])
+    xt = x.clone()
+    xt[:, :, : N // 3] = xt[:, :, :1]                      # massive exact ties
+    xd = xt.to(DEV)
+    a = G.knn_graph(xd, k, k)[0]
+    b = G.knn_graph(xd, k, k, brute_force=True)[0]
+    # tied points are interchangeable: compare the distance profile, and exact equality away from the ties
+    sc = orc.knn_scores(xt[:1])
+    check_knn_rows(a[:1], b[:1].cpu(), sc, knn_tau(xt[:1]))
+    srt = a.sort(dim=2)[0]
+    assert bool((srt[:, :, 1:] != srt[:, :, :-1]).all())
+
+
 def test_normal_edge_head_golden(golden_dir):
     """conv_normal head (M4:584-587, 691-693) against the fixture made from the reference's
     get_graph_feature_with_normals_g; forward 1e-4, weight gradients 2e-3 relative."""
