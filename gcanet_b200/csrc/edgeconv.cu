@@ -25,6 +25,9 @@
 
 namespace gcanet {
 
+// gemm_tc.cu: C[M][N] = A[M][K] Bt[N][K]^T on the tensor cores; -1 = shape not covered, use the CUDA-core GEMM
+int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K, cudaStream_t st);
+
 constexpr unsigned FULLM = 0xffffffffu;
 constexpr int kGWarps = 8;           // warps per CTA in the per-point kernels
 constexpr int kPtsPerWarp = 4;       // points each warp handles
@@ -747,7 +750,7 @@ static size_t plan_saved(const gcanet_edgeconv_desc *d, void *base, Saved *s) {
 }
 
 struct FwdWs {
-    float *wcat;
+    float *wcat, *wcatT;
     double *part;
 };
 
@@ -755,13 +758,14 @@ static size_t plan_fwd(const gcanet_edgeconv_desc *d, void *base, FwdWs *w) {
     Carver cv(base);
     int nblk = ceil_div(d->N, kPtsPerCta);
     float *wcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
+    float *wcatT = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
     double *part = cv.take<double>((size_t)d->B * nblk * d->groups * 2);
-    if (w) { w->wcat = wcat; w->part = part; }
+    if (w) { w->wcat = wcat; w->wcatT = wcatT; w->part = part; }
     return cv.off;
 }
 
 struct BwdWs {
-    float *wcatT, *dpq, *part, *coef, *dwcat, *dwpart, *xt;
+    float *wcatT, *wcat, *dpq, *part, *coef, *dwcat, *dwpart, *xt;
     int *deg;
     double *sbc;
 };
@@ -780,7 +784,8 @@ static size_t plan_bwd(const gcanet_edgeconv_desc *d, void *base, BwdWs *w) {
     float *dwcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
     float *dwpart = cv.take<float>((size_t)tn_splits(M, 2 * d->Cout, d->ldx) * d->ldx * 2 * d->Cout);
     float *xt = cv.take<float>(d->ldx <= 8 ? bn * d->ldx : 0);
-    if (w) { w->xt = xt; w->wcatT = wcatT; w->dpq = dpq; w->deg = deg; w->part = part; w->sbc = sbc; w->coef = coef; w->dwcat = dwcat; w->dwpart = dwpart; }
+    float *wcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
+    if (w) { w->xt = xt; w->wcat = wcat; w->wcatT = wcatT; w->dpq = dpq; w->deg = deg; w->part = part; w->sbc = sbc; w->coef = coef; w->dwcat = dwcat; w->dwpart = dwpart; }
     return cv.off;
 }
 
@@ -805,9 +810,11 @@ static int run_forward(const gcanet_edgeconv_desc *d, const float *x_nc, const i
                        const FwdWs &w, cudaStream_t st) {
     const int M = d->B * d->N, Cout = d->Cout;
     int total = d->ldx * 2 * Cout;
-    prep_wcat_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, w.wcat, nullptr, d->C, d->ldx, Cout);
+    prep_wcat_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, w.wcat, w.wcatT, d->C, d->ldx, Cout);
     GCANET_LAUNCH_OK("prep_wcat_kernel");
-    int rc = launch_sgemm_nn(x_nc, w.wcat, sv.pq, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, 2 * Cout, st);
+    // [P|Q] = X Wcat: tensor cores (bf16x3 split, fp32-accurate) for the feature layers, CUDA cores for the xyz layer
+    int rc = gemm_tc_try(x_nc, d->ldx, w.wcatT, d->ldx, sv.pq, 2 * Cout, M, 2 * Cout, d->ldx, st);
+    if (rc < 0) rc = launch_sgemm_nn(x_nc, w.wcat, sv.pq, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, 2 * Cout, st);
     if (rc) return rc;
     FwdArgs fa{sv.pq, idx, gamma, sv.ysel, sv.ysum, sv.arg, w.part, d->N, Cout, d->k, d->groups};
     const int nblk = ceil_div(d->N, kPtsPerCta);
@@ -830,7 +837,7 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     const size_t bn = (size_t)M;
     const int nblk = ceil_div(d->N, kPtsPerCta);
     int total = d->ldx * 2 * Cout;
-    prep_wcat_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, nullptr, w.wcatT, d->C, d->ldx, Cout);
+    prep_wcat_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, w.wcat, w.wcatT, d->C, d->ldx, Cout);
     GCANET_LAUNCH_OK("prep_wcat_kernel");
     GCANET_CUDA_OK(cudaMemsetAsync(w.dpq, 0, bn * 2 * Cout * sizeof(float), st));
     GCANET_CUDA_OK(cudaMemsetAsync(w.deg, 0, bn * sizeof(int), st));
@@ -872,7 +879,8 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     unprep_dw_kernel<<<ceil_div(Cout * d->C, 256), 256, 0, st>>>(w.dwcat, grad_weight, d->C, Cout);
     GCANET_LAUNCH_OK("unprep_dw_kernel");
     if (grad_x_nc) {
-        rc = launch_sgemm_nn(w.dpq, w.wcatT, grad_x_nc, M, d->ldx, 2 * Cout, 2 * Cout, d->ldx, d->ldx, st);
+        rc = gemm_tc_try(w.dpq, 2 * Cout, w.wcat, 2 * Cout, grad_x_nc, d->ldx, M, d->ldx, 2 * Cout, st);
+        if (rc < 0) rc = launch_sgemm_nn(w.dpq, w.wcatT, grad_x_nc, M, d->ldx, 2 * Cout, 2 * Cout, d->ldx, d->ldx, st);
         if (rc) return rc;
     }
     return GCANET_OK;

@@ -1,0 +1,227 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores for the EdgeConv projections:
+//   PQ = X Wcat            [M][K] x [K][N],  K = C  (64),      N = 2 Cout (128 / 256)
+//   dX = dPQ Wcat^T        [M][K] x [K][N],  K = 2 Cout,       N = C (64)
+// with M = B * N_points (160 000 rows).  C[M][N] = A[M][K] * Bt[N][K]^T, all fp32 in memory.
+//
+// Both operands are split x = hi + lo (bf16 each) while they are staged into shared memory, and
+// hi*hi + hi*lo + lo*hi is accumulated in fp32 TMEM by tcgen05.mma (error ~2^-16 |a||b| per product, the
+// level of fp32 summation error at these K).  No bf16 copy of the activations ever exists in HBM:
+//   warps 0-3  load fp32 rows of A (coalesced 16-byte loads), split them, and write the two bf16 tiles in the
+//              128-byte-swizzled K-major layout the UMMA descriptors expect (what TMA would have produced)
+//   warp  8    issues the MMAs (one elected thread), accumulators double-buffered in TMEM
+//   warps 4-7  drain the accumulators: one row per thread, 128-byte segments straight to global memory
+// The weight matrix (<= 64 KB as hi|lo bf16) is staged once per CTA; CTAs are persistent over the M tiles.
+// The kernel is memory-bound (reads A once, writes C once), which is the point: the CUDA-core sgemm it
+// replaces ran at ~33 TFLOP/s fp32 and was compute-bound.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+#include <stdlib.h>
+
+namespace gcanet {
+
+constexpr int GT_BM = 128;            // rows per tile (UMMA M)
+constexpr int GT_KB = 64;             // bf16 elements per 128-byte swizzle row = K chunk per pipeline stage
+constexpr int GT_STAGES = 2;          // A stages
+constexpr int GT_THREADS = 288;       // 4 loader warps, 4 epilogue warps, 1 MMA warp
+
+__host__ __device__ constexpr uint32_t tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512))); }
+
+// byte offset of element (row r, column kc < 64) inside a [rows][64] bf16 tile with the 128-byte swizzle:
+// 16-byte chunk index XOR (row mod 8)
+__device__ __forceinline__ uint32_t sw128_offset(int r, int kc) {
+    return (uint32_t)(r * 128 + ((((kc >> 3) ^ (r & 7)) << 4) | ((kc & 7) << 1)));
+}
+
+// four consecutive floats -> four bf16 hi + four bf16 lo, stored as two 8-byte words at (r, kc .. kc+3)
+__device__ __forceinline__ void split_store4(uint8_t *hi_tile, uint8_t *lo_tile, int r, int kc, float4 v) {
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = __float2bfloat16_rn(f[i]);
+        l[i] = __float2bfloat16_rn(f[i] - __bfloat162float(h[i]));
+    }
+    const uint32_t off = sw128_offset(r, kc);
+    uint2 hw, lw;
+    hw.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    hw.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    lw.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+    lw.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2 *>(hi_tile + off) = hw;
+    *reinterpret_cast<uint2 *>(lo_tile + off) = lw;
+}
+
+template <int K, int N>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bt, int ldb, float *__restrict__ C, int ldc, int M) {
+    static_assert(K % GT_KB == 0 && N % 32 == 0 && N <= 256, "unsupported GEMM shape");
+    constexpr int KCH = K / GT_KB;                      // K chunks
+    constexpr int A_TILE = GT_BM * 128;                 // one [128][64] bf16 tile: 16 KB
+    constexpr int A_STAGE = 2 * A_TILE;                 // hi + lo
+    constexpr int B_BLK = N * 128;                      // one [N][64] bf16 block
+    constexpr int B_BYTES = 2 * KCH * B_BLK;            // hi blocks, then lo blocks
+    constexpr uint32_t IDESC = umma_idesc_bf16(GT_BM, N);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *sBm = smem;                                // weights
+    uint8_t *sA = smem + B_BYTES;                       // GT_STAGES x (hi | lo)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + GT_STAGES * A_STAGE);
+    uint64_t *a_full = bars;                            // [STAGES] loaders -> MMA   (128 arrivals)
+    uint64_t *a_empty = bars + GT_STAGES;               // [STAGES] MMA -> loaders
+    uint64_t *t_full = bars + 2 * GT_STAGES;            // [2] MMA -> epilogue
+    uint64_t *t_empty = t_full + 2;                     // [2] epilogue -> MMA       (4 arrivals)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = (M + GT_BM - 1) / GT_BM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, tmem_cols(2 * N));
+    // weights: Bt[n][k] fp32 -> hi / lo bf16 blocks, swizzled (every thread helps; N*K/4 float4 items)
+    for (int e = threadIdx.x; e < N * K / 4; e += GT_THREADS) {
+        const int n = e / (K / 4), k4 = (e % (K / 4)) * 4;
+        const float4 v = *reinterpret_cast<const float4 *>(Bt + (size_t)n * ldb + k4);
+        const int kb = k4 / GT_KB, kc = k4 % GT_KB;
+        split_store4(sBm + kb * B_BLK, sBm + (KCH + kb) * B_BLK, n, kc, v);
+    }
+    fence_proxy_async();                                // generic-proxy writes above are read by the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===================== loaders: fp32 rows -> swizzled bf16 hi / lo tiles =====================
+        const int tid = threadIdx.x;                    // 0..127
+        const int rsub = tid >> 4, c4 = tid & 15;       // 8 rows x 16 float4 per sweep
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m0 = tile * GT_BM;
+            for (int kc = 0; kc < KCH; ++kc) {
+                mbar_wait(&a_empty[stage], phase ^ 1);
+                uint8_t *hi_tile = sA + stage * A_STAGE, *lo_tile = hi_tile + A_TILE;
+                float4 v[16];
+#pragma unroll
+                for (int it = 0; it < 16; ++it) {
+                    const int r = it * 8 + rsub;
+                    v[it] = m0 + r < M ? __ldg(reinterpret_cast<const float4 *>(A + (size_t)(m0 + r) * lda + kc * GT_KB) + c4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int it = 0; it < 16; ++it) split_store4(hi_tile, lo_tile, it * 8 + rsub, c4 * 4, v[it]);
+                fence_proxy_async();
+                mbar_arrive(&a_full[stage]);
+                if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 8) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t b_addr = smem_u32(sBm);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, accphase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait(&t_empty[acc], accphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * N;
+                uint32_t accum = 0;
+                for (int kc = 0; kc < KCH; ++kc) {
+                    mbar_wait(&a_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE);
+#pragma unroll
+                    for (int ks = 0; ks < GT_KB / 16; ++ks) {
+                        const uint32_t koff = ks * 32;
+                        const uint64_t a_hi = make_kmajor_sw128_desc(a_addr + koff);
+                        const uint64_t a_lo = make_kmajor_sw128_desc(a_addr + A_TILE + koff);
+                        const uint64_t b_hi = make_kmajor_sw128_desc(b_addr + kc * B_BLK + koff);
+                        const uint64_t b_lo = make_kmajor_sw128_desc(b_addr + (KCH + kc) * B_BLK + koff);
+                        umma_bf16(d_tmem, a_hi, b_hi, IDESC, accum);
+                        accum = 1;
+                        umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1);
+                        umma_bf16(d_tmem, a_lo, b_hi, IDESC, 1);
+                    }
+                    umma_commit(&a_empty[stage]);
+                    if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&t_full[acc]);
+                if (++acc == 2) { acc = 0; accphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: one row per thread =====================
+        const int ew = warp & 3;                          // TMEM lane quarter (warps 4..7 -> 0..3)
+        int acc = 0;
+        uint32_t accphase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int row = tile * GT_BM + ew * 32 + lane;
+            mbar_wait(&t_full[acc], accphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * N;
+            float *crow = C + (size_t)row * ldc;
+#pragma unroll 1
+            for (int ch = 0; ch < N / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(taddr + ch * 32, v);
+                tmem_ld_wait();
+                if (row < M) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4 *>(crow + ch * 32 + q * 4) =
+                            make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                                        __uint_as_float(v[q * 4 + 3]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[acc]);
+            if (++acc == 2) { acc = 0; accphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols(2 * N));
+    }
+}
+
+template <int K, int N>
+static int launch_gemm_tc(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, cudaStream_t st) {
+    constexpr int KCH = K / GT_KB;
+    const size_t smem = 1024 + (size_t)2 * KCH * N * 128 + (size_t)GT_STAGES * 2 * GT_BM * 128 + 16 * sizeof(uint64_t);
+    auto kern = gemm_tc_kernel<K, N>;
+    GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = ceil_div(M, GT_BM);
+    kern<<<ntiles < kNumSMs ? ntiles : kNumSMs, GT_THREADS, smem, st>>>(A, lda, Bt, ldb, C, ldc, M);
+    GCANET_LAUNCH_OK("gemm_tc_kernel");
+    return GCANET_OK;
+}
+
+// C[M][N] = A[M][K] Bt[N][K]^T on the tensor cores when the shape is one the EdgeConv layers use
+// (K, N in {64, 128, 256}, 16-byte aligned rows); returns -1 when the caller should use the CUDA-core GEMM.
+int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K, cudaStream_t st) {
+    if (M < 1024 || lda % 4 || ldb % 4 || ldc % 4) return -1;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt) | reinterpret_cast<uintptr_t>(C)) & 15) return -1;
+    if (getenv("GCANET_NO_TC_GEMM")) return -1;        // measurement aid
+#define GT_CASE(KK, NN) if (K == KK && N == NN) return launch_gemm_tc<KK, NN>(A, lda, Bt, ldb, C, ldc, M, st)
+    GT_CASE(64, 128);
+    GT_CASE(64, 256);
+    GT_CASE(128, 128);
+    GT_CASE(128, 64);
+    GT_CASE(256, 64);
+    GT_CASE(256, 128);
+    GT_CASE(64, 64);
+#undef GT_CASE
+    return -1;
+}
+
+}  // namespace gcanet
