@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(XW * 32) knn_xyz_kernel(XyzArgs a) {
     //   pass 1: every other tile, only if its AABB lower bound is within the largest threshold.
     int lo_t, hi_t;
     {
-        int half = (a.k + XT - 1) / XT + 2;
+        int half = (a.k + XT - 1) / XT;
         lo_t = max(0, tile0 - half);
         hi_t = min(tiles - 1, tile0 + half);
         while ((hi_t - lo_t + 1) * XT < a.k + 2 * XT && (lo_t > 0 || hi_t < tiles - 1)) {
