@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
                     cnt[r] += __popc(m);
                     if (cnt[r] > CAP - 32) {
                         __syncwarp();
-                        cnt[r] = shrink_list<SL>(my_ld + r * CAP, my_li + r * CAP, cnt[r], a.k, CAP - 32, lane, thr[r]);
+                        float t = thr[r];      // by-reference argument of a non-inlined call: keep thr[] itself in registers
+                        cnt[r] = shrink_list<SL>(my_ld + r * CAP, my_li + r * CAP, cnt[r], a.k, CAP - 32, lane, t);
+                        thr[r] = t;
                     }
                 }
             });
