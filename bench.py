@@ -284,8 +284,8 @@ def run_ours(args):
         achieved = flop / (avg_ms * 1e-3) / 1e12
         peak = float(peaks["bf16_tflops_sustained"])
         roofline = {"bound": "tensor",
-                    "kernel": "feature-space kNN C=64: prep + knn_tc_scan_kernel (tcgen05) + exact re-rank, "
-                              "algorithmic 2*N^2*C FLOP per cloud",
+                    "kernel": "feature-space kNN C=64: PCA/Morton prep + knn_tcp_scan_kernel (tcgen05, box-pruned) + exact "
+                              "re-rank, algorithmic 2*N^2*C FLOP per cloud",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "ms_per_launch": avg_ms, "launches_per_step": len(knn_ms) / args.steps,
                     "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)"}
