@@ -102,9 +102,11 @@ GCANET_API int gcanet_nc_to_cn(const float *x_nc, float *x_cn, int B, int C, int
  * Distances are fp32 with the reference's expansion arithmetic; no N x N matrix is
  * ever written to memory.  For C = 64 / 128 (L2 metric, k2 <= 128, N >= 128) candidates are
  * pruned on the tensor cores (tcgen05, bf16x3 split) and the survivors re-ranked in exact
- * fp32; xyz clouds (C = 3 L2, C = 6 points x normals, N >= 256) are Morton-sorted and scanned
- * with AABB pruning; every other shape runs the brute-force CUDA-core scan.  The result does not
- * depend on the path. */
+ * fp32 -- for N >= 1024 and k2 <= 64 after sorting the cloud along its three leading principal
+ * directions, so that key tiles whose bounding box cannot hold a neighbour are never read
+ * (GCANET_KNN_FLAG_NO_PRUNE scans every tile); xyz clouds (C = 3 L2, C = 6 points x normals,
+ * N >= 256) are Morton-sorted and scanned with AABB pruning; every other shape runs the
+ * brute-force CUDA-core scan.  The result does not depend on the path. */
 GCANET_API int gcanet_knn_graph_columns(int k1, int k2);
 GCANET_API size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric);
 GCANET_API int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int k2, int metric,
