@@ -22,7 +22,11 @@ namespace gcanet {
 
 constexpr int GT_BM = 128;            // rows per tile (UMMA M)
 constexpr int GT_KB = 64;             // bf16 elements per 128-byte swizzle row = K chunk per pipeline stage
-constexpr int GT_STAGES = 2;          // A stages
+// A stages: as many 32 KB (hi | lo) stages as fit next to the weights, at most 4
+__host__ __device__ constexpr int gt_stages(int K, int N) {
+    const int left = 200 * 1024 - 2 * (K / 64) * N * 128;
+    return left >= 4 * 32768 ? 4 : (left >= 3 * 32768 ? 3 : 2);
+}
 constexpr int GT_THREADS = 288;       // 4 loader warps, 4 epilogue warps, 1 MMA warp
 
 __host__ __device__ constexpr uint32_t tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512))); }
@@ -57,6 +61,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bt, int ldb, float *__restrict__ C, int ldc, int M) {
     static_assert(K % GT_KB == 0 && N % 32 == 0 && N <= 256, "unsupported GEMM shape");
     constexpr int KCH = K / GT_KB;                      // K chunks
+    constexpr int GT_STAGES = gt_stages(K, N);
     constexpr int A_TILE = GT_BM * 128;                 // one [128][64] bf16 tile: 16 KB
     constexpr int A_STAGE = 2 * A_TILE;                 // hi + lo
     constexpr int B_BLK = N * 128;                      // one [N][64] bf16 block
@@ -102,20 +107,33 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
         const int rsub = tid >> 4, c4 = tid & 15;       // 8 rows x 16 float4 per sweep
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int m0 = tile * GT_BM;
-            for (int kc = 0; kc < KCH; ++kc) {
+        // work items = (tile, K chunk) in order; the loads of item i+1 are in flight while item i is split and stored
+        const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int items = my_tiles * KCH;
+        auto issue = [&](int item, float4 (&v)[16]) {
+            const int m0 = (blockIdx.x + (item / KCH) * gridDim.x) * GT_BM, kc = item % KCH;
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int r = it * 8 + rsub;
+                v[it] = m0 + r < M ? __ldg(reinterpret_cast<const float4 *>(A + (size_t)(m0 + r) * lda + kc * GT_KB) + c4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 va[16], vb[16];
+        if (items > 0) issue(0, va);
+        for (int item = 0; item < items; item += 2) {
+            // even item from va (prefetch odd into vb), then odd item from vb (prefetch next even into va)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int cur = item + half;
+                if (cur >= items) break;
+                float4 (&vc)[16] = half == 0 ? va : vb;
+                float4 (&vn)[16] = half == 0 ? vb : va;
+                if (cur + 1 < items) issue(cur + 1, vn);
                 mbar_wait(&a_empty[stage], phase ^ 1);
                 uint8_t *hi_tile = sA + stage * A_STAGE, *lo_tile = hi_tile + A_TILE;
-                float4 v[16];
 #pragma unroll
-                for (int it = 0; it < 16; ++it) {
-                    const int r = it * 8 + rsub;
-                    v[it] = m0 + r < M ? __ldg(reinterpret_cast<const float4 *>(A + (size_t)(m0 + r) * lda + kc * GT_KB) + c4)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int it = 0; it < 16; ++it) split_store4(hi_tile, lo_tile, it * 8 + rsub, c4 * 4, v[it]);
+                for (int it = 0; it < 16; ++it) split_store4(hi_tile, lo_tile, it * 8 + rsub, c4 * 4, vc[it]);
                 fence_proxy_async();
                 mbar_arrive(&a_full[stage]);
                 if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
@@ -197,7 +215,8 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
 template <int K, int N>
 static int launch_gemm_tc(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, cudaStream_t st) {
     constexpr int KCH = K / GT_KB;
-    const size_t smem = 1024 + (size_t)2 * KCH * N * 128 + (size_t)GT_STAGES * 2 * GT_BM * 128 + 16 * sizeof(uint64_t);
+    constexpr int GT_STAGES = gt_stages(K, N);
+    const size_t smem = 1024 + (size_t)2 * KCH * N * 128 + (size_t)GT_STAGES * 2 * GT_BM * 128 + 32 * sizeof(uint64_t);
     auto kern = gemm_tc_kernel<K, N>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = ceil_div(M, GT_BM);
