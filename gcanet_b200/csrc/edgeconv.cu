@@ -521,37 +521,45 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_reduce_kernel(BwdArgs a
     }
 }
 
-// per cloud: S1[c] = sum_i du, S2[c] = sum_i du*yhat  ->  sbc[b][c][2] (double) and coef[b][g] = (A_g, K_g)
-// One CTA per cloud; each warp reduces a channel at a time over the per-CTA partials (fixed order).
-__global__ void edge_bwd_coef_kernel(const float *__restrict__ part, const float *__restrict__ stats,
-                                     const float *__restrict__ gamma, double *__restrict__ sbc,
-                                     float *__restrict__ coef, int nblk, int Cout, int G, double count) {
-    extern __shared__ double sh[];      // [Cout][2] weighted by gamma
-    const int b = blockIdx.x;
-    const int cpg = Cout / G;
+// per cloud: S1[c] = sum_i du, S2[c] = sum_i du*yhat  ->  sbc[b][c][2] (double).  One warp per (cloud, channel)
+// reduces the per-CTA partials in a fixed order (grid = (Cout / warps per CTA, B): fp64 adds are slow, spread them).
+__global__ void edge_bwd_chansum_kernel(const float *__restrict__ part, double *__restrict__ sbc, int nblk, int Cout) {
+    const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (int c = warp; c < Cout; c += nwarp) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int i = lane; i < nblk; i += 32) {
-            s1 += (double)part[(((size_t)b * nblk + i) * Cout + c) * 2 + 0];
-            s2 += (double)part[(((size_t)b * nblk + i) * Cout + c) * 2 + 1];
-        }
-        for (int o = 16; o; o >>= 1) {
-            s1 += __shfl_xor_sync(FULLM, s1, o);
-            s2 += __shfl_xor_sync(FULLM, s2, o);
-        }
-        if (lane == 0) {
-            sbc[((size_t)b * Cout + c) * 2 + 0] = s1;
-            sbc[((size_t)b * Cout + c) * 2 + 1] = s2;
-            sh[c * 2 + 0] = s1 * (double)gamma[c];
-            sh[c * 2 + 1] = s2 * (double)gamma[c];
-        }
+    const int c = blockIdx.x * nwarp + warp;
+    if (c >= Cout) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = lane; i < nblk; i += 32) {
+        const float2 v = *reinterpret_cast<const float2 *>(part + (((size_t)b * nblk + i) * Cout + c) * 2);
+        s1 += (double)v.x;
+        s2 += (double)v.y;
     }
-    __syncthreads();
-    if (threadIdx.x < G) {
-        const int g = threadIdx.x;
-        double m1 = 0.0, m2 = 0.0;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { m1 += sh[c * 2]; m2 += sh[c * 2 + 1]; }
+    for (int o = 16; o; o >>= 1) {
+        s1 += __shfl_xor_sync(FULLM, s1, o);
+        s2 += __shfl_xor_sync(FULLM, s2, o);
+    }
+    if (lane == 0) {
+        sbc[((size_t)b * Cout + c) * 2 + 0] = s1;
+        sbc[((size_t)b * Cout + c) * 2 + 1] = s2;
+    }
+}
+
+// coef[b][g] = (A_g, K_g) from the gamma-weighted channel sums of the group; one warp per (cloud, group)
+__global__ void edge_bwd_coef_kernel(const double *__restrict__ sbc, const float *__restrict__ stats,
+                                     const float *__restrict__ gamma, float *__restrict__ coef, int Cout, int G, double count) {
+    const int b = blockIdx.x;
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cpg = Cout / G;
+    double m1 = 0.0, m2 = 0.0;
+    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {      // fixed order: lane-strided, then the shuffle tree
+        m1 += sbc[((size_t)b * Cout + c) * 2 + 0] * (double)gamma[c];
+        m2 += sbc[((size_t)b * Cout + c) * 2 + 1] * (double)gamma[c];
+    }
+    for (int o = 16; o; o >>= 1) {
+        m1 += __shfl_xor_sync(FULLM, m1, o);
+        m2 += __shfl_xor_sync(FULLM, m2, o);
+    }
+    if (lane == 0) {
         m1 /= count; m2 /= count;
         const double mean = stats[((size_t)b * G + g) * 2 + 0], rstd = stats[((size_t)b * G + g) * 2 + 1];
         coef[((size_t)b * G + g) * 2 + 0] = (float)(-rstd * m1 + rstd * rstd * m2 * mean);
@@ -849,8 +857,9 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     edge_bwd_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
     GCANET_LAUNCH_OK("edge_bwd_reduce_kernel");
     double count = (double)(Cout / d->groups) * d->N * d->k;
-    edge_bwd_coef_kernel<<<d->B, 512, Cout * 2 * sizeof(double), st>>>(w.part, sv.stats, gamma, w.sbc, w.coef, nblk, Cout,
-                                                                      d->groups, count);
+    edge_bwd_chansum_kernel<<<dim3(ceil_div(Cout, 8), d->B), 256, 0, st>>>(w.part, w.sbc, nblk, Cout);
+    GCANET_LAUNCH_OK("edge_bwd_chansum_kernel");
+    edge_bwd_coef_kernel<<<d->B, 32 * d->groups, 0, st>>>(w.sbc, sv.stats, gamma, w.coef, Cout, d->groups, count);
     GCANET_LAUNCH_OK("edge_bwd_coef_kernel");
     edge_bwd_affine_kernel<<<ceil_div(Cout, 128), 128, 0, st>>>(w.sbc, grad_gamma, grad_beta, d->B, Cout);
     GCANET_LAUNCH_OK("edge_bwd_affine_kernel");
@@ -1196,8 +1205,9 @@ static int run_nbackward(const gcanet_normal_edge_desc *d, const float *x_nc, co
     edge_bwd_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
     GCANET_LAUNCH_OK("edge_bwd_reduce_kernel");
     double count = (double)(Cout / d->groups) * d->N * d->k;
-    edge_bwd_coef_kernel<<<d->B, 512, Cout * 2 * sizeof(double), st>>>(w.rpart, sv.stats, gamma, w.sbc, w.coef, nblk, Cout,
-                                                                      d->groups, count);
+    edge_bwd_chansum_kernel<<<dim3(ceil_div(Cout, 8), d->B), 256, 0, st>>>(w.rpart, w.sbc, nblk, Cout);
+    GCANET_LAUNCH_OK("edge_bwd_chansum_kernel");
+    edge_bwd_coef_kernel<<<d->B, 32 * d->groups, 0, st>>>(w.sbc, sv.stats, gamma, w.coef, Cout, d->groups, count);
     GCANET_LAUNCH_OK("edge_bwd_coef_kernel");
     edge_bwd_affine_kernel<<<ceil_div(Cout, 128), 128, 0, st>>>(w.sbc, grad_gamma, grad_beta, d->B, Cout);
     GCANET_LAUNCH_OK("edge_bwd_affine_kernel");

@@ -401,7 +401,7 @@ int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metri
     int rc = launch_sqnorm_public(x, norm, B, C, 3, N, st);
     if (rc) return rc;
     GCANET_CUDA_OK(cudaMemsetAsync(fallback, 0, B * sizeof(int), st));
-    xyz_bbox_kernel<<<B, 256, 0, st>>>(x, bbox, C, N);
+    xyz_bbox_kernel<<<B, 1024, 0, st>>>(x, bbox, C, N);
     GCANET_LAUNCH_OK("xyz_bbox_kernel");
     xyz_code_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(x, bbox, keys_in, vals_in, C, N);
     GCANET_LAUNCH_OK("xyz_code_kernel");
