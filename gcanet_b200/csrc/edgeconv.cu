@@ -147,12 +147,23 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A,
 }
 
 // sums `splits` partial [rows][ld] matrices
-__global__ void reduce_splits_kernel(const float *__restrict__ part, float *__restrict__ out, int count, int splits) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
+// (eight warps per 32 outputs, each a strided eighth of the splits with coalesced loads, combined in a fixed order
+// through shared memory: the sum is deterministic and no thread walks all `splits` partials serially)
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const float *__restrict__ part, float *__restrict__ out, int count, int splits) {
+    __shared__ double red[8][32];
+    const int sub = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 32 + lane;
     double s = 0.0;
-    for (int z = 0; z < splits; ++z) s += (double)part[(size_t)z * count + t];
-    out[t] = (float)s;
+    if (t < count)
+        for (int z = sub; z < splits; z += 8) s += (double)part[(size_t)z * count + t];
+    red[sub][lane] = s;
+    __syncthreads();
+    if (sub == 0 && t < count) {
+        double r = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) r += red[w][lane];
+        out[t] = (float)r;
+    }
 }
 
 static int launch_sgemm_nn(const float *A, const float *Bm, float *Cm, int M, int N, int K, int lda, int ldb, int ldc,
@@ -273,7 +284,7 @@ static int launch_sgemm_tn(const float *A, const float *Bm, float *out, float *p
         GCANET_LAUNCH_OK("sgemm_tn64_kernel");
     }
     int count = K * N;
-    reduce_splits_kernel<<<ceil_div(count, 256), 256, 0, st>>>(part, out, count, splits);
+    reduce_splits_kernel<<<ceil_div(count, 32), 256, 0, st>>>(part, out, count, splits);
     GCANET_LAUNCH_OK("reduce_splits_kernel");
     return GCANET_OK;
 }

@@ -576,6 +576,36 @@ def test_knn_pruned_path_shapes_and_ties(B, N, k):
     assert bool((srt[:, :, 1:] != srt[:, :, :-1]).all())
 
 
+def test_knn_and_edgeconv_are_graph_capturable():
+    """The C-ABI never allocates or synchronises (include/gcanet_b200.h), so a kNN + EdgeConv forward can be
+    captured in a CUDA graph and replayed on new inputs of the same shape."""
+    x1, _ = _layer_activations(2, 2000, seed=3)
+    a, b = x1.to(DEV), x1.flip(2).contiguous().to(DEV)
+    w = torch.randn(64, 128, generator=torch.Generator().manual_seed(1)).to(DEV) * 0.1
+    gm, bt = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
+
+    def run(x):
+        with torch.no_grad():
+            idx = G.knn_graph(x, 20, 20, want64=False, want32=True, ordered=False)[1]
+            out_nc, out_cn = gb.edgeconv(G.to_point_major(x), idx, w, gm, bt, 64, groups=2)
+        return idx, out_cn
+
+    static_x = a.clone()
+    for _ in range(2):
+        run(static_x)                                   # warm-up: workspaces, function attributes
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        idx_g, out_g = run(static_x)
+    for src in (a, b):
+        static_x.copy_(src)
+        g.replay()
+        torch.cuda.synchronize()
+        idx_e, out_e = run(src)
+        assert torch.equal(idx_g.sort(dim=2)[0], idx_e.sort(dim=2)[0])
+        assert torch.allclose(out_g, out_e, rtol=1e-5, atol=1e-6)
+
+
 def test_normal_edge_head_golden(golden_dir):
     """conv_normal head (M4:584-587, 691-693) against the fixture made from the reference's
     get_graph_feature_with_normals_g; forward 1e-4, weight gradients 2e-3 relative."""
