@@ -151,7 +151,7 @@ struct XyzArgs {
 };
 
 template <int CDIM, bool PN, int SL>
-__global__ void __launch_bounds__(XW * 32) knn_xyz_kernel(XyzArgs a) {
+__global__ void __launch_bounds__(XW * 32, 3) knn_xyz_kernel(XyzArgs a) {   // 80 registers: three CTAs (24 warps) per SM hide the list latency better than two
     extern __shared__ __align__(16) float smem[];
     constexpr int CAP = 32 * SL;
     float *s_aabb = smem;                                     // [tiles][6]
