@@ -2,19 +2,25 @@
 //
 //   prep      x[B][C][N] fp32 -> xs[B][N][2C] bf16 = (hi | lo) with hi = bf16(x), lo = bf16(x - hi),
 //             x_nc[B][N][C] fp32 (point-major, for the exact re-rank), |x|^2 (reference order)
-//   scan      one CTA per (cloud, 128-query tile), warp-specialised:
-//               warp 0    TMA producer: query tile once, then 128-key tiles through an mbarrier ring
-//               warp 1    tcgen05.mma issuer: D[128 x 128] (TMEM, fp32) = Qhi Khi^T + Qhi Klo^T + Qlo Khi^T
-//                         (bf16 x 3 split, |error| <= ~2^-14 |q||k|), double-buffered accumulators
-//               warps 2-5 epilogue: tcgen05.ld one accumulator row per thread, d~ = |k|^2 - 2 q.k,
-//                         threshold filter, survivors appended to the row's candidate list;
-//                         a full list is compacted by the warp (bisection for an upper bound of the
-//                         k-th smallest, keep everything below bound + margin)
-//             Every key whose approximate distance is within `margin` (>= 2 x the error bound) of the
-//             approximate k-th survives, so the exact k nearest are always among the candidates.
-//   rerank    one warp per query: exact fp32 distances of the <= ~k+slack candidates in the
-//             reference's expansion arithmetic, rank by (distance, index), write the k best in order.
-//   fallback  rows whose candidate list overflowed (massive ties) are redone by the CUDA-core scan.
+//   scan      approximate distances d~ = |k|^2 - 2 q.k for 128-query x 64-key tiles:
+//               TMA producer warp: query tile once, then key tiles through an mbarrier ring
+//               tcgen05.mma issuer: D (TMEM, fp32) = Qhi Khi^T + Qhi Klo^T + Qlo Khi^T
+//                         (bf16 x 3 split, |error| <= ~2^-14 |q||k|), accumulators ring-buffered in TMEM
+//               epilogue warps: tcgen05.ld accumulator rows, threshold filter, survivors appended to the row's
+//                         candidate list.  Every key whose approximate distance is within `margin` (>= 2 x the
+//                         error bound) of the approximate k-th survives, so the exact k nearest are always
+//                         among the candidates.
+//             Two kernels:
+//               knn_tcp_scan_kernel (N >= 1024, k <= 64; the default): the cloud is sorted along a Morton curve in
+//                         the space of its three leading principal directions, every 64-key tile has a bounding
+//                         box there, and a query tile walks the key tiles nearest-box-first and stops when no
+//                         row's bound can be beaten.  Pass A finds each row's threshold from per-column-slot
+//                         minima held in registers, pass B collects the candidates below it.
+//               knn_tc_scan_kernel (small clouds, k > 64, or GCANET_KNN_FLAG_NO_PRUNE): every tile once, in a
+//                         strided order, streaming threshold with warp-cooperative list compaction.
+//   rerank    one warp per query: exact fp32 distances of the candidates whose membership is in doubt, in the
+//             reference's expansion arithmetic, ranked by (distance, index).
+//   fallback  rows whose candidate list overflowed (massive ties) are listed and redone by the CUDA-core scan.
 //
 // No N x N matrix and no approximate distance ever decides the result: tensor cores only prune.
 #include "common.cuh"
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
 // ---------------------------------------------------------------------------------
 constexpr int TCP_MIN_N = 1024;
 constexpr int TCP_SPLIT = 8;          // partial Gram matrices per cloud
-constexpr int TCP_PRE = 8;            // tiles of the threshold pre-pass
+constexpr int TCP_PRE = 8;            // nearest tiles every query tile reads unconditionally (first bound refresh after them)
 constexpr int TCP_ITERS = 5;          // subspace iterations (lambda_3 / lambda_4 is ~4 on layer activations: 4^5 = 1000x)
 constexpr uint32_t TCP_END = 0xffffffffu;
 constexpr int TCP_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
@@ -945,27 +951,6 @@ struct TcpScanArgs {
     int qtiles;
 };
 
-// thread-local selection over the 64 slot minima: smallest bound with count(m <= bound) >= k found by bisection
-__device__ __forceinline__ float slot_bound(const float (&m)[TC_BN], int k, int iters) {
-    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-    int nf = 0;
-#pragma unroll
-    for (int s = 0; s < TC_BN; ++s) {
-        mn = fminf(mn, m[s]);
-        if (m[s] < CUDART_INF_F) { mx = fmaxf(mx, m[s]); ++nf; }
-    }
-    if (nf < k) return CUDART_INF_F;
-    float lo = mn, hi = mx;
-    for (int it = 0; it < iters; ++it) {
-        const float mid = 0.5f * lo + 0.5f * hi;
-        int c = 0;
-#pragma unroll
-        for (int s = 0; s < TC_BN; ++s) c += (m[s] <= mid) ? 1 : 0;
-        if (c >= k) hi = mid; else lo = mid;
-    }
-    return hi;
-}
-
 template <int C>
 __global__ void __launch_bounds__(TCP_THREADS, C == 64 ? 2 : 1)
 knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
@@ -997,8 +982,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     volatile int *s_end = reinterpret_cast<volatile int *>(s_kt + STAGES);   // [2] stream position of the pass A / pass B end marker
     volatile float *s_wthr = reinterpret_cast<volatile float *>(const_cast<int *>(s_end) + 2);   // [8] max true-distance threshold per epilogue warp
     int *s_cnt = reinterpret_cast<int *>(const_cast<float *>(s_wthr) + 8);      // [2][128] final half-list counts (-1 = overflowed)
-    int *s_ovf = s_cnt + TC_BM;                                                   //   (second half of s_cnt)
-    volatile float *s_xf = reinterpret_cast<volatile float *>(s_ovf + TC_BM);     // [2][2][128] pair exchange (double-buffered)
+    volatile float *s_xf = reinterpret_cast<volatile float *>(s_cnt + 2 * TC_BM); // [2][2][128] pair exchange (double-buffered)
     // [P] (bf16-truncated lower bound << 16) | tile, ascending; 8 bytes per entry while it is being sorted;
     // followed by [4][P] bf16-truncated lower bounds of the same tiles against each 32-row group of the query tile
     uint32_t *s_ord = reinterpret_cast<uint32_t *>(smem + ((reinterpret_cast<uint8_t *>(const_cast<float *>(s_xf) + 4 * TC_BM) - smem + 7) & ~(size_t)7));
