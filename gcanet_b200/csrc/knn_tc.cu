@@ -38,7 +38,9 @@ constexpr unsigned FULLW = 0xffffffffu;
 constexpr int TC_BM = 128;            // queries per CTA  (UMMA M)
 constexpr int TC_BN = 64;             // keys per tile    (UMMA N); 64 keeps a CTA at ~66 KB so three share an SM
 constexpr int TC_KB = 64;             // bf16 elements per 128-byte swizzle row
-constexpr int TC_CAP = 256;           // candidate list capacity per query
+constexpr int TC_CAP = 256;           // candidate list capacity per query (full scan)
+constexpr int TCP_CAP = 512;          // ... on the box-pruned path: dense feature regions hold hundreds of keys within the
+                                      // margin of the k-th distance, and they must not overflow into the slow fallback
 constexpr int TC_SLACK = 8;           // bisection stops once the bound keeps <= k + slack entries
 constexpr int TC_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int TC_NRING = 8;           // key-norm ring slots (producer is never more than 4 tiles ahead of the epilogue)
@@ -419,7 +421,8 @@ struct RerankArgs {
     int N, k, step, kout;
     int unordered;         // 1: the caller only needs the neighbour SET (EdgeConv is order-invariant)
     const int *perm;       // pruned path: rows and candidates are sorted positions, perm[b][s] = original index; else null
-    int split;             // 1: a row's list is two halves of TC_CAP / 2 entries with counts cand_cnt[2 row], cand_cnt[2 row + 1]
+    int cap;               // entries per row in `cand`
+    int split;             // 1: a row's list is two halves of cap / 2 entries with counts cand_cnt[2 row], cand_cnt[2 row + 1]
     int *fb_list;          // [B][N] rows left to the CUDA-core fallback (overflowed lists), fb_count [B] (zeroed by the host)
     int *fb_count;
 };
@@ -481,7 +484,7 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
         ad[s] = CUDART_INF_F;
         aj[s] = 0;
         if (e < n) {
-            uint2 t = cand[e < n0 ? e : e - n0 + TC_CAP / 2];      // second half-list starts at TC_CAP / 2 (n0 = n: one list)
+            uint2 t = cand[e < n0 ? e : e - n0 + (a.cap >> 1)];    // second half-list starts at cap / 2 (n0 = n: one list)
             ad[s] = __uint_as_float(t.x);
             aj[s] = (int)t.y;                                       // scan-order id; mapped through perm only if it survives
         }
@@ -594,8 +597,8 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
 template <int C>
 __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
     constexpr int VEC = C / 32;
-    __shared__ int s_idx[8][TC_CAP];
-    __shared__ float s_d[8][TC_CAP];
+    __shared__ int s_idx[8][TCP_CAP];
+    __shared__ float s_d[8][TCP_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int qs = blockIdx.x * 8 + warp;                 // row in the scan's order
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
     }
     const int n0 = a.split ? a.cand_cnt[2 * srow] : a.cand_cnt[srow];
     const int n = a.split ? n0 + a.cand_cnt[2 * srow + 1] : n0;
-    const uint2 *cand = a.cand + srow * TC_CAP;
+    const uint2 *cand = a.cand + srow * a.cap;
     const float *xb = a.x_nc + (size_t)b * a.N * C;
     const float *nb = a.norm + (size_t)b * a.N;
     float qv[VEC];
@@ -619,7 +622,8 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
     const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
     // short lists (the pruned scan's fixed thresholds leave ~2k entries) take the narrow instantiation
     if (n <= 128) rerank_row<C, 4>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
-    else rerank_row<C, TC_CAP / 32>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+    else if (n <= 256) rerank_row<C, 8>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+    else rerank_row<C, TCP_CAP / 32>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
 }
 
 // ---------------------------------------------------------------------------------
@@ -638,7 +642,7 @@ constexpr int TCP_PRE = 8;            // nearest tiles every query tile reads un
 constexpr int TCP_ITERS = 5;          // subspace iterations (lambda_3 / lambda_4 is ~4 on layer activations: 4^5 = 1000x)
 constexpr uint32_t TCP_END = 0xffffffffu;
 constexpr int TCP_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-constexpr int TCP_HCAP = TC_CAP / 2;  // each of a row's two epilogue threads owns half of its candidate list
+constexpr int TCP_HCAP = TCP_CAP / 2; // each of a row's two epilogue threads owns half of its candidate list
 constexpr int TCP_ACC = 4;            // TMEM accumulator stages (4 x 64 columns)
 constexpr int TCP_NRING = 16;         // key-norm ring: the producer runs at most STAGES + ACC + 1 tiles ahead of the epilogue
 __host__ __device__ constexpr int tcp_stages(int C) { return C == 64 ? 4 : 3; }
@@ -942,7 +946,7 @@ struct TcpScanArgs {
     const float *boxes;     // [B][tiles][6]
     const float *boxes32;   // [B][2 * tiles][6] boxes of the 32-point halves (= the rows of one epilogue warp)
     const int *perm;        // [B][N] sorted position -> original index
-    uint2 *cand;            // [B][N][TC_CAP]  rows in sorted order, key ids are sorted positions
+    uint2 *cand;            // [B][N][TCP_CAP] rows in sorted order, key ids are sorted positions
     int *cand_cnt;          // [B][N]          rows in sorted order
     int *overflow;          // [B][N]          rows in ORIGINAL order (consumed by the fallback scan)
     int *visited;           // [B][query tiles] statistics: key tiles scanned in the main pass (may be null)
@@ -1226,7 +1230,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int q = q0 + row;                               // sorted position
         const bool active = q < a.N;
         const size_t srow = (size_t)b * a.N + (active ? q : 0);
-        uint2 *buf = a.cand + srow * TC_CAP;
+        uint2 *buf = a.cand + srow * TCP_CAP;
         const float qn = active ? a.norm_pad[(size_t)b * a.Npad + q] : 0.f;
         const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
         float thr = active ? CUDART_INF_F : -CUDART_INF_F;
@@ -1336,7 +1340,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         // half of the row's list (capacity TCP_HCAP): no shared counter, and a half that fills up is compacted by
         // its warp exactly like in the full scan (its k-th smallest entry is a valid bound for the whole row).
         uint2 *hbuf = buf + hf * TCP_HCAP;
-        // The half-list is 1 KB and 1 KB-aligned, so appending only ever changes the low 32 address bits: the write
+        // The half-list is 2 KB and 2 KB-aligned, so appending only ever changes the low 32 address bits: the write
         // pointer is kept as a (running low word, constant high word) pair -- one predicated add per append instead
         // of a 64-bit index computation.
         const uint32_t hb_lo0 = (uint32_t)reinterpret_cast<uintptr_t>(hbuf);
@@ -1493,7 +1497,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += align_up(bn * sizeof(float));                   // norm
     t += align_up((size_t)B * (ceil_div(N, TC_BN) * TC_BN) * sizeof(float));   // norm_pad
     t += align_up((size_t)B * sizeof(float));            // nmax
-    t += align_up(bn * TC_CAP * sizeof(uint2));          // cand
+    t += align_up(bn * TCP_CAP * sizeof(uint2));         // cand (the full scan uses TC_CAP entries per row of it)
     t += align_up(2 * bn * sizeof(int));                 // cand_cnt (two halves per row on the pruned path)
     t += align_up(bn * sizeof(int));                     // overflow
     return t;
@@ -1595,7 +1599,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     const int Npad = ceil_div(N, TC_BN) * TC_BN;
     float *norm_pad = cv.take<float>((size_t)B * Npad);
     float *nmax = cv.take<float>(B);
-    uint2 *cand = cv.take<uint2>(bn * TC_CAP);
+    uint2 *cand = cv.take<uint2>(bn * TCP_CAP);
     int *cand_cnt = cv.take<int>(2 * bn);
     int *overflow = cv.take<int>(bn);
 
@@ -1656,7 +1660,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         }
         TcpScanArgs sa{norm_pad, Npad, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, N, k2, tiles, pre, P, qtiles};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
-                      (unordered && k1 == k2) ? 1 : 0, perm, 1, fb_list, fb_count};
+                      (unordered && k1 == k2) ? 1 : 0, perm, TCP_CAP, 1, fb_list, fb_count};
         rc = C == 64 ? launch_tcp<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128>(tmap_q, tmap_k, sa, ra, B, st);
         if (rc) return rc;
         const char *stats = getenv("GCANET_TC_STATS");
@@ -1696,7 +1700,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     const int dbg_mode = (dbg && dbg[0] >= '1' && dbg[0] <= '3') ? dbg[0] - '0' : 0;
     TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, dbg_mode, stride};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
-                  (unordered && k1 == k2) ? 1 : 0, nullptr, 0, fb_list, fb_count};
+                  (unordered && k1 == k2) ? 1 : 0, nullptr, TC_CAP, 0, fb_list, fb_count};
     if (dbg_mode >= 2 && C == 64)
         rc = dbg_mode == 2 ? launch_tc<64, 2>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<64, 3>(tmap_q, tmap_k, sa, ra, B, st);
     else
