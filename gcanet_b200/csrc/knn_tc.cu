@@ -11,12 +11,12 @@
 //                         error bound) of the approximate k-th survives, so the exact k nearest are always
 //                         among the candidates.
 //             Two kernels:
-//               knn_tcp_scan_kernel (N >= 1024, k <= 64; the default): the cloud is sorted along a Morton curve in
+//               knn_tcp_scan_kernel (N >= 1024, k <= 128; the default): the cloud is sorted along a Morton curve in
 //                         the space of its three leading principal directions, every 64-key tile has a bounding
 //                         box there, and a query tile walks the key tiles nearest-box-first and stops when no
 //                         row's bound can be beaten.  Pass A finds each row's threshold from per-column-slot
 //                         minima held in registers, pass B collects the candidates below it.
-//               knn_tc_scan_kernel (small clouds, k > 64, or GCANET_KNN_FLAG_NO_PRUNE): every tile once, in a
+//               knn_tc_scan_kernel (clouds under 1024 points, or GCANET_KNN_FLAG_NO_PRUNE): every tile once, in a
 //                         strided order, streaming threshold with warp-cooperative list compaction.
 //   rerank    one warp per query: exact fp32 distances of the candidates whose membership is in doubt, in the
 //             reference's expansion arithmetic, ranked by (distance, index).
@@ -955,8 +955,10 @@ struct TcpScanArgs {
     int qtiles;
 };
 
-template <int C>
-__global__ void __launch_bounds__(TCP_THREADS, C == 64 ? 2 : 1)
+// SM = 1: k <= 64, one minimum per column slot.  SM = 2: k <= 128, the two smallest per slot (128 distinct keys; the
+// 64 extra registers cost the second resident CTA).
+template <int C, int SM>
+__global__ void __launch_bounds__(TCP_THREADS, (C == 64 && SM == 1) ? 2 : 1)
 knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int NH = C / TC_KB;
@@ -1250,11 +1252,11 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             return other;
         };
         // smallest bound with count(slot minima of the row <= bound) >= k, by bisection over both threads' 32 slots
-        auto row_bound = [&](const float (&m)[32], int iters) -> float {
+        auto row_bound = [&](const float (&m)[32 * SM], int iters) -> float {
             float mn = CUDART_INF_F, mx = -CUDART_INF_F;
             int nf = 0;
 #pragma unroll
-            for (int s = 0; s < 32; ++s) {
+            for (int s = 0; s < 32 * SM; ++s) {
                 mn = fminf(mn, m[s]);
                 if (m[s] < CUDART_INF_F) { mx = fmaxf(mx, m[s]); ++nf; }
             }
@@ -1271,7 +1273,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const float mid = 0.5f * lo + 0.5f * hi;
                 int c = 0;
 #pragma unroll
-                for (int s = 0; s < 32; ++s) c += (m[s] <= mid) ? 1 : 0;
+                for (int s = 0; s < 32 * SM; ++s) c += (m[s] <= mid) ? 1 : 0;
                 c += (int)pair_exchange((float)c);
                 if (c >= a.k) { hi = mid; c_hi = c; } else lo = mid;
             }
@@ -1279,11 +1281,12 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         };
 
         // ---- pass A: per-column-slot minima over the visited tiles.  The 64 slot minima of a row belong to 64
-        // different keys, so the k-th smallest of them bounds the row's k-th distance from above; nothing is stored.
+        // different keys (SM = 2: the two smallest per slot, 128 keys), so the k-th smallest of them bounds the
+        // row's k-th distance from above; nothing is stored.
         {
-            float m[32];
+            float m[32 * SM];
 #pragma unroll
-            for (int s = 0; s < 32; ++s) m[s] = CUDART_INF_F;
+            for (int s = 0; s < 32 * SM; ++s) m[s] = CUDART_INF_F;
             int done = 0, refresh_at = pre > 0 ? pre : 8;
             for (;; ++seq) {
                 mbar_wait(&t_full[acc], accphase);
@@ -1302,8 +1305,11 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         const float4 n4 = rn[c4];
                         const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            m[c4 * 4 + e] = fminf(m[c4 * 4 + e], fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]));
+                        for (int e = 0; e < 4; ++e) {
+                            const float d = fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]);
+                            if constexpr (SM == 2) m[32 + c4 * 4 + e] = fminf(m[32 + c4 * 4 + e], fmaxf(m[c4 * 4 + e], d));   // second smallest
+                            m[c4 * 4 + e] = fminf(m[c4 * 4 + e], d);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -1474,7 +1480,7 @@ static int tcp_axis_bits(int B) {
     return bits > 10 ? 10 : bits;
 }
 static bool tcp_supported(int B, int N, int k2) {
-    return N >= TCP_MIN_N && k2 <= TC_BN && ceil_div(N, TC_BN) <= 2048 && tcp_axis_bits(B) >= 5;
+    return N >= TCP_MIN_N && k2 <= 2 * TC_BN && ceil_div(N, TC_BN) <= 2048 && tcp_axis_bits(B) >= 5;
 }
 
 size_t knn_tc_workspace_bytes(int B, int C, int N) {
@@ -1530,13 +1536,13 @@ static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcSca
     return GCANET_OK;
 }
 
-template <int C>
+template <int C, int SM>
 static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpScanArgs sa, RerankArgs ra, int B, cudaStream_t st) {
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int STAGES = tcp_stages(C);
     const size_t smem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)STAGES * NBLK * TC_BN * 128 +
                         TCP_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t) + 6 * TC_BM * sizeof(float) + (size_t)sa.P * 16;
-    auto kern = knn_tcp_scan_kernel<C>;
+    auto kern = knn_tcp_scan_kernel<C, SM>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(sa.N, TC_BM) * B);
     kern<<<grid, TCP_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
@@ -1661,7 +1667,8 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         TcpScanArgs sa{norm_pad, Npad, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, N, k2, tiles, pre, P, qtiles};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                       (unordered && k1 == k2) ? 1 : 0, perm, TCP_CAP, 1, fb_list, fb_count};
-        rc = C == 64 ? launch_tcp<64>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128>(tmap_q, tmap_k, sa, ra, B, st);
+        if (k2 <= TC_BN) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, ra, B, st);
+        else rc = C == 64 ? launch_tcp<64, 2>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128, 2>(tmap_q, tmap_k, sa, ra, B, st);
         if (rc) return rc;
         const char *stats = getenv("GCANET_TC_STATS");
         if (stats && stats[0] == '1') {            // measurement aid: synchronises

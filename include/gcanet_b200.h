@@ -102,7 +102,7 @@ GCANET_API int gcanet_nc_to_cn(const float *x_nc, float *x_cn, int B, int C, int
  * Distances are fp32 with the reference's expansion arithmetic; no N x N matrix is
  * ever written to memory.  For C = 64 / 128 (L2 metric, k2 <= 128, N >= 128) candidates are
  * pruned on the tensor cores (tcgen05, bf16x3 split) and the survivors re-ranked in exact
- * fp32 -- for N >= 1024 and k2 <= 64 after sorting the cloud along its three leading principal
+ * fp32 -- for N >= 1024 after sorting the cloud along its three leading principal
  * directions, so that key tiles whose bounding box cannot hold a neighbour are never read
  * (GCANET_KNN_FLAG_NO_PRUNE scans every tile); xyz clouds (C = 3 L2, C = 6 points x normals,
  * N >= 256) are Morton-sorted and scanned with AABB pruning; every other shape runs the

@@ -519,7 +519,7 @@ def _layer_activations(B, N, seed, k=20):
     return x1, x2
 
 
-@pytest.mark.parametrize("N,k,B", [(10000, 50, 2), (4097, 20, 2), (1025, 64, 1), (3000, 50, 3)])
+@pytest.mark.parametrize("N,k,B", [(10000, 50, 2), (4097, 20, 2), (1025, 64, 1), (3000, 50, 3), (6000, 80, 2), (2500, 128, 1)])
 def test_knn_pruned_tensor_core_path_equals_full_scan(N, k, B):
     """Sorting the cloud along its principal directions and skipping key tiles by bounding box must not
     change a single index: same lists as the full tensor-core scan, ordered and unordered, on real
