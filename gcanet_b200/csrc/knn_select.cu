@@ -56,6 +56,7 @@ struct ScanArgs {
     int TR;                 // reference tile (multiple of 32)
     const int *qlist;       // optional [B][Nq] + qcount [B]: only the listed queries are computed / written (the
     const int *qcount;      //   tensor-core path's overflow rows); CTAs then stride over the list
+    int list_min;           // list mode: clouds with fewer listed rows than this are left alone (0 = no limit)
     const int *cloud_filter;  // optional [B]: only clouds with a non-zero flag are computed
 };
 
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kThreads) knn_scan_kernel(ScanArgs a) {
     // list mode: slot s of this cloud's work is query qlist[b][s]; otherwise slot = query
     const int *ql = a.qlist ? a.qlist + (size_t)b * a.Nq : nullptr;
     const int nq = ql ? a.qcount[b] : a.Nq;
+    if (ql && a.list_min > 0 && nq < a.list_min) return;      // few listed rows: knn_row_kernel took them
     for (int vbx = blockIdx.x; vbx * QPB < nq; vbx += gridDim.x) {
     const int q0 = vbx * QPB + warp * R;
     __syncthreads();   // shared memory of the previous round is free
@@ -426,11 +428,169 @@ int launch_sqnorm_public(const float *x, float *out, int B, int C, int Cuse, int
 }
 
 static int scan_self(const float *x, const float *norms, const int *qlist, const int *qcount, int B, int C, int N, int k1, int k2,
-                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st, const int *cloud_filter = nullptr);
+                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st, const int *cloud_filter = nullptr,
+                     int list_min = 0);
+
+// ---------------------------------------------------------------------------------
+// One CTA per listed query (the tensor-core path's overflow rows: massive ties).  The batched scan above needs
+// ~1 ms per CTA whatever the number of queries it holds, which made a handful of overflow rows cost more than the
+// rest of the call.  Here all N distances of the query go to shared memory (same arithmetic as the scan: fma chain
+// over the channels, fl(fl(|x_j|^2 - 2 t) + |x_i|^2)), the k smallest by (distance, index) are found by block-wide
+// bisection -- on the distance, then on the index among the points tied at the k-th distance -- and ranked.
+// ---------------------------------------------------------------------------------
+constexpr int kRowFallbackMax = 512;    // listed rows per cloud up to which the per-row kernel is used
+
+struct RowArgs {
+    const float *x;         // [B][C][N]
+    const float *norm;      // [B][N]
+    const int *qlist;       // [B][N]
+    const int *qcount;      // [B]
+    int C, N, k, step, kout;
+    int64_t *idx64;
+    int32_t *idx32;
+};
+
+__device__ __forceinline__ int block_sum_256(int v, int *s_red) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    __syncthreads();                                   // s_red free again
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) knn_row_kernel(RowArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float *sd = smem;                                   // [N] distances of the current query
+    float *s_q = sd + a.N;                              // [C]
+    float *s_seld = s_q + a.C;                          // [k]
+    int *s_selj = reinterpret_cast<int *>(s_seld + a.k);// [k]
+    __shared__ int s_red[8];
+    __shared__ float s_fred[2][8];
+    __shared__ int s_cnt;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int N = a.N, C = a.C, k = a.k;
+    const float *xb = a.x + (size_t)b * C * N;
+    const float *nb = a.norm + (size_t)b * N;
+    const int nq = a.qcount[b];
+    if (nq > kRowFallbackMax) return;                   // many rows: the batched scan (launched next) is cheaper per row
+    for (int slot = blockIdx.x; slot < nq; slot += gridDim.x) {
+        const int q = a.qlist[(size_t)b * N + slot];
+        __syncthreads();
+        for (int c = tid; c < C; c += 256) s_q[c] = xb[(size_t)c * N + q];
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        const float qn = nb[q];
+        float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+        for (int j0 = tid; j0 < N; j0 += 4 * 256) {         // four points per thread and step: four independent fma chains
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            int jj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) jj[u] = min(j0 + u * 256, N - 1);
+#pragma unroll 8
+            for (int c = 0; c < C; ++c) {                    // (unrolled: 32 independent loads in flight per thread)
+                const float qc = s_q[c];
+                const float *xr = xb + (size_t)c * N;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] = fmaf(qc, __ldg(xr + jj[u]), acc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + u * 256 < N) {
+                    const float d = __fadd_rn(fmaf(-2.f, acc[u], nb[jj[u]]), qn);
+                    sd[jj[u]] = d;
+                    mn = fminf(mn, d);
+                    mx = fmaxf(mx, d);
+                }
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+        }
+        if ((tid & 31) == 0) { s_fred[0][tid >> 5] = mn; s_fred[1][tid >> 5] = mx; }
+        __syncthreads();
+        mn = s_fred[0][0]; mx = s_fred[1][0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_fred[0][w]); mx = fmaxf(mx, s_fred[1][w]); }
+        // distance bisection: hi keeps count(d <= hi) >= k, lo keeps count(d <= lo) < k (or lo = min)
+        float lo = mn, hi = mx;
+        int c_hi = N;
+        for (int it = 0; it < 80 && c_hi > k; ++it) {
+            const float mid = 0.5f * lo + 0.5f * hi;
+            if (!(mid > lo && mid < hi)) break;
+            int c = 0;
+            for (int j = tid; j < N; j += 256) c += (sd[j] <= mid) ? 1 : 0;
+            c = block_sum_256(c, s_red);
+            if (c >= k) { hi = mid; c_hi = c; } else lo = mid;
+        }
+        // ties at hi: everything strictly below hi is in (count below), the rest of the k come from the points with
+        // d == hi in index order.  (If the loop ended with c_hi == k there is nothing to cut: J = N.)
+        int J = N;
+        if (c_hi > k) {
+            int below = 0;
+            for (int j = tid; j < N; j += 256) below += (sd[j] < hi) ? 1 : 0;
+            below = block_sum_256(below, s_red);
+            if (below >= k) {
+                // only when lo was never proven (count(d <= min) >= k): the ties sit at the minimum itself
+                hi = lo;
+                below = 0;
+                for (int j = tid; j < N; j += 256) below += (sd[j] < hi) ? 1 : 0;
+                below = block_sum_256(below, s_red);
+            }
+            const int need = k - below;                     // >= 1
+            int jl = -1, jh = N - 1;                        // count(d == hi && j <= jh) >= need
+            while (jh - jl > 1) {
+                const int jm = (jl + jh) >> 1;
+                int c = 0;
+                for (int j = tid; j < N; j += 256) c += (sd[j] == hi && j <= jm) ? 1 : 0;
+                c = block_sum_256(c, s_red);
+                if (c >= need) jh = jm; else jl = jm;
+            }
+            J = jh;
+        }
+        __syncthreads();
+        for (int j = tid; j < N; j += 256) {
+            const float d = sd[j];
+            if (d < hi || (d == hi && j <= J)) {
+                const int p = atomicAdd(&s_cnt, 1);
+                if (p < k) { s_seld[p] = d; s_selj[p] = j; }
+            }
+        }
+        __syncthreads();
+        const int m = min(s_cnt, k);
+        for (int e = tid; e < m; e += 256) {
+            const float d = s_seld[e];
+            const int j = s_selj[e];
+            int rank = 0;
+            for (int f = 0; f < m; ++f) {
+                const float od = s_seld[f];
+                const int oj = s_selj[f];
+                rank += (od < d || (od == d && oj < j)) ? 1 : 0;
+            }
+            if (rank % a.step == 0) {
+                const size_t o = ((size_t)b * N + q) * a.kout + rank / a.step;
+                if (a.idx64) a.idx64[o] = j;
+                if (a.idx32) a.idx32[o] = j;
+            }
+        }
+    }
+}
 
 // re-runs the CUDA-core scan for the queries listed in qlist[b][0 .. qcount[b]) (tensor-core path overflow)
 int knn_fallback_rows(const float *x, const float *norms, const int *qlist, const int *qcount, int B, int C, int N, int k1, int k2,
                       int64_t *idx64, int32_t *idx32, cudaStream_t st) {
+    const size_t smem = ((size_t)N + C + 2 * (size_t)k2) * sizeof(float);
+    if (smem <= 200 * 1024) {
+        RowArgs a{x, norms, qlist, qcount, C, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2), idx64, idx32};
+        if (smem > 48 * 1024) GCANET_CUDA_OK(cudaFuncSetAttribute(knn_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_row_kernel<<<dim3(64, B), 256, smem, st>>>(a);
+        GCANET_LAUNCH_OK("knn_row_kernel");
+        // clouds with more than kRowFallbackMax listed rows (degenerate inputs) take the batched scan instead
+        return scan_self(x, norms, qlist, qcount, B, C, N, k1, k2, GCANET_METRIC_L2, idx64, idx32, st, nullptr, kRowFallbackMax + 1);
+    }
     return scan_self(x, norms, qlist, qcount, B, C, N, k1, k2, GCANET_METRIC_L2, idx64, idx32, st);
 }
 
@@ -442,10 +602,11 @@ int knn_graph_cuda_cores(const float *x, int B, int C, int N, int k1, int k2, in
 }
 
 static int scan_self(const float *x, const float *norms, const int *qlist, const int *qcount, int B, int C, int N, int k1, int k2,
-                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st, const int *cloud_filter) {
+                     int metric, int64_t *idx64, int32_t *idx32, cudaStream_t st, const int *cloud_filter, int list_min) {
     ScanArgs a{};
     a.qlist = qlist;
     a.qcount = qcount;
+    a.list_min = list_min;
     a.cloud_filter = cloud_filter;
     a.ref = x; a.qry = x; a.ref_norm = norms; a.qry_norm = norms;
     a.C = C; a.Nr = N; a.Nq = N; a.k = k2;
