@@ -423,6 +423,8 @@ struct RerankArgs {
     const int *perm;       // pruned path: rows and candidates are sorted positions, perm[b][s] = original index; else null
     int cap;               // entries per row in `cand`
     int split;             // 1: a row's list is two halves of cap / 2 entries with counts cand_cnt[2 row], cand_cnt[2 row + 1]
+    int *big_list;         // [B][N] rows (scan order) with more than TC_CAP candidates, big_count [B] (zeroed by the host)
+    int *big_count;
     int *fb_list;          // [B][N] rows left to the CUDA-core fallback (overflowed lists), fb_count [B] (zeroed by the host)
     int *fb_count;
 };
@@ -594,36 +596,51 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
     (void)q;
 }
 
-template <int C>
+// BIG = false: one warp per row of the scan; rows with more than TC_CAP candidates (dense near-tie regions on the
+// pruned path, whose lists hold up to TCP_CAP) are only listed.  BIG = true: a second, usually empty launch takes
+// the listed rows with the wide instantiation -- its registers and shared memory would otherwise cost every row
+// an occupancy step.
+template <int C, bool BIG>
 __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
     constexpr int VEC = C / 32;
-    __shared__ int s_idx[8][TCP_CAP];
-    __shared__ float s_d[8][TCP_CAP];
+    constexpr int SCAP = BIG ? TCP_CAP : TC_CAP;
+    __shared__ int s_idx[8][SCAP];
+    __shared__ float s_d[8][SCAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    const int qs = blockIdx.x * 8 + warp;                 // row in the scan's order
-    if (qs >= a.N) return;
-    const size_t srow = (size_t)b * a.N + qs;
     const int *perm = a.perm ? a.perm + (size_t)b * a.N : nullptr;
-    const int q = perm ? perm[qs] : qs;                   // original point index
-    const size_t grow = (size_t)b * a.N + q;
-    if (a.overflow[grow]) {                               // the fallback kernel writes this row
-        if (lane == 0) a.fb_list[(size_t)b * a.N + atomicAdd(&a.fb_count[b], 1)] = q;
-        return;
-    }
-    const int n0 = a.split ? a.cand_cnt[2 * srow] : a.cand_cnt[srow];
-    const int n = a.split ? n0 + a.cand_cnt[2 * srow + 1] : n0;
-    const uint2 *cand = a.cand + srow * a.cap;
     const float *xb = a.x_nc + (size_t)b * a.N * C;
     const float *nb = a.norm + (size_t)b * a.N;
-    float qv[VEC];
-    load_row<VEC>(xb + (size_t)q * C + lane * VEC, qv);
-    const float qn = nb[q];
-    const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
-    // short lists (the pruned scan's fixed thresholds leave ~2k entries) take the narrow instantiation
-    if (n <= 128) rerank_row<C, 4>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
-    else if (n <= 256) rerank_row<C, 8>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
-    else rerank_row<C, TCP_CAP / 32>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+    const int rows = BIG ? a.big_count[b] : a.N;
+    for (int slot = blockIdx.x * 8 + warp; slot < rows; slot += gridDim.x * 8) {
+        const int qs = BIG ? a.big_list[(size_t)b * a.N + slot] : slot;       // row in the scan's order
+        const size_t srow = (size_t)b * a.N + qs;
+        const int q = perm ? perm[qs] : qs;               // original point index
+        const size_t grow = (size_t)b * a.N + q;
+        if (!BIG && a.overflow[grow]) {                   // the fallback kernel writes this row
+            if (lane == 0) a.fb_list[(size_t)b * a.N + atomicAdd(&a.fb_count[b], 1)] = q;
+            continue;
+        }
+        const int n0 = a.split ? a.cand_cnt[2 * srow] : a.cand_cnt[srow];
+        const int n = a.split ? n0 + a.cand_cnt[2 * srow + 1] : n0;
+        if (!BIG && n > TC_CAP) {
+            if (lane == 0) a.big_list[(size_t)b * a.N + atomicAdd(&a.big_count[b], 1)] = qs;
+            continue;
+        }
+        const uint2 *cand = a.cand + srow * a.cap;
+        float qv[VEC];
+        load_row<VEC>(xb + (size_t)q * C + lane * VEC, qv);
+        const float qn = nb[q];
+        const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
+        if constexpr (BIG) {
+            rerank_row<C, TCP_CAP / 32>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+        } else {
+            // short lists (the pruned scan's fixed thresholds leave ~1.5 k entries) take the narrow instantiation
+            if (n <= 128) rerank_row<C, 4>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+            else rerank_row<C, 8>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+        }
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -1497,7 +1514,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += 3 * align_up((size_t)B * ceil_div(N, TC_BN) * 6 * sizeof(float));   // tile boxes + boxes of their 32-point halves
     t += align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));          // visited-tile statistics
     t += 2 * align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));      // launch order of the query tiles + its sort keys
-    t += align_up(bn * sizeof(int)) + align_up((size_t)B * sizeof(int));  // fallback row list + counts
+    t += 2 * align_up(bn * sizeof(int)) + align_up(2 * (size_t)B * sizeof(int));  // fallback / wide re-rank row lists + counts
     t += align_up(bn * 2 * C * sizeof(__nv_bfloat16));   // xs
     t += align_up(bn * C * sizeof(float));               // x_nc
     t += align_up(bn * sizeof(float));                   // norm
@@ -1531,7 +1548,7 @@ static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcSca
     GCANET_LAUNCH_OK("knn_tc_scan_kernel");
     if (sa.debug_no_append) return GCANET_OK;      // measurement aid: scan pipeline only
     dim3 rgrid(ceil_div(sa.N, 8), B);
-    knn_tc_rerank_kernel<C><<<rgrid, 256, 0, st>>>(ra);
+    knn_tc_rerank_kernel<C, false><<<rgrid, 256, 0, st>>>(ra);
     GCANET_LAUNCH_OK("knn_tc_rerank_kernel");
     return GCANET_OK;
 }
@@ -1548,8 +1565,10 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
     kern<<<grid, TCP_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
     GCANET_LAUNCH_OK("knn_tcp_scan_kernel");
     dim3 rgrid(ceil_div(sa.N, 8), B);
-    knn_tc_rerank_kernel<C><<<rgrid, 256, 0, st>>>(ra);
+    knn_tc_rerank_kernel<C, false><<<rgrid, 256, 0, st>>>(ra);
     GCANET_LAUNCH_OK("knn_tc_rerank_kernel");
+    knn_tc_rerank_kernel<C, true><<<dim3(32, B), 256, 0, st>>>(ra);       // rows with more than TC_CAP candidates (usually none)
+    GCANET_LAUNCH_OK("knn_tc_rerank_kernel<big>");
     return GCANET_OK;
 }
 
@@ -1595,8 +1614,10 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     int *work_buf = cv.take<int>((size_t)B * ceil_div(N, TC_BM));
     unsigned *wkey = cv.take<unsigned>((size_t)B * ceil_div(N, TC_BM));
     int *fb_list = cv.take<int>(bn);
-    int *fb_count = cv.take<int>(B);
-    GCANET_CUDA_OK(cudaMemsetAsync(fb_count, 0, B * sizeof(int), st));
+    int *big_list = cv.take<int>(bn);
+    int *fb_count = cv.take<int>(2 * (size_t)B);          // fallback rows | wide re-rank rows
+    int *big_count = fb_count + B;
+    GCANET_CUDA_OK(cudaMemsetAsync(fb_count, 0, 2 * B * sizeof(int), st));
     const char *env_np = getenv("GCANET_TC_NO_PRUNE");
     const bool prune = !no_prune && tcp_supported(B, N, k2) && !(env_np && env_np[0] == '1') && !getenv("GCANET_TC_DEBUG");
     __nv_bfloat16 *xs = cv.take<__nv_bfloat16>(bn * 2 * C);
@@ -1666,7 +1687,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         }
         TcpScanArgs sa{norm_pad, Npad, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, N, k2, tiles, pre, P, qtiles};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
-                      (unordered && k1 == k2) ? 1 : 0, perm, TCP_CAP, 1, fb_list, fb_count};
+                      (unordered && k1 == k2) ? 1 : 0, perm, TCP_CAP, 1, big_list, big_count, fb_list, fb_count};
         if (k2 <= TC_BN) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, ra, B, st);
         else rc = C == 64 ? launch_tcp<64, 2>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128, 2>(tmap_q, tmap_k, sa, ra, B, st);
         if (rc) return rc;
@@ -1707,7 +1728,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     const int dbg_mode = (dbg && dbg[0] >= '1' && dbg[0] <= '3') ? dbg[0] - '0' : 0;
     TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, dbg_mode, stride};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
-                  (unordered && k1 == k2) ? 1 : 0, nullptr, TC_CAP, 0, fb_list, fb_count};
+                  (unordered && k1 == k2) ? 1 : 0, nullptr, TC_CAP, 0, big_list, big_count, fb_list, fb_count};
     if (dbg_mode >= 2 && C == 64)
         rc = dbg_mode == 2 ? launch_tc<64, 2>(tmap_q, tmap_k, sa, ra, B, st) : launch_tc<64, 3>(tmap_q, tmap_k, sa, ra, B, st);
     else
