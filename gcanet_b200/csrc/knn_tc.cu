@@ -1535,7 +1535,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += align_up(bn * sizeof(float));                   // norm
     t += align_up((size_t)B * (ceil_div(N, TC_BN) * TC_BN) * sizeof(float));   // norm_pad
     t += align_up((size_t)B * sizeof(float));            // nmax
-    t += align_up(bn * TCP_CAP * sizeof(uint2));         // cand (the full scan uses TC_CAP entries per row of it)
+    t += align_up((bn * TCP_CAP + 512) * sizeof(uint2)); // cand, 4 KB-aligned rows (the full scan uses TC_CAP entries per row of it)
     t += align_up(2 * bn * sizeof(int));                 // cand_cnt (two halves per row on the pruned path)
     t += align_up(bn * sizeof(int));                     // overflow
     return t;
@@ -1641,7 +1641,11 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     const int Npad = ceil_div(N, TC_BN) * TC_BN;
     float *norm_pad = cv.take<float>((size_t)B * Npad);
     float *nmax = cv.take<float>(B);
-    uint2 *cand = cv.take<uint2>(bn * TCP_CAP);
+    // rows of the candidate buffer start on 4 KB boundaries whatever the caller's workspace alignment: the scan
+    // advances a half-list's write pointer in the low address word only, so a half-list (2 KB, 2 KB-aligned)
+    // must never straddle a 4 GB boundary
+    uint2 *cand = cv.take<uint2>(bn * TCP_CAP + 512);
+    cand = reinterpret_cast<uint2 *>((reinterpret_cast<uintptr_t>(cand) + 4095) & ~(uintptr_t)4095);
     int *cand_cnt = cv.take<int>(2 * bn);
     int *overflow = cv.take<int>(bn);
 
