@@ -116,6 +116,10 @@ struct TcScanArgs {
     int debug_no_append; // measurement aid (GCANET_TC_DEBUG=1): thresholds start at -inf, nothing is ever appended
     int tile_stride;     // key tiles are visited as (t * tile_stride) % tiles, stride coprime to tiles:
                          // a spatially sorted cloud then looks like a random stream to the thresholds
+    // hybrid launch next to the box-pruned kernel (which takes the clouds with structured[b] != 0):
+    const int *structured;  // null, or [B]: this kernel only takes the clouds with structured[b] == 0
+    int cap;                // row stride of `cand` in entries (TC_CAP, or TCP_CAP in the hybrid launch)
+    int split_counts;       // 1: counts are written as (cnt, 0) pairs at cand_cnt[2 row], the pruned path's layout
 };
 
 // Bisection over a warp-distributed list (entries e = s*32 + lane, +inf padding): returns hi with
@@ -231,6 +235,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int b = blockIdx.y;
     const int q0 = blockIdx.x * TC_BM;
     const int tiles = a.tiles;
+    if (a.structured != nullptr && a.structured[b] != 0) return;     // the box-pruned kernel has this cloud
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -311,7 +316,7 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int q = q0 + row;
         const bool active = q < a.N;
         const size_t grow = (size_t)b * a.N + (active ? q : 0);
-        uint2 *buf = a.cand + grow * TC_CAP;
+        uint2 *buf = a.cand + grow * a.cap;
         const float qn = active ? a.norm[grow] : 0.f;
         const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
         float thr = (active && !a.debug_no_append) ? CUDART_INF_F : -CUDART_INF_F;   // inactive rows never append
@@ -393,7 +398,8 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
         // the last shrink of each list happens in the re-rank kernel (one warp per row, full occupancy)
         if (active) {
-            a.cand_cnt[grow] = ovf ? 0 : cnt;
+            if (a.split_counts) { a.cand_cnt[2 * grow] = ovf ? 0 : cnt; a.cand_cnt[2 * grow + 1] = 0; }
+            else a.cand_cnt[grow] = ovf ? 0 : cnt;
             a.overflow[grow] = (ovf || cnt < a.k) ? 1 : 0;
         }
     }
@@ -654,6 +660,7 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
 // no pruning); how well they capture the variance only decides how much is skipped.
 // ---------------------------------------------------------------------------------
 constexpr int TCP_MIN_N = 1024;
+constexpr int TCP_FULL_MIN_N = 32768;  // unstructured clouds at least this large take the single-pass full scan
 constexpr int TCP_SPLIT = 8;          // partial Gram matrices per cloud
 constexpr int TCP_PRE = 8;            // nearest tiles every query tile reads unconditionally (first bound refresh after them)
 constexpr int TCP_ITERS = 5;          // subspace iterations (lambda_3 / lambda_4 is ~4 on layer activations: 4^5 = 1000x)
@@ -714,8 +721,14 @@ __global__ void __launch_bounds__(256) tcp_moments_kernel(const float *__restric
 
 // pca[b] = { V[3][C], m[3] = V mu, sigma_1 }  (3*C + 4 floats): three orthonormal directions spanning (approximately)
 // the leading principal subspace of the cloud, by subspace iteration on its covariance.  One CTA per cloud.
+// structured[b] = 1: the box-pruned two-pass scan takes the cloud.  Large clouds (n_full >= TCP_FULL_MIN_N) whose three
+// directions carry less than half of the variance (e.g. i.i.d. Gaussian features: nothing can be skipped, and at
+// that size the repeated tensor-core pass costs more than the list compactions it avoids) get 0: their directions
+// are zeroed -- all sort keys equal, the stable sort keeps the original order -- and the single-pass full scan
+// takes them.  (At 10 000 points the two-pass scan is the faster one even without any structure: 2.3 vs 3.0 ms.)
 template <int C>
-__global__ void __launch_bounds__(256) tcp_pca_kernel(const float *__restrict__ part, float *__restrict__ pca, int N) {
+__global__ void __launch_bounds__(256) tcp_pca_kernel(const float *__restrict__ part, float *__restrict__ pca,
+                                                      int *__restrict__ structured, int N, int n_full) {
     extern __shared__ float sm[];
     float *cov = sm;                  // [C][C+1]
     float *mu = cov + C * (C + 1);    // [C]
@@ -805,7 +818,12 @@ __global__ void __launch_bounds__(256) tcp_pca_kernel(const float *__restrict__ 
                 const float want = i == j ? 1.f : 0.f;
                 if (!(fabsf(d - want) <= 1e-4f)) ok = false;
             }
-        if (lane == 0) s_ok = ok ? 1 : 0;
+        // explained variance: lambda_i ~ |cov v_i| of the last iteration against the trace
+        float tr = 0.f;
+        for (int c = lane; c < C; c += 32) tr += cov[c * (C + 1) + c];
+        for (int o = 16; o; o >>= 1) tr += __shfl_xor_sync(FULLW, tr, o);
+        if (n_full >= TCP_FULL_MIN_N && !(s_lambda[0] + s_lambda[1] + s_lambda[2] >= 0.5f * tr)) ok = false;
+        if (lane == 0) { s_ok = ok ? 1 : 0; structured[blockIdx.x] = ok ? 1 : 0; }
     }
     __syncthreads();
     float *o = pca + (size_t)b * (3 * C + 4);
@@ -983,6 +1001,7 @@ struct TcpScanArgs {
     int *overflow;          // [B][N]          rows in ORIGINAL order (consumed by the fallback scan)
     int *visited;           // [B][query tiles] statistics: key tiles scanned in the main pass (may be null)
     const int *work;        // [B * qtiles] query tiles (b * qtiles + qt) in launch order, or null = natural order
+    const int *structured;  // [B] 1 = this kernel takes the cloud, 0 = the full scan does
     int N, k, tiles, pre, P;  // P = tiles rounded up to a power of two (sort width)
     int qtiles;
 };
@@ -1029,6 +1048,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // CTAs take the query tiles in the order of a.work (largest bounding box first: those scan the most key tiles,
     // and starting them last would leave the tail of the grid to a few long-running CTAs)
     const int item = a.work ? a.work[blockIdx.x] : (int)blockIdx.x;
+    if (a.structured[item / a.qtiles] == 0) return;       // no low-dimensional structure: the full scan has this cloud
     const int b = item / a.qtiles;
     const int qt = item - b * a.qtiles;
     const int q0 = qt * TC_BM;
@@ -1521,6 +1541,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     // pruned path
     t += align_up((size_t)B * TCP_SPLIT * (C * C + C) * sizeof(float));   // partial moments
     t += align_up((size_t)B * (3 * C + 4) * sizeof(float));               // pca
+    t += align_up((size_t)B * sizeof(int));                               // structured flags
     t += align_up(3 * bn * sizeof(float));                                // projections
     t += 2 * align_up(bn * sizeof(unsigned));                             // keys in/out
     t += 2 * align_up(bn * sizeof(int));                                  // vals in/out
@@ -1569,7 +1590,8 @@ static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcSca
 }
 
 template <int C, int SM>
-static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpScanArgs sa, RerankArgs ra, int B, cudaStream_t st) {
+static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpScanArgs sa, TcScanArgs fa, RerankArgs ra, int B,
+                      cudaStream_t st) {
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int STAGES = tcp_stages(C);
     const size_t smem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)STAGES * NBLK * TC_BN * 128 +
@@ -1579,6 +1601,16 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
     dim3 grid(ceil_div(sa.N, TC_BM) * B);
     kern<<<grid, TCP_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
     GCANET_LAUNCH_OK("knn_tcp_scan_kernel");
+    {
+        // clouds without low-dimensional structure (their sorted order is the original order): single-pass full scan
+        constexpr int FS_STAGES = 2;
+        const size_t fsmem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)FS_STAGES * NBLK * TC_BN * 128 +
+                             TC_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t);
+        auto fkern = knn_tc_scan_kernel<C, 0>;
+        GCANET_CUDA_OK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        fkern<<<dim3(ceil_div(sa.N, TC_BM), B), TC_THREADS, fsmem, st>>>(tmap_q, tmap_k, fa);
+        GCANET_LAUNCH_OK("knn_tc_scan_kernel");
+    }
     dim3 rgrid(ceil_div(sa.N, 8), B);
     knn_tc_rerank_kernel<C, false><<<rgrid, 256, 0, st>>>(ra);
     GCANET_LAUNCH_OK("knn_tc_rerank_kernel");
@@ -1588,7 +1620,7 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
 }
 
 template <int C>
-static int launch_tcp_prep(const float *x, float *part, float *pca, float *proj, unsigned *keys, int *vals,
+static int launch_tcp_prep(const float *x, float *part, float *pca, int *structured, float *proj, unsigned *keys, int *vals,
                            int B, int N, cudaStream_t st) {
     int stride = N / 1024;
     stride = stride < 1 ? 1 : (stride > 8 ? 8 : stride);
@@ -1598,7 +1630,7 @@ static int launch_tcp_prep(const float *x, float *part, float *pca, float *proj,
     const size_t smem = ((size_t)C * (C + 1) + 7 * C) * sizeof(float);
     auto kern = tcp_pca_kernel<C>;
     if (smem > 48 * 1024) GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, 256, smem, st>>>(part, pca, Ns);
+    kern<<<B, 256, smem, st>>>(part, pca, structured, Ns, N);
     GCANET_LAUNCH_OK("tcp_pca_kernel");
     tcp_project_kernel<C><<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(x, pca, proj, keys, vals, B, N, tcp_axis_bits(B));
     GCANET_LAUNCH_OK("tcp_project_kernel");
@@ -1613,6 +1645,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     Carver cv(ws);
     float *part = cv.take<float>((size_t)B * TCP_SPLIT * (C * C + C));
     float *pca = cv.take<float>((size_t)B * (3 * C + 4));
+    int *structured = cv.take<int>(B);
     float *proj = cv.take<float>(3 * bn);
     unsigned *keys_in = cv.take<unsigned>(bn);
     unsigned *keys_out = cv.take<unsigned>(bn);
@@ -1653,8 +1686,8 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     if (rc) return rc;
     const int tiles = ceil_div(N, TC_BN);
     if (prune) {
-        rc = C == 64 ? launch_tcp_prep<64>(x, part, pca, proj, keys_in, vals_in, B, N, st)
-                     : launch_tcp_prep<128>(x, part, pca, proj, keys_in, vals_in, B, N, st);
+        rc = C == 64 ? launch_tcp_prep<64>(x, part, pca, structured, proj, keys_in, vals_in, B, N, st)
+                     : launch_tcp_prep<128>(x, part, pca, structured, proj, keys_in, vals_in, B, N, st);
         if (rc) return rc;
         GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
         count_launch();
@@ -1698,6 +1731,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         if (pre > tiles) pre = tiles;
         if (pre < 0) pre = 0;
         const int qtiles = ceil_div(N, TC_BM);
+        if (getenv("GCANET_TC_STATS")) GCANET_CUDA_OK(cudaMemsetAsync(visited, 0, (size_t)B * qtiles * sizeof(int), st));
         const int *work = nullptr;
         if (B * qtiles <= TCP_MAX_WORK && !getenv("GCANET_TC_NO_ORDER")) {
             tcp_work_key_kernel<<<dim3(ceil_div(qtiles, 8), B), 256, 0, st>>>(boxes, wkey, tiles, qtiles);
@@ -1706,14 +1740,19 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
             GCANET_LAUNCH_OK("tcp_work_order_kernel");
             work = work_buf;
         }
-        TcpScanArgs sa{norm_pad, Npad, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, N, k2, tiles, pre, P, qtiles};
+        TcpScanArgs sa{norm_pad, Npad, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, structured, N, k2, tiles, pre, P, qtiles};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                       (unordered && k1 == k2) ? 1 : 0, perm, TCP_CAP, 1, big_list, big_count, fb_list, fb_count};
-        if (k2 <= TC_BN) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, ra, B, st);
-        else rc = C == 64 ? launch_tcp<64, 2>(tmap_q, tmap_k, sa, ra, B, st) : launch_tcp<128, 2>(tmap_q, tmap_k, sa, ra, B, st);
+        int fstride = (int)(tiles * 0.381966f);
+        if (fstride < 1) fstride = 1;
+        auto gcd2 = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+        while (gcd2(fstride, tiles) != 1) ++fstride;
+        TcScanArgs fa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, 0, fstride, structured, TCP_CAP, 1};
+        if (k2 <= TC_BN) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, fa, ra, B, st);
+        else rc = C == 64 ? launch_tcp<64, 2>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 2>(tmap_q, tmap_k, sa, fa, ra, B, st);
         if (rc) return rc;
         const char *stats = getenv("GCANET_TC_STATS");
-        if (stats && stats[0] == '1') {            // measurement aid: synchronises
+        if (stats && stats[0] == '1') {            // measurement aid: synchronises (clouds left to the full scan report 0 tiles)
             const int nq = B * ceil_div(N, TC_BM);
             int *h = (int *)malloc(nq * sizeof(int));
             GCANET_CUDA_OK(cudaStreamSynchronize(st));
@@ -1747,7 +1786,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     // and stop after it -- gives the TMA + MMA + TMEM-read + compare floor of the kernel.
     const char *dbg = getenv("GCANET_TC_DEBUG");
     const int dbg_mode = (dbg && dbg[0] >= '1' && dbg[0] <= '3') ? dbg[0] - '0' : 0;
-    TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, dbg_mode, stride};
+    TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, dbg_mode, stride, nullptr, TC_CAP, 0};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                   (unordered && k1 == k2) ? 1 : 0, nullptr, TC_CAP, 0, big_list, big_count, fb_list, fb_count};
     if (dbg_mode >= 2 && C == 64)
