@@ -69,6 +69,23 @@ def test_argument_validation_without_device():
     assert L.gcanet_edgeconv_workspace_bytes(ctypes.byref(d)) > 0
 
 
+def test_flag_constants_match_the_header_and_unknown_flags_are_rejected():
+    from gcanet_b200 import functional as G
+    text = open(os.path.join(ROOT, "include", "gcanet_b200.h")).read()
+    for name, val in (("GCANET_KNN_FLAG_BRUTE_FORCE", G.KNN_FLAG_BRUTE_FORCE), ("GCANET_KNN_FLAG_UNORDERED", G.KNN_FLAG_UNORDERED),
+                      ("GCANET_KNN_FLAG_NO_PRUNE", G.KNN_FLAG_NO_PRUNE)):
+        m = re.search(r"#define\s+" + name + r"\s+(0x[0-9a-fA-F]+)", text)
+        assert m and int(m.group(1), 16) == val, name
+    L = _cabi.lib()
+    null, one = ctypes.c_void_p(0), ctypes.c_void_p(256)
+    # every known flag combination passes validation (and then fails on the missing workspace, never on the flags)
+    for flags in (0x100, 0x200, 0x400, 0x600, 0x700):
+        assert L.gcanet_knn_graph(one, 1, 64, 2048, 20, 20, flags, one, null, null, 0, null) == -2
+        assert L.gcanet_knn_graph_workspace_bytes(1, 64, 2048, 20, flags) > 0
+    assert L.gcanet_knn_graph(one, 1, 64, 2048, 20, 20, 0x800, one, null, one, 1 << 30, null) == -1
+    assert b"unknown flag" in L.gcanet_last_error()
+
+
 def test_cpu_tensors_are_refused():
     x = torch.randn(1, 3, 32)
     for fn in (lambda: gb.knn(x, 4, 4), lambda: gb.get_graph_feature(x, 4, 4),
