@@ -1339,7 +1339,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             float m[32 * SM];
 #pragma unroll
             for (int s = 0; s < 32 * SM; ++s) m[s] = CUDART_INF_F;
-            int done = 0, refresh_at = pre > 0 ? pre : 8;
+            int done = 0, refresh_at = 12;
             for (;; ++seq) {
                 mbar_wait(&t_full[acc], accphase);
                 if (seq == s_end[0]) break;
@@ -1369,8 +1369,9 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 if (lane == 0) mbar_arrive(&t_empty[acc]);
                 if (++acc == ACC) { acc = 0; accphase ^= 1; }
                 if (++done == refresh_at) {
-                    // let the producer start skipping: publish the bound reached so far (after pre, 2 pre, 4 pre tiles)
-                    refresh_at = refresh_at < 4 * (pre > 0 ? pre : 8) ? refresh_at * 2 : 0x7fffffff;
+                    // let the producer start skipping: publish the bound reached so far (after 12 and 36 tiles: each
+                    // refresh costs about as much as six tiles of this pass)
+                    refresh_at = refresh_at < 36 ? refresh_at * 3 : 0x7fffffff;
                     const float bd = row_bound(m, 6);
                     float wt = active ? bd + margin + qn : -CUDART_INF_F;
                     for (int o = 16; o; o >>= 1) wt = fmaxf(wt, __shfl_xor_sync(FULLW, wt, o));
