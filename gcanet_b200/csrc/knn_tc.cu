@@ -642,7 +642,8 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
             rerank_row<C, TCP_CAP / 32>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
         } else {
             // short lists (the pruned scan's fixed thresholds leave ~1.5 k entries) take the narrow instantiation
-            if (n <= 128) rerank_row<C, 4>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+            if (n <= 96) rerank_row<C, 3>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+            else if (n <= 128) rerank_row<C, 4>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
             else rerank_row<C, 8>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
         }
         __syncwarp();
