@@ -1010,7 +1010,7 @@ struct TcpScanArgs {
 // SM = 1: k <= 64, one minimum per column slot.  SM = 2: k <= 128, the two smallest per slot (128 distinct keys; the
 // 64 extra registers cost the second resident CTA).
 template <int C, int SM>
-__global__ void __launch_bounds__(TCP_THREADS, (C == 64 && SM == 1) ? 2 : 1)
+__global__ void __launch_bounds__(TCP_THREADS, C == 64 ? 2 : 1)
 knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int NH = C / TC_KB;
@@ -1349,19 +1349,39 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 // could lower any of them: its slot minima are not needed (the final bound is the same without them)
                 if (__uint_as_float((uint32_t)lbw[seq] << 16) <= wbound) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_BN + hf * 32;
-                    uint32_t v[32];
-                    tmem_ld32(taddr, v);
-                    tmem_ld_wait();
                     const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + hf * 32);
+                    if constexpr (SM == 1) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr, v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4) {
-                        const float4 n4 = rn[c4];
-                        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 n4 = rn[c4];
+                            const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float d = fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]);
-                            if constexpr (SM == 2) m[32 + c4 * 4 + e] = fminf(m[32 + c4 * 4 + e], fmaxf(m[c4 * 4 + e], d));   // second smallest
-                            m[c4 * 4 + e] = fminf(m[c4 * 4 + e], d);
+                            for (int e = 0; e < 4; ++e)
+                                m[c4 * 4 + e] = fminf(m[c4 * 4 + e], fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]));
+                        }
+                    } else {
+                        // 64 slot registers: the accumulator chunk is read 16 columns at a time to stay within the
+                        // register budget of two CTAs per SM
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t v[16];
+                            tmem_ld16(taddr + h * 16, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; ++c4) {
+                                const float4 n4 = rn[h * 4 + c4];
+                                const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int sl = h * 16 + c4 * 4 + e;
+                                    const float d = fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]);
+                                    m[32 + sl] = fminf(m[32 + sl], fmaxf(m[sl], d));      // second smallest of the slot
+                                    m[sl] = fminf(m[sl], d);
+                                }
+                            }
                         }
                     }
                 }
