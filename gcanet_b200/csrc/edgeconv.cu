@@ -426,11 +426,13 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
         const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
         if (i >= a.N) break;
         // z = sign(gamma) * y: one running max covers both signs (y itself is exact: only a sign flip)
+        // with sq = sg * q:  z = fma(sg, p, sq) = sg * fl(p + q) exactly (sg = +-1, rounding is symmetric), sum_k y =
+        // sg * sum_k z and y^2 = z^2 -- one instruction per edge and channel less than forming y first
         float q[VEC], zmax[VEC], vsum[VEC], vsq[VEC];
         int kbest[VEC];
         VecIO<VEC>::ld(pq + (size_t)i * 2 * Cout + Cout + c0, q);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { zmax[v] = -CUDART_INF_F; vsum[v] = 0.f; vsq[v] = 0.f; kbest[v] = 0; }
+        for (int v = 0; v < VEC; ++v) { zmax[v] = -CUDART_INF_F; vsum[v] = 0.f; vsq[v] = 0.f; kbest[v] = 0; q[v] *= sg[v]; }
         const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
         for (int base = 0; base < k; base += 32) {
             const int cnt = min(32, k - base);
@@ -447,11 +449,10 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
                 for (int u = 0; u < 8; ++u)
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
-                        const float y = p[u][v] + q[v];
-                        const float z = sg[v] * y;
+                        const float z = fmaf(sg[v], p[u][v], q[v]);
                         if (z > zmax[v]) { zmax[v] = z; kbest[v] = base + t + u; }
-                        vsum[v] += y;
-                        vsq[v] = fmaf(y, y, vsq[v]);
+                        vsum[v] += z;
+                        vsq[v] = fmaf(z, z, vsq[v]);
                     }
             }
             for (; t < cnt; ++t) {
@@ -460,18 +461,17 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
                 VecIO<VEC>::ld(pq + (size_t)j * 2 * Cout + c0, p);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    const float y = p[v] + q[v];
-                    const float z = sg[v] * y;
+                    const float z = fmaf(sg[v], p[v], q[v]);
                     if (z > zmax[v]) { zmax[v] = z; kbest[v] = base + t; }
-                    vsum[v] += y;
-                    vsq[v] = fmaf(y, y, vsq[v]);
+                    vsum[v] += z;
+                    vsq[v] = fmaf(z, z, vsq[v]);
                 }
             }
         }
         const size_t o = ((size_t)b * a.N + i) * Cout + c0;
         float ys[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) ys[v] = sg[v] * zmax[v];
+        for (int v = 0; v < VEC; ++v) { ys[v] = sg[v] * zmax[v]; vsum[v] *= sg[v]; }     // back from z to y
         VecIO<VEC>::st(a.ysel + o, ys);
         VecIO<VEC>::st(a.ysum + o, vsum);
 #pragma unroll
