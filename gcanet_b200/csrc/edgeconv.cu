@@ -416,6 +416,10 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
     const int Cout = a.Cout, k = a.k;
     const int c0 = lane * VEC;
     const float *pq = a.pq + (size_t)b * a.N * 2 * Cout;
+    // rows are addressed with 32-bit element offsets inside the cloud's [N][2 Cout] matrix (N * 2 Cout < 2^30, checked
+    // by check_desc): two instructions per edge instead of a seven-instruction 64-bit multiply
+    const float *pq_c0 = pq + c0;
+    const unsigned row_stride = 2u * (unsigned)Cout;
     double s1 = 0.0, s2 = 0.0;
     float sg[VEC];
     VecIO<VEC>::ld(a.gamma + c0, sg);
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     int j = __shfl_sync(FULLM, myj, t + u);
-                    VecIO<VEC>::ld(pq + (size_t)j * 2 * Cout + c0, p[u]);
+                    VecIO<VEC>::ld(pq_c0 + (unsigned)j * row_stride, p[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
             for (; t < cnt; ++t) {
                 float p[VEC];
                 int j = __shfl_sync(FULLM, myj, t);
-                VecIO<VEC>::ld(pq + (size_t)j * 2 * Cout + c0, p);
+                VecIO<VEC>::ld(pq_c0 + (unsigned)j * row_stride, p);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     const float z = fmaf(sg[v], p[v], q[v]);
@@ -678,6 +682,8 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_kernel(BwdArgs 
     VecIO<VEC>::ld(a.beta + c0, bt);
     float *dpq = a.dpq + (size_t)b * a.N * 2 * Cout;
     const float *pq = a.pq + (size_t)b * a.N * 2 * Cout;
+    float *dpq_c0 = dpq + c0;                              // 32-bit row offsets, as in the gather
+    const unsigned row_stride = 2u * (unsigned)Cout;
     for (int pi = 0; pi < kPtsPerWarp; ++pi) {
         const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
         if (i >= a.N) break;
@@ -709,7 +715,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_kernel(BwdArgs 
                 float val[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) val[v] = T[v] + (ak[v] == base + t ? s[v] : 0.f);
-                VecIO<VEC>::red(dpq + (size_t)j * 2 * Cout + c0, val);
+                VecIO<VEC>::red(dpq_c0 + (unsigned)j * row_stride, val);
             }
         }
     }
@@ -895,6 +901,8 @@ static int check_desc(const gcanet_edgeconv_desc *d) {
     GCANET_REQUIRE(d->groups >= 1 && d->Cout % d->groups == 0 && 32 % d->groups == 0,
                    "edgeconv: groups=%d must divide 32 and Cout=%d", d->groups, d->Cout);
     GCANET_REQUIRE(d->eps > 0.f, "edgeconv: eps must be positive");
+    GCANET_REQUIRE((long long)d->N * 2 * d->Cout < (1ll << 30), "edgeconv: N * 2 * Cout = %lld exceeds 2^30 (32-bit row offsets)",
+                   (long long)d->N * 2 * d->Cout);
     return GCANET_OK;
 }
 
