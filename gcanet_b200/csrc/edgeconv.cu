@@ -21,6 +21,7 @@
 // 2*B*N*C*2Cout FLOP, k times fewer than the per-edge formulation.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <math_constants.h>
 
 namespace gcanet {
@@ -811,6 +812,86 @@ __global__ void edge_bwd_degfix_small_kernel(float *__restrict__ dpq, const floa
     *o = make_float4(out[0], out[1], out[2], out[3]);
 }
 
+// C = 64 feeding Cout > 64 (layer 3): the same split as the small-C variant, with the X~ scatter as one 16-byte
+// reduction per lane -- each half-warp owns one edge (16 lanes x 4 floats = the 64-float row of x_i) -- so an edge costs
+// 256 B of L2 reductions instead of 4 Cout, and the dense term comes back as one tensor-core GEMM  X~ Wq^T  whose
+// result edge_bwd_degfix_mid_kernel folds in.
+template <int VEC>
+__global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_mid_kernel(BwdArgs a) {
+    constexpr int LDX = 64;
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Cout = a.Cout, k = a.k, c0 = lane * VEC;
+    const int cpg = Cout / a.G;
+    const int g = c0 / cpg;
+    const float mean = a.stats[((size_t)b * a.G + g) * 2 + 0], rstd = a.stats[((size_t)b * a.G + g) * 2 + 1];
+    const float Ag = a.coef[((size_t)b * a.G + g) * 2 + 0], Kg = a.coef[((size_t)b * a.G + g) * 2 + 1];
+    float gm[VEC], bt[VEC];
+    VecIO<VEC>::ld(a.gamma + c0, gm);
+    VecIO<VEC>::ld(a.beta + c0, bt);
+    float *dpq = a.dpq + (size_t)b * a.N * 2 * Cout;
+    const float *xb = a.x_nc + (size_t)b * a.N * LDX;
+    const int half = lane >> 4;
+    float *xt_l = a.xt + (size_t)b * a.N * LDX + (lane & 15) * 4;
+    float *dpq_c0 = dpq + c0;
+    const unsigned row_stride = 2u * (unsigned)Cout;
+    for (int pi = 0; pi < kPtsPerWarp; ++pi) {
+        const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
+        if (i >= a.N) break;
+        const size_t o = ((size_t)b * a.N + i) * Cout + c0;
+        float ys[VEC], gg[VEC], ysum[VEC], s[VEC], dq[VEC];
+        VecIO<VEC>::ld(a.ysel + o, ys);
+        VecIO<VEC>::ld(a.gout + o, gg);
+        VecIO<VEC>::ld(a.ysum + o, ysum);
+        const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const int ak = a.arg[o + v];
+            float yh = (ys[v] - mean) * rstd;
+            float u = yh * gm[v] + bt[v];
+            float du = u > 0.f ? gg[v] : gg[v] * a.slope;
+            s[v] = rstd * gm[v] * du;
+            dq[v] = s[v] + (float)k * Ag + Kg * ysum[v];
+            atomicAdd(dpq_c0 + (unsigned)ip[ak] * row_stride + v, s[v]);
+        }
+        VecIO<VEC>::st(dpq + (size_t)i * 2 * Cout + Cout + c0, dq);
+        float xi[4];
+        VecIO<4>::ld(xb + (size_t)i * LDX + (lane & 15) * 4, xi);
+        for (int base = 0; base < k; base += 32) {
+            const int cnt = min(32, k - base);
+            const int myj = lane < cnt ? ip[base + lane] : 0;
+            if (lane < cnt) atomicAdd(a.deg + (size_t)b * a.N + myj, 1);
+            for (int t = 0; t < cnt; t += 2) {
+                const int j = __shfl_sync(FULLM, myj, t + half);
+                if (t + half < cnt) VecIO<4>::red(xt_l + (unsigned)j * LDX, xi);
+            }
+        }
+    }
+}
+
+// dP[j][c] += deg_j (A_g + K_g P[j][c]) + K_g (X~ Wq^T)[j][c]
+__global__ void edge_bwd_degfix_mid_kernel(float *__restrict__ dpq, const float *__restrict__ pq, const int *__restrict__ deg,
+                                           const float *__restrict__ coef, const float *__restrict__ xq, int N, int Cout,
+                                           int G, long long total4) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total4) return;
+    const int c4 = Cout / 4;
+    long long bn = t / c4;
+    int c = (int)(t % c4) * 4;
+    int b = (int)(bn / N);
+    const float Ag = coef[((size_t)b * G + c / (Cout / G)) * 2 + 0], Kg = coef[((size_t)b * G + c / (Cout / G)) * 2 + 1];
+    const float dg = (float)deg[bn];
+    float4 p = *reinterpret_cast<const float4 *>(pq + bn * 2 * Cout + c);
+    float4 x = *reinterpret_cast<const float4 *>(xq + bn * Cout + c);
+    float4 *o = reinterpret_cast<float4 *>(dpq + bn * 2 * Cout + c);
+    float4 v = *o;
+    v.x += dg * fmaf(Kg, p.x, Ag) + Kg * x.x;
+    v.y += dg * fmaf(Kg, p.y, Ag) + Kg * x.y;
+    v.z += dg * fmaf(Kg, p.z, Ag) + Kg * x.z;
+    v.w += dg * fmaf(Kg, p.w, Ag) + Kg * x.w;
+    *o = v;
+}
+
 // dP[j][c] += deg_j * K_g * P[j][c]
 __global__ void edge_bwd_degfix_kernel(float *__restrict__ dpq, const float *__restrict__ pq, const int *__restrict__ deg,
                                        const float *__restrict__ coef, int N, int Cout, int G, long long total4) {
@@ -865,10 +946,17 @@ static size_t plan_fwd(const gcanet_edgeconv_desc *d, void *base, FwdWs *w) {
 }
 
 struct BwdWs {
-    float *wcatT, *wcat, *dpq, *part, *coef, *dwcat, *dwpart, *xt;
+    float *wcatT, *wcat, *dpq, *part, *coef, *dwcat, *dwpart, *xt, *xq;
     int *deg;
     double *sbc;
 };
+
+// layer-3 shape: 64 input channels feeding more output channels -- scatter X~ instead of the Cout-wide dense term
+// (at Cout = 64 the split loses: 0.65 ms against 0.55 ms for the layer's backward)
+static bool bwd_mid_path(const gcanet_edgeconv_desc *d) {
+    static const bool off = getenv("GCANET_NO_MID_SCATTER") != nullptr;
+    return !off && d->ldx == 64 && d->C == 64 && d->Cout >= 128 && d->Cout <= 256 && (long long)d->B * d->N >= 1024;
+}
 
 static size_t plan_bwd(const gcanet_edgeconv_desc *d, void *base, BwdWs *w) {
     Carver cv(base);
@@ -883,9 +971,11 @@ static size_t plan_bwd(const gcanet_edgeconv_desc *d, void *base, BwdWs *w) {
     float *coef = cv.take<float>((size_t)d->B * d->groups * 2);
     float *dwcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
     float *dwpart = cv.take<float>((size_t)tn_splits(M, 2 * d->Cout, d->ldx) * d->ldx * 2 * d->Cout);
-    float *xt = cv.take<float>(d->ldx <= 8 ? bn * d->ldx : 0);
+    const bool mid = bwd_mid_path(d);
+    float *xt = cv.take<float>(d->ldx <= 8 || mid ? bn * d->ldx : 0);
+    float *xq = cv.take<float>(mid ? bn * d->Cout : 0);
     float *wcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
-    if (w) { w->xt = xt; w->wcat = wcat; w->wcatT = wcatT; w->dpq = dpq; w->deg = deg; w->part = part; w->sbc = sbc; w->coef = coef; w->dwcat = dwcat; w->dwpart = dwpart; }
+    if (w) { w->xt = xt; w->xq = xq; w->wcat = wcat; w->wcatT = wcatT; w->dpq = dpq; w->deg = deg; w->part = part; w->sbc = sbc; w->coef = coef; w->dwcat = dwcat; w->dwpart = dwpart; }
     return cv.off;
 }
 
@@ -945,7 +1035,8 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     GCANET_CUDA_OK(cudaMemsetAsync(w.deg, 0, bn * sizeof(int), st));
 
     const bool small = d->ldx == 4 || d->ldx == 8;
-    if (small) GCANET_CUDA_OK(cudaMemsetAsync(w.xt, 0, bn * d->ldx * sizeof(float), st));
+    const bool mid = bwd_mid_path(d);
+    if (small || mid) GCANET_CUDA_OK(cudaMemsetAsync(w.xt, 0, bn * d->ldx * sizeof(float), st));
     BwdArgs ba{sv.pq, sv.ysel, sv.ysum, sv.stats, gamma, beta, gout, sv.arg, idx, w.part, w.coef, w.dpq, w.deg,
                d->N, Cout, d->k, d->groups, d->slope, x_nc, w.xt};
     edge_bwd_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
@@ -969,6 +1060,18 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
             edge_bwd_degfix_small_kernel<8><<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, w.xt, w.wcatT,
                                                                                            d->N, Cout, d->groups, total4);
         GCANET_LAUNCH_OK("edge_bwd_degfix_small_kernel");
+    } else if (mid) {
+        if constexpr (VEC >= 4) {
+            edge_bwd_scatter_mid_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
+            GCANET_LAUNCH_OK("edge_bwd_scatter_mid_kernel");
+            // X~ Wq^T: rows Cout.. of wcatT are Wq
+            int rq = gemm_tc_try(w.xt, d->ldx, w.wcatT + (size_t)Cout * d->ldx, d->ldx, w.xq, Cout, M, Cout, d->ldx, st);
+            if (rq < 0) rq = launch_sgemm_nn(w.xt, w.wcat + Cout, w.xq, M, Cout, d->ldx, d->ldx, 2 * Cout, Cout, st);
+            if (rq) return rq;
+            edge_bwd_degfix_mid_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, w.xq, d->N,
+                                                                                        Cout, d->groups, total4);
+            GCANET_LAUNCH_OK("edge_bwd_degfix_mid_kernel");
+        }
     } else {
         edge_bwd_scatter_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
         GCANET_LAUNCH_OK("edge_bwd_scatter_kernel");
