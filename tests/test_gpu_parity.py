@@ -334,7 +334,8 @@ def test_grouping_operation_forward_backward():
 
 # ------------------------------------------------------------------------------ fused EdgeConv
 @pytest.mark.parametrize("C,Cout,N,k,groups", [(3, 64, 257, 20, 2), (6, 64, 300, 16, 2), (64, 64, 200, 50, 2),
-                                               (64, 128, 190, 33, 2), (64, 32, 64, 8, 4), (16, 256, 70, 5, 8)])
+                                               (64, 128, 190, 33, 2), (64, 32, 64, 8, 4), (16, 256, 70, 5, 8),
+                                               (64, 128, 700, 50, 2), (64, 256, 600, 20, 4)])   # X~ scatter path
 def test_edgeconv_forward_backward_vs_oracle(C, Cout, N, k, groups):
     g = torch.Generator().manual_seed(C + Cout + N)
     B = 2
