@@ -28,6 +28,8 @@ namespace gcanet {
 
 // gemm_tc.cu: C[M][N] = A[M][K] Bt[N][K]^T on the tensor cores; -1 = shape not covered, use the CUDA-core GEMM
 int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K, cudaStream_t st);
+int gemm_tn_tc_try(const float *X, int ldx, const float *Y, int ldy, float *part, int M, int N, int K, int max_splits, int *splits_out,
+                   cudaStream_t st);
 
 constexpr unsigned FULLM = 0xffffffffu;
 constexpr int kGWarps = 8;           // warps per CTA in the per-point kernels
@@ -343,6 +345,15 @@ static int tn_splits(int M, int N, int K) {
 static int launch_sgemm_tn(const float *A, const float *Bm, float *out, float *part, int M, int N, int K, int lda,
                            int ldb, cudaStream_t st) {
     int splits = tn_splits(M, N, K);
+    // feature layers: tensor cores (bf16x3 split, fp32 accumulate)
+    int tc_splits = 0;
+    const int rc_tc = gemm_tn_tc_try(A, lda, Bm, ldb, part, M, N, K, splits, &tc_splits, st);
+    if (rc_tc < 0) return rc_tc;
+    if (rc_tc == GCANET_OK) {
+        reduce_splits_kernel<<<ceil_div(K * N, 32), 256, 0, st>>>(part, out, K * N, tc_splits);
+        GCANET_LAUNCH_OK("reduce_splits_kernel");
+        return GCANET_OK;
+    }
     int rows = ceil_div(ceil_div(M, splits), TN_BK) * TN_BK;
     splits = ceil_div(M, rows);
     if (K <= 8 && N <= 256) {

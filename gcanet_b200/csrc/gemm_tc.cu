@@ -243,4 +243,194 @@ int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int
     return -1;
 }
 
+// =================================================================================
+// Weight gradient: out[64][NY] = X[M][64]^T Y[M][NY], the reduction running over the M = B * N points.
+// Split over M, one CTA per split; each CTA accumulates  D[n][m] = sum_p Y[p][n] X[p][m]  (two 128-row accumulators at
+// NY = 256) in TMEM with the same bf16 hi/lo split as above, and writes its partial as part[split][m][n].
+// Both operands are "MN-major" in memory (the reduction index p is the slow one); instead of MN-major descriptors the
+// loaders transpose while they stage: a thread owns one row (n or m) and eight consecutive points, i.e. exactly one
+// 16-byte chunk of the swizzled K-major tile, so global loads stay coalesced across the warp (consecutive n) and the
+// shared-memory stores are conflict-free (eight consecutive rows hit eight different chunk positions).
+// All 16 warps load; thread 0 issues the MMAs of a stage after the block-wide barrier; two stages.
+// =================================================================================
+constexpr int GTN_THREADS = 512;
+
+__device__ __forceinline__ void split_pack8(const float *v, uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+        const float2 hf = __bfloat1622float2(hh);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * q] - hf.x, v[2 * q + 1] - hf.y);
+        h[q] = *reinterpret_cast<const uint32_t *>(&hh);
+        l[q] = *reinterpret_cast<const uint32_t *>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int NY>
+__global__ void __launch_bounds__(GTN_THREADS, 1)
+gemm_tn_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ Y, int ldy, float *__restrict__ part, int M,
+                  int rows_per_split) {
+    static_assert(NY == 128 || NY == 256, "unsupported width");
+    constexpr int TA = NY / 128;                        // accumulator tiles (128 rows of n each)
+    constexpr int A_TILE = 128 * 128;                   // [128 n][64 p] bf16
+    constexpr int B_TILE = 64 * 128;                    // [64 m][64 p] bf16
+    constexpr int STAGE = 2 * TA * A_TILE + 2 * B_TILE; // A hi tiles, A lo tiles, B hi, B lo
+    constexpr int UA = NY * 8 / GTN_THREADS;            // (row, chunk) units of Y per thread
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, 64);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE);
+    uint64_t *empty = bars;                             // [2] MMA -> loaders
+    uint64_t *done = bars + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3);
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int start = blockIdx.x * rows_per_split;
+    const int end = min(M, start + rows_per_split);
+    const int nkb = (end - start + 63) / 64;
+
+    if (t == 0) {
+        mbar_init(&empty[0], 1);
+        mbar_init(&empty[1], 1);
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 15) tmem_alloc(tmem_slot, tmem_cols(TA * 64));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // this thread's units: Y (n, chunk) x UA, X (m, chunk) x 1
+    const int xm = t & 63, xc = t >> 6;
+    auto issue = [&](int kb, float (&ya)[UA][8], float (&xa)[8]) {
+        const int p0 = start + kb * 64;
+#pragma unroll
+        for (int i = 0; i < UA; ++i) {
+            const int u = t + GTN_THREADS * i, n = u % NY, c = u / NY;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int p = p0 + 8 * c + j;
+                ya[i][j] = p < end ? __ldg(Y + (size_t)p * ldy + n) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p = p0 + 8 * xc + j;
+            xa[j] = p < end ? __ldg(X + (size_t)p * ldx + xm) : 0.f;
+        }
+    };
+    auto store = [&](uint8_t *st, const float (&ya)[UA][8], const float (&xa)[8]) {
+        uint4 hi, lo;
+#pragma unroll
+        for (int i = 0; i < UA; ++i) {
+            const int u = t + GTN_THREADS * i, n = u % NY, c = u / NY;
+            const int tile = n >> 7, r = n & 127;
+            const uint32_t off = (uint32_t)(tile * A_TILE + r * 128 + ((c ^ (r & 7)) << 4));
+            split_pack8(ya[i], hi, lo);
+            *reinterpret_cast<uint4 *>(st + off) = hi;
+            *reinterpret_cast<uint4 *>(st + TA * A_TILE + off) = lo;
+        }
+        const uint32_t off = (uint32_t)(xm * 128 + ((xc ^ (xm & 7)) << 4));
+        split_pack8(xa, hi, lo);
+        *reinterpret_cast<uint4 *>(st + 2 * TA * A_TILE + off) = hi;
+        *reinterpret_cast<uint4 *>(st + 2 * TA * A_TILE + B_TILE + off) = lo;
+    };
+    auto mma_stage = [&](uint8_t *st, uint32_t accum) {
+        const uint32_t a_addr = smem_u32(st), b_addr = a_addr + 2 * TA * A_TILE;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t koff = ks * 32;
+            const uint64_t b_hi = make_kmajor_sw128_desc(b_addr + koff);
+            const uint64_t b_lo = make_kmajor_sw128_desc(b_addr + B_TILE + koff);
+#pragma unroll
+            for (int ta = 0; ta < TA; ++ta) {
+                const uint64_t a_hi = make_kmajor_sw128_desc(a_addr + ta * A_TILE + koff);
+                const uint64_t a_lo = make_kmajor_sw128_desc(a_addr + (TA + ta) * A_TILE + koff);
+                const uint32_t d = tmem_base + ta * 64;
+                umma_bf16(d, a_hi, b_hi, IDESC, (ks == 0) ? accum : 1u);
+                umma_bf16(d, a_hi, b_lo, IDESC, 1);
+                umma_bf16(d, a_lo, b_hi, IDESC, 1);
+            }
+        }
+    };
+
+    float ya0[UA][8], xa0[8], ya1[UA][8], xa1[8];
+    if (nkb > 0) issue(0, ya0, xa0);
+    for (int kb = 0; kb < nkb; kb += 2) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int cur = kb + half;
+            if (cur >= nkb) break;
+            float (&yc)[UA][8] = half == 0 ? ya0 : ya1;
+            float (&xcur)[8] = half == 0 ? xa0 : xa1;
+            float (&yn)[UA][8] = half == 0 ? ya1 : ya0;
+            float (&xn)[8] = half == 0 ? xa1 : xa0;
+            if (cur + 1 < nkb) issue(cur + 1, yn, xn);
+            uint8_t *st = smem + half * STAGE;           // stage = cur & 1 = half (kb is even)
+            const int use = cur >> 1;                    // how often this stage has been filled before
+            if (use > 0) mbar_wait(&empty[half], (uint32_t)((use - 1) & 1));
+            store(st, yc, xcur);
+            fence_proxy_async();
+            __syncthreads();
+            if (t == 0) {
+                tc_fence_after();
+                mma_stage(st, cur == 0 ? 0u : 1u);
+                umma_commit(&empty[half]);
+            }
+        }
+    }
+    if (t == 0) umma_commit(done);
+    mbar_wait(done, 0);
+    tc_fence_after();
+
+    // epilogue: thread = one output column n, 64 values of m; for each m a warp writes 32 consecutive n
+    if (warp < 4 * TA) {
+        const int tile = warp >> 2, q = warp & 3;
+        const int n = tile * 128 + q * 32 + lane;
+        float *po = part + (size_t)blockIdx.x * 64 * NY + n;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tile * 64;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(taddr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int m = 0; m < 32; ++m) po[(size_t)(ch * 32 + m) * NY] = nkb > 0 ? __uint_as_float(v[m]) : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 15) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols(TA * 64));
+    }
+}
+
+// part[split][64][N] partials of X[M][64]^T Y[M][N] on the tensor cores; *splits_out = the number of splits written
+// (<= max_splits, the caller reduces them).  Returns +1 when the shape is not one this kernel covers.
+int gemm_tn_tc_try(const float *X, int ldx, const float *Y, int ldy, float *part, int M, int N, int K, int max_splits,
+                   int *splits_out, cudaStream_t st) {
+    if (K != 64 || (N != 128 && N != 256) || M < 8192 || max_splits < 1) return 1;
+    if (ldx % 4 || ldy % 4 || getenv("GCANET_NO_TC_GEMM")) return 1;
+    int splits = max_splits < kNumSMs ? max_splits : kNumSMs;
+    const int rows = ceil_div(ceil_div(M, splits), 64) * 64;
+    splits = ceil_div(M, rows);
+    const size_t smem = 1024 + (size_t)2 * (2 * (N / 128) * 128 * 128 + 2 * 64 * 128) + 64;
+    if (N == 256) {
+        GCANET_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tn_tc_kernel<256><<<splits, GTN_THREADS, smem, st>>>(X, ldx, Y, ldy, part, M, rows);
+    } else {
+        GCANET_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tn_tc_kernel<128><<<splits, GTN_THREADS, smem, st>>>(X, ldx, Y, ldy, part, M, rows);
+    }
+    GCANET_LAUNCH_OK("gemm_tn_tc_kernel");
+    *splits_out = splits;
+    return GCANET_OK;
+}
+
 }  // namespace gcanet

@@ -362,6 +362,38 @@ def test_edgeconv_forward_backward_vs_oracle(C, Cout, N, k, groups):
         assert rel_err(a, b) < 2e-3, f"{name}: rel err {rel_err(a, b):.3e}"
 
 
+@pytest.mark.parametrize("Cout,N,k", [(128, 4501, 8), (64, 4200, 6)])
+def test_edgeconv_backward_large_m_vs_oracle(Cout, N, k):
+    """M = B * N >= 8192 rows: the weight gradient runs on the tensor cores (gemm_tn_tc_kernel) and every projection GEMM
+    takes its tensor-core path.  At ~10^6 (point, channel) outputs a handful sit within fp32 rounding of a LeakyReLU kink
+    or of an arg-max tie, where the gradient is discontinuous (the oracle and any fp32 implementation may land on
+    different sides): dx is therefore compared per point with a bounded fraction of outliers, the summed gradients with a
+    tolerance that absorbs a few such flips (one flip moves a row of dW by up to ~1e-2 of the largest entry)."""
+    C, B, groups = 64, 2, 2
+    g = torch.Generator().manual_seed(Cout + N)
+    x = torch.randn(B, C, N, generator=g)
+    W = torch.randn(Cout, 2 * C, generator=g) / (2 * C) ** 0.5
+    gamma = torch.randn(Cout, generator=g) * 0.7 + 0.2
+    beta = torch.randn(Cout, generator=g) * 0.3
+    idx = orc.knn(x, k, k)
+    cot = torch.randn(B, Cout, N, generator=g)
+    xo, Wo, go, bo = (t.clone().requires_grad_(True) for t in (x, W, gamma, beta))
+    out_o = orc.edgeconv_block(orc.get_graph_feature(xo, k, k, idx=idx), Wo, go, bo, groups=groups)
+    (out_o * cot).sum().backward()
+    xg, Wg, gg, bg = (t.to(DEV).requires_grad_(True) for t in (x, W, gamma, beta))
+    out_nc, out_cn = gb.edgeconv(G._ToPointMajor.apply(xg, C), idx.int().to(DEV), Wg, gg, bg, C, groups=groups)
+    assert float((out_cn.cpu() - out_o).abs().max()) <= 2e-4 * float(out_o.detach().abs().max())
+    (out_cn * cot.to(DEV)).sum().backward()
+    per_point = (xg.grad.cpu() - xo.grad).abs().amax(dim=1)                   # [B, N]
+    outliers = float((per_point > 2e-3 * float(xo.grad.abs().max())).float().mean())
+    assert outliers < 3e-3, f"dx: {outliers:.2e} of the points differ"
+    for name, a, b in (("dW", Wg.grad, Wo.grad), ("dgamma", gg.grad, go.grad), ("dbeta", bg.grad, bo.grad)):
+        assert rel_err(a, b) < 3e-2, f"{name}: rel err {rel_err(a, b):.3e}"
+    # a flip touches one row of dW (one output channel); the rest agrees to fp32-GEMM accuracy
+    dw_err = (Wg.grad.cpu() - Wo.grad).abs().flatten() / float(Wo.grad.abs().max())
+    assert float(dw_err.median()) < 2e-5 and float(dw_err.quantile(0.9)) < 2e-4, (float(dw_err.median()), float(dw_err.quantile(0.9)))
+
+
 @pytest.mark.parametrize("mode", [0, 5])
 def test_encoder_edge_stack_golden(golden_dir, mode):
     """DGCNNEncoderGn with the fixture's weights: x1|x2|x3 and the hot-path parameter gradients
