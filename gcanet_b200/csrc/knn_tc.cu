@@ -477,9 +477,12 @@ __device__ __forceinline__ void kth_bracket(const float (&dv)[SL], int k, float 
 
 template <int C, int SL>
 __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *cand, int n, int n0, const int *perm, const float *xb,
-                                           const float *nb, int q, float qn, const float (&qv)[C / 32], float margin,
-                                           size_t grow, int *sl, float *sd, int lane) {
-    constexpr int VEC = C / 32;
+                                           const float *nb, int q, float qn, const float (&qv)[16], float margin,
+                                           size_t grow, unsigned long long *skey, int lane) {
+    constexpr int LPC = C / 16;                         // lanes per candidate in the exact pass (16 channels each)
+    constexpr int SCAP_ROW = SL * 32;
+    int *sl = reinterpret_cast<int *>(skey);            // survivors' point ids, then (step 3) the keys overwrite both
+    float *sd = reinterpret_cast<float *>(skey) + SCAP_ROW;
     // 1. last shrink of the list on the approximate distances (same bound + margin rule as the scan).
     //    In set-only mode entries with d~ <= lo - margin, where fewer than k entries have d~ <= lo, are
     //    certainly among the exact k nearest (anything that could beat them also lies below lo): they are
@@ -527,66 +530,69 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
     const int k_left = a.k - n_sure;                    // >= 1: fewer than k entries lie below lo
     __syncwarp();
 
-    // 2. exact fp32 distances of the m survivors, four at a time (coalesced row loads, one
-    //    6-shuffle transposing reduction per four candidates)
-    for (int e0 = 0; e0 < m; e0 += 4) {
-        float part[4];
-        int jj[4];
+    // 2. exact fp32 distances of the m survivors, 32 / LPC at a time: LPC lanes share a candidate, each with 16 channels
+    //    as four 16-byte loads (the lanes of a candidate read LPC * 16 contiguous bytes per load), the query's matching
+    //    channels stay in registers, log2(LPC) shuffles finish the dot product
+    {
+        constexpr int CPP = 32 / LPC;                   // candidates per pass
+        const int u = lane / LPC, w = lane % LPC;
+        for (int e0 = 0; e0 < m; e0 += CPP) {
+            const int j = sl[min(e0 + u, m - 1)];
+            const float4 *xr = reinterpret_cast<const float4 *>(xb + (size_t)j * C) + w;
+            float4 xv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            jj[u] = sl[min(e0 + u, m - 1)];
-            float xv[VEC];
-            load_row<VEC>(xb + (size_t)jj[u] * C + lane * VEC, xv);
-            float p = 0.f;
+            for (int it = 0; it < 4; ++it) xv[it] = __ldg(xr + it * LPC);
+            float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) p = fmaf(qv[v], xv[v], p);
-            part[u] = p;
-        }
-        const bool h16 = lane & 16, h8 = lane & 8;
-        float k0 = h16 ? part[2] : part[0], k1 = h16 ? part[3] : part[1];
-        const float s0 = h16 ? part[0] : part[2], s1 = h16 ? part[1] : part[3];
-        k0 += __shfl_xor_sync(FULLW, s0, 16);
-        k1 += __shfl_xor_sync(FULLW, s1, 16);
-        float kk = h8 ? k1 : k0;
-        const float ss = h8 ? k0 : k1;
-        kk += __shfl_xor_sync(FULLW, ss, 8);
-        kk += __shfl_xor_sync(FULLW, kk, 4);
-        kk += __shfl_xor_sync(FULLW, kk, 2);
-        kk += __shfl_xor_sync(FULLW, kk, 1);
-        // lanes 8u .. 8u+7 now hold the dot product of candidate e0 + u
-        const int u = lane >> 3;
-        if ((lane & 7) == 0 && e0 + u < m) {
-            const int j = u == 0 ? jj[0] : (u == 1 ? jj[1] : (u == 2 ? jj[2] : jj[3]));
+            for (int it = 0; it < 4; it += 2) {
+                p0 = fmaf(qv[it * 4 + 0], xv[it].x, p0);
+                p1 = fmaf(qv[it * 4 + 4], xv[it + 1].x, p1);
+                p0 = fmaf(qv[it * 4 + 1], xv[it].y, p0);
+                p1 = fmaf(qv[it * 4 + 5], xv[it + 1].y, p1);
+                p0 = fmaf(qv[it * 4 + 2], xv[it].z, p0);
+                p1 = fmaf(qv[it * 4 + 6], xv[it + 1].z, p1);
+                p0 = fmaf(qv[it * 4 + 3], xv[it].w, p0);
+                p1 = fmaf(qv[it * 4 + 7], xv[it + 1].w, p1);
+            }
+            float kk = p0 + p1;
+#pragma unroll
+            for (int o = LPC / 2; o; o >>= 1) kk += __shfl_xor_sync(FULLW, kk, o);
             // reference arithmetic: fl(fl(|x_j|^2 - 2 t) + |x_i|^2)
-            sd[e0 + u] = __fadd_rn(fmaf(-2.f, kk, nb[j]), qn);
+            if (w == 0 && e0 + u < m) sd[e0 + u] = __fadd_rn(fmaf(-2.f, kk, nb[j]), qn);
         }
     }
     __syncwarp();
 
-    // 3. rank the survivors by (distance, index) and write the k best in order
-    float dv[SL];
-    int di[SL], rank[SL];
+    // 3. rank the survivors by (distance, index) and write the k best in order.  (distance, index) is packed into one
+    //    64-bit key -- the float mapped to an order-preserving unsigned -- so a comparison is one 64-bit compare and
+    //    the broadcast read one 8-byte load
+    unsigned long long key[SL];
+    int rank[SL];
 #pragma unroll
     for (int s = 0; s < SL; ++s) {
         const int e = s * 32 + lane;
-        dv[s] = e < m ? sd[e] : CUDART_INF_F;
-        di[s] = e < m ? sl[e] : 0x7fffffff;
+        key[s] = ~0ull;
         rank[s] = 0;
-    }
-    if (m <= 32) {
-        for (int e = 0; e < m; ++e) {
-            const float od = sd[e];
-            const int oi = sl[e];
-            rank[0] += (od < dv[0] || (od == dv[0] && oi < di[0])) ? 1 : 0;
+        if (e < m) {
+            unsigned bits = __float_as_uint(sd[e]);
+            bits ^= (unsigned)((int)bits >> 31) | 0x80000000u;
+            key[s] = ((unsigned long long)bits << 32) | (unsigned)sl[e];
         }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < SL; ++s)
+        if (s * 32 + lane < m) skey[s * 32 + lane] = key[s];
+    __syncwarp();
+    if (m <= 32) {
+        for (int e = 0; e < m; ++e) rank[0] += (skey[e] < key[0]) ? 1 : 0;
     } else {
         for (int e = 0; e < m; ++e) {
-            const float od = sd[e];
-            const int oi = sl[e];
+            const unsigned long long ok = skey[e];
 #pragma unroll
             for (int s = 0; s < SL; ++s) {
                 if (s * 32 >= m) break;
-                rank[s] += (od < dv[s] || (od == dv[s] && oi < di[s])) ? 1 : 0;
+                rank[s] += (ok < key[s]) ? 1 : 0;
             }
         }
     }
@@ -595,8 +601,9 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
         const int e = s * 32 + lane;
         if (e < m && rank[s] < k_left && rank[s] % a.step == 0) {
             const size_t o = grow * a.kout + n_sure + rank[s] / a.step;
-            if (a.idx64) a.idx64[o] = di[s];
-            if (a.idx32) a.idx32[o] = di[s];
+            const int jo = (int)(unsigned)key[s];
+            if (a.idx64) a.idx64[o] = jo;
+            if (a.idx32) a.idx32[o] = jo;
         }
     }
     (void)q;
@@ -608,10 +615,9 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
 // an occupancy step.
 template <int C, bool BIG>
 __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
-    constexpr int VEC = C / 32;
+    constexpr int LPC = C / 16;
     constexpr int SCAP = BIG ? TCP_CAP : TC_CAP;
-    __shared__ int s_idx[8][SCAP];
-    __shared__ float s_d[8][SCAP];
+    __shared__ unsigned long long s_key[8][SCAP];       // per warp: survivors' ids | exact distances, then the packed keys
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int *perm = a.perm ? a.perm + (size_t)b * a.N : nullptr;
@@ -634,17 +640,21 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
             continue;
         }
         const uint2 *cand = a.cand + srow * a.cap;
-        float qv[VEC];
-        load_row<VEC>(xb + (size_t)q * C + lane * VEC, qv);
+        float qv[16];                                    // this lane's 16 channels of the query (layout of the exact pass)
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)q * C) + it * LPC + lane % LPC);
+            qv[it * 4] = t.x; qv[it * 4 + 1] = t.y; qv[it * 4 + 2] = t.z; qv[it * 4 + 3] = t.w;
+        }
         const float qn = nb[q];
         const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
         if constexpr (BIG) {
-            rerank_row<C, TCP_CAP / 32>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+            rerank_row<C, TCP_CAP / 32>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_key[warp], lane);
         } else {
             // short lists (the pruned scan's fixed thresholds leave ~1.5 k entries) take the narrow instantiation
-            if (n <= 96) rerank_row<C, 3>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
-            else if (n <= 128) rerank_row<C, 4>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
-            else rerank_row<C, 8>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_idx[warp], s_d[warp], lane);
+            if (n <= 96) rerank_row<C, 3>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_key[warp], lane);
+            else if (n <= 128) rerank_row<C, 4>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_key[warp], lane);
+            else rerank_row<C, 8>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_key[warp], lane);
         }
         __syncwarp();
     }
