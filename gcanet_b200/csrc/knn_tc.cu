@@ -614,7 +614,7 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
 // the listed rows with the wide instantiation -- its registers and shared memory would otherwise cost every row
 // an occupancy step.
 template <int C, bool BIG>
-__global__ void __launch_bounds__(256) knn_tc_rerank_kernel(RerankArgs a) {
+__global__ void __launch_bounds__(256, BIG ? 1 : 6) knn_tc_rerank_kernel(RerankArgs a) {
     constexpr int LPC = C / 16;
     constexpr int SCAP = BIG ? TCP_CAP : TC_CAP;
     __shared__ unsigned long long s_key[8][SCAP];       // per warp: survivors' ids | exact distances, then the packed keys
