@@ -627,19 +627,14 @@ __global__ void __launch_bounds__(256, BIG ? 1 : 6) knn_tc_rerank_kernel(RerankA
     for (int slot = blockIdx.x * 8 + warp; slot < rows; slot += gridDim.x * 8) {
         const int qs = BIG ? a.big_list[(size_t)b * a.N + slot] : slot;       // row in the scan's order
         const size_t srow = (size_t)b * a.N + qs;
+        // the row waits on chains of dependent loads: everything that only needs qs is issued first, everything that
+        // needs the point id next, before any of it is tested
         const int q = perm ? perm[qs] : qs;               // original point index
-        const size_t grow = (size_t)b * a.N + q;
-        if (!BIG && a.overflow[grow]) {                   // the fallback kernel writes this row
-            if (lane == 0) a.fb_list[(size_t)b * a.N + atomicAdd(&a.fb_count[b], 1)] = q;
-            continue;
-        }
         const int n0 = a.split ? a.cand_cnt[2 * srow] : a.cand_cnt[srow];
-        const int n = a.split ? n0 + a.cand_cnt[2 * srow + 1] : n0;
-        if (!BIG && n > TC_CAP) {
-            if (lane == 0) a.big_list[(size_t)b * a.N + atomicAdd(&a.big_count[b], 1)] = qs;
-            continue;
-        }
-        const uint2 *cand = a.cand + srow * a.cap;
+        const int n1 = a.split ? a.cand_cnt[2 * srow + 1] : 0;
+        const float nmax = a.nmax[b];
+        const size_t grow = (size_t)b * a.N + q;
+        const int ovf = BIG ? 0 : a.overflow[grow];
         float qv[16];                                    // this lane's 16 channels of the query (layout of the exact pass)
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -647,7 +642,17 @@ __global__ void __launch_bounds__(256, BIG ? 1 : 6) knn_tc_rerank_kernel(RerankA
             qv[it * 4] = t.x; qv[it * 4 + 1] = t.y; qv[it * 4 + 2] = t.z; qv[it * 4 + 3] = t.w;
         }
         const float qn = nb[q];
-        const float margin = TC_MARGIN * sqrtf(qn * a.nmax[b]);
+        if (ovf) {                                        // the fallback kernel writes this row
+            if (lane == 0) a.fb_list[(size_t)b * a.N + atomicAdd(&a.fb_count[b], 1)] = q;
+            continue;
+        }
+        const int n = n0 + n1;
+        if (!BIG && n > TC_CAP) {
+            if (lane == 0) a.big_list[(size_t)b * a.N + atomicAdd(&a.big_count[b], 1)] = qs;
+            continue;
+        }
+        const uint2 *cand = a.cand + srow * a.cap;
+        const float margin = TC_MARGIN * sqrtf(qn * nmax);
         if constexpr (BIG) {
             rerank_row<C, TCP_CAP / 32>(a, cand, n, n0, perm, xb, nb, q, qn, qv, margin, grow, s_key[warp], lane);
         } else {
