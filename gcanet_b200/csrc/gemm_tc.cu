@@ -6,10 +6,10 @@
 // Both operands are split x = hi + lo (bf16 each) while they are staged into shared memory, and
 // hi*hi + hi*lo + lo*hi is accumulated in fp32 TMEM by tcgen05.mma (error ~2^-16 |a||b| per product, the
 // level of fp32 summation error at these K).  No bf16 copy of the activations ever exists in HBM:
-//   warps 0-3  load fp32 rows of A (coalesced 16-byte loads), split them, and write the two bf16 tiles in the
-//              128-byte-swizzled K-major layout the UMMA descriptors expect (what TMA would have produced)
-//   warp  8    issues the MMAs (one elected thread), accumulators double-buffered in TMEM
-//   warps 4-7  drain the accumulators: one row per thread, 128-byte segments straight to global memory
+//   warps 0-7  load fp32 rows of A (coalesced 16-byte loads, two work items ahead), split them, and write the two bf16
+//              tiles in the 128-byte-swizzled K-major layout the UMMA descriptors expect (what TMA would have produced)
+//   warp  12   issues the MMAs (one elected thread), accumulators double-buffered in TMEM
+//   warps 8-11 drain the accumulators: one row per thread, 128-byte segments straight to global memory
 // The weight matrix (<= 64 KB as hi|lo bf16) is staged once per CTA; CTAs are persistent over the M tiles.
 // The kernel is memory-bound (reads A once, writes C once), which is the point: the CUDA-core sgemm it
 // replaces ran at ~33 TFLOP/s fp32 and was compute-bound.
@@ -27,7 +27,8 @@ __host__ __device__ constexpr int gt_stages(int K, int N) {
     const int left = 200 * 1024 - 2 * (K / 64) * N * 128;
     return left >= 4 * 32768 ? 4 : (left >= 3 * 32768 ? 3 : 2);
 }
-constexpr int GT_THREADS = 288;       // 4 loader warps, 4 epilogue warps, 1 MMA warp
+constexpr int GT_LOADERS = 256;       // loader threads (8 warps)
+constexpr int GT_THREADS = GT_LOADERS + 128 + 32;   // 8 loader warps, 4 epilogue warps, 1 MMA warp
 
 __host__ __device__ constexpr uint32_t tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512))); }
 
@@ -83,11 +84,11 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
     const int ntiles = (M + GT_BM - 1) / GT_BM;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&a_full[s], GT_LOADERS); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, tmem_cols(2 * N));
+    if (warp == GT_THREADS / 32 - 1) tmem_alloc(tmem_slot, tmem_cols(2 * N));
     // weights: Bt[n][k] fp32 -> hi / lo bf16 blocks, swizzled (every thread helps; N*K/4 float4 items)
     for (int e = threadIdx.x; e < N * K / 4; e += GT_THREADS) {
         const int n = e / (K / 4), k4 = (e % (K / 4)) * 4;
@@ -101,45 +102,48 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < GT_LOADERS / 32) {
         // ===================== loaders: fp32 rows -> swizzled bf16 hi / lo tiles =====================
-        const int tid = threadIdx.x;                    // 0..127
-        const int rsub = tid >> 4, c4 = tid & 15;       // 8 rows x 16 float4 per sweep
+        const int tid = threadIdx.x;                    // 0..255
+        const int rsub = tid >> 4, c4 = tid & 15;       // 16 rows x 16 float4 per sweep, 8 sweeps per tile
         int stage = 0;
         uint32_t phase = 0;
-        // work items = (tile, K chunk) in order; the loads of item i+1 are in flight while item i is split and stored
+        // work items = (tile, K chunk) in order; three register buffers: while item i is split and stored the loads of
+        // items i+1 and i+2 are in flight (64 KB per SM -- the kernel is bound by how many bytes it keeps in flight)
         const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int items = my_tiles * KCH;
-        auto issue = [&](int item, float4 (&v)[16]) {
+        auto issue = [&](int item, float4 (&v)[8]) {
             const int m0 = (blockIdx.x + (item / KCH) * gridDim.x) * GT_BM, kc = item % KCH;
 #pragma unroll
-            for (int it = 0; it < 16; ++it) {
-                const int r = it * 8 + rsub;
+            for (int it = 0; it < 8; ++it) {
+                const int r = it * 16 + rsub;
                 v[it] = m0 + r < M ? __ldg(reinterpret_cast<const float4 *>(A + (size_t)(m0 + r) * lda + kc * GT_KB) + c4)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        float4 va[16], vb[16];
-        if (items > 0) issue(0, va);
-        for (int item = 0; item < items; item += 2) {
-            // even item from va (prefetch odd into vb), then odd item from vb (prefetch next even into va)
+        auto consume = [&](const float4 (&v)[8]) {
+            mbar_wait(&a_empty[stage], phase ^ 1);
+            uint8_t *hi_tile = sA + stage * A_STAGE, *lo_tile = hi_tile + A_TILE;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int cur = item + half;
-                if (cur >= items) break;
-                float4 (&vc)[16] = half == 0 ? va : vb;
-                float4 (&vn)[16] = half == 0 ? vb : va;
-                if (cur + 1 < items) issue(cur + 1, vn);
-                mbar_wait(&a_empty[stage], phase ^ 1);
-                uint8_t *hi_tile = sA + stage * A_STAGE, *lo_tile = hi_tile + A_TILE;
-#pragma unroll
-                for (int it = 0; it < 16; ++it) split_store4(hi_tile, lo_tile, it * 8 + rsub, c4 * 4, vc[it]);
-                fence_proxy_async();
-                mbar_arrive(&a_full[stage]);
-                if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
-            }
+            for (int it = 0; it < 8; ++it) split_store4(hi_tile, lo_tile, it * 16 + rsub, c4 * 4, v[it]);
+            fence_proxy_async();
+            mbar_arrive(&a_full[stage]);
+            if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
+        };
+        float4 v0[8], v1[8], v2[8];
+        if (items > 0) issue(0, v0);
+        if (items > 1) issue(1, v1);
+        for (int item = 0; item < items; item += 3) {
+            if (item + 2 < items) issue(item + 2, v2);
+            consume(v0);
+            if (item + 1 >= items) break;
+            if (item + 3 < items) issue(item + 3, v0);
+            consume(v1);
+            if (item + 2 >= items) break;
+            if (item + 4 < items) issue(item + 4, v1);
+            consume(v2);
         }
-    } else if (warp == 8) {
+    } else if (warp == GT_THREADS / 32 - 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t b_addr = smem_u32(sBm);
@@ -175,7 +179,7 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
         }
     } else {
         // ===================== epilogue: one row per thread =====================
-        const int ew = warp & 3;                          // TMEM lane quarter (warps 4..7 -> 0..3)
+        const int ew = warp & 3;                          // TMEM lane quarter (warps 8..11 -> 0..3)
         int acc = 0;
         uint32_t accphase = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -206,7 +210,7 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == GT_THREADS / 32 - 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols(2 * N));
     }
