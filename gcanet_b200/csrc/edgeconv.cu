@@ -581,6 +581,51 @@ __global__ void edge_finish_kernel(const float *__restrict__ ysel, const float *
     }
 }
 
+// Same with 64 x 64 tiles and 16-byte accesses on all three streams (Cout % 64 == 0, N % 4 == 0).
+__global__ void __launch_bounds__(256) edge_finish_wide_kernel(const float *__restrict__ ysel, const float *__restrict__ stats,
+                                                               const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                               float *__restrict__ out_nc, float *__restrict__ out_cn, int N,
+                                                               int Cout, int G, float slope) {
+    __shared__ float tile[64][65];
+    const int b = blockIdx.z;
+    const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int cpg = Cout / G;
+    {
+        const int c = c0 + (threadIdx.x & 15) * 4;         // the same four channels in all four sweeps
+        const float4 gm = __ldg(reinterpret_cast<const float4 *>(gamma + c)), bt = __ldg(reinterpret_cast<const float4 *>(beta + c));
+        float mean[4], rstd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            mean[j] = stats[((size_t)b * G + (c + j) / cpg) * 2 + 0];
+            rstd[j] = stats[((size_t)b * G + (c + j) / cpg) * 2 + 1];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int n = (threadIdx.x >> 4) + 16 * i, cl = (threadIdx.x & 15) * 4;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + n < N) {
+                const size_t e = ((size_t)b * N + n0 + n) * Cout + c;
+                const float4 y = __ldg(reinterpret_cast<const float4 *>(ysel + e));
+                o.x = lrelu((y.x - mean[0]) * rstd[0] * gm.x + bt.x, slope);
+                o.y = lrelu((y.y - mean[1]) * rstd[1] * gm.y + bt.y, slope);
+                o.z = lrelu((y.z - mean[2]) * rstd[2] * gm.z + bt.z, slope);
+                o.w = lrelu((y.w - mean[3]) * rstd[3] * gm.w + bt.w, slope);
+                *reinterpret_cast<float4 *>(out_nc + e) = o;
+            }
+            tile[cl][n] = o.x; tile[cl + 1][n] = o.y; tile[cl + 2][n] = o.z; tile[cl + 3][n] = o.w;
+        }
+    }
+    if (out_cn == nullptr) return;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = threadIdx.x + 256 * i, c = e >> 4, n = (e & 15) * 4;
+        if (n0 + n < N)
+            *reinterpret_cast<float4 *>(out_cn + ((size_t)b * Cout + c0 + c) * N + n0 + n) =
+                make_float4(tile[c][n], tile[c][n + 1], tile[c][n + 2], tile[c][n + 3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------
@@ -1042,9 +1087,17 @@ static int run_forward(const gcanet_edgeconv_desc *d, const float *x_nc, const i
     double count = (double)(Cout / d->groups) * d->N * d->k;
     gn_stats_kernel<<<d->B, 32 * d->groups, 0, st>>>(w.part, sv.stats, nblk, d->groups, count, d->eps);
     GCANET_LAUNCH_OK("gn_stats_kernel");
-    dim3 fg(ceil_div(d->N, 32), Cout / 32, d->B), fb(32, 8);
-    edge_finish_kernel<<<fg, fb, 0, st>>>(sv.ysel, sv.stats, gamma, beta, out_nc, out_cn, d->N, Cout, d->groups, d->slope);
-    GCANET_LAUNCH_OK("edge_finish_kernel");
+    const uintptr_t align_bits = reinterpret_cast<uintptr_t>(out_nc) | reinterpret_cast<uintptr_t>(out_cn) |
+                                 reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta);
+    if (Cout % 64 == 0 && d->N % 4 == 0 && (align_bits & 15) == 0) {
+        edge_finish_wide_kernel<<<dim3(ceil_div(d->N, 64), Cout / 64, d->B), 256, 0, st>>>(sv.ysel, sv.stats, gamma, beta, out_nc,
+                                                                                         out_cn, d->N, Cout, d->groups, d->slope);
+        GCANET_LAUNCH_OK("edge_finish_wide_kernel");
+    } else {
+        dim3 fg(ceil_div(d->N, 32), Cout / 32, d->B), fb(32, 8);
+        edge_finish_kernel<<<fg, fb, 0, st>>>(sv.ysel, sv.stats, gamma, beta, out_nc, out_cn, d->N, Cout, d->groups, d->slope);
+        GCANET_LAUNCH_OK("edge_finish_kernel");
+    }
     return GCANET_OK;
 }
 

@@ -171,7 +171,7 @@ GCANET_API int gcanet_group_points_grad(int b, int c, int n, int npoints, int ns
  *   saved  opaque, gcanet_edgeconv_saved_bytes(); must be kept untouched until backward
  *   ws     scratch, gcanet_edgeconv_workspace_bytes()
  * Constraints: Cout % 32 == 0, Cout <= 256, Cout % groups == 0, (Cout/groups) % (Cout/32) == 0,
- * C <= 256, 1 <= k <= 255.
+ * C <= 256, 1 <= k <= 255, N * 2 * Cout < 2^30 per cloud (rows are addressed with 32-bit offsets).
  *
  * backward: grad_out_nc [B][N][Cout] -> grad_x_nc [B][N][ldx] (or NULL to skip; padding
  * columns are zeroed), grad_weight [Cout][2C], grad_gamma, grad_beta [Cout], all overwritten. */

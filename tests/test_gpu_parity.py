@@ -332,6 +332,21 @@ def test_grouping_operation_forward_backward():
     assert torch.equal(ii[:, :, 0].cpu(), torch.arange(50, dtype=torch.int32).expand(3, 50))
 
 
+@pytest.mark.parametrize("C,N", [(64, 1000), (128, 4100), (96, 260), (64, 257), (3, 1000), (6, 64), (40, 36)])
+def test_to_point_major_layout(C, N):
+    """[B][C][N] -> [B][N][ld] (zero-padded to a multiple of 4 channels): the 64 x 64 tile kernel (N % 4 == 0, ld >= 32,
+    with partial tiles in both directions) and the 32 x 32 one for everything else; exact copy, and its autograd."""
+    x = torch.randn(3, C, N, generator=torch.Generator().manual_seed(C * N)).to(DEV).requires_grad_(True)
+    ld = (C + 3) // 4 * 4
+    y = G._ToPointMajor.apply(x, ld)
+    assert y.shape == (3, N, ld)
+    assert torch.equal(y[:, :, :C], x.detach().transpose(1, 2))
+    assert not y[:, :, C:].any()
+    cot = torch.randn_like(y)
+    (y * cot).sum().backward()
+    assert torch.equal(x.grad, cot[:, :, :C].transpose(1, 2))
+
+
 # ------------------------------------------------------------------------------ fused EdgeConv
 @pytest.mark.parametrize("C,Cout,N,k,groups", [(3, 64, 257, 20, 2), (6, 64, 300, 16, 2), (64, 64, 200, 50, 2),
                                                (64, 128, 190, 33, 2), (64, 32, 64, 8, 4), (16, 256, 70, 5, 8),
