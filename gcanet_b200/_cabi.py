@@ -41,6 +41,7 @@ SIGNATURES = {
     "gcanet_launch_count": (ctypes.c_ulonglong, []),
     "gcanet_check_device": (c_int, []),
     "gcanet_cn_to_nc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "gcanet_cn_to_nc_add": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "gcanet_nc_to_cn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "gcanet_knn_graph_columns": (c_int, [c_int, c_int]),
     "gcanet_knn_graph_workspace_bytes": (c_size_t, [c_int] * 5),

@@ -64,7 +64,7 @@ struct Carver {
 inline cudaStream_t as_stream(gcanet_stream_t s) { return static_cast<cudaStream_t>(s); }
 
 // layout.cu
-int launch_cn_to_nc(const float *x_cn, float *x_nc, int B, int C, int N, int ld, cudaStream_t st);
+int launch_cn_to_nc(const float *x_cn, float *x_nc, int B, int C, int N, int ld, cudaStream_t st, const float *add_nc = nullptr);
 int launch_nc_to_cn(const float *x_nc, float *x_cn, int B, int C, int N, int ld, cudaStream_t st);
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }

@@ -19,8 +19,10 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-// x_cn [B][C][N] -> x_nc [B][N][ld]; columns C..ld-1 are zero-filled.
-__global__ void cn_to_nc_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int N, int ld) {
+// x_cn [B][C][N] -> x_nc [B][N][ld]; columns C..ld-1 are zero-filled.  ADD: dst = transpose(src) + add, with
+// add [B][N][ld] laid out like dst (the sum of a channel-major and a point-major incoming gradient in one pass).
+template <bool ADD>
+__global__ void cn_to_nc_kernel(const float *__restrict__ src, const float *__restrict__ add, float *__restrict__ dst, int C, int N, int ld) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -33,18 +35,33 @@ __global__ void cn_to_nc_kernel(const float *__restrict__ src, float *__restrict
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int n = n0 + r, c = c0 + threadIdx.x;
-        if (n < N && c < ld) d[(size_t)n * ld + c] = tile[threadIdx.x][r];
+        if (n < N && c < ld) {
+            float v = tile[threadIdx.x][r];
+            if (ADD) v += __ldg(add + (size_t)b * N * ld + (size_t)n * ld + c);
+            d[(size_t)n * ld + c] = v;
+        }
     }
 }
 
 // Same, 64 x 64 tiles with 16-byte global accesses on both sides (N % 4 == 0, ld % 4 == 0, 16-byte aligned bases):
 // four times the bytes per thread of the 32 x 32 kernel, which was latency-bound at ~55 % of the HBM rate.
-__global__ void __launch_bounds__(256) cn_to_nc_wide_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int N, int ld) {
+template <bool ADD>
+__global__ void __launch_bounds__(256) cn_to_nc_wide_kernel(const float *__restrict__ src, const float *__restrict__ add, float *__restrict__ dst, int C, int N, int ld) {
     __shared__ float tile[64][65];
     const int b = blockIdx.z;
     const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
     const float *s = src + (size_t)b * C * N;
     float *d = dst + (size_t)b * N * ld;
+    float4 a[4];
+    if (ADD) {   // issued before the transposing loads so both streams are in flight together
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = threadIdx.x + 256 * i, n = e >> 4, c = (e & 15) * 4;
+            a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + n < N && c0 + c < ld)
+                a[i] = __ldg(reinterpret_cast<const float4 *>(add + (size_t)b * N * ld + (size_t)(n0 + n) * ld + c0 + c));
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int e = threadIdx.x + 256 * i, c = e >> 4, n = (e & 15) * 4;
@@ -56,9 +73,11 @@ __global__ void __launch_bounds__(256) cn_to_nc_wide_kernel(const float *__restr
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int e = threadIdx.x + 256 * i, n = e >> 4, c = (e & 15) * 4;
-        if (n0 + n < N && c0 + c < ld)
-            *reinterpret_cast<float4 *>(d + (size_t)(n0 + n) * ld + c0 + c) =
-                make_float4(tile[c][n], tile[c + 1][n], tile[c + 2][n], tile[c + 3][n]);
+        if (n0 + n < N && c0 + c < ld) {
+            float4 v = make_float4(tile[c][n], tile[c + 1][n], tile[c + 2][n], tile[c + 3][n]);
+            if (ADD) { v.x += a[i].x; v.y += a[i].y; v.z += a[i].z; v.w += a[i].w; }
+            *reinterpret_cast<float4 *>(d + (size_t)(n0 + n) * ld + c0 + c) = v;
+        }
     }
 }
 
@@ -80,14 +99,18 @@ __global__ void nc_to_cn_kernel(const float *__restrict__ src, float *__restrict
     }
 }
 
-int launch_cn_to_nc(const float *x_cn, float *x_nc, int B, int C, int N, int ld, cudaStream_t st) {
-    if (ld >= 32 && N % 4 == 0 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(x_cn) | reinterpret_cast<uintptr_t>(x_nc)) & 15) == 0) {
-        cn_to_nc_wide_kernel<<<dim3(ceil_div(N, 64), ceil_div(ld, 64), B), 256, 0, st>>>(x_cn, x_nc, C, N, ld);
+int launch_cn_to_nc(const float *x_cn, float *x_nc, int B, int C, int N, int ld, cudaStream_t st, const float *add_nc) {
+    const uintptr_t bases = reinterpret_cast<uintptr_t>(x_cn) | reinterpret_cast<uintptr_t>(x_nc) | reinterpret_cast<uintptr_t>(add_nc);
+    if (ld >= 32 && N % 4 == 0 && ld % 4 == 0 && (bases & 15) == 0) {
+        const dim3 grid(ceil_div(N, 64), ceil_div(ld, 64), B);
+        if (add_nc) cn_to_nc_wide_kernel<true><<<grid, 256, 0, st>>>(x_cn, add_nc, x_nc, C, N, ld);
+        else cn_to_nc_wide_kernel<false><<<grid, 256, 0, st>>>(x_cn, nullptr, x_nc, C, N, ld);
         GCANET_LAUNCH_OK("cn_to_nc_wide_kernel");
         return GCANET_OK;
     }
     dim3 grid(ceil_div(N, 32), ceil_div(ld, 32), B), block(32, 8);
-    cn_to_nc_kernel<<<grid, block, 0, st>>>(x_cn, x_nc, C, N, ld);
+    if (add_nc) cn_to_nc_kernel<true><<<grid, block, 0, st>>>(x_cn, add_nc, x_nc, C, N, ld);
+    else cn_to_nc_kernel<false><<<grid, block, 0, st>>>(x_cn, nullptr, x_nc, C, N, ld);
     GCANET_LAUNCH_OK("cn_to_nc_kernel");
     return GCANET_OK;
 }
@@ -136,6 +159,14 @@ extern "C" int gcanet_cn_to_nc(const float *x_cn, float *x_nc, int B, int C, int
     GCANET_REQUIRE(B >= 1 && C >= 1 && N >= 1 && ld >= C, "cn_to_nc: bad shape B=%d C=%d N=%d ld=%d", B, C, N, ld);
     GCANET_REQUIRE(B <= 65535, "cn_to_nc: B > 65535");
     return launch_cn_to_nc(x_cn, x_nc, B, C, N, ld, as_stream(stream));
+}
+
+extern "C" int gcanet_cn_to_nc_add(const float *x_cn, const float *add_nc, float *x_nc, int B, int C, int N, int ld,
+                                   gcanet_stream_t stream) {
+    GCANET_REQUIRE(x_cn && x_nc && add_nc, "cn_to_nc_add: null pointer");
+    GCANET_REQUIRE(B >= 1 && C >= 1 && N >= 1 && ld >= C, "cn_to_nc_add: bad shape B=%d C=%d N=%d ld=%d", B, C, N, ld);
+    GCANET_REQUIRE(B <= 65535, "cn_to_nc_add: B > 65535");
+    return launch_cn_to_nc(x_cn, x_nc, B, C, N, ld, as_stream(stream), add_nc);
 }
 
 extern "C" int gcanet_nc_to_cn(const float *x_nc, float *x_cn, int B, int C, int N, int ld, gcanet_stream_t stream) {

@@ -301,14 +301,21 @@ def group_points(group_size, point_cloud, query_cloud, point_features=None):
 # ----------------------------------------------------------------------------------
 # fused EdgeConv block
 # ----------------------------------------------------------------------------------
-def to_point_major(x_cn: torch.Tensor, ld: int | None = None) -> torch.Tensor:
-    """[B, C, N] -> [B, N, ld] (ld = C rounded up to a multiple of 4 by default, zero padded)."""
+def to_point_major(x_cn: torch.Tensor, ld: int | None = None, add: torch.Tensor | None = None) -> torch.Tensor:
+    """[B, C, N] -> [B, N, ld] (ld = C rounded up to a multiple of 4 by default, zero padded);
+    with ``add`` [B, N, ld] the result is transpose(x) + add in the same pass."""
     require_cuda(x_cn, "x", torch.float32)
     B, C, N = x_cn.shape
     ld = ld or (C + 3) // 4 * 4
     with torch.cuda.device(x_cn.device):
         out = torch.empty((B, N, ld), dtype=torch.float32, device=x_cn.device)
-        call("gcanet_cn_to_nc", ptr(x_cn), ptr(out), B, C, N, ld, stream())
+        if add is None:
+            call("gcanet_cn_to_nc", ptr(x_cn), ptr(out), B, C, N, ld, stream())
+        else:
+            require_cuda(add, "add", torch.float32)
+            if tuple(add.shape) != (B, N, ld):
+                raise RuntimeError(f"add must be [B, N, ld] = {(B, N, ld)} (got {tuple(add.shape)})")
+            call("gcanet_cn_to_nc_add", ptr(x_cn), ptr(add), ptr(out), B, C, N, ld, stream())
     return out
 
 
@@ -376,12 +383,9 @@ class _EdgeConv(torch.autograd.Function):
         desc = ctx.desc
         L = _cabi.lib()
         with torch.cuda.device(x_nc.device):
-            g = None
-            if g_nc is not None:
-                g = g_nc.contiguous()
+            g = g_nc.contiguous() if g_nc is not None else None
             if g_cn is not None:
-                t = to_point_major(g_cn.contiguous(), desc.Cout)
-                g = t if g is None else g + t
+                g = to_point_major(g_cn.contiguous(), desc.Cout, add=g)
             if g is None:
                 g = torch.zeros((desc.B, desc.N, desc.Cout), dtype=torch.float32, device=x_nc.device)
             need_x = ctx.needs_input_grad[0]

@@ -90,6 +90,11 @@ GCANET_API int gcanet_check_device(void);
  * written as zero by cn_to_nc and ignored by nc_to_cn). */
 GCANET_API int gcanet_cn_to_nc(const float *x_cn, float *x_nc, int B, int C, int N, int ld, gcanet_stream_t stream);
 GCANET_API int gcanet_nc_to_cn(const float *x_nc, float *x_cn, int B, int C, int N, int ld, gcanet_stream_t stream);
+/* x_nc = transpose(x_cn) + add_nc, add_nc [B][N][ld] laid out like x_nc (may alias x_nc): the sum of a channel-major
+ * and a point-major incoming gradient in one pass (autograd's accumulation at x1/x2, M4:497-507, without the
+ * intermediate tensor). */
+GCANET_API int gcanet_cn_to_nc_add(const float *x_cn, const float *add_nc, float *x_nc, int B, int C, int N, int ld,
+                                   gcanet_stream_t stream);
 
 /* ------------------------------------------------------------------ kNN graph (torch path)
  * Replaces knn(x,k1,k2) M4:30-47, knn_points_normals(x,k1,k2) M4:50-90 and

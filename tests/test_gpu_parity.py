@@ -345,6 +345,10 @@ def test_to_point_major_layout(C, N):
     cot = torch.randn_like(y)
     (y * cot).sum().backward()
     assert torch.equal(x.grad, cot[:, :, :C].transpose(1, 2))
+    # transpose + accumulate in one pass (the two incoming gradients of x1 / x2): bit-identical to the two-step sum
+    add = torch.randn(3, N, ld, generator=torch.Generator().manual_seed(7)).to(DEV)
+    z = G.to_point_major(x.detach(), ld, add=add)
+    assert torch.equal(z, y.detach() + add)
 
 
 # ------------------------------------------------------------------------------ fused EdgeConv
