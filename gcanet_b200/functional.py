@@ -375,6 +375,7 @@ class _EdgeConv(torch.autograd.Function):
         ctx.save_for_backward(x_nc, idx32, weight, gamma, beta, saved)
         ctx.desc = desc
         ctx.want_cn = want_cn
+        ctx.set_materialize_grads(False)      # an unused layout of the output hands back None, not a zero tensor to add
         return out_nc, out_cn
 
     @staticmethod
