@@ -67,28 +67,36 @@ class GradBucket:
             self.offsets.append(n)
             n += p.numel()
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._zeros = None
 
     def all_reduce_mean(self, group=None, async_op: bool = False):
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world == 1:
             return None
-        for p, o in zip(self.params, self.offsets):
-            dst = self.flat[o:o + p.numel()]
-            if p.grad is None:
-                dst.zero_()
-            else:
-                dst.copy_(p.grad.reshape(-1))
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        # pack with one kernel (absent gradients go in as zeros), average inside the collective where the backend can
+        if self._zeros is None:
+            self._zeros = [torch.zeros(p.numel(), dtype=torch.float32, device=self.flat.device) for p in self.params]
+        srcs = [z if p.grad is None else p.grad.reshape(-1) for p, z in zip(self.params, self._zeros)]
+        torch.cat(srcs, out=self.flat)
+        in_collective = dist.get_backend(group) == "nccl"
+        op = dist.ReduceOp.AVG if in_collective else dist.ReduceOp.SUM
+        work = dist.all_reduce(self.flat, op=op, group=group, async_op=async_op)
+        div = 1 if in_collective else world
         if async_op:
-            return _Pending(self, work, world)
-        self._scatter_back(world)
+            return _Pending(self, work, div)
+        self._scatter_back(div)
         return None
 
     def _scatter_back(self, world: int):
-        self.flat.div_(world)
+        if world != 1:
+            self.flat.div_(world)
+        dsts, views = [], []
         for p, o in zip(self.params, self.offsets):
             if p.grad is not None:
-                p.grad.copy_(self.flat[o:o + p.numel()].view_as(p.grad))
+                dsts.append(p.grad)
+                views.append(self.flat[o:o + p.numel()].view_as(p.grad))
+        if dsts:
+            torch._foreach_copy_(dsts, views)          # one multi-tensor kernel
 
 
 class _Pending:
