@@ -3,7 +3,7 @@
 // arithmetic, ties resolved by (distance, original index) -- but only a fraction of the
 // N x N pairs is evaluated:
 //
-//   1. per cloud: bounding box -> 30-bit Morton code per point -> radix sort (CUB) of
+//   1. per cloud: bounding box -> Morton code per point (up to 10 bits per axis) -> radix sort (CUB) of
 //      (cloud, code) keys; coordinates, norms and the permutation are gathered into sorted
 //      SoA arrays; every 32 consecutive sorted points form a tile with an AABB.
 //   2. one CTA per query tile (8 warps x 4 queries).  A warp first scans its own tile and the
@@ -78,23 +78,27 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {   // 10 bits -> every
     return v;
 }
 
+// key = (cloud << 3*ab) | Morton code with `ab` bits per axis: fits a 32-bit radix key (four 8-bit passes at B = 16,
+// ab = 9, instead of five over 64-bit keys); 512 cells per axis are far finer than the point spacing of a 10 k cloud,
+// and the order only shapes the tiles -- exactness rests on their AABBs
 __global__ void xyz_code_kernel(const float *__restrict__ x, const float *__restrict__ bbox,
-                                unsigned long long *__restrict__ keys, int *__restrict__ vals, int C, int N) {
+                                unsigned *__restrict__ keys, int *__restrict__ vals, int C, int N, int ab) {
     const int b = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const float *p = x + (size_t)b * C * N;
     const float *bb = bbox + b * 8;
     const float ext = fmaxf(fmaxf(bb[3] - bb[0], bb[4] - bb[1]), fmaxf(bb[5] - bb[2], 1e-30f));
-    const float sc = 1023.f / ext;
+    const float top = (float)((1 << ab) - 1);
+    const float sc = top / ext;
     unsigned code = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float t = (p[(size_t)c * N + n] - bb[c]) * sc;
-        unsigned q = (unsigned)fminf(fmaxf(t, 0.f), 1023.f);
+        unsigned q = (unsigned)fminf(fmaxf(t, 0.f), top);
         code |= spread10(q) << c;
     }
-    keys[(size_t)b * N + n] = ((unsigned long long)b << 32) | code;
+    keys[(size_t)b * N + n] = ((unsigned)b << (3 * ab)) | code;
     vals[(size_t)b * N + n] = n;
 }
 
@@ -323,16 +327,21 @@ __global__ void __launch_bounds__(XW * 32, 3) knn_xyz_kernel(XyzArgs a) {   // 8
 // ---------------------------------------------------------------------------------
 static size_t cub_temp_bytes(size_t n, int end_bit) {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned *)nullptr, (unsigned *)nullptr,
                                     (const int *)nullptr, (int *)nullptr, (int)n, 0, end_bit);
     return bytes;
 }
 
-static int key_bits(int B) {
-    int bits = 32;
-    while ((1 << (bits - 32)) < B) ++bits;
+static int cloud_bits(int B) {
+    int bits = 0;
+    while ((1 << bits) < B) ++bits;
     return bits;
 }
+static int axis_bits(int B) {                 // B <= 65535 (checked by the caller): at least 5 bits per axis
+    const int ab = (32 - cloud_bits(B)) / 3;
+    return ab > 10 ? 10 : ab;
+}
+static int key_bits(int B) { return cloud_bits(B) + 3 * axis_bits(B); }
 
 bool knn_xyz_supported(int C, int N, int k2, int metric) {
     if (!((metric == GCANET_METRIC_L2 && C == 3) || (metric == GCANET_METRIC_POINTS_NORMALS && C == 6))) return false;
@@ -345,7 +354,7 @@ size_t knn_xyz_workspace_bytes(int B, int C, int N) {
     size_t t = 0;
     t += align_up(bn * sizeof(float));                     // norm (reference order, original positions)
     t += align_up((size_t)B * 8 * sizeof(float));          // bbox
-    t += 2 * align_up(bn * sizeof(unsigned long long));    // keys in/out
+    t += 2 * align_up(bn * sizeof(unsigned));              // keys in/out
     t += 2 * align_up(bn * sizeof(int));                   // vals in/out
     t += align_up(cub_temp_bytes(bn, key_bits(B)));        // cub temp
     t += align_up(bn * C * sizeof(float));                 // sorted coords
@@ -386,8 +395,8 @@ int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metri
     Carver cv(ws);
     float *norm = cv.take<float>(bn);
     float *bbox = cv.take<float>((size_t)B * 8);
-    unsigned long long *keys_in = cv.take<unsigned long long>(bn);
-    unsigned long long *keys_out = cv.take<unsigned long long>(bn);
+    unsigned *keys_in = cv.take<unsigned>(bn);
+    unsigned *keys_out = cv.take<unsigned>(bn);
     int *vals_in = cv.take<int>(bn);
     int *vals_out = cv.take<int>(bn);
     size_t temp_bytes = cub_temp_bytes(bn, end_bit);
@@ -403,7 +412,7 @@ int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metri
     GCANET_CUDA_OK(cudaMemsetAsync(fallback, 0, B * sizeof(int), st));
     xyz_bbox_kernel<<<B, 1024, 0, st>>>(x, bbox, C, N);
     GCANET_LAUNCH_OK("xyz_bbox_kernel");
-    xyz_code_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(x, bbox, keys_in, vals_in, C, N);
+    xyz_code_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(x, bbox, keys_in, vals_in, C, N, axis_bits(B));
     GCANET_LAUNCH_OK("xyz_code_kernel");
     GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
     count_launch();
