@@ -169,6 +169,104 @@ def run_reference_arm(args):
     return 0
 
 
+
+# ---------------------------------------------------------------------------- same-GPU reference + other configs
+def gpu_reference_leg(dev):
+    """The reference torch path (oracle restatement, bit-identical to the reference source on the golden fixtures)
+    on THIS GPU: DGCNNEncoderGn.edge_stack forward+backward, mode 0, k = 50, B as large as fits (the path
+    materialises [B,N,N] distances and [B,2C,N,k] edge tensors, M4:36-41, M4:120-123).  SURVEY 8(d) / BASELINE.md 3.3:
+    the GPU-vs-GPU bar.  torch defaults (matmul fp32, cuDNN conv TF32 allowed), as the reference would run."""
+    from oracle import dgcnn_oracle as orc
+    from gcanet_b200.synth import abc_like_batch
+    torch.manual_seed(0)
+    enc = orc.DGCNNEncoderGn(mode=0, nn_nb=KNN, input_channels=6).to(dev)
+    for B in (16, 8, 4, 2, 1):
+        try:
+            x = torch.from_numpy(abc_like_batch(B, NPTS, seed=1234)).to(dev)
+            cot = [torch.randn(B, c, NPTS, device=dev) for c in (64, 64, 128)]
+
+            def step():
+                enc.zero_grad(set_to_none=True)
+                outs = enc.edge_stack(x)
+                torch.autograd.backward(outs, cot)
+
+            step()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                step()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 3
+            peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+            del x, cot
+            torch.cuda.empty_cache()
+            return {"value": B / (ms / 1e3), "unit": UNIT, "batch": B, "ms_per_step": ms, "steps": 3,
+                    "peak_memory_gb": round(peak_gb, 1),
+                    "what": "oracle (restated reference torch path: matmul + topk + gather + conv2d + group_norm + max, "
+                            "autograd backward) on cuda, fp32, same clouds / k / layers as `value`"}
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            continue
+    return None
+
+
+def _median_ms(fn, reps=7, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def extra_configs(enc, dev, G):
+    """BASELINE configs[2] (kNN sweep C = 3/64/128, k = 20/50, B = 16 x 10k, the public `knn` call: ordered int64 lists)
+    and configs[4] (large-cloud stress, B = 4 x 100k, k = 50: the three-layer stack forward+backward)."""
+    import gcanet_b200 as gb
+    from gcanet_b200.synth import abc_like_batch
+    out = {}
+    x = torch.from_numpy(abc_like_batch(B_PER_GPU, NPTS, seed=1234)).to(dev)
+    with torch.no_grad():
+        x1, x2, x3 = enc.edge_stack(x)
+    sweep = {}
+    for C, t in ((3, x), (64, x1.contiguous()), (128, x3.contiguous())):
+        for k in (20, 50):
+            ms = _median_ms(lambda: gb.knn(t, k, k))
+            sweep[f"C={C},k={k}"] = {"ms": round(ms, 4), "tflops_algorithmic": round(2.0 * NPTS * NPTS * C * B_PER_GPU / ms / 1e9, 1)}
+    out["config3_knn_sweep"] = {"workload": "knn(x,k,k), B=16 x 10k pts; xyz clouds (C=3), layer-1 (C=64) and layer-3 (C=128) "
+                                            "activations of this encoder; nearest-first int64 lists; median of 7 calls",
+                                "results": sweep}
+    del x1, x2, x3
+    # config 5
+    B5, N5 = 4, 100000
+    x5 = torch.from_numpy(abc_like_batch(B5, N5, seed=555)).to(dev)
+    cot5 = [torch.randn(B5, c, N5, device=dev) for c in (64, 64, 128)]
+    hot = [p for n, p in enc.named_parameters() if n.split(".")[0] in ("conv1", "conv2", "conv3", "bn1", "bn2", "bn3")]
+
+    def step5():
+        for p in hot:
+            p.grad = None
+        outs = enc.edge_stack(x5)
+        torch.autograd.backward(outs, cot5)
+
+    ms5 = _median_ms(step5, reps=5, warm=2)
+    knn5 = _median_ms(lambda: G.knn_graph(x5, KNN, KNN, want64=False, want32=True, ordered=False), reps=5, warm=1)
+    out["config5_large_clouds"] = {"workload": "kNN+EdgeConv stack fwd+bwd, B=4 x 100k pts, k=50, mode 0; median of 5 steps",
+                                   "ms_per_step": round(ms5, 3), "clouds_per_s": round(B5 / (ms5 / 1e3), 1),
+                                   "points_per_s": round(B5 * N5 / (ms5 / 1e3)), "xyz_knn_ms": round(knn5, 3)}
+    del x5, cot5
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------- GPU path
 def run_ours(args):
     import torch.distributed as dist
@@ -190,7 +288,7 @@ def run_ours(args):
     enc = gb.DGCNNEncoderGn(mode=0, nn_nb=KNN, input_channels=6).to(dev)
     hot = [p for n, p in enc.named_parameters()
            if n.split(".")[0] in ("conv1", "conv2", "conv3", "bn1", "bn2", "bn3")]
-    bucket = GradBucket(hot) if world > 1 else None
+    bucket = GradBucket(hot, assume_uniform=True) if world > 1 else None
 
     # each rank owns its own 16 clouds (weak scaling); cloud seeds are disjoint across ranks
     x_host = torch.from_numpy(abc_like_batch(B_PER_GPU, NPTS, seed=1234, first_cloud=rank * B_PER_GPU)).pin_memory()
@@ -216,19 +314,22 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """(total ms, median ms of one step): CUDA events on the launching stream, barrier + synchronize on both sides,
+        max over ranks.  The total over exactly `steps` steps gives `value`; the per-step median is reported beside it."""
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
+        evs[0].record()
+        for i in range(steps):
             fn()
-        b.record()
+            evs[i + 1].record()
         barrier()
-        ms = a.elapsed_time(b)
+        ms = evs[0].elapsed_time(evs[-1])
+        med = statistics.median(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
         if world > 1:
-            t = torch.tensor([ms], device=dev)
+            t = torch.tensor([ms, med], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t[0])
-        return ms
+            ms, med = float(t[0]), float(t[1])
+        return ms, med
 
     for _ in range(max(args.warmup, 3)):
         step(x_dev)
@@ -240,7 +341,7 @@ def run_ours(args):
         sampler.start()
     G.enable_kernel_timing(True)
     l0 = _cabi.launch_count()
-    ms_total = timed(lambda: step(x_dev), args.steps)
+    ms_total, ms_median = timed(lambda: step(x_dev), args.steps)
     launches = _cabi.launch_count() - l0
     per_call = G.kernel_timings_ms()
     G.enable_kernel_timing(False)
@@ -256,8 +357,32 @@ def run_ours(args):
 
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    ms_e2e_total, ms_e2e_median = timed(e2e_step, args.steps)
+    ms_e2e = ms_e2e_total / args.steps
     e2e_value = world * B_PER_GPU / (ms_e2e / 1e3)
+
+    # --- N > 1: the collective itself, checked on the hardware (outside the timed regions): every rank's own gradients
+    # are all-gathered and averaged with torch ops, and must equal what GradBucket.all_reduce_mean left in p.grad
+    allreduce_check = None
+    if world > 1:
+        for p in hot:
+            p.grad = None
+        outs = enc.edge_stack(x_dev)
+        torch.autograd.backward(outs, cot)
+        mine = torch.cat([p.grad.reshape(-1) for p in hot]).clone()
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        want = torch.stack(gathered).double().mean(0)
+        bucket.all_reduce_mean()
+        got = torch.cat([p.grad.reshape(-1) for p in hot]).double()
+        err = ((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).reshape(1)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        differ = (torch.stack(gathered).std(0).max() > 0).float().reshape(1)      # ranks really hold different gradients
+        allreduce_check = {"max_rel_err": float(err[0]), "ranks_differ": bool(differ[0] > 0), "floats": int(mine.numel())}
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = extra_configs(enc, dev, G)
 
     if world > 1:
         dist.barrier()
@@ -271,13 +396,19 @@ def run_ours(args):
     tag = "knn_graph[C=64,metric=0]"
     knn_ms = per_call.get(tag, [])
     roofline = None
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_dominant_kernel.json")) as f:
-            dk = json.load(f)
-        traffic = int(dk["dram_bytes_read"]) + int(dk["dram_bytes_write"])      # one ncu --set full capture
-    except Exception:
-        pass
+    # `traffic` is by definition a profiler counter (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full
+    # capture of this kernel, per launch): it cannot be measured inside an un-profiled run, so it is read from the newest
+    # committed capture and the file is named in `traffic_source`; null when no capture of the current kernel exists
+    traffic, traffic_source = None, None
+    for name in ("r02_dominant_kernel.json", "r01_dominant_kernel.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                dk = json.load(f)
+            traffic = int(dk["dram_bytes_read"]) + int(dk["dram_bytes_write"])
+            traffic_source = f"profiles/{name} (ncu --set full, {dk.get('kernel', 'dominant kernel')}, per launch)"
+            break
+        except Exception:
+            continue
     if knn_ms:
         avg_ms = sum(knn_ms) / len(knn_ms)
         flop = 2.0 * NPTS * NPTS * 64 * B_PER_GPU                 # 2*N^2*C per cloud
@@ -287,9 +418,13 @@ def run_ours(args):
                     "kernel": "feature-space kNN C=64: PCA/Morton prep + knn_tcp_scan_kernel (tcgen05, box-pruned) + exact "
                               "re-rank, algorithmic 2*N^2*C FLOP per cloud",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic, "ms_per_launch": avg_ms, "launches_per_step": len(knn_ms) / args.steps,
+                    "traffic": traffic, "traffic_source": traffic_source, "ms_per_launch": avg_ms, "launches_per_step": len(knn_ms) / args.steps,
                     "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)"}
     step_tflops = GFLOP_PER_CLOUD * 1e9 * B_PER_GPU / (ms_step * 1e-3) / 1e12
+
+    gpu_reference = None
+    if world == 1 and not args.no_extras:
+        gpu_reference = gpu_reference_leg(dev)
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -301,7 +436,8 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_step_median": ms_median,
+        "value_from_median": world * B_PER_GPU / (ms_median / 1e3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DGCNN kNN+EdgeConv stack fwd+bwd, B=16 x 10k pts, k=50, mode 0 (BASELINE configs[1])",
                    "batch_per_gpu": B_PER_GPU, "global_batch": world * B_PER_GPU, "points": NPTS, "k": KNN,
@@ -309,7 +445,7 @@ def run_ours(args):
                    if world > 1 else "single GPU",
                    "l2": "no flush needed: one step streams >1 GB of activations/neighbour lists, far above the 126 MB L2"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "ms_per_step_median": ms_e2e_median,
                 "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "roofline": roofline,
@@ -317,7 +453,10 @@ def run_ours(args):
         "step_frac_of_tensor_peak": step_tflops / float(peaks["bf16_tflops_sustained"]),
         "breakdown_ms_per_step": breakdown,
         "cpu_baseline": cpu_baseline,
+        "gpu_reference": gpu_reference,
+        "allreduce_check": allreduce_check,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
     return 0
 
@@ -329,6 +468,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~15 s CPU leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the same-GPU reference leg and the config 3 / config 5 keys (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -52,6 +52,16 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
     if not sources:
         raise RuntimeError(f"no CUDA sources under {CSRC}")
     os.makedirs(OBJ, exist_ok=True)
+    # objects built with other flags (e.g. --aids) are stale whatever their age
+    stamp = os.path.join(OBJ, ".flags")
+    flags_now = " ".join([*NVCC_FLAGS, *[f for f in extra_flags if f not in ("-Xptxas", "-v")]])
+    try:
+        with open(stamp) as f:
+            force = force or f.read() != flags_now
+    except OSError:
+        force = True
+    with open(stamp, "w") as f:
+        f.write(flags_now)
     nvcc = None
     jobs = []
     for src in sources:
@@ -91,6 +101,10 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--ptxas-v", action="store_true", help="print registers / spills / shared memory per kernel")
+    ap.add_argument("--aids", action="store_true",
+                    help="compile the measurement knobs in (GCANET_* environment variables, see DESIGN.md section 7)")
     a = ap.parse_args()
     extra = ["-Xptxas", "-v"] if a.ptxas_v else []
-    print(build_library(force=a.force or a.ptxas_v, verbose=a.verbose or a.ptxas_v, extra_flags=extra))
+    if a.aids:
+        extra.append("-DGCANET_MEASUREMENT_AIDS")
+    print(build_library(force=a.force or a.ptxas_v or a.aids, verbose=a.verbose or a.ptxas_v, extra_flags=extra))

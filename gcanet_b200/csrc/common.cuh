@@ -41,6 +41,16 @@ void count_launch();   // statistics only: bumps the counter gcanet_launch_count
         }                                                                               \
     } while (0)
 
+// Measurement knobs (environment variables that switch a path off for A/B timing or print statistics) exist only in
+// builds made with -DGCANET_MEASUREMENT_AIDS (python -m gcanet_b200.build --aids); the shipped library never reads the
+// environment, so no call can be steered into a debug mode that leaves its outputs unwritten.
+#ifdef GCANET_MEASUREMENT_AIDS
+#include <stdlib.h>
+#define GCANET_AID_ENV(name) getenv(name)
+#else
+#define GCANET_AID_ENV(name) (static_cast<const char *>(nullptr))
+#endif
+
 constexpr int kNumSMs = 148;          // B200
 constexpr size_t kAlign = 256;        // every workspace sub-buffer starts on this boundary
 

@@ -1026,7 +1026,7 @@ struct BwdWs {
 // layer-3 shape: 64 input channels feeding more output channels -- scatter X~ instead of the Cout-wide dense term
 // (at Cout = 64 the split loses: 0.65 ms against 0.55 ms for the layer's backward)
 static bool bwd_mid_path(const gcanet_edgeconv_desc *d) {
-    static const bool off = getenv("GCANET_NO_MID_SCATTER") != nullptr;
+    static const bool off = GCANET_AID_ENV("GCANET_NO_MID_SCATTER") != nullptr;
     return !off && d->ldx == 64 && d->C == 64 && d->Cout >= 128 && d->Cout <= 256 && (long long)d->B * d->N >= 1024;
 }
 
@@ -1063,6 +1063,9 @@ static int check_desc(const gcanet_edgeconv_desc *d) {
     GCANET_REQUIRE(d->groups >= 1 && d->Cout % d->groups == 0 && 32 % d->groups == 0,
                    "edgeconv: groups=%d must divide 32 and Cout=%d", d->groups, d->Cout);
     GCANET_REQUIRE(d->eps > 0.f, "edgeconv: eps must be positive");
+    // max_k LReLU(GN(y)) = LReLU(GN(max or min of y)) needs a non-decreasing activation
+    GCANET_REQUIRE(d->slope >= 0.f, "edgeconv: negative_slope=%g < 0 (the fused max/min selection needs a non-decreasing activation)", (double)d->slope);
+    GCANET_REQUIRE((long long)d->B * d->N < 2147483647ll, "edgeconv: B * N = %lld does not fit 32-bit row counts", (long long)d->B * d->N);
     GCANET_REQUIRE((long long)d->N * 2 * d->Cout < (1ll << 30), "edgeconv: N * 2 * Cout = %lld exceeds 2^30 (32-bit row offsets)",
                    (long long)d->N * 2 * d->Cout);
     return GCANET_OK;
@@ -1078,7 +1081,7 @@ static int run_forward(const gcanet_edgeconv_desc *d, const float *x_nc, const i
     GCANET_LAUNCH_OK("prep_wcat_kernel");
     // [P|Q] = X Wcat: tensor cores (bf16x3 split, fp32-accurate) for the feature layers, CUDA cores for the xyz layer
     int rc = gemm_tc_try(x_nc, d->ldx, w.wcatT, d->ldx, sv.pq, 2 * Cout, M, 2 * Cout, d->ldx, st);
-    if (rc < 0) rc = launch_sgemm_nn(x_nc, w.wcat, sv.pq, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, 2 * Cout, st);
+    if (rc > 0) rc = launch_sgemm_nn(x_nc, w.wcat, sv.pq, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, 2 * Cout, st);
     if (rc) return rc;
     FwdArgs fa{sv.pq, idx, gamma, sv.ysel, sv.ysum, sv.arg, w.part, d->N, Cout, d->k, d->groups};
     const int nblk = ceil_div(d->N, kPtsPerCta);
@@ -1146,7 +1149,7 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
             GCANET_LAUNCH_OK("edge_bwd_scatter_mid_kernel");
             // X~ Wq^T: rows Cout.. of wcatT are Wq
             int rq = gemm_tc_try(w.xt, d->ldx, w.wcatT + (size_t)Cout * d->ldx, d->ldx, w.xq, Cout, M, Cout, d->ldx, st);
-            if (rq < 0) rq = launch_sgemm_nn(w.xt, w.wcat + Cout, w.xq, M, Cout, d->ldx, d->ldx, 2 * Cout, Cout, st);
+            if (rq > 0) rq = launch_sgemm_nn(w.xt, w.wcat + Cout, w.xq, M, Cout, d->ldx, d->ldx, 2 * Cout, Cout, st);
             if (rq) return rq;
             edge_bwd_degfix_mid_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, w.xq, d->N,
                                                                                         Cout, d->groups, total4);
@@ -1166,7 +1169,7 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     GCANET_LAUNCH_OK("unprep_dw_kernel");
     if (grad_x_nc) {
         rc = gemm_tc_try(w.dpq, 2 * Cout, w.wcat, 2 * Cout, grad_x_nc, d->ldx, M, d->ldx, 2 * Cout, st);
-        if (rc < 0) rc = launch_sgemm_nn(w.dpq, w.wcatT, grad_x_nc, M, d->ldx, 2 * Cout, 2 * Cout, d->ldx, d->ldx, st);
+        if (rc > 0) rc = launch_sgemm_nn(w.dpq, w.wcatT, grad_x_nc, M, d->ldx, 2 * Cout, 2 * Cout, d->ldx, d->ldx, st);
         if (rc) return rc;
     }
     return GCANET_OK;
@@ -1449,6 +1452,8 @@ static int check_ndesc(const gcanet_normal_edge_desc *d) {
     GCANET_REQUIRE(d->Cout == 32 || d->Cout == 64 || d->Cout == 128, "normal_edgeconv: Cout=%d must be 32, 64 or 128", d->Cout);
     GCANET_REQUIRE(d->groups >= 1 && d->Cout % d->groups == 0 && 32 % d->groups == 0, "normal_edgeconv: groups=%d must divide 32 and Cout", d->groups);
     GCANET_REQUIRE(d->eps > 0.f, "normal_edgeconv: eps must be positive");
+    GCANET_REQUIRE(d->slope >= 0.f, "normal_edgeconv: negative_slope=%g < 0", (double)d->slope);
+    GCANET_REQUIRE((long long)d->B * d->N < 2147483647ll, "normal_edgeconv: B * N = %lld does not fit 32-bit row counts", (long long)d->B * d->N);
     return GCANET_OK;
 }
 

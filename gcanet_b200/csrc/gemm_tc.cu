@@ -230,11 +230,13 @@ static int launch_gemm_tc(const float *A, int lda, const float *Bt, int ldb, flo
 }
 
 // C[M][N] = A[M][K] Bt[N][K]^T on the tensor cores when the shape is one the EdgeConv layers use
-// (K, N in {64, 128, 256}, 16-byte aligned rows); returns -1 when the caller should use the CUDA-core GEMM.
+// (K, N in {64, 128, 256}, 16-byte aligned rows); returns +1 (GEMM_TC_NOT_COVERED, never a
+// negative gcanet_status) when the shape is not covered and the caller should use the CUDA-core GEMM; a negative return is
+// a real error and must be propagated.
 int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K, cudaStream_t st) {
-    if (M < 1024 || lda % 4 || ldb % 4 || ldc % 4) return -1;
-    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt) | reinterpret_cast<uintptr_t>(C)) & 15) return -1;
-    if (getenv("GCANET_NO_TC_GEMM")) return -1;        // measurement aid
+    if (M < 1024 || lda % 4 || ldb % 4 || ldc % 4) return 1;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt) | reinterpret_cast<uintptr_t>(C)) & 15) return 1;
+    if (GCANET_AID_ENV("GCANET_NO_TC_GEMM")) return 1;        // measurement aid
 #define GT_CASE(KK, NN) if (K == KK && N == NN) return launch_gemm_tc<KK, NN>(A, lda, Bt, ldb, C, ldc, M, st)
     GT_CASE(64, 128);
     GT_CASE(64, 256);
@@ -244,7 +246,7 @@ int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int
     GT_CASE(256, 128);
     GT_CASE(64, 64);
 #undef GT_CASE
-    return -1;
+    return 1;
 }
 
 // =================================================================================
@@ -420,7 +422,7 @@ gemm_tn_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict_
 int gemm_tn_tc_try(const float *X, int ldx, const float *Y, int ldy, float *part, int M, int N, int K, int max_splits,
                    int *splits_out, cudaStream_t st) {
     if (K != 64 || (N != 128 && N != 256) || M < 8192 || max_splits < 1) return 1;
-    if (ldx % 4 || ldy % 4 || getenv("GCANET_NO_TC_GEMM")) return 1;
+    if (ldx % 4 || ldy % 4 || GCANET_AID_ENV("GCANET_NO_TC_GEMM")) return 1;
     int splits = max_splits < kNumSMs ? max_splits : kNumSMs;
     const int rows = ceil_div(ceil_div(M, splits), 64) * 64;
     splits = ceil_div(M, rows);

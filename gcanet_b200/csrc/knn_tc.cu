@@ -1743,8 +1743,8 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     int *fb_count = cv.take<int>(2 * (size_t)B);          // fallback rows | wide re-rank rows
     int *big_count = fb_count + B;
     GCANET_CUDA_OK(cudaMemsetAsync(fb_count, 0, 2 * B * sizeof(int), st));
-    const char *env_np = getenv("GCANET_TC_NO_PRUNE");
-    const bool prune = !no_prune && tcp_supported(B, N, k2) && !(env_np && env_np[0] == '1') && !getenv("GCANET_TC_DEBUG");
+    const char *env_np = GCANET_AID_ENV("GCANET_TC_NO_PRUNE");
+    const bool prune = !no_prune && tcp_supported(B, N, k2) && !(env_np && env_np[0] == '1') && !GCANET_AID_ENV("GCANET_TC_DEBUG");
     __nv_bfloat16 *xs = cv.take<__nv_bfloat16>(bn * 2 * C);
     float *x_nc = cv.take<float>(bn * C);
     float *norm = cv.take<float>(bn);
@@ -1810,13 +1810,13 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         int P = 16;
         while (P < tiles) P <<= 1;
         int pre = TCP_PRE;
-        if (const char *e = getenv("GCANET_TC_PRE")) pre = atoi(e);          // measurement aid
+        if (const char *e = GCANET_AID_ENV("GCANET_TC_PRE")) pre = atoi(e);          // measurement aid
         if (pre > tiles) pre = tiles;
         if (pre < 0) pre = 0;
         const int qtiles = ceil_div(N, TC_BM);
-        if (getenv("GCANET_TC_STATS")) GCANET_CUDA_OK(cudaMemsetAsync(visited, 0, (size_t)B * qtiles * sizeof(int), st));
+        if (GCANET_AID_ENV("GCANET_TC_STATS")) GCANET_CUDA_OK(cudaMemsetAsync(visited, 0, (size_t)B * qtiles * sizeof(int), st));
         const int *work = nullptr;
-        if (B * qtiles <= TCP_MAX_WORK && !getenv("GCANET_TC_NO_ORDER")) {
+        if (B * qtiles <= TCP_MAX_WORK && !GCANET_AID_ENV("GCANET_TC_NO_ORDER")) {
             tcp_work_key_kernel<<<dim3(ceil_div(qtiles, 8), B), 256, 0, st>>>(boxes, wkey, tiles, qtiles);
             GCANET_LAUNCH_OK("tcp_work_key_kernel");
             tcp_work_order_kernel<<<ceil_div(B * qtiles, 8), 256, 0, st>>>(wkey, work_buf, B * qtiles);
@@ -1834,7 +1834,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         if (k2 <= TC_BN) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, fa, ra, B, st);
         else rc = C == 64 ? launch_tcp<64, 2>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 2>(tmap_q, tmap_k, sa, fa, ra, B, st);
         if (rc) return rc;
-        const char *stats = getenv("GCANET_TC_STATS");
+        const char *stats = GCANET_AID_ENV("GCANET_TC_STATS");
         if (stats && stats[0] == '1') {            // measurement aid: synchronises (clouds left to the full scan report 0 tiles)
             const int nq = B * ceil_div(N, TC_BM);
             int *h = (int *)malloc(nq * sizeof(int));
@@ -1867,7 +1867,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     while (gcd(stride, tiles) != 1) ++stride;
     // GCANET_TC_DEBUG=1 (measurement aid, tools/time_knn.py): run the scan pipeline with appends disabled
     // and stop after it -- gives the TMA + MMA + TMEM-read + compare floor of the kernel.
-    const char *dbg = getenv("GCANET_TC_DEBUG");
+    const char *dbg = GCANET_AID_ENV("GCANET_TC_DEBUG");
     const int dbg_mode = (dbg && dbg[0] >= '1' && dbg[0] <= '3') ? dbg[0] - '0' : 0;
     TcScanArgs sa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, dbg_mode, stride, nullptr, TC_CAP, 0};
     RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),

@@ -44,11 +44,17 @@ class DGCNNEncoderGn(nn.Module):
         self.conv3 = nn.Sequential(nn.Conv2d(64 * 2, 128, kernel_size=1, bias=False), self.bn3, act)
         self.mlp1 = nn.Conv1d(256, 1024, 1)
         self.bnmlp1 = nn.GroupNorm(8, 1024)
+        # set keep_graphs = True to have edge_stack leave its three neighbour lists (int32 [B, N, k], the SETS the
+        # layers used, order unspecified) in last_graphs: the parity tests feed them to the oracle's idx= argument
+        self.keep_graphs = False
+        self.last_graphs = []
 
     # -- hot path ------------------------------------------------------------------
     def _block(self, x_nc, x_cn, conv, C, metric):
         """One EdgeConv layer: graph on x_cn (no gradient, M4:33), fused conv/GN/act/max on x_nc."""
         _, idx32 = G.knn_graph(x_cn, self.k, self.k, metric, want64=False, want32=True, ordered=False)   # max over k is order-invariant
+        if self.keep_graphs:
+            self.last_graphs.append(idx32)
         gn = conv[1]
         return G.edgeconv(x_nc, idx32, conv[0].weight, gn.weight, gn.bias, C, groups=gn.num_groups, eps=gn.eps,
                           slope=conv[2].negative_slope, want_cn=True)
@@ -62,6 +68,7 @@ class DGCNNEncoderGn(nn.Module):
         if 2 * C != self.conv1[0].in_channels:
             raise RuntimeError(f"conv1 expects {self.conv1[0].in_channels} edge channels, input has C={C}")
         metric = G.METRIC_POINTS_NORMALS if self.mode == 5 else G.METRIC_L2
+        self.last_graphs = []
         x_nc = G._ToPointMajor.apply(x, (C + 3) // 4 * 4)
         x1_nc, x1 = self._block(x_nc, x, self.conv1, C, metric)
         x2_nc, x2 = self._block(x1_nc, x1, self.conv2, 64, G.METRIC_L2)

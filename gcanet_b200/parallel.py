@@ -51,12 +51,20 @@ class GradBucket:
     """One flat buffer for the gradients of ``params``; ``all_reduce_mean()`` sums it over
     the ranks in a single collective and writes the averages back into ``p.grad``.
 
-    Parameters whose ``.grad`` is None (the reference's declared-but-unused ``bn4``/``bn5``,
-    M4:466-467) are skipped on every rank alike, so ranks never disagree on the layout:
-    the layout is fixed by the parameter list, absent gradients are sent as zeros.
+    The layout is fixed by the parameter list, so ranks never disagree on it.  A parameter whose
+    ``.grad`` is None (the reference's declared-but-unused ``bn4``/``bn5``, M4:466-467) is sent as
+    zeros, followed by one presence flag per parameter; after the collective a parameter that got a
+    gradient on ANY rank has the average written back on EVERY rank (``p.grad`` is created where it was
+    missing), so replicas cannot drift apart when a gradient is absent on some ranks only.  Reading the
+    flags costs one small device-to-host copy per step; ``assume_uniform=True`` skips it for callers
+    that know every rank produces the same set of gradients (bench.py's hot-path parameters).
+
+    The average is a mean of per-rank means: it equals the global-batch gradient when every rank holds
+    the same number of clouds (what ``shard_range`` gives when world divides the global batch);
+    otherwise scale each rank's loss by ``local_batch * world / global_batch`` before backward.
     """
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], assume_uniform: bool = False):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("GradBucket needs at least one trainable parameter")
@@ -66,43 +74,72 @@ class GradBucket:
         for p in self.params:
             self.offsets.append(n)
             n += p.numel()
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.numel = n
+        self.assume_uniform = assume_uniform
+        # gradients, then one presence flag per parameter
+        self.flat = torch.zeros(n + len(self.params), dtype=torch.float32, device=dev)
         self._zeros = None
+        self._flag_cache = {}
+
+    def _flags(self, present):
+        key = tuple(present)
+        t = self._flag_cache.get(key)
+        if t is None:
+            t = torch.tensor([1.0 if f else 0.0 for f in present], dtype=torch.float32, device=self.flat.device)
+            self._flag_cache[key] = t
+        return t
 
     def all_reduce_mean(self, group=None, async_op: bool = False):
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world == 1:
-            return None
+            return _Done() if async_op else None
         # pack with one kernel (absent gradients go in as zeros), average inside the collective where the backend can
         if self._zeros is None:
             self._zeros = [torch.zeros(p.numel(), dtype=torch.float32, device=self.flat.device) for p in self.params]
+        present = [p.grad is not None for p in self.params]
         srcs = [z if p.grad is None else p.grad.reshape(-1) for p, z in zip(self.params, self._zeros)]
-        torch.cat(srcs, out=self.flat)
+        torch.cat(srcs + [self._flags(present)], out=self.flat)
         in_collective = dist.get_backend(group) == "nccl"
         op = dist.ReduceOp.AVG if in_collective else dist.ReduceOp.SUM
         work = dist.all_reduce(self.flat, op=op, group=group, async_op=async_op)
         div = 1 if in_collective else world
         if async_op:
-            return _Pending(self, work, div)
-        self._scatter_back(div)
+            return _Pending(self, work, div, present)
+        self._scatter_back(div, present)
         return None
 
-    def _scatter_back(self, world: int):
+    def _scatter_back(self, world: int, present):
         if world != 1:
             self.flat.div_(world)
+        if self.assume_uniform:
+            anywhere = present
+        else:
+            anywhere = (self.flat[self.numel:] > 0).tolist()          # one small D2H copy
         dsts, views = [], []
-        for p, o in zip(self.params, self.offsets):
-            if p.grad is not None:
+        for p, o, here, some in zip(self.params, self.offsets, present, anywhere):
+            if not some:
+                continue
+            view = self.flat[o:o + p.numel()].view_as(p)
+            if here:
                 dsts.append(p.grad)
-                views.append(self.flat[o:o + p.numel()].view_as(p.grad))
+                views.append(view.view_as(p.grad))
+            else:
+                p.grad = view.clone()             # absent here, present elsewhere: take the average all the same
         if dsts:
             torch._foreach_copy_(dsts, views)          # one multi-tensor kernel
 
 
 class _Pending:
-    def __init__(self, bucket, work, world):
-        self.bucket, self.work, self.world = bucket, work, world
+    def __init__(self, bucket, work, world, present):
+        self.bucket, self.work, self.world, self.present = bucket, work, world, present
 
     def wait(self):
         self.work.wait()
-        self.bucket._scatter_back(self.world)
+        self.bucket._scatter_back(self.world, self.present)
+
+
+class _Done:
+    """What ``all_reduce_mean(async_op=True)`` returns in a single-process run: nothing to wait for."""
+
+    def wait(self):
+        return None

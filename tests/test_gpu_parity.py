@@ -513,8 +513,10 @@ def test_large_cloud_stress_100k():
     st = torch.gather(score, 1, idx[0, rows]).double()
     kth = torch.gather(score, 1, io).double().min(dim=1)[0]
     assert bool((st >= (kth - tau).unsqueeze(-1)).all())
-    same = (idx[0, rows].sort(dim=1)[0] == io.sort(dim=1)[0]).all(dim=1)
-    assert float(same.float().mean()) > 0.95
+    # rows whose set differs from the chunked oracle's: every one passed the tau check above; report and bound the count
+    n_diff = int((idx[0, rows].sort(dim=1)[0] != io.sort(dim=1)[0]).any(dim=1).sum())
+    print(f"100k xyz: {n_diff} of {rows.numel()} sampled rows needed the tie tolerance")
+    assert n_diff <= max(2, rows.numel() // 25)
 
 
 def test_knn_xyz_pruned_path_cloud_edges():
@@ -705,7 +707,8 @@ def test_large_cloud_feature_space_100k():
     st = torch.gather(score, 1, idx[0, rows]).double()
     kth = torch.gather(score, 1, io).double().min(dim=1)[0]
     assert bool((st >= (kth - tau).unsqueeze(-1)).all())
-    same = (idx[0, rows].sort(dim=1)[0] == io.sort(dim=1)[0]).all(dim=1)
-    assert float(same.float().mean()) > 0.95
+    n_diff = int((idx[0, rows].sort(dim=1)[0] != io.sort(dim=1)[0]).any(dim=1).sum())
+    print(f"100k C=64: {n_diff} of {rows.numel()} sampled rows needed the tie tolerance")
+    assert n_diff <= 1                                    # Gaussian features: distances are well separated
     srt = idx.sort(dim=2)[0]
     assert bool((srt[:, :, 1:] != srt[:, :, :-1]).all())

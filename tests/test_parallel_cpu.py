@@ -56,6 +56,13 @@ def _worker(rank, world, port, out):
         bucket.all_reduce_mean(async_op=True).wait()
         for a, b in zip(out[rank], [p.grad for p in lin.parameters()]):
             assert torch.allclose(a, b)
+        # a gradient that exists on rank 0 only: every rank must end up with the average (replicas diverged)
+        lonely = torch.nn.Parameter(torch.zeros(3))
+        b2 = GradBucket([lonely])
+        if rank == 0:
+            lonely.grad = torch.full((3,), 4.0)
+        b2.all_reduce_mean()
+        assert lonely.grad is not None and torch.allclose(lonely.grad, torch.full((3,), 4.0 / world))
     finally:
         dist.destroy_process_group()
 
@@ -82,5 +89,6 @@ def test_single_process_bucket_is_a_no_op():
     lin(torch.ones(1, 2)).sum().backward()
     before = [p.grad.clone() for p in lin.parameters()]
     assert GradBucket(lin.parameters()).all_reduce_mean() is None
+    GradBucket(lin.parameters()).all_reduce_mean(async_op=True).wait()       # a no-op handle, not None
     for a, b in zip(before, [p.grad for p in lin.parameters()]):
         assert torch.equal(a, b)
