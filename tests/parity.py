@@ -71,3 +71,45 @@ def check_knn_rows(idx_test: torch.Tensor, idx_oracle: torch.Tensor, scores: tor
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def argmax_ambiguity(feat: torch.Tensor, weight: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, idx: torch.Tensor,
+                     groups: int = 2, eps: float = 1e-5, rel: float = 2e-5):
+    """Which points' input gradient is decided by a near-tie.
+
+    EdgeConv's backward is discontinuous in two places: the max over k hands the whole gradient of (point i, channel c)
+    to ONE neighbour, and LeakyReLU switches slope at 0.  Two correct fp32 implementations that round the pre-norm
+    activation y differently (here: P_j + Q_i against the reference's W [x_j - x_i; x_i]) pick different neighbours when
+    the two largest y of a row are closer than their rounding, and the gradient then lands on another point.  This
+    helper recomputes y in fp64 and returns a bool mask [B, N] of the points whose dX can legitimately differ:
+
+      * every neighbour j whose (sign(gamma)-oriented) y is within ``rel * max|y|`` of the row's extreme, whenever a
+        row has more than one such neighbour (the gradient of that (i, c) may land on any of them);
+      * every point i with a channel whose post-norm value is within ``rel * max|u|`` of the LeakyReLU kink, and the
+        neighbour that attains that row's extreme.
+
+    feat [B, 2C, N, k] (the oracle's edge tensor), weight [Cout, 2C], idx [B, N, k].  Returns (mask, n_rows_tied)."""
+    B, _, N, k = feat.shape
+    w = weight.reshape(weight.shape[0], -1).double()
+    y = torch.einsum("oc,bcnk->bonk", w, feat.double())                        # [B, Cout, N, k]
+    Cout = y.shape[1]
+    sg = torch.where(gamma.double() < 0, -1.0, 1.0).view(1, Cout, 1, 1)
+    z = y * sg                                                                   # the extreme that survives is max_k z
+    zmax = z.max(dim=3, keepdim=True)[0]
+    tol = rel * float(y.abs().max())
+    near = z >= zmax - tol                                                       # [B, Cout, N, k]
+    tied_rows = near.sum(dim=3) > 1                                              # [B, Cout, N]
+    yg = y.view(B, groups, Cout // groups, N, k)
+    mean = yg.mean(dim=(2, 3, 4), keepdim=True)
+    var = yg.var(dim=(2, 3, 4), unbiased=False, keepdim=True)
+    u = ((yg - mean) / torch.sqrt(var + eps)).view(B, Cout, N, k) * gamma.double().view(1, Cout, 1, 1) \
+        + beta.double().view(1, Cout, 1, 1)
+    u_sel = torch.gather(u, 3, z.argmax(dim=3, keepdim=True)).squeeze(3)         # [B, Cout, N]
+    kink_rows = u_sel.abs() <= rel * float(u.abs().max())
+    mask = torch.zeros(B, N, dtype=torch.bool)
+    hit = near & (tied_rows | kink_rows).unsqueeze(3)                            # neighbours that may receive / lose it
+    hit_nk = hit.any(dim=1)                                                      # [B, N, k]
+    for b in range(B):
+        mask[b, idx[b][hit_nk[b]]] = True
+    mask |= kink_rows.any(dim=1)
+    return mask, int(tied_rows.sum()) + int(kink_rows.sum())
