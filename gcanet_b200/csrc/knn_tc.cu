@@ -939,13 +939,20 @@ __global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restric
     vals[o] = n;
 }
 
+// Extension operand of a 64-key tile: [64 keys][16 bf16] in the interleaved (no-swizzle) K-major layout of
+// make_kmajor_interleaved_desc -- 8-row groups of 256 bytes, inside a group the two 16-byte column blocks 128 bytes apart.
+constexpr int TCP_KEXT_BYTES = TC_BN * 32;
+__host__ __device__ __forceinline__ uint32_t tcp_kext_offset(int r, int chunk) {
+    return (uint32_t)((r >> 3) * 256 + chunk * 128 + (r & 7) * 16);
+}
+
 // one warp per 64-key tile of the sorted order: perm / inverse permutation, sorted key norms (+inf padding),
 // tile AABB in the projected space
 __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ sorted_vals, const float *__restrict__ norm,
                                                         const float *__restrict__ proj, int *__restrict__ perm,
                                                         int *__restrict__ inv, float *__restrict__ norm_pad,
                                                         float *__restrict__ boxes, float *__restrict__ boxes32,
-                                                        unsigned *__restrict__ nmax_bits,
+                                                        unsigned *__restrict__ nmax_bits, uint8_t *__restrict__ kext,
                                                         int B, int N, int Npad, int tiles) {
     const int b = blockIdx.y;
     const int wl = threadIdx.x >> 5;
@@ -957,12 +964,14 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
     for (int h = 0; h < TC_BN / 32; ++h) {
         const int s = t * TC_BN + h * 32 + lane;
         float hmn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hmx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+        float nkey = CUDART_INF_F;                             // +inf masks the zero-filled keys past N
         if (s < N) {
             const int o = sorted_vals[(size_t)b * N + s];
             perm[(size_t)b * N + s] = o;
             inv[(size_t)b * N + o] = s;
             const float nv = norm[(size_t)b * N + o];
             norm_pad[(size_t)b * Npad + s] = nv;
+            nkey = nv;
             nm = fmaxf(nm, nv);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -972,6 +981,25 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
             }
         } else if (s < Npad) {
             norm_pad[(size_t)b * Npad + s] = CUDART_INF_F;
+        }
+        {
+            // |k|^2 as three bf16 terms (hi + mid + lo = all 24 bits of the fp32 norm) in column 0..2 of a K = 16 operand
+            // step: the scan adds the norm to -2 q.k on the tensor cores (one more MMA per tile).  Written as the
+            // shared-memory image of the tile (interleaved K-major, tcp_kext_offset), fetched with one bulk copy.
+            const int r = h * 32 + lane;
+            __nv_bfloat16 e0 = __float2bfloat16_rn(nkey), e1 = __float2bfloat16_rn(0.f), e2 = e1;
+            if (nkey < CUDART_INF_F) {
+                const float r1 = nkey - __bfloat162float(e0);
+                e1 = __float2bfloat16_rn(r1);
+                e2 = __float2bfloat16_rn(r1 - __bfloat162float(e1));
+            }
+            uint4 c0;
+            c0.x = (unsigned)__bfloat16_as_ushort(e0) | ((unsigned)__bfloat16_as_ushort(e1) << 16);
+            c0.y = (unsigned)__bfloat16_as_ushort(e2);
+            c0.z = 0u; c0.w = 0u;
+            uint8_t *img = kext + ((size_t)b * tiles + t) * TCP_KEXT_BYTES;
+            *reinterpret_cast<uint4 *>(img + tcp_kext_offset(r, 0)) = c0;
+            *reinterpret_cast<uint4 *>(img + tcp_kext_offset(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
         }
         // box of this 32-point half (the rows one epilogue warp of the scan owns), then merged into the tile's box
 #pragma unroll
@@ -1048,6 +1076,7 @@ __global__ void __launch_bounds__(256) tcp_work_order_kernel(const unsigned *__r
 struct TcpScanArgs {
     const float *norm_pad;  // [B][Npad] key norms in sorted order, +inf past N
     int Npad;
+    const uint8_t *kext;    // [B][tiles][TCP_KEXT_BYTES] the same norms as a K = 16 bf16 operand step (tcp_tiles_kernel)
     const float *nmax;      // [B]
     const float *boxes;     // [B][tiles][6]
     const float *boxes32;   // [B][2 * tiles][6] boxes of the 32-point halves (= the rows of one epilogue warp)
@@ -1060,7 +1089,18 @@ struct TcpScanArgs {
     const int *structured;  // [B] 1 = this kernel takes the cloud, 0 = the full scan does
     int N, k, tiles, pre, P;  // P = tiles rounded up to a power of two (sort width)
     int qtiles;
+    long long *prof;        // [B * qtiles][16] per-CTA cycle counters (measurement builds, GCANET_TC_PROF=1), else null
 };
+
+#ifdef GCANET_MEASUREMENT_AIDS
+#define TCP_PROF_T0() const long long prof_t0__ = clock64()
+#define TCP_PROF_ADD(acc) acc += clock64() - prof_t0__
+#define TCP_PROF_NOW() clock64()
+#else
+#define TCP_PROF_T0() do { } while (0)
+#define TCP_PROF_ADD(acc) do { } while (0)
+#define TCP_PROF_NOW() 0ll
+#endif
 
 // SM = 1: k <= 64, one minimum per column slot.  SM = 2: k <= 128, the two smallest per slot (128 distinct keys; the
 // 64 extra registers cost the second resident CTA).
@@ -1082,15 +1122,20 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *sA = smem;
     uint8_t *sB = smem + A_BYTES;
-    float *s_rn = reinterpret_cast<float *>(sB + STAGES * TILE_BYTES);      // [TCP_NRING][TC_BN] key norms
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_rn + TCP_NRING * TC_BN);
+    // The key norms ride on the tensor cores: the query operand is scaled by -2 after it lands (exact in bf16), and one
+    // extra K = 16 step multiplies a constant (1, 1, 1, 0, ...) query row with (|k|^2 hi, mid, lo, 0, ...) of every key,
+    // so the accumulator holds  |k|^2 - 2 q.k  itself and the epilogue spends no instruction on forming it.
+    uint8_t *sKe = sB + STAGES * TILE_BYTES;                // [STAGES][TCP_KEXT_BYTES] norm operand of the stage's key tile
+    uint8_t *sQe = sKe + STAGES * TCP_KEXT_BYTES;           // 256 B: one 8-row group of the constant query operand (SBO = 0)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sQe + 256);
     uint64_t *full = bars;
     uint64_t *empty = bars + STAGES;
     uint64_t *a_full = bars + 2 * STAGES;
     uint64_t *t_full = a_full + 1;
     uint64_t *t_empty = t_full + ACC;
     uint64_t *thr_ready = t_empty + ACC;                    // [1] epilogue -> producer: final thresholds of pass A are published
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(thr_ready + 1);
+    uint64_t *a_ready = thr_ready + 1;                      // [1] epilogue -> MMA: the query tile has been scaled by -2
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
     uint32_t *s_kt = tmem_slot + 1;                         // [STAGES] key tile in the stage, TCP_END = end-of-pass marker
     volatile int *s_end = reinterpret_cast<volatile int *>(s_kt + STAGES);   // [2] stream position of the pass A / pass B end marker
     volatile float *s_wthr = reinterpret_cast<volatile float *>(const_cast<int *>(s_end) + 2);   // [8] max true-distance threshold per epilogue warp
@@ -1101,6 +1146,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint32_t *s_ord = reinterpret_cast<uint32_t *>(smem + ((reinterpret_cast<uint8_t *>(const_cast<float *>(s_xf) + 4 * TC_BM) - smem + 7) & ~(size_t)7));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long prof_start = TCP_PROF_NOW();
     // CTAs take the query tiles in the order of a.work (largest bounding box first: those scan the most key tiles,
     // and starting them last would leave the tail of the grid to a few long-running CTAs)
     const int item = a.work ? a.work[blockIdx.x] : (int)blockIdx.x;
@@ -1118,12 +1164,20 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         mbar_init(a_full, 1);
         for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
         mbar_init(thr_ready, 8);
+        mbar_init(a_ready, 8);
         s_end[0] = 0x7fffffff;
         s_end[1] = 0x7fffffff;
         for (int s = 0; s < 8; ++s) s_wthr[s] = CUDART_INF_F;
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, ACC * TC_BN);
+    if (threadIdx.x >= 64 && threadIdx.x < 80) {
+        // constant query operand of the norm step: rows (1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8) in bf16; one 8-row group serves
+        // all 128 rows (stride between groups = 0)
+        const int i = threadIdx.x - 64;
+        reinterpret_cast<uint4 *>(sQe)[i] = i < 8 ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+    }
 
     // ---- tile order: lower bound of every key tile against this CTA's query box, ascending
     {
@@ -1238,6 +1292,9 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const long long prof_sorted = TCP_PROF_NOW();
+    long long *prof = a.prof ? a.prof + (size_t)item * 16 : nullptr;
+    long long pw0 = 0, pw1 = 0;        // per-role wait cycles (measurement builds)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -1245,7 +1302,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_expect_tx(a_full, A_BYTES);
 #pragma unroll
             for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(sA + kb * ABLK_BYTES, &tmap_q, a_full, kb * TC_KB, q0, b);
-            const float *rn_g = a.norm_pad + (size_t)b * a.Npad;
+            const uint8_t *ke_g = a.kext + (size_t)b * tiles * TCP_KEXT_BYTES;
             int stage = 0, seq = 0, nvis = 0;
             uint32_t phase = 0;
             // pass A feeds the threshold search (slot minima), pass B the candidate collection; both walk the tiles
@@ -1255,7 +1312,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     const uint32_t e = s_ord[i];
                     // pass B re-reads the `pre` nearest tiles whatever the bounds turn out to be, so they are
                     // requested while the epilogue is still finishing pass A; only then wait for its final bounds
-                    if (pass == 1 && i == pre) mbar_wait_backoff(thr_ready, 0);
+                    if (pass == 1 && i == pre) { TCP_PROF_T0(); mbar_wait_backoff(thr_ready, 0); TCP_PROF_ADD(pw1); }
                     if (i >= pre) {
                         // thresholds only ever decrease: a stale (larger) value is safe
                         const float thr = fmaxf(fmaxf(fmaxf(s_wthr[0], s_wthr[1]), fmaxf(s_wthr[2], s_wthr[3])),
@@ -1263,13 +1320,13 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         if (__uint_as_float(e & 0xffff0000u) > thr) break;     // every later tile has a larger bound
                     }
                     const int kt = (int)(e & 0xffffu);
-                    mbar_wait_backoff(&empty[stage], phase ^ 1);
+                    { TCP_PROF_T0(); mbar_wait_backoff(&empty[stage], phase ^ 1); TCP_PROF_ADD(pw0); }
                     s_kt[stage] = (uint32_t)kt;
-                    mbar_expect_tx(&full[stage], TILE_BYTES + TC_BN * sizeof(float));
+                    mbar_expect_tx(&full[stage], TILE_BYTES + TCP_KEXT_BYTES);
                     uint8_t *dst = sB + stage * TILE_BYTES;
 #pragma unroll
                     for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(dst + kb * BLK_BYTES, &tmap_k, &full[stage], kb * TC_KB, kt * TC_BN, b);
-                    bulk_load_1d(s_rn + (seq % TCP_NRING) * TC_BN, rn_g + (size_t)kt * TC_BN, TC_BN * sizeof(float), &full[stage]);
+                    bulk_load_1d(sKe + stage * TCP_KEXT_BYTES, ke_g + (size_t)kt * TCP_KEXT_BYTES, TCP_KEXT_BYTES, &full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     ++seq;
                     if (pass == 1) ++nvis;
@@ -1283,18 +1340,20 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 if (pass == 1 && tiles <= pre) mbar_wait_backoff(thr_ready, 0);   // (not yet waited for above)
             }
             if (a.visited) a.visited[(size_t)b * a.qtiles + qt] = nvis;
+            if (prof) { prof[8] = pw0; prof[9] = pw1; prof[10] = seq; prof[11] = TCP_PROF_NOW() - prof_start; }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            mbar_wait(a_full, 0);
+            mbar_wait(a_ready, 0);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(sA);
+            const uint64_t q_ext = make_kmajor_interleaved_desc(smem_u32(sQe), 128, 0);
             int stage = 0, acc = 0, seq = 0, markers = 0;
             uint32_t phase = 0, accphase = 0;
             for (;; ++seq) {
-                mbar_wait_backoff(&t_empty[acc], accphase ^ 1);
-                mbar_wait_backoff(&full[stage], phase);
+                { TCP_PROF_T0(); mbar_wait_backoff(&t_empty[acc], accphase ^ 1); TCP_PROF_ADD(pw0); }
+                { TCP_PROF_T0(); mbar_wait_backoff(&full[stage], phase); TCP_PROF_ADD(pw1); }
                 if (s_kt[stage] == TCP_END) {
                     s_end[markers] = seq;                    // visible to the epilogue through the arrive below
                     mbar_arrive(&empty[stage]);
@@ -1323,11 +1382,13 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         umma_bf16(d_tmem, a_lo, b_hi, kIdesc, 1);
                     }
                 }
+                umma_bf16(d_tmem, q_ext, make_kmajor_interleaved_desc(smem_u32(sKe + stage * TCP_KEXT_BYTES), 128, 256), kIdesc, 1);
                 umma_commit(&empty[stage]);
                 umma_commit(&t_full[acc]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 if (++acc == ACC) { acc = 0; accphase ^= 1; }
             }
+            if (prof) { prof[12] = pw0; prof[13] = pw1; prof[14] = TCP_PROF_NOW() - prof_start; }
         }
     } else {
         // ===================== epilogue: two threads per query row, 32 key columns each =====================
@@ -1350,6 +1411,26 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint16_t *lbw = s_lbw + lg * a.P;               // this warp's lower bound of the i-th tile of the order
         float wbound = CUDART_INF_F;                          // largest true-distance bound among this warp's rows
         const int pair_bar = 1 + lg;                          // named barrier shared by the two warps of a lane quarter
+
+        // the query tile, hi and lo blocks alike, times -2 (exact: a sign and an exponent step), so that the MMAs
+        // accumulate -2 q.k; element-wise, hence independent of the swizzle
+        {
+            mbar_wait(a_full, 0);
+            const __nv_bfloat162 m2 = __float2bfloat162_rn(-2.f);
+            uint4 *pa = reinterpret_cast<uint4 *>(sA);
+            for (int e = threadIdx.x - 64; e < A_BYTES / 16; e += 256) {
+                uint4 w = pa[e];
+                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&w);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) h[u] = __hmul2(h[u], m2);
+                pa[e] = w;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        }
+        const long long prof_scaled = TCP_PROF_NOW();
+        long long prof_refresh = 0;
 
         // the two threads of a row combine a value (sum for counts, min / max for ranges) through shared memory
         auto pair_exchange = [&](float mine) -> float {
@@ -1397,26 +1478,19 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             for (int s = 0; s < 32 * SM; ++s) m[s] = CUDART_INF_F;
             int done = 0, refresh_at = 12;
             for (;; ++seq) {
-                mbar_wait(&t_full[acc], accphase);
+                { TCP_PROF_T0(); mbar_wait(&t_full[acc], accphase); TCP_PROF_ADD(pw0); }
                 if (seq == s_end[0]) break;
                 tc_fence_after();
                 // a tile whose bound against this warp's 32 rows exceeds all their current bounds holds no key that
                 // could lower any of them: its slot minima are not needed (the final bound is the same without them)
                 if (__uint_as_float((uint32_t)lbw[seq] << 16) <= wbound) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_BN + hf * 32;
-                    const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + hf * 32);
                     if constexpr (SM == 1) {
                         uint32_t v[32];
                         tmem_ld32(taddr, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            const float4 n4 = rn[c4];
-                            const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                m[c4 * 4 + e] = fminf(m[c4 * 4 + e], fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]));
-                        }
+                        for (int s = 0; s < 32; ++s) m[s] = fminf(m[s], __uint_as_float(v[s]));     // |k|^2 - 2 q.k, +inf past N
                     } else {
                         // 64 slot registers: the accumulator chunk is read 16 columns at a time to stay within the
                         // register budget of two CTAs per SM
@@ -1426,16 +1500,11 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                             tmem_ld16(taddr + h * 16, v);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int c4 = 0; c4 < 4; ++c4) {
-                                const float4 n4 = rn[h * 4 + c4];
-                                const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int sl = h * 16 + c4 * 4 + e;
-                                    const float d = fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]);
-                                    m[32 + sl] = fminf(m[32 + sl], fmaxf(m[sl], d));      // second smallest of the slot
-                                    m[sl] = fminf(m[sl], d);
-                                }
+                            for (int e = 0; e < 16; ++e) {
+                                const int sl = h * 16 + e;
+                                const float d = __uint_as_float(v[e]);
+                                m[32 + sl] = fminf(m[32 + sl], fmaxf(m[sl], d));      // second smallest of the slot
+                                m[sl] = fminf(m[sl], d);
                             }
                         }
                     }
@@ -1448,7 +1517,9 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     // let the producer start skipping: publish the bound reached so far (after 12 and 36 tiles: each
                     // refresh costs about as much as six tiles of this pass)
                     refresh_at = refresh_at < 36 ? refresh_at * 3 : 0x7fffffff;
+                    TCP_PROF_T0();
                     const float bd = row_bound(m, 6);
+                    TCP_PROF_ADD(prof_refresh);
                     float wt = active ? bd + margin + qn : -CUDART_INF_F;
                     for (int o = 16; o; o >>= 1) wt = fmaxf(wt, __shfl_xor_sync(FULLW, wt, o));
                     if (lane == 0) s_wthr[ewi] = wt;
@@ -1456,6 +1527,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 }
             }
             // end marker of pass A: final thresholds (bit-identical in the two threads of a row)
+            const long long prof_a_end = TCP_PROF_NOW();
             const float bd = row_bound(m, 11);
             if (active) thr = bd + margin;
             float wt = active ? thr + qn : -CUDART_INF_F;
@@ -1469,7 +1541,13 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (++acc == ACC) { acc = 0; accphase ^= 1; }
             ++seq;
             wbound = wt;
+            if (prof && ewi == 0 && lane == 0) {
+                prof[0] = prof_sorted - prof_start; prof[1] = prof_scaled - prof_sorted; prof[2] = prof_a_end - prof_scaled;
+                prof[3] = TCP_PROF_NOW() - prof_a_end; prof[4] = pw0; prof[5] = prof_refresh;
+            }
+            pw0 = 0;
         }
+        const long long prof_b_start = TCP_PROF_NOW();
 
         // ---- pass B: same order again, every key below the row's threshold becomes a candidate.  Each thread owns
         // half of the row's list (capacity TCP_HCAP): no shared counter, and a half that fills up is compacted by
@@ -1483,7 +1561,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         int cnt = 0;
         bool ovf = false;
         for (int i = 0;; ++i, ++seq) {
-            mbar_wait(&t_full[acc], accphase);
+            { TCP_PROF_T0(); mbar_wait(&t_full[acc], accphase); TCP_PROF_ADD(pw0); }
             if (seq == s_end[1]) break;
             tc_fence_after();
             if (__uint_as_float((uint32_t)lbw[i] << 16) > wbound) {
@@ -1500,14 +1578,11 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             tmem_ld32(taddr, v);
             tmem_ld_wait();
             const int jbase = kt * TC_BN + hf * 32;
-            const float4 *rn = reinterpret_cast<const float4 *>(s_rn + (seq % TCP_NRING) * TC_BN + hf * 32);
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
-                const float4 n4 = rn[c4];
-                const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float d = fmaf(-2.f, __uint_as_float(v[c4 * 4 + e]), nn[e]);   // +inf for keys >= N
+                    const float d = __uint_as_float(v[c4 * 4 + e]);                      // |k|^2 - 2 q.k, +inf for keys >= N
                     // if (d < thr) { *wp = (d, index); ++wp; } as two predicated instructions: only the low address
                     // word ever changes (see above)
                     asm volatile(
@@ -1551,6 +1626,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
         }
 
+        if (prof && ewi == 0 && lane == 0) { prof[6] = TCP_PROF_NOW() - prof_b_start; prof[7] = pw0; }
         // the row's two halves meet through shared memory: both must be done before the totals are written
         s_cnt[hf * TC_BM + row] = ovf ? -1 : cnt;
         named_bar_sync(5, 256);
@@ -1627,11 +1703,13 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += 3 * align_up((size_t)B * ceil_div(N, TC_BN) * 6 * sizeof(float));   // tile boxes + boxes of their 32-point halves
     t += align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));          // visited-tile statistics
     t += 2 * align_up((size_t)B * ceil_div(N, TC_BM) * sizeof(int));      // launch order of the query tiles + its sort keys
+    t += align_up((size_t)B * ceil_div(N, TC_BM) * 16 * sizeof(long long)); // per-CTA cycle counters (measurement builds)
     t += 2 * align_up(bn * sizeof(int)) + align_up(2 * (size_t)B * sizeof(int));  // fallback / wide re-rank row lists + counts
     t += align_up(bn * 2 * C * sizeof(__nv_bfloat16));   // xs
     t += align_up(bn * C * sizeof(float));               // x_nc
     t += align_up(bn * sizeof(float));                   // norm
     t += align_up((size_t)B * (ceil_div(N, TC_BN) * TC_BN) * sizeof(float));   // norm_pad
+    t += align_up((size_t)B * ceil_div(N, TC_BN) * TCP_KEXT_BYTES);            // key norms as an operand step
     t += align_up((size_t)B * sizeof(float));            // nmax
     t += align_up((bn * TCP_CAP + 512) * sizeof(uint2)); // cand, 4 KB-aligned rows (the full scan uses TC_CAP entries per row of it)
     t += align_up(2 * bn * sizeof(int));                 // cand_cnt (two halves per row on the pruned path)
@@ -1672,7 +1750,7 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int STAGES = tcp_stages(C);
     const size_t smem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)STAGES * NBLK * TC_BN * 128 +
-                        TCP_NRING * TC_BN * sizeof(float) + 32 * sizeof(uint64_t) + 6 * TC_BM * sizeof(float) + (size_t)sa.P * 16;
+                        (size_t)STAGES * TCP_KEXT_BYTES + 256 + 32 * sizeof(uint64_t) + 6 * TC_BM * sizeof(float) + (size_t)sa.P * 16;
     auto kern = knn_tcp_scan_kernel<C, SM>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(sa.N, TC_BM) * B);
@@ -1737,6 +1815,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     float *boxes32 = cv.take<float>((size_t)B * ceil_div(N, TC_BN) * 12);
     int *visited = cv.take<int>((size_t)B * ceil_div(N, TC_BM));
     int *work_buf = cv.take<int>((size_t)B * ceil_div(N, TC_BM));
+    long long *prof_buf = cv.take<long long>((size_t)B * ceil_div(N, TC_BM) * 16);
     unsigned *wkey = cv.take<unsigned>((size_t)B * ceil_div(N, TC_BM));
     int *fb_list = cv.take<int>(bn);
     int *big_list = cv.take<int>(bn);
@@ -1750,6 +1829,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     float *norm = cv.take<float>(bn);
     const int Npad = ceil_div(N, TC_BN) * TC_BN;
     float *norm_pad = cv.take<float>((size_t)B * Npad);
+    uint8_t *kext = cv.take<uint8_t>((size_t)B * ceil_div(N, TC_BN) * TCP_KEXT_BYTES);
     float *nmax = cv.take<float>(B);
     // rows of the candidate buffer start on 4 KB boundaries whatever the caller's workspace alignment: the scan
     // advances a half-list's write pointer in the low address word only, so a half-list (2 KB, 2 KB-aligned)
@@ -1770,7 +1850,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         count_launch();
         GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
         tcp_tiles_kernel<<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes, boxes32,
-                                                                      reinterpret_cast<unsigned *>(nmax), B, N, Npad, tiles);
+                                                                      reinterpret_cast<unsigned *>(nmax), kext, B, N, Npad, tiles);
         GCANET_LAUNCH_OK("tcp_tiles_kernel");
     }
     {
@@ -1823,7 +1903,9 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
             GCANET_LAUNCH_OK("tcp_work_order_kernel");
             work = work_buf;
         }
-        TcpScanArgs sa{norm_pad, Npad, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, structured, N, k2, tiles, pre, P, qtiles};
+        long long *prof = GCANET_AID_ENV("GCANET_TC_PROF") ? prof_buf : nullptr;
+        if (prof) GCANET_CUDA_OK(cudaMemsetAsync(prof, 0, (size_t)B * qtiles * 16 * sizeof(long long), st));
+        TcpScanArgs sa{norm_pad, Npad, kext, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, structured, N, k2, tiles, pre, P, qtiles, prof};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                       (unordered && k1 == k2) ? 1 : 0, perm, TCP_CAP, 1, big_list, big_count, fb_list, fb_count};
         int fstride = (int)(tiles * 0.381966f);
@@ -1834,6 +1916,19 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         if (k2 <= TC_BN) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, fa, ra, B, st);
         else rc = C == 64 ? launch_tcp<64, 2>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 2>(tmap_q, tmap_k, sa, fa, ra, B, st);
         if (rc) return rc;
+        if (prof) {                                // measurement aid: synchronises; mean cycles per CTA and role
+            const int nq = B * qtiles;
+            long long *h = (long long *)malloc((size_t)nq * 16 * sizeof(long long));
+            GCANET_CUDA_OK(cudaStreamSynchronize(st));
+            GCANET_CUDA_OK(cudaMemcpy(h, prof, (size_t)nq * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+            double m[16] = {0};
+            for (int i = 0; i < nq; ++i) for (int j = 0; j < 16; ++j) m[j] += (double)h[(size_t)i * 16 + j] / nq;
+            fprintf(stderr, "[gcanet] scan CTA cycles (mean of %d): prologue %.0f | A-scale %.0f | pass A %.0f (wait t_full %.0f, refresh %.0f) | "
+                    "final bound %.0f | pass B %.0f (wait t_full %.0f) || producer: total %.0f, wait empty %.0f, wait thr %.0f, steps %.1f || "
+                    "mma: total %.0f, wait t_empty %.0f, wait full %.0f\n",
+                    nq, m[0], m[1], m[2], m[4], m[5], m[3], m[6], m[7], m[11], m[8], m[9], m[10], m[14], m[12], m[13]);
+            free(h);
+        }
         const char *stats = GCANET_AID_ENV("GCANET_TC_STATS");
         if (stats && stats[0] == '1') {            // measurement aid: synchronises (clouds left to the full scan report 0 tiles)
             const int nq = B * ceil_div(N, TC_BM);

@@ -129,6 +129,17 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
     return d;
 }
+// K-major operand tile without swizzle ("interleaved" canonical layout, cute/atom/mma_traits_sm100.hpp:
+// ((8,m),(T,2)):((1T,SBO),(1,LBO))): core matrices of 8 rows x 16 bytes stored as 128 contiguous bytes, the two
+// 16-byte column blocks of a K = 16 step `lbo` bytes apart, consecutive 8-row groups `sbo` bytes apart.
+__device__ __forceinline__ uint64_t make_kmajor_interleaved_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                 // version
+    return d;                               // layout type 0 = SWIZZLE_NONE
+}
 // Instruction descriptor of tcgen05.mma kind::f16 with A = B = bf16, D = fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
