@@ -723,7 +723,10 @@ constexpr int TCP_ITERS = 5;          // subspace iterations (lambda_3 / lambda_
 constexpr uint32_t TCP_END = 0xffffffffu;
 constexpr int TCP_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int TCP_HCAP = TCP_CAP / 2; // each of a row's two epilogue threads owns half of its candidate list
-constexpr int TCP_ACC = 4;            // TMEM accumulator stages (4 x 64 columns)
+// TMEM accumulator stages (64 columns each) behind the query tile, which lives in TMEM as well (C columns: hi | lo):
+// C = 64: 64 + 3 x 64 = 256 columns, so two CTAs still share an SM's 512; C = 128: 128 + 4 x 64 = 384 (one CTA per SM)
+__host__ __device__ constexpr int tcp_acc(int C) { return C == 64 ? 3 : 4; }
+__host__ __device__ constexpr int tcp_tmem_cols(int C) { return C == 64 ? 256 : 512; }
 constexpr int TCP_NRING = 16;         // key-norm ring: the producer runs at most STAGES + ACC + 1 tiles ahead of the epilogue
 __host__ __device__ constexpr int tcp_stages(int C) { return C == 64 ? 4 : 3; }
 
@@ -1076,6 +1079,7 @@ __global__ void __launch_bounds__(256) tcp_work_order_kernel(const unsigned *__r
 struct TcpScanArgs {
     const float *norm_pad;  // [B][Npad] key norms in sorted order, +inf past N
     int Npad;
+    const __nv_bfloat16 *xs; // [B][N][2C] hi | lo operands in sorted order (the array the key tensor map covers)
     const uint8_t *kext;    // [B][tiles][TCP_KEXT_BYTES] the same norms as a K = 16 bf16 operand step (tcp_tiles_kernel)
     const float *nmax;      // [B]
     const float *boxes;     // [B][tiles][6]
@@ -1106,35 +1110,35 @@ struct TcpScanArgs {
 // 64 extra registers cost the second resident CTA).
 template <int C, int SM>
 __global__ void __launch_bounds__(TCP_THREADS, C == 64 ? 2 : 1)
-knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
+knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int NH = C / TC_KB;
-    constexpr int ABLK_BYTES = TC_BM * 128;
-    constexpr int A_BYTES = NBLK * ABLK_BYTES;
     constexpr int BLK_BYTES = TC_BN * 128;
     constexpr int TILE_BYTES = NBLK * BLK_BYTES;
     // The hand-offs (TMA -> MMA -> epilogue -> MMA -> TMA) each cost a barrier round trip of ~1 us under load, so the
     // rings are deep: the epilogue should never wait for an accumulator.  C = 64: 32 + 4*16 KB -> two CTAs per SM.
     constexpr int STAGES = tcp_stages(C);
-    constexpr int ACC = TCP_ACC;
+    constexpr int ACC = tcp_acc(C);
+    constexpr int ACOLS = C;                                // TMEM columns of the query tile: C/2 hi, C/2 lo (two bf16 each)
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *sA = smem;
-    uint8_t *sB = smem + A_BYTES;
-    // The key norms ride on the tensor cores: the query operand is scaled by -2 after it lands (exact in bf16), and one
-    // extra K = 16 step multiplies a constant (1, 1, 1, 0, ...) query row with (|k|^2 hi, mid, lo, 0, ...) of every key,
-    // so the accumulator holds  |k|^2 - 2 q.k  itself and the epilogue spends no instruction on forming it.
+    uint8_t *sB = smem;
+    // The query tile never touches shared memory: each row is read once from global memory, scaled by -2 (exact in
+    // bf16) and stored into TMEM, from where every MMA takes its A operand.  With both operands in shared memory an
+    // M = 128, N = 64 step reads 6 KB per 32-cycle tensor slot -- 1.5x what shared memory delivers (measured: the MMA
+    // issuer busy 85 % of a CTA's life, tensor pipe 45 % active); with A in TMEM it reads 2 KB.
+    // The key norms ride on the tensor cores too: one extra K = 16 step multiplies a constant (1, 1, 1, 0, ...) query
+    // row with (|k|^2 hi, mid, lo, 0, ...) of every key, so the accumulator holds  |k|^2 - 2 q.k  itself.
     uint8_t *sKe = sB + STAGES * TILE_BYTES;                // [STAGES][TCP_KEXT_BYTES] norm operand of the stage's key tile
     uint8_t *sQe = sKe + STAGES * TCP_KEXT_BYTES;           // 256 B: one 8-row group of the constant query operand (SBO = 0)
     uint64_t *bars = reinterpret_cast<uint64_t *>(sQe + 256);
     uint64_t *full = bars;
     uint64_t *empty = bars + STAGES;
-    uint64_t *a_full = bars + 2 * STAGES;
-    uint64_t *t_full = a_full + 1;
+    uint64_t *t_full = bars + 2 * STAGES;
     uint64_t *t_empty = t_full + ACC;
     uint64_t *thr_ready = t_empty + ACC;                    // [1] epilogue -> producer: final thresholds of pass A are published
-    uint64_t *a_ready = thr_ready + 1;                      // [1] epilogue -> MMA: the query tile has been scaled by -2
+    uint64_t *a_ready = thr_ready + 1;                      // [1] epilogue -> MMA: the query tile is in TMEM
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
     uint32_t *s_kt = tmem_slot + 1;                         // [STAGES] key tile in the stage, TCP_END = end-of-pass marker
     volatile int *s_end = reinterpret_cast<volatile int *>(s_kt + STAGES);   // [2] stream position of the pass A / pass B end marker
@@ -1158,19 +1162,17 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int pre = a.pre;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_k);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(a_full, 1);
         for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
         mbar_init(thr_ready, 8);
-        mbar_init(a_ready, 8);
+        mbar_init(a_ready, 4);
         s_end[0] = 0x7fffffff;
         s_end[1] = 0x7fffffff;
         for (int s = 0; s < 8; ++s) s_wthr[s] = CUDART_INF_F;
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, ACC * TC_BN);
+    if (warp == 1) tmem_alloc(tmem_slot, tcp_tmem_cols(C));
     if (threadIdx.x >= 64 && threadIdx.x < 80) {
         // constant query operand of the norm step: rows (1, 1, 1, 0, 0, 0, 0, 0 | 0 x 8) in bf16; one 8-row group serves
         // all 128 rows (stride between groups = 0)
@@ -1299,9 +1301,6 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(a_full, A_BYTES);
-#pragma unroll
-            for (int kb = 0; kb < NBLK; ++kb) tma_load_3d(sA + kb * ABLK_BYTES, &tmap_q, a_full, kb * TC_KB, q0, b);
             const uint8_t *ke_g = a.kext + (size_t)b * tiles * TCP_KEXT_BYTES;
             int stage = 0, seq = 0, nvis = 0;
             uint32_t phase = 0;
@@ -1344,51 +1343,59 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp walks the loop converged and one elected lane issues (see elect_one_sync): the issuing thread's
+        // own instruction stream was the bottleneck of this kernel -- 13 MMAs per tile, each wrapped in an election loop
+        // plus two descriptor computations, ~1 300 cycles per tile against 450 cycles of tensor-pipe work.
+        {
             mbar_wait(a_ready, 0);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(sA);
             const uint64_t q_ext = make_kmajor_interleaved_desc(smem_u32(sQe), 128, 0);
+            const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(sB));
+            const uint64_t k_desc0 = make_kmajor_interleaved_desc(smem_u32(sKe), 128, 256);
             int stage = 0, acc = 0, seq = 0, markers = 0;
             uint32_t phase = 0, accphase = 0;
             for (;; ++seq) {
                 { TCP_PROF_T0(); mbar_wait_backoff(&t_empty[acc], accphase ^ 1); TCP_PROF_ADD(pw0); }
                 { TCP_PROF_T0(); mbar_wait_backoff(&full[stage], phase); TCP_PROF_ADD(pw1); }
                 if (s_kt[stage] == TCP_END) {
-                    s_end[markers] = seq;                    // visible to the epilogue through the arrive below
-                    mbar_arrive(&empty[stage]);
-                    mbar_arrive(&t_full[acc]);
+                    if (elect_one_sync()) {
+                        s_end[markers] = seq;                    // visible to the epilogue through the arrive below
+                        mbar_arrive(&empty[stage]);
+                        mbar_arrive(&t_full[acc]);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     if (++acc == ACC) { acc = 0; accphase ^= 1; }
                     if (++markers == 2) break;
                     continue;
                 }
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(sB + stage * TILE_BYTES);
-                const uint32_t d_tmem = tmem_base + acc * TC_BN;
-                uint32_t accum = 0;
+                if (elect_one_sync()) {
+                    const uint64_t b_desc = desc_advance(b_desc0, stage * TILE_BYTES);
+                    const uint32_t d_tmem = tmem_base + ACOLS + acc * TC_BN;
 #pragma unroll
-                for (int hb = 0; hb < NH; ++hb) {
+                    for (int hb = 0; hb < NH; ++hb) {
 #pragma unroll
-                    for (int ks = 0; ks < TC_KB / 16; ++ks) {
-                        const uint32_t koff = ks * 32;
-                        const uint64_t a_hi = make_kmajor_sw128_desc(a_addr + hb * ABLK_BYTES + koff);
-                        const uint64_t a_lo = make_kmajor_sw128_desc(a_addr + (NH + hb) * ABLK_BYTES + koff);
-                        const uint64_t b_hi = make_kmajor_sw128_desc(b_addr + hb * BLK_BYTES + koff);
-                        const uint64_t b_lo = make_kmajor_sw128_desc(b_addr + (NH + hb) * BLK_BYTES + koff);
-                        umma_bf16(d_tmem, a_hi, b_hi, kIdesc, accum);
-                        accum = 1;
-                        umma_bf16(d_tmem, a_hi, b_lo, kIdesc, 1);
-                        umma_bf16(d_tmem, a_lo, b_hi, kIdesc, 1);
+                        for (int ks = 0; ks < TC_KB / 16; ++ks) {
+                            // A from TMEM: a K = 16 step is 8 columns; hi in columns [0, C/2), lo in [C/2, C)
+                            const uint32_t a_hi = tmem_base + hb * (TC_KB / 2) + ks * 8;
+                            const uint32_t a_lo = a_hi + C / 2;
+                            const uint64_t b_hi = desc_advance(b_desc, hb * BLK_BYTES + ks * 32);
+                            const uint64_t b_lo = desc_advance(b_desc, (NH + hb) * BLK_BYTES + ks * 32);
+                            umma_bf16_ts(d_tmem, a_hi, b_hi, kIdesc, (hb | ks) ? 1u : 0u);
+                            umma_bf16_ts(d_tmem, a_hi, b_lo, kIdesc, 1);
+                            umma_bf16_ts(d_tmem, a_lo, b_hi, kIdesc, 1);
+                        }
                     }
+                    umma_bf16(d_tmem, q_ext, desc_advance(k_desc0, stage * TCP_KEXT_BYTES), kIdesc, 1);
+                    umma_commit(&empty[stage]);
+                    umma_commit(&t_full[acc]);
                 }
-                umma_bf16(d_tmem, q_ext, make_kmajor_interleaved_desc(smem_u32(sKe + stage * TCP_KEXT_BYTES), 128, 256), kIdesc, 1);
-                umma_commit(&empty[stage]);
-                umma_commit(&t_full[acc]);
+                __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 if (++acc == ACC) { acc = 0; accphase ^= 1; }
             }
-            if (prof) { prof[12] = pw0; prof[13] = pw1; prof[14] = TCP_PROF_NOW() - prof_start; }
+            if (prof && lane == 0) { prof[12] = pw0; prof[13] = pw1; prof[14] = TCP_PROF_NOW() - prof_start; }
         }
     } else {
         // ===================== epilogue: two threads per query row, 32 key columns each =====================
@@ -1412,20 +1419,27 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         float wbound = CUDART_INF_F;                          // largest true-distance bound among this warp's rows
         const int pair_bar = 1 + lg;                          // named barrier shared by the two warps of a lane quarter
 
-        // the query tile, hi and lo blocks alike, times -2 (exact: a sign and an exponent step), so that the MMAs
-        // accumulate -2 q.k; element-wise, hence independent of the swizzle
-        {
-            mbar_wait(a_full, 0);
+        // the query tile: one thread per row (the column-half-0 warps; a warp owns the TMEM lanes of its quarter) reads
+        // the row's hi | lo operand (2C bf16), multiplies by -2 (exact: a sign and an exponent step) so that the MMAs
+        // accumulate -2 q.k, and stores it into TMEM columns [0, C): one 32-bit column = two consecutive bf16 along K
+        if (hf == 0) {
             const __nv_bfloat162 m2 = __float2bfloat162_rn(-2.f);
-            uint4 *pa = reinterpret_cast<uint4 *>(sA);
-            for (int e = threadIdx.x - 64; e < A_BYTES / 16; e += 256) {
-                uint4 w = pa[e];
-                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&w);
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.xs + ((size_t)b * a.N + (active ? q : 0)) * 2 * C);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) h[u] = __hmul2(h[u], m2);
-                pa[e] = w;
+            for (int blk = 0; blk < ACOLS / 32; ++blk) {
+                uint32_t w[32];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint4 t = active ? __ldg(src + blk * 8 + u) : make_uint4(0u, 0u, 0u, 0u);
+                    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], m2);
+                    w[u * 4 + 0] = t.x; w[u * 4 + 1] = t.y; w[u * 4 + 2] = t.z; w[u * 4 + 3] = t.w;
+                }
+                tmem_st32(tmem_base + ((uint32_t)(lg * 32) << 16) + blk * 32, w);
             }
-            fence_proxy_async();
+            tmem_st_wait();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
         }
@@ -1484,7 +1498,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 // a tile whose bound against this warp's 32 rows exceeds all their current bounds holds no key that
                 // could lower any of them: its slot minima are not needed (the final bound is the same without them)
                 if (__uint_as_float((uint32_t)lbw[seq] << 16) <= wbound) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_BN + hf * 32;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + ACOLS + acc * TC_BN + hf * 32;
                     if constexpr (SM == 1) {
                         uint32_t v[32];
                         tmem_ld32(taddr, v);
@@ -1573,7 +1587,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 continue;
             }
             const int kt = (int)(s_ord[i] & 0xffffu);
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_BN + hf * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + ACOLS + acc * TC_BN + hf * 32;
             uint32_t v[32];
             tmem_ld32(taddr, v);
             tmem_ld_wait();
@@ -1643,7 +1657,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, ACC * TC_BN);
+        tmem_dealloc(tmem_base, tcp_tmem_cols(C));
     }
 }
 
@@ -1749,12 +1763,12 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
                       cudaStream_t st) {
     constexpr int NBLK = 2 * C / TC_KB;
     constexpr int STAGES = tcp_stages(C);
-    const size_t smem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)STAGES * NBLK * TC_BN * 128 +
+    const size_t smem = 1024 + (size_t)STAGES * NBLK * TC_BN * 128 +
                         (size_t)STAGES * TCP_KEXT_BYTES + 256 + 32 * sizeof(uint64_t) + 6 * TC_BM * sizeof(float) + (size_t)sa.P * 16;
     auto kern = knn_tcp_scan_kernel<C, SM>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(sa.N, TC_BM) * B);
-    kern<<<grid, TCP_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
+    kern<<<grid, TCP_THREADS, smem, st>>>(tmap_k, sa);
     GCANET_LAUNCH_OK("knn_tcp_scan_kernel");
     {
         // clouds without low-dimensional structure (their sorted order is the original order): single-pass full scan
@@ -1905,7 +1919,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         }
         long long *prof = GCANET_AID_ENV("GCANET_TC_PROF") ? prof_buf : nullptr;
         if (prof) GCANET_CUDA_OK(cudaMemsetAsync(prof, 0, (size_t)B * qtiles * 16 * sizeof(long long), st));
-        TcpScanArgs sa{norm_pad, Npad, kext, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, structured, N, k2, tiles, pre, P, qtiles, prof};
+        TcpScanArgs sa{norm_pad, Npad, xs, kext, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, structured, N, k2, tiles, pre, P, qtiles, prof};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                       (unordered && k1 == k2) ? 1 : 0, perm, TCP_CAP, 1, big_list, big_count, fb_list, fb_count};
         int fstride = (int)(tiles * 0.381966f);

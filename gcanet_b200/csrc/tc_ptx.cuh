@@ -87,6 +87,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with the A operand read from tensor memory (lane = row, one 32-bit column = two consecutive bf16 along K):
+// only B travels through shared memory -- at M = 128, N = 64 an SS-mode MMA reads 6 KB of operands per 32-cycle slot,
+// more than the 128 B / cycle shared memory delivers; with A resident in TMEM it reads 2 KB.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -112,6 +124,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// 32 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -129,6 +154,26 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
     return d;
 }
+// One lane of a converged warp.  tcgen05.mma / tcgen05.commit issued under this predicate compile to a single
+// predicated instruction; issued under `if (lane == 0)` the compiler cannot prove that one thread is active and wraps
+// every one of them in an ELECT / BRA.U.ANY loop (~6 extra instructions each on the uniform datapath).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// descriptor of the tile `byte_off` bytes further on (byte_off % 16 == 0; the 14-bit address field cannot carry: shared
+// memory addresses stay below 256 KB)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t byte_off) {
+    return (d & 0xFFFFFFFF00000000ull) | (uint32_t)((uint32_t)d + (byte_off >> 4));
+}
+
 // K-major operand tile without swizzle ("interleaved" canonical layout, cute/atom/mma_traits_sm100.hpp:
 // ((8,m),(T,2)):((1T,SBO),(1,LBO))): core matrices of 8 rows x 16 bytes stored as 128 contiguous bytes, the two
 // 16-byte column blocks of a K = 16 step `lbo` bytes apart, consecutive 8-row groups `sbo` bytes apart.
