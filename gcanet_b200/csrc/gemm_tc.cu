@@ -145,35 +145,40 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
         }
     } else if (warp == GT_THREADS / 32 - 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t b_addr = smem_u32(sBm);
+        // whole warp converged, one elected lane issues (tc_ptx.cuh: elect_one_sync), descriptors advanced from a base
+        {
+            const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(sBm));
+            const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(sA));
             int stage = 0, acc = 0;
             uint32_t phase = 0, accphase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 mbar_wait(&t_empty[acc], accphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * N;
-                uint32_t accum = 0;
                 for (int kc = 0; kc < KCH; ++kc) {
                     mbar_wait(&a_full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE);
+                    if (elect_one_sync()) {
+                        const uint64_t a_desc = desc_advance(a_desc0, stage * A_STAGE);
 #pragma unroll
-                    for (int ks = 0; ks < GT_KB / 16; ++ks) {
-                        const uint32_t koff = ks * 32;
-                        const uint64_t a_hi = make_kmajor_sw128_desc(a_addr + koff);
-                        const uint64_t a_lo = make_kmajor_sw128_desc(a_addr + A_TILE + koff);
-                        const uint64_t b_hi = make_kmajor_sw128_desc(b_addr + kc * B_BLK + koff);
-                        const uint64_t b_lo = make_kmajor_sw128_desc(b_addr + (KCH + kc) * B_BLK + koff);
-                        umma_bf16(d_tmem, a_hi, b_hi, IDESC, accum);
-                        accum = 1;
-                        umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1);
-                        umma_bf16(d_tmem, a_lo, b_hi, IDESC, 1);
+                        for (int ks = 0; ks < GT_KB / 16; ++ks) {
+                            const uint32_t koff = ks * 32;
+                            const uint64_t a_hi = desc_advance(a_desc, koff);
+                            const uint64_t a_lo = desc_advance(a_desc, A_TILE + koff);
+                            const uint64_t b_hi = desc_advance(b_desc0, kc * B_BLK + koff);
+                            const uint64_t b_lo = desc_advance(b_desc0, (KCH + kc) * B_BLK + koff);
+                            umma_bf16(d_tmem, a_hi, b_hi, IDESC, (kc | ks) ? 1u : 0u);
+                            umma_bf16(d_tmem, a_hi, b_lo, IDESC, 1);
+                            umma_bf16(d_tmem, a_lo, b_hi, IDESC, 1);
+                        }
+                        umma_commit(&a_empty[stage]);
+                        // tcgen05.commit covers the MMAs of the EXECUTING thread: the accumulator's commit must come from
+                        // the lane that issued them, i.e. from inside the same elected block
+                        if (kc == KCH - 1) umma_commit(&t_full[acc]);
                     }
-                    umma_commit(&a_empty[stage]);
+                    __syncwarp();
                     if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&t_full[acc]);
                 if (++acc == 2) { acc = 0; accphase ^= 1; }
             }
         }
@@ -383,14 +388,21 @@ gemm_tn_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict_
             store(st, yc, xcur);
             fence_proxy_async();
             __syncthreads();
-            if (t == 0) {
+            if (warp == 0) {
                 tc_fence_after();
-                mma_stage(st, cur == 0 ? 0u : 1u);
-                umma_commit(&empty[half]);
+                if (elect_one_sync()) {
+                    mma_stage(st, cur == 0 ? 0u : 1u);
+                    umma_commit(&empty[half]);
+                    if (cur == nkb - 1) umma_commit(done);      // same lane as the MMAs it has to cover
+                }
+                __syncwarp();
             }
         }
     }
-    if (t == 0) umma_commit(done);
+    if (nkb <= 0 && warp == 0) {                                // nothing was issued: release the waiters
+        if (elect_one_sync()) umma_commit(done);
+        __syncwarp();
+    }
     mbar_wait(done, 0);
     tc_fence_after();
 

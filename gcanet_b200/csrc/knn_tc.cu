@@ -315,36 +315,39 @@ knn_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // whole warp converged, one elected lane issues (tc_ptx.cuh: elect_one_sync), descriptors advanced from a base
+        {
             mbar_wait(a_full, 0);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(sA);
+            const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(sA));
+            const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(sB));
             int stage = 0, acc = 0;
             uint32_t phase = 0, accphase = 0;
             for (int t = 0; t < tiles; ++t) {
                 mbar_wait_backoff(&t_empty[acc], accphase ^ 1);
                 mbar_wait_backoff(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(sB + stage * TILE_BYTES);
-                const uint32_t d_tmem = tmem_base + acc * TC_BN;
-                uint32_t accum = 0;
+                if (elect_one_sync()) {
+                    const uint64_t b_desc = desc_advance(b_desc0, stage * TILE_BYTES);
+                    const uint32_t d_tmem = tmem_base + acc * TC_BN;
 #pragma unroll
-                for (int hb = 0; hb < NH; ++hb) {
+                    for (int hb = 0; hb < NH; ++hb) {
 #pragma unroll
-                    for (int ks = 0; ks < TC_KB / 16; ++ks) {
-                        const uint32_t koff = ks * 32;        // 16 bf16 = 32 bytes inside the swizzled row
-                        const uint64_t a_hi = make_kmajor_sw128_desc(a_addr + hb * ABLK_BYTES + koff);
-                        const uint64_t a_lo = make_kmajor_sw128_desc(a_addr + (NH + hb) * ABLK_BYTES + koff);
-                        const uint64_t b_hi = make_kmajor_sw128_desc(b_addr + hb * BLK_BYTES + koff);
-                        const uint64_t b_lo = make_kmajor_sw128_desc(b_addr + (NH + hb) * BLK_BYTES + koff);
-                        umma_bf16(d_tmem, a_hi, b_hi, kIdesc, accum);
-                        accum = 1;
-                        umma_bf16(d_tmem, a_hi, b_lo, kIdesc, 1);
-                        umma_bf16(d_tmem, a_lo, b_hi, kIdesc, 1);
+                        for (int ks = 0; ks < TC_KB / 16; ++ks) {
+                            const uint32_t koff = ks * 32;        // 16 bf16 = 32 bytes inside the swizzled row
+                            const uint64_t a_hi = desc_advance(a_desc0, hb * ABLK_BYTES + koff);
+                            const uint64_t a_lo = desc_advance(a_desc0, (NH + hb) * ABLK_BYTES + koff);
+                            const uint64_t b_hi = desc_advance(b_desc, hb * BLK_BYTES + koff);
+                            const uint64_t b_lo = desc_advance(b_desc, (NH + hb) * BLK_BYTES + koff);
+                            umma_bf16(d_tmem, a_hi, b_hi, kIdesc, (hb | ks) ? 1u : 0u);
+                            umma_bf16(d_tmem, a_hi, b_lo, kIdesc, 1);
+                            umma_bf16(d_tmem, a_lo, b_hi, kIdesc, 1);
+                        }
                     }
+                    umma_commit(&empty[stage]);      // smem slot reusable once these MMAs have read it
+                    umma_commit(&t_full[acc]);       // accumulator ready for the epilogue
                 }
-                umma_commit(&empty[stage]);      // smem slot reusable once these MMAs have read it
-                umma_commit(&t_full[acc]);       // accumulator ready for the epilogue
+                __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 if (++acc == ACC) { acc = 0; accphase ^= 1; }
             }

