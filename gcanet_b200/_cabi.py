@@ -33,6 +33,13 @@ class NormalEdgeDesc(ctypes.Structure):
 
 _NDESC_P = ctypes.POINTER(NormalEdgeDesc)
 
+
+class GlobalFeatureDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("N", c_int), ("K", c_int), ("Cout", c_int), ("groups", c_int), ("eps", c_float)]
+
+
+_GDESC_P = ctypes.POINTER(GlobalFeatureDesc)
+
 # name -> (restype, argtypes); mirrors include/gcanet_b200.h one to one
 SIGNATURES = {
     "gcanet_abi_version": (c_int, []),
@@ -67,6 +74,10 @@ SIGNATURES = {
     "gcanet_normal_edgeconv_workspace_bytes": (c_size_t, [_NDESC_P]),
     "gcanet_normal_edgeconv_forward": (c_int, [_NDESC_P] + [c_void_p] * 9 + [c_size_t, c_void_p]),
     "gcanet_normal_edgeconv_backward": (c_int, [_NDESC_P] + [c_void_p] * 11 + [c_size_t, c_void_p]),
+    "gcanet_global_feature_saved_bytes": (c_size_t, [_GDESC_P]),
+    "gcanet_global_feature_workspace_bytes": (c_size_t, [_GDESC_P]),
+    "gcanet_global_feature_forward": (c_int, [_GDESC_P] + [c_void_p] * 8 + [c_size_t, c_void_p]),
+    "gcanet_global_feature_backward": (c_int, [_GDESC_P] + [c_void_p] * 13 + [c_size_t, c_void_p]),
 }
 
 _lib = None

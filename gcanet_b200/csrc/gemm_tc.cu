@@ -59,7 +59,14 @@ __device__ __forceinline__ void split_store4(uint8_t *hi_tile, uint8_t *lo_tile,
 
 template <int K, int N>
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bt, int ldb, float *__restrict__ C, int ldc, int M) {
+gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bt, int ldb, float *__restrict__ C, int ldc, int M,
+               long long batch_a, long long batch_b, long long batch_c, const float *__restrict__ cbias, int batch_bias) {
+    // batched use (blockIdx.y = batch): every batch has its own M x K rows of A, its own weights and, optionally, a row
+    // vector cbias[batch][N] added to every output row; element strides between batches are passed in
+    A += (size_t)blockIdx.y * batch_a;
+    Bt += (size_t)blockIdx.y * batch_b;
+    C += (size_t)blockIdx.y * batch_c;
+    if (cbias) cbias += (size_t)blockIdx.y * batch_bias;
     static_assert(K % GT_KB == 0 && N % 32 == 0 && N <= 256, "unsupported GEMM shape");
     constexpr int KCH = K / GT_KB;                      // K chunks
     constexpr int GT_STAGES = gt_stages(K, N);
@@ -200,10 +207,15 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
                 tmem_ld_wait();
                 if (row < M) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<float4 *>(crow + ch * 32 + q * 4) =
-                            make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                                        __uint_as_float(v[q * 4 + 3]));
+                    for (int q = 0; q < 8; ++q) {
+                        float4 o = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                                               __uint_as_float(v[q * 4 + 3]));
+                        if (cbias) {
+                            const float4 cb = __ldg(reinterpret_cast<const float4 *>(cbias + ch * 32 + q * 4));
+                            o.x += cb.x; o.y += cb.y; o.z += cb.z; o.w += cb.w;
+                        }
+                        *reinterpret_cast<float4 *>(crow + ch * 32 + q * 4) = o;
+                    }
                 }
             }
             tc_fence_before();
@@ -222,14 +234,18 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
 }
 
 template <int K, int N>
-static int launch_gemm_tc(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, cudaStream_t st) {
+static int launch_gemm_tc(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, cudaStream_t st,
+                          int batches = 1, long long batch_a = 0, long long batch_b = 0, long long batch_c = 0,
+                          const float *cbias = nullptr, int batch_bias = 0) {
     constexpr int KCH = K / GT_KB;
     constexpr int GT_STAGES = gt_stages(K, N);
     const size_t smem = 1024 + (size_t)2 * KCH * N * 128 + (size_t)GT_STAGES * 2 * GT_BM * 128 + 32 * sizeof(uint64_t);
     auto kern = gemm_tc_kernel<K, N>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = ceil_div(M, GT_BM);
-    kern<<<ntiles < kNumSMs ? ntiles : kNumSMs, GT_THREADS, smem, st>>>(A, lda, Bt, ldb, C, ldc, M);
+    int ctas = ntiles < kNumSMs ? ntiles : kNumSMs;
+    if (batches > 1) ctas = ctas < ceil_div(2 * kNumSMs, batches) ? ctas : ceil_div(2 * kNumSMs, batches);
+    kern<<<dim3(ctas, batches), GT_THREADS, smem, st>>>(A, lda, Bt, ldb, C, ldc, M, batch_a, batch_b, batch_c, cbias, batch_bias);
     GCANET_LAUNCH_OK("gemm_tc_kernel");
     return GCANET_OK;
 }
@@ -250,6 +266,24 @@ int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int
     GT_CASE(256, 64);
     GT_CASE(256, 128);
     GT_CASE(64, 64);
+#undef GT_CASE
+    return 1;
+}
+
+// Batched form: C[b] = A[b] Bt[b]^T (+ cbias[b] on every row), b < batches; same shapes and return convention.
+int gemm_tc_batched_try(const float *A, int lda, long long batch_a, const float *Bt, int ldb, long long batch_b, float *C, int ldc,
+                        long long batch_c, const float *cbias, int batch_bias, int M, int N, int K, int batches, cudaStream_t st) {
+    if (lda % 4 || ldb % 4 || ldc % 4 || batches < 1 || batches > 65535) return 1;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt) | reinterpret_cast<uintptr_t>(C) |
+         reinterpret_cast<uintptr_t>(cbias)) & 15) return 1;
+    if ((batch_a | batch_b | batch_c | batch_bias) & 3) return 1;
+#define GT_CASE(KK, NN) if (K == KK && N == NN) return launch_gemm_tc<KK, NN>(A, lda, Bt, ldb, C, ldc, M, st, batches, batch_a, batch_b, batch_c, cbias, batch_bias)
+    GT_CASE(256, 64);
+    GT_CASE(256, 128);
+    GT_CASE(128, 64);
+    GT_CASE(128, 128);
+    GT_CASE(64, 64);
+    GT_CASE(64, 128);
 #undef GT_CASE
     return 1;
 }
@@ -283,7 +317,11 @@ __device__ __forceinline__ void split_pack8(const float *v, uint4 &hi, uint4 &lo
 template <int NY>
 __global__ void __launch_bounds__(GTN_THREADS, 1)
 gemm_tn_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ Y, int ldy, float *__restrict__ part, int M,
-                  int rows_per_split) {
+                  int rows_per_split, long long batch_x, long long batch_y) {
+    // batched use (blockIdx.y = batch): M rows per batch, partials laid out [batch][split][64][NY]
+    X += (size_t)blockIdx.y * batch_x;
+    Y += (size_t)blockIdx.y * batch_y;
+    part += (size_t)blockIdx.y * gridDim.x * 64 * NY;
     static_assert(NY == 128 || NY == 256, "unsupported width");
     constexpr int TA = NY / 128;                        // accumulator tiles (128 rows of n each)
     constexpr int A_TILE = 128 * 128;                   // [128 n][64 p] bf16
@@ -441,13 +479,27 @@ int gemm_tn_tc_try(const float *X, int ldx, const float *Y, int ldy, float *part
     const size_t smem = 1024 + (size_t)2 * (2 * (N / 128) * 128 * 128 + 2 * 64 * 128) + 64;
     if (N == 256) {
         GCANET_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_tn_tc_kernel<256><<<splits, GTN_THREADS, smem, st>>>(X, ldx, Y, ldy, part, M, rows);
+        gemm_tn_tc_kernel<256><<<splits, GTN_THREADS, smem, st>>>(X, ldx, Y, ldy, part, M, rows, 0, 0);
     } else {
         GCANET_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_tn_tc_kernel<128><<<splits, GTN_THREADS, smem, st>>>(X, ldx, Y, ldy, part, M, rows);
+        gemm_tn_tc_kernel<128><<<splits, GTN_THREADS, smem, st>>>(X, ldx, Y, ldy, part, M, rows, 0, 0);
     }
     GCANET_LAUNCH_OK("gemm_tn_tc_kernel");
     *splits_out = splits;
+    return GCANET_OK;
+}
+
+// Batched Gram-type product: part[b][split][64][256] partials of X[b][M][64]^T Y[b][M][256] with `splits` splits of the
+// M rows of every batch (the caller reduces them); rows per split are a multiple of 64.
+int gemm_tn_tc_batched(const float *X, int ldx, long long batch_x, const float *Y, int ldy, long long batch_y, float *part, int M,
+                       int splits, int batches, cudaStream_t st) {
+    if (ldx % 4 || ldy % 4 || splits < 1 || batches < 1 || batches > 65535) return 1;
+    const int rows = ceil_div(ceil_div(M, splits), 64) * 64;
+    if (ceil_div(M, rows) != splits) return 1;              // the caller sized `part` for exactly this many
+    const size_t smem = 1024 + (size_t)2 * (2 * 2 * 128 * 128 + 2 * 64 * 128) + 64;
+    GCANET_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tn_tc_kernel<256><<<dim3(splits, batches), GTN_THREADS, smem, st>>>(X, ldx, Y, ldy, part, M, rows, batch_x, batch_y);
+    GCANET_LAUNCH_OK("gemm_tn_tc_kernel<batched>");
     return GCANET_OK;
 }
 

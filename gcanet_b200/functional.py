@@ -13,7 +13,7 @@ import ctypes as _ct
 import torch
 
 from . import _cabi
-from ._cabi import EdgeConvDesc, NormalEdgeDesc, call, ptr, require_cuda, stream, workspace
+from ._cabi import EdgeConvDesc, GlobalFeatureDesc, NormalEdgeDesc, call, ptr, require_cuda, stream, workspace
 
 METRIC_L2 = 0
 METRIC_POINTS_NORMALS = 1
@@ -465,3 +465,61 @@ def normal_edgeconv(points, idx32, weight, gamma, beta, groups=2, eps=1e-5, slop
     x_nc = to_point_major(points.detach().float().contiguous(), 8)
     return _NormalEdgeConv.apply(x_nc, idx32, weight.reshape(weight.shape[0], -1), gamma, beta, int(groups),
                                  float(eps), float(slope))
+
+
+# ----------------------------------------------------------------------------------
+# encoder tail: Conv1d(256 -> 1024) + GroupNorm + ReLU + max over the points, fused
+# ----------------------------------------------------------------------------------
+class _GlobalFeature(torch.autograd.Function):
+    """x4 [B, Cout] = max_n relu(GroupNorm(Conv1d(x)))  from point-major x_nc [B, N, K]."""
+
+    @staticmethod
+    def forward(ctx, x_nc, weight, bias, gamma, beta, groups, eps):
+        require_cuda(x_nc, "x_nc", torch.float32)
+        weight, gamma, beta = weight.contiguous(), gamma.contiguous(), beta.contiguous()
+        bias = None if bias is None else bias.contiguous()
+        for t, nme in ((weight, "weight"), (gamma, "gamma"), (beta, "beta")):
+            require_cuda(t, nme, torch.float32)
+        B, N, K = x_nc.shape
+        Cout = weight.shape[0]
+        if weight.shape[1] != K:
+            raise RuntimeError(f"weight must be [Cout, {K}] (got {tuple(weight.shape)})")
+        desc = GlobalFeatureDesc(B, N, K, Cout, groups, eps)
+        L = _cabi.lib()
+        with torch.cuda.device(x_nc.device):
+            saved_bytes = L.gcanet_global_feature_saved_bytes(_ct.byref(desc))
+            if saved_bytes == 0:
+                raise RuntimeError("gcanet_b200 global_feature: " + L.gcanet_last_error().decode())
+            saved = workspace(saved_bytes, x_nc.device)
+            ws = workspace(L.gcanet_global_feature_workspace_bytes(_ct.byref(desc)), x_nc.device)
+            out = torch.empty((B, Cout), dtype=torch.float32, device=x_nc.device)
+            with _timed(f"global_feature_fwd[K={K},Cout={Cout}]"):
+                call("gcanet_global_feature_forward", _ct.byref(desc), ptr(x_nc), ptr(weight), ptr(bias), ptr(gamma), ptr(beta),
+                     ptr(out), ptr(saved), ptr(ws), ws.numel(), stream())
+        ctx.save_for_backward(x_nc, weight, gamma, beta, saved)
+        ctx.bias = bias
+        ctx.desc = desc
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x_nc, weight, gamma, beta, saved = ctx.saved_tensors
+        bias, desc = ctx.bias, ctx.desc
+        L = _cabi.lib()
+        with torch.cuda.device(x_nc.device):
+            g = g.contiguous().float()
+            gx = torch.empty_like(x_nc) if ctx.needs_input_grad[0] else None
+            gw, gg, gb = torch.empty_like(weight), torch.empty_like(gamma), torch.empty_like(beta)
+            gbias = None if bias is None else torch.empty_like(bias)
+            ws = workspace(L.gcanet_global_feature_workspace_bytes(_ct.byref(desc)), x_nc.device)
+            with _timed(f"global_feature_bwd[K={desc.K},Cout={desc.Cout}]"):
+                call("gcanet_global_feature_backward", _ct.byref(desc), ptr(x_nc), ptr(weight), ptr(bias), ptr(gamma), ptr(beta),
+                     ptr(g), ptr(saved), ptr(gx), ptr(gw), ptr(gbias), ptr(gg), ptr(gb), ptr(ws), ws.numel(), stream())
+        return gx, gw, gbias, gg, gb, None, None
+
+
+def global_feature(x_nc, weight, bias, gamma, beta, groups=8, eps=1e-5):
+    """Fused replacement of ``relu(bnmlp1(mlp1(x_features))).max(dim=2)[0]`` (M4:507-510): x_nc [B, N, 256] point-major
+    concatenation of x1 | x2 | x3, weight [1024, 256] (or the Conv1d's [1024, 256, 1]), bias [1024] or None.
+    Returns x4 [B, Cout]; differentiable in x_nc, weight, bias, gamma, beta.  The [B, Cout, N] activation is never formed."""
+    return _GlobalFeature.apply(x_nc, weight.reshape(weight.shape[0], -1), bias, gamma, beta, int(groups), float(eps))

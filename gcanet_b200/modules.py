@@ -22,8 +22,9 @@ class DGCNNEncoderGn(nn.Module):
 
     forward(x [B, 3 or 6, N]) -> [B, 1280, N].  The three EdgeConv blocks and their dynamic
     kNN graphs (M4:493-505 / M4:514-527) run through ``gcanet_b200.functional.edgeconv``;
-    the tail (Conv1d 256->1024 + GroupNorm + ReLU + global max + concat, M4:507-511) is the
-    consumer of the hot path and stays on torch (cuBLAS), see SURVEY.md 8(a) a7.
+    the tail (Conv1d 256->1024 + GroupNorm + ReLU + global max, M4:507-510) through
+    ``gcanet_b200.functional.global_feature`` (one fused tcgen05 GEMM, SURVEY.md 8(a) a7);
+    only the final concat into the reference's [B, 1280, N] layout is a torch op.
     """
 
     def __init__(self, mode=0, nn_nb=80, input_channels=3):
@@ -59,8 +60,8 @@ class DGCNNEncoderGn(nn.Module):
         return G.edgeconv(x_nc, idx32, conv[0].weight, gn.weight, gn.bias, C, groups=gn.num_groups, eps=gn.eps,
                           slope=conv[2].negative_slope, want_cn=True)
 
-    def edge_stack(self, x):
-        """x [B, C, N] -> (x1 [B,64,N], x2 [B,64,N], x3 [B,128,N]) -- the path bench.py times."""
+    def _stack(self, x):
+        """x [B, C, N] -> ((x1, x2, x3) channel-major, (x1_nc, x2_nc, x3_nc) point-major)."""
         if not x.is_cuda:
             raise RuntimeError("gcanet_b200.DGCNNEncoderGn has no CPU path")
         x = x.float().contiguous()
@@ -72,20 +73,38 @@ class DGCNNEncoderGn(nn.Module):
         x_nc = G._ToPointMajor.apply(x, (C + 3) // 4 * 4)
         x1_nc, x1 = self._block(x_nc, x, self.conv1, C, metric)
         x2_nc, x2 = self._block(x1_nc, x1, self.conv2, 64, G.METRIC_L2)
-        _, x3 = self._block(x2_nc, x2, self.conv3, 64, G.METRIC_L2)
-        return x1, x2, x3
+        x3_nc, x3 = self._block(x2_nc, x2, self.conv3, 64, G.METRIC_L2)
+        return (x1, x2, x3), (x1_nc, x2_nc, x3_nc)
 
-    # -- consumer (torch) ------------------------------------------------------------
+    def edge_stack(self, x):
+        """x [B, C, N] -> (x1 [B,64,N], x2 [B,64,N], x3 [B,128,N]) -- the path bench.py times."""
+        return self._stack(x)[0]
+
+    # -- consumer: encoder tail (M4:507-511) ---------------------------------------------
+    def global_feature(self, x1_nc, x2_nc, x3_nc):
+        """x4 [B, 1024] = max over the points of relu(bnmlp1(mlp1(x1 | x2 | x3))) -- one fused tcgen05 GEMM with the
+        GroupNorm statistics and the max in its epilogue; the [B, 1024, N] activation is never formed."""
+        xcat = torch.cat((x1_nc, x2_nc, x3_nc), dim=2)
+        gn = self.bnmlp1
+        return G.global_feature(xcat, self.mlp1.weight, self.mlp1.bias, gn.weight, gn.bias, groups=gn.num_groups, eps=gn.eps)
+
+    def forward_global(self, x):
+        """(x4 [B, 1024], x_features [B, 256, N]): the two pieces of the reference's [B, 1280, N] output without the
+        N-fold repeat -- a consumer folds W[:, :1024] x4 into its bias."""
+        (x1, x2, x3), ncs = self._stack(x)
+        return self.global_feature(*ncs), torch.cat((x1, x2, x3), dim=1)
+
     def tail(self, x1, x2, x3):
-        batch_size, num_points = x1.shape[0], x1.shape[2]
-        x_features = torch.cat((x1, x2, x3), dim=1)
-        x = F.relu(self.bnmlp1(self.mlp1(x_features)))
-        x4 = x.max(dim=2)[0]
-        x4 = x4.view(batch_size, 1024, 1).repeat(1, 1, num_points)
-        return torch.cat([x4, x_features], 1)
+        """Reference-layout tail on channel-major inputs (for callers that hold only x1, x2, x3)."""
+        ncs = [G._ToPointMajor.apply(t.contiguous(), t.shape[1]) for t in (x1, x2, x3)]
+        x4 = self.global_feature(*ncs)
+        num_points = x1.shape[2]
+        return torch.cat([x4.unsqueeze(2).expand(-1, -1, num_points), x1, x2, x3], 1)
 
     def forward(self, x):
-        return self.tail(*self.edge_stack(x))
+        """[B, 1280, N] exactly like the reference (M4:511), the first 1024 channels being x4 repeated over the points."""
+        x4, x_features = self.forward_global(x)
+        return torch.cat([x4.unsqueeze(2).expand(-1, -1, x_features.shape[2]), x_features], 1)
 
 
 class SoftProjection(nn.Module):

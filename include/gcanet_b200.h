@@ -225,6 +225,32 @@ GCANET_API int gcanet_normal_edgeconv_backward(const gcanet_normal_edge_desc *d,
                                                float *grad_gamma, float *grad_beta, void *ws, size_t ws_bytes,
                                                gcanet_stream_t stream);
 
+/* ------------------------------------------------------------------ encoder tail (global feature)
+ * Replaces  x = relu(bnmlp1(mlp1(cat(x1, x2, x3))));  x4 = x.max(dim=2)[0]   (M4:507-510: Conv1d(256 -> 1024, 1, bias) ->
+ * GroupNorm(8, 1024) -> ReLU -> max over the N points) and its autograd backward, without forming the [B][Cout][N]
+ * activation (the reference keeps three copies of it).  The broadcast + concat of M4:510-511 into [B][1280][N] is left
+ * to the caller: 1024 of those channels are one value per cloud (fold them into the next layer's bias).
+ *   x_nc   [B][N][K]   point-major concatenation of x1 | x2 | x3 (K = 256), 16-byte aligned
+ *   weight [Cout][K]   mlp1.weight viewed as a matrix;  bias [Cout] or NULL;  gamma, beta [Cout]
+ *   out    [B][Cout]   x4
+ * backward: grad_out [B][Cout] -> grad_x_nc [B][N][K] (or NULL to skip), grad_weight [Cout][K], grad_bias [Cout] (or NULL),
+ * grad_gamma, grad_beta [Cout]; all overwritten.  Constraints: K = 256, Cout % 128 == 0, Cout % groups == 0. */
+typedef struct {
+    int B, N, K, Cout, groups;
+    float eps;
+} gcanet_global_feature_desc;
+
+GCANET_API size_t gcanet_global_feature_saved_bytes(const gcanet_global_feature_desc *d);
+GCANET_API size_t gcanet_global_feature_workspace_bytes(const gcanet_global_feature_desc *d);
+GCANET_API int gcanet_global_feature_forward(const gcanet_global_feature_desc *d, const float *x_nc, const float *weight,
+                                             const float *bias, const float *gamma, const float *beta, float *out, void *saved,
+                                             void *ws, size_t ws_bytes, gcanet_stream_t stream);
+GCANET_API int gcanet_global_feature_backward(const gcanet_global_feature_desc *d, const float *x_nc, const float *weight,
+                                              const float *bias, const float *gamma, const float *beta, const float *grad_out,
+                                              const void *saved, float *grad_x_nc, float *grad_weight, float *grad_bias,
+                                              float *grad_gamma, float *grad_beta, void *ws, size_t ws_bytes,
+                                              gcanet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
