@@ -216,3 +216,77 @@ class NormalEdgeHead(nn.Module):
     def forward(self, points, idx=None):
         f = get_graph_feature_with_normals_g(points, k1=self.k, k2=self.k, idx=idx)
         return self.conv_normal(f).max(dim=-1, keepdim=False)[0]
+
+
+# --------------------------------------------------------------------------
+# offset-prediction block: cos_dist M4:326-342, KPAM M4:351-373,
+# OFFSET_PRED_MODULE M4:376-452
+# --------------------------------------------------------------------------
+def cos_dist(feat: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
+    """feat [B, N, C], keys [B, K, C] -> [B, N, K] = -(1 - cosine similarity)  (larger = more similar)."""
+    fn = feat / feat.norm(dim=-1, keepdim=True)
+    kn = keys / keys.norm(dim=-1, keepdim=True)
+    return -(1 - torch.einsum('bnc,bkc->bnk', fn, kn))
+
+
+def offset_key_indices(num_points: int, count: int) -> torch.Tensor:
+    """The reference re-seeds numpy with 1234 on every call, shuffles arange(N) and keeps the first `count`
+    (M4:403-406): the same `count` points of every cloud, every step.  RandomState(1234) is the same MT19937 stream as
+    the seeded global generator, without the side effect on it."""
+    order = np.arange(num_points)
+    np.random.RandomState(1234).shuffle(order)
+    return torch.from_numpy(order[:count].copy()).long()
+
+
+class KPAM(nn.Module):
+    """Attention over the k neighbours from their similarity values: softmax_k(W2 relu(W1 d))."""
+
+    def __init__(self, C):
+        super().__init__()
+        self.dim = C
+        self.conv1 = nn.Sequential(nn.Conv1d(C, C, kernel_size=1, bias=False), nn.ReLU(),
+                                   nn.Conv1d(C, C, kernel_size=1, bias=False))
+
+    def forward(self, x, sims):
+        """x [B, N, k, F], sims [B, N, k] -> x scaled per (point, neighbour)."""
+        w = self.conv1(sims.permute(0, 2, 1)).permute(0, 2, 1)
+        w = torch.softmax(w, dim=2).unsqueeze(-1)
+        return w * x
+
+
+class OffsetPredModule(nn.Module):
+    """Same parameter names / shapes as OFFSET_PRED_MODULE (M4:376-452): ``bn1``, ``conv1.0.weight`` [128, 131, 1, 1],
+    ``attention.conv1.{0,2}.weight`` [k, k, 1], ``mlp_offset.{weight,bias}`` [3, 256, 1] / [3]."""
+
+    def __init__(self, nn_nb=30, sampling_ratio=120):
+        super().__init__()
+        self.k = nn_nb
+        self.sampling_ratio = sampling_ratio
+        self.bn1 = nn.GroupNorm(2, 128)
+        self.conv1 = nn.Sequential(nn.Conv2d(131, 128, kernel_size=1, bias=False), self.bn1,
+                                   nn.LeakyReLU(negative_slope=LEAKY_SLOPE))
+        self.attention = KPAM(nn_nb)
+        self.mlp_offset = nn.Conv1d(256, 3, 1)
+
+    def forward(self, points, feature, instance_feature):
+        """points [B, N, 3], feature [B, N, 128], instance_feature [B, N, E] -> offsets [B, 3, N]."""
+        B, N, _ = points.shape
+        sub = offset_key_indices(N, self.sampling_ratio).to(points.device)
+        key_points = points[:, sub]                                  # [B, S, 3]
+        key_feat = feature[:, sub]                                   # [B, S, 128]
+        key_inst = instance_feature[:, sub]                          # [B, S, E]
+        sims = cos_dist(instance_feature, key_inst)                  # [B, N, S]
+        top_val, top_idx = torch.topk(sims, self.k, dim=2, largest=True)
+        # gather through an N-fold repeat of the key tables, as the reference does (M4:425-430): its backward sums the
+        # N copies in that order, which is what makes the gradients bit-identical to the reference's
+        def pick(table):                                             # [B, S, F] -> [B, N, k, F]
+            rep = table.unsqueeze(1).repeat(1, N, 1, 1)
+            return torch.gather(rep, 2, top_idx.unsqueeze(-1).expand(-1, -1, -1, table.shape[2]))
+        nb_points = pick(key_points)                                 # [B, N, k, 3]
+        nb_feat = pick(key_feat)                                     # [B, N, k, 128]
+        edge = torch.cat([nb_feat, nb_points - points.unsqueeze(2)], 3)          # [B, N, k, 131]
+        edge = self.attention(edge, top_val)
+        y = self.conv1(edge.permute(0, 3, 2, 1))                     # [B, 128, k, N]
+        y = y.max(dim=-2, keepdim=False)[0]                          # [B, 128, N]
+        y = torch.cat([y, feature.permute(0, 2, 1)], dim=1)          # [B, 256, N]
+        return self.mlp_offset(y)

@@ -172,6 +172,45 @@ def make_normal_head_fixture(ns, out_dir):
     np.savez_compressed(os.path.join(out_dir, "normal_head_small.npz"), **fix)
 
 
+def make_offset_fixture(ref_root, out_dir):
+    """OFFSET_PRED_MODULE + KPAM + cos_dist: the reference's own text (M4:326-452) against oracle.OffsetPredModule."""
+    print("[offset prediction block]")
+    with open(os.path.join(ref_root, M4)) as f:
+        lines = f.read().split("\n")
+    text = "\n".join(lines[325:452]) + "\n"
+    ns = {"torch": torch, "np": np, "nn": nn, "F": F}
+    exec(compile(text, os.path.join(ref_root, M4), "exec"), ns)
+    B, N, E = 2, 300, 64
+    g = torch.Generator().manual_seed(21)
+    pts = torch.from_numpy(abc_like_batch(B, N, seed=55)).transpose(1, 2).contiguous()      # [B, N, 3]
+    feat = torch.randn(B, N, 128, generator=g)
+    feat = torch.where(feat > 0, feat, 0.2 * feat)
+    inst = torch.randn(B, N, E, generator=g)
+    torch.manual_seed(4)
+    ref = ns["OFFSET_PRED_MODULE"](nn_nb=30, sampling_ratio=120)
+    randomise_affine(ref, torch.Generator().manual_seed(17))
+    mine = orc.OffsetPredModule(nn_nb=30, sampling_ratio=120)
+    mine.load_state_dict(ref.state_dict())
+    same(orc.cos_dist(inst, inst[:, :7]), ns["cos_dist"](inst, inst[:, :7]), "cos_dist")
+    ins_r = [t.clone().requires_grad_(True) for t in (feat, inst)]
+    ins_m = [t.clone().requires_grad_(True) for t in (feat, inst)]
+    out_ref = ref(pts, *ins_r)
+    out = mine(pts, *ins_m)
+    same(out, out_ref, "OFFSET_PRED_MODULE forward")
+    cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(8))
+    (out_ref * cot).sum().backward()
+    (out * cot).sum().backward()
+    fix = {"points": pts.numpy(), "feature": feat.numpy(), "inst": inst.numpy(), "out": out_ref.detach().numpy(),
+           "cot": cot.numpy(), "grad.feature": ins_r[0].grad.numpy(), "grad.inst": ins_r[1].grad.numpy()}
+    same(ins_m[0].grad, ins_r[0].grad, "grad feature")
+    same(ins_m[1].grad, ins_r[1].grad, "grad instance_feature")
+    for (name, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
+        same(q.grad, p.grad, f"grad {name}")
+        fix[f"param.{name}"] = p.detach().numpy()
+        fix[f"grad.{name}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(out_dir, "offset_small.npz"), **fix)
+
+
 def extract_search_knn_golden(ref_root, out_dir):
     print("[search_knn.py hand-written golden vectors]")
     path = os.path.join(ref_root, "models/search_knn.py")
@@ -205,9 +244,10 @@ def main():
     make_knn_fixture(ns, out_dir)
     make_encoder_fixture(ns, out_dir)
     make_normal_head_fixture(ns, out_dir)
+    make_offset_fixture(args.reference, out_dir)
     extract_search_knn_golden(args.reference, out_dir)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "threads": 1,
-            "reference_files": [M4 + ":30-205", M4 + ":455-534", "models/search_knn.py:180-244"]}
+            "reference_files": [M4 + ":30-205", M4 + ":326-452", M4 + ":455-534", "models/search_knn.py:180-244"]}
     with open(os.path.join(out_dir, "META.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("done ->", out_dir)

@@ -107,6 +107,28 @@ def test_normal_head_matches_fixture(golden_dir):
     torch.testing.assert_close(out, _t(fx["out"]), rtol=1e-5, atol=1e-5)
 
 
+def test_offset_module_matches_fixture(golden_dir):
+    """OffsetPredModule / KPAM / cos_dist against the values the reference's own text (M4:326-452) produced."""
+    fx = np.load(os.path.join(golden_dir, "offset_small.npz"))
+    mod = orc.OffsetPredModule(nn_nb=30, sampling_ratio=120)
+    with torch.no_grad():
+        for name, p in mod.named_parameters():
+            p.copy_(_t(fx[f"param.{name}"]))
+    feat = _t(fx["feature"]).requires_grad_(True)
+    inst = _t(fx["inst"]).requires_grad_(True)
+    out = mod(_t(fx["points"]), feat, inst)
+    torch.testing.assert_close(out, _t(fx["out"]), rtol=1e-5, atol=1e-5)
+    (out * _t(fx["cot"])).sum().backward()
+    torch.testing.assert_close(feat.grad, _t(fx["grad.feature"]), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(inst.grad, _t(fx["grad.inst"]), rtol=1e-4, atol=1e-5)
+    for name, p in mod.named_parameters():
+        torch.testing.assert_close(p.grad, _t(fx[f"grad.{name}"]), rtol=1e-4, atol=1e-4)
+    # the key points are the same for every call and every cloud (numpy re-seeded with 1234, M4:403-406)
+    sub = orc.offset_key_indices(300, 120)
+    assert sub.shape == (120,) and len(set(sub.tolist())) == 120 and int(sub.max()) < 300
+    assert torch.equal(sub, orc.offset_key_indices(300, 120))
+
+
 # ---------------------------------------------------------------- native path
 @pytest.fixture(scope="module")
 def sk_golden(golden_dir):
