@@ -10,6 +10,7 @@ from .functional import (  # noqa: F401
     get_graph_feature,
     get_graph_feature_with_normals,
     get_graph_feature_with_normals_g,
+    global_feature,
     group_points,
     grouping_operation,
     knn,
@@ -19,11 +20,12 @@ from .functional import (  # noqa: F401
     knn_point,
     knn_points_normals,
     normal_edgeconv,
+    offset_pred,
     splinenet_get_graph_feature,
     splinenet_knn,
     to_channel_major,
     to_point_major,
 )
-from .modules import DGCNNEncoderGn, NormalEdgeHead, SoftProjection  # noqa: F401
+from .modules import KPAM, OFFSET_PRED_MODULE, DGCNNEncoderGn, NormalEdgeHead, SoftProjection  # noqa: F401
 
 __version__ = "0.1.0"

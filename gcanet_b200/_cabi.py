@@ -40,6 +40,14 @@ class GlobalFeatureDesc(ctypes.Structure):
 
 _GDESC_P = ctypes.POINTER(GlobalFeatureDesc)
 
+
+class OffsetDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("N", c_int), ("S", c_int), ("k", c_int), ("E", c_int), ("groups", c_int),
+                ("eps", c_float), ("slope", c_float)]
+
+
+_ODESC_P = ctypes.POINTER(OffsetDesc)
+
 # name -> (restype, argtypes); mirrors include/gcanet_b200.h one to one
 SIGNATURES = {
     "gcanet_abi_version": (c_int, []),
@@ -78,6 +86,10 @@ SIGNATURES = {
     "gcanet_global_feature_workspace_bytes": (c_size_t, [_GDESC_P]),
     "gcanet_global_feature_forward": (c_int, [_GDESC_P] + [c_void_p] * 8 + [c_size_t, c_void_p]),
     "gcanet_global_feature_backward": (c_int, [_GDESC_P] + [c_void_p] * 13 + [c_size_t, c_void_p]),
+    "gcanet_offset_pred_saved_bytes": (c_size_t, [_ODESC_P]),
+    "gcanet_offset_pred_workspace_bytes": (c_size_t, [_ODESC_P]),
+    "gcanet_offset_pred_forward": (c_int, [_ODESC_P] + [c_void_p] * 14 + [c_size_t, c_void_p]),
+    "gcanet_offset_pred_backward": (c_int, [_ODESC_P] + [c_void_p] * 23 + [c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ import ctypes as _ct
 import torch
 
 from . import _cabi
-from ._cabi import EdgeConvDesc, GlobalFeatureDesc, NormalEdgeDesc, call, ptr, require_cuda, stream, workspace
+from ._cabi import EdgeConvDesc, GlobalFeatureDesc, NormalEdgeDesc, OffsetDesc, call, ptr, require_cuda, stream, workspace
 
 METRIC_L2 = 0
 METRIC_POINTS_NORMALS = 1
@@ -523,3 +523,60 @@ def global_feature(x_nc, weight, bias, gamma, beta, groups=8, eps=1e-5):
     concatenation of x1 | x2 | x3, weight [1024, 256] (or the Conv1d's [1024, 256, 1]), bias [1024] or None.
     Returns x4 [B, Cout]; differentiable in x_nc, weight, bias, gamma, beta.  The [B, Cout, N] activation is never formed."""
     return _GlobalFeature.apply(x_nc, weight.reshape(weight.shape[0], -1), bias, gamma, beta, int(groups), float(eps))
+
+
+# ----------------------------------------------------------------------------------
+# offset-prediction block (OFFSET_PRED_MODULE + KPAM + cos_dist, M4:326-452), fused
+# ----------------------------------------------------------------------------------
+class _OffsetPred(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, feature, inst, key_index, conv_w, gamma, beta, w1, w2, off_w, off_b, k, groups, eps, slope):
+        for t, nme in ((points, "points"), (feature, "feature"), (inst, "instance_feature")):
+            require_cuda(t, nme, torch.float32)
+        require_cuda(key_index, "key_index", torch.int32)
+        params = [t.contiguous() for t in (conv_w, gamma, beta, w1, w2, off_w, off_b)]
+        B, N, _ = points.shape
+        if tuple(points.shape) != (B, N, 3) or tuple(feature.shape) != (B, N, 128) or inst.shape[:2] != (B, N):
+            raise RuntimeError(f"offset_pred: points [B,N,3], feature [B,N,128], instance_feature [B,N,E] expected "
+                               f"(got {tuple(points.shape)}, {tuple(feature.shape)}, {tuple(inst.shape)})")
+        desc = OffsetDesc(B, N, key_index.numel(), k, inst.shape[2], groups, eps, slope)
+        L = _cabi.lib()
+        with torch.cuda.device(points.device):
+            saved_bytes = L.gcanet_offset_pred_saved_bytes(_ct.byref(desc))
+            if saved_bytes == 0:
+                raise RuntimeError("gcanet_b200 offset_pred: " + L.gcanet_last_error().decode())
+            saved = workspace(saved_bytes, points.device)
+            ws = workspace(L.gcanet_offset_pred_workspace_bytes(_ct.byref(desc)), points.device)
+            out = torch.empty((B, 3, N), dtype=torch.float32, device=points.device)
+            with _timed("offset_pred_fwd"):
+                call("gcanet_offset_pred_forward", _ct.byref(desc), ptr(points), ptr(feature), ptr(inst), ptr(key_index),
+                     *[ptr(t) for t in params], ptr(out), ptr(saved), ptr(ws), ws.numel(), stream())
+        ctx.save_for_backward(points, feature, inst, key_index, saved, *params)
+        ctx.desc = desc
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        points, feature, inst, key_index, saved, *params = ctx.saved_tensors
+        desc = ctx.desc
+        L = _cabi.lib()
+        with torch.cuda.device(points.device):
+            g = g.contiguous().float()
+            gf, gi = torch.empty_like(feature), torch.empty_like(inst)
+            gp = [torch.empty_like(t) for t in params]
+            ws = workspace(L.gcanet_offset_pred_workspace_bytes(_ct.byref(desc)), points.device)
+            with _timed("offset_pred_bwd"):
+                call("gcanet_offset_pred_backward", _ct.byref(desc), ptr(points), ptr(feature), ptr(inst), ptr(key_index),
+                     *[ptr(t) for t in params], ptr(g), ptr(saved), ptr(gf), ptr(gi), *[ptr(t) for t in gp], ptr(ws),
+                     ws.numel(), stream())
+        return (None, gf, gi, None, *gp, None, None, None, None)
+
+
+def offset_pred(points, feature, instance_feature, key_index, conv_w, gamma, beta, att_w1, att_w2, off_w, off_b, k=30,
+                groups=2, eps=1e-5, slope=0.2):
+    """Fused ``OFFSET_PRED_MODULE.forward`` (M4:398-452): points [B, N, 3] (data), feature [B, N, 128], instance_feature
+    [B, N, E], key_index [S] int32 -> offsets [B, 3, N]; differentiable in feature, instance_feature and all parameters."""
+    return _OffsetPred.apply(points.contiguous(), feature.contiguous(), instance_feature.contiguous(), key_index,
+                             conv_w.reshape(conv_w.shape[0], -1), gamma, beta, att_w1.reshape(att_w1.shape[0], -1),
+                             att_w2.reshape(att_w2.shape[0], -1), off_w.reshape(off_w.shape[0], -1), off_b, int(k), int(groups),
+                             float(eps), float(slope))

@@ -162,6 +162,57 @@ class SoftProjection(nn.Module):
         return torch.sum(grouped_points * weights, dim=3)
 
 
+class KPAM(nn.Module):
+    """Parameter container with the reference's names (``conv1.0.weight``, ``conv1.2.weight`` [k, k, 1], M4:351-363); the
+    attention itself runs inside the fused offset kernel."""
+
+    def __init__(self, C):
+        super().__init__()
+        self.dim = C
+        self.conv1 = nn.Sequential(nn.Conv1d(C, C, kernel_size=1, bias=False), nn.ReLU(),
+                                   nn.Conv1d(C, C, kernel_size=1, bias=False))
+
+
+class OFFSET_PRED_MODULE(nn.Module):
+    """Drop-in for ``OFFSET_PRED_MODULE`` (M4:376-452), same constructor, parameter names and
+    ``forward(points [B,N,3], feature [B,N,128], instance_feature [B,N,E]) -> offsets [B,3,N]``; the whole block is one
+    fused kernel sequence (``gcanet_b200.functional.offset_pred``)."""
+
+    def __init__(self, nn_nb=30, sampling_ratio=120):
+        super().__init__()
+        self.k = nn_nb
+        self.dilation_factor = 1
+        self.drop = 0.0
+        self.sampling_ratio = sampling_ratio
+        self.bn1 = nn.GroupNorm(2, 128)
+        self.conv1 = nn.Sequential(nn.Conv2d(131, 128, kernel_size=1, bias=False), self.bn1,
+                                   nn.LeakyReLU(negative_slope=LEAKY_SLOPE))
+        self.attention = KPAM(nn_nb)
+        self.mlp_offset = torch.nn.Conv1d(256, 3, 1)
+        self._keys = {}
+
+    def key_index(self, num_points, device):
+        """The reference's key points: numpy re-seeded with 1234, arange(N) shuffled, first ``sampling_ratio`` (M4:403-406)
+        -- the same indices for every cloud and every call, so they are computed once per (N, device)."""
+        import numpy as np
+        k = (int(num_points), str(device))
+        if k not in self._keys:
+            order = np.arange(num_points)
+            np.random.RandomState(1234).shuffle(order)
+            self._keys[k] = torch.from_numpy(order[:self.sampling_ratio].astype(np.int32)).to(device)
+        return self._keys[k]
+
+    def forward(self, points, feature, instance_feature):
+        if not points.is_cuda:
+            raise RuntimeError("gcanet_b200.OFFSET_PRED_MODULE has no CPU path")
+        gn = self.bn1
+        return G.offset_pred(points.detach().float(), feature.float(), instance_feature.float(),
+                             self.key_index(points.shape[1], points.device), self.conv1[0].weight, gn.weight, gn.bias,
+                             self.attention.conv1[0].weight, self.attention.conv1[2].weight, self.mlp_offset.weight,
+                             self.mlp_offset.bias, k=self.k, groups=gn.num_groups, eps=gn.eps,
+                             slope=self.conv1[2].negative_slope)
+
+
 class NormalEdgeHead(nn.Module):
     """The 4th EdgeConv of the reference, on normals: ``conv_normal`` (M4:584-587) applied to
     ``get_graph_feature_with_normals_g(points, k, k)`` and reduced with max over k (M4:691-693).

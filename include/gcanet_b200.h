@@ -251,6 +251,38 @@ GCANET_API int gcanet_global_feature_backward(const gcanet_global_feature_desc *
                                               float *grad_gamma, float *grad_beta, void *ws, size_t ws_bytes,
                                               gcanet_stream_t stream);
 
+/* ------------------------------------------------------------------ offset-prediction block
+ * Replaces OFFSET_PRED_MODULE.forward with KPAM and cos_dist (M4:326-452) and its autograd backward: per cloud S key
+ * points (the caller passes their indices; the reference re-seeds numpy with 1234 and takes the first S of a shuffle,
+ * M4:403-406), cosine similarity of every point's instance feature to the keys', the k most similar keys (descending,
+ * ties by key index), attention softmax_k(W2 relu(W1 d)) on the similarity values, edge feature
+ * a_ik (f_j ; p_j - p_i) -> Conv2d(131 -> 128, no bias) -> GroupNorm -> LeakyReLU -> max over k, concatenated with the
+ * point's own feature, Conv1d(256 -> 3).  Nothing of size N x S x C or N x k x C is stored.
+ *   points [B][N][3], feature [B][N][128], inst [B][N][E] (point-major, as the module receives them)
+ *   key_index [S] int32;  conv_w [128][131];  gamma, beta [128];  att_w1, att_w2 [k][k];  off_w [3][256];  off_b [3]
+ *   out [B][3][N]
+ * backward: grad_out [B][3][N] -> grad_feature [B][N][128], grad_inst [B][N][E] and all parameter gradients (overwritten);
+ * points are data.  Constraints: S % 4 == 0, S <= 128, k <= min(32, S), E % 4 == 0, E <= 256 (E <= 64 for the backward's
+ * shared-memory budget at S = 120). */
+typedef struct {
+    int B, N, S, k, E, groups;
+    float eps, slope;
+} gcanet_offset_desc;
+
+GCANET_API size_t gcanet_offset_pred_saved_bytes(const gcanet_offset_desc *d);
+GCANET_API size_t gcanet_offset_pred_workspace_bytes(const gcanet_offset_desc *d);
+GCANET_API int gcanet_offset_pred_forward(const gcanet_offset_desc *d, const float *points, const float *feature, const float *inst,
+                                          const int32_t *key_index, const float *conv_w, const float *gamma, const float *beta,
+                                          const float *att_w1, const float *att_w2, const float *off_w, const float *off_b,
+                                          float *out, void *saved, void *ws, size_t ws_bytes, gcanet_stream_t stream);
+GCANET_API int gcanet_offset_pred_backward(const gcanet_offset_desc *d, const float *points, const float *feature, const float *inst,
+                                           const int32_t *key_index, const float *conv_w, const float *gamma, const float *beta,
+                                           const float *att_w1, const float *att_w2, const float *off_w, const float *off_b,
+                                           const float *grad_out, const void *saved, float *grad_feature, float *grad_inst,
+                                           float *grad_conv_w, float *grad_gamma, float *grad_beta, float *grad_att_w1,
+                                           float *grad_att_w2, float *grad_off_w, float *grad_off_b, void *ws, size_t ws_bytes,
+                                           gcanet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,96 @@
+"""GPU suite, part 4: the fused offset-prediction block (OFFSET_PRED_MODULE + KPAM + cos_dist, M4:326-452) against the
+fixture produced by the reference's own text and against the oracle at N = 10 000.
+
+Tolerances: forward <= 2e-4 of the largest entry (a (T_j - q_i) instead of W [a f_j ; a (p_j - p_i)] changes rounding;
+a near-tie at the rank-30 boundary of the similarities or at the arg-max swaps a neighbour: bounded fraction of points);
+gradients: median error below 1e-4 .. 5e-4 of the largest entry; single entries up to 5e-2 (one swapped neighbour moves a whole
+channel gradient from one key to another; the 600-point fixture has one such point).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gcanet_b200 as gb
+from oracle import dgcnn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _compare(name, got, want, tol_max, tol_med):
+    e = (got.detach().cpu().double() - want.double()).abs() / float(want.abs().max())
+    print(f"{name}: max {float(e.max()):.2e}, median {float(e.median()):.2e}")
+    assert float(e.max()) < tol_max and float(e.median()) < tol_med, f"{name}: max {float(e.max()):.3e} median {float(e.median()):.3e}"
+
+
+def test_offset_module_golden_fixture(golden_dir):
+    fx = np.load(os.path.join(golden_dir, "offset_small.npz"))
+    mod = gb.OFFSET_PRED_MODULE(nn_nb=30, sampling_ratio=120)
+    with torch.no_grad():
+        for name, p in mod.named_parameters():
+            p.copy_(_t(fx[f"param.{name}"]))
+    mod.to(DEV)
+    feat = _t(fx["feature"]).to(DEV).requires_grad_(True)
+    inst = _t(fx["inst"]).to(DEV).requires_grad_(True)
+    out = mod(_t(fx["points"]).to(DEV), feat, inst)
+    want = _t(fx["out"])
+    assert out.shape == want.shape
+    d = (out.detach().cpu() - want).abs() / float(want.abs().max())
+    print(f"forward: max {float(d.max()):.2e}, points above 2e-4: {float((d.amax(dim=1) > 2e-4).float().mean()):.2%}")
+    assert float((d.amax(dim=1) > 2e-4).float().mean()) < 0.02
+    (out * _t(fx["cot"]).to(DEV)).sum().backward()
+    _compare("grad feature", feat.grad, _t(fx["grad.feature"]), 5e-2, 1e-4)
+    _compare("grad inst", inst.grad, _t(fx["grad.inst"]), 5e-2, 1e-4)
+    for name, p in mod.named_parameters():
+        _compare(f"grad {name}", p.grad, _t(fx[f"grad.{name}"]), 2e-2, 2e-4)
+    assert torch.equal(mod.key_index(300, DEV).cpu().long(), orc.offset_key_indices(300, 120))
+
+
+def test_offset_module_vs_oracle_10k_points():
+    B, N, E = 2, 10000, 64
+    from gcanet_b200.synth import abc_like_batch
+    g = torch.Generator().manual_seed(3)
+    pts = torch.from_numpy(abc_like_batch(B, N, seed=77)).transpose(1, 2).contiguous()
+    feat = torch.randn(B, N, 128, generator=g)
+    feat = torch.where(feat > 0, feat, 0.2 * feat)
+    # instance features with cluster structure (points of a primitive share an embedding direction)
+    centres = torch.randn(B, 9, E, generator=g)
+    inst = centres[torch.arange(B).view(B, 1), torch.randint(0, 9, (B, N), generator=g)] + 0.3 * torch.randn(B, N, E, generator=g)
+    torch.manual_seed(1)
+    ref = orc.OffsetPredModule()
+    with torch.no_grad():
+        ref.bn1.weight.copy_(torch.randn(128) * 0.7 + 0.2)
+        ref.bn1.bias.copy_(torch.randn(128) * 0.3)
+    mod = gb.OFFSET_PRED_MODULE()
+    mod.load_state_dict(ref.state_dict())
+    mod.to(DEV)
+    fo, io = feat.clone().requires_grad_(True), inst.clone().requires_grad_(True)
+    fg, ig = feat.to(DEV).requires_grad_(True), inst.to(DEV).requires_grad_(True)
+    out_o = ref(pts, fo, io)
+    out_g = mod(pts.to(DEV), fg, ig)
+    d = (out_g.detach().cpu() - out_o.detach()).abs() / float(out_o.detach().abs().max())
+    frac = float((d.amax(dim=1) > 2e-4).float().mean())
+    print(f"forward: max {float(d.max()):.2e}, points above 2e-4: {frac:.2%}")
+    assert frac < 0.02
+    cot = torch.randn(out_o.shape, generator=g)
+    (out_o * cot).sum().backward()
+    (out_g * cot.to(DEV)).sum().backward()
+    _compare("grad feature", fg.grad, fo.grad, 5e-2, 1e-4)
+    _compare("grad inst", ig.grad, io.grad, 5e-2, 2e-4)
+    g_ref = dict(ref.named_parameters())
+    for name, p in mod.named_parameters():
+        _compare(f"grad {name}", p.grad, g_ref[name].grad, 2e-2, 5e-4)
+
+
+def test_offset_module_errors():
+    mod = gb.OFFSET_PRED_MODULE().to(DEV)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        mod(torch.zeros(1, 200, 3), torch.zeros(1, 200, 128), torch.zeros(1, 200, 64))
+    with pytest.raises(RuntimeError):
+        mod(torch.zeros(1, 200, 3, device=DEV), torch.zeros(1, 200, 64, device=DEV), torch.zeros(1, 200, 64, device=DEV))
