@@ -264,7 +264,43 @@ def extra_configs(enc, dev, G):
                                    "points_per_s": round(B5 * N5 / (ms5 / 1e3)), "xyz_knn_ms": round(knn5, 3)}
     del x5, cot5
     torch.cuda.empty_cache()
+    out["config4_full_step"] = full_step_leg(dev, B_PER_GPU)
     return out
+
+
+def full_step_leg(dev, batch, steps=10):
+    """BASELINE configs[3] as SURVEY 8(d) defines it for this environment: the three-layer stack + encoder tail + per-point
+    heads + normals EdgeConv + offset-prediction block + NLL / offset-L1 losses, forward + backward (everything of
+    forward_train before the proposal grouping, which needs spconv / softgroup.ops)."""
+    import gcanet_b200 as gb
+    from gcanet_b200.model import PrimitivesEmbeddingPerPoint, nll_loss, offset_l1_loss
+    from gcanet_b200.synth import abc_like_batch
+    torch.manual_seed(0)
+    net = PrimitivesEmbeddingPerPoint(emb_size=64, num_primitives=10, mode=5, num_channels=6, nn_nb=KNN).to(dev)
+    c = torch.from_numpy(abc_like_batch(batch, NPTS, seed=4321, with_normals=True)).to(dev)
+    pts, nrm = c[:, :3].transpose(1, 2).contiguous(), c[:, 3:].transpose(1, 2).contiguous()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    t_gt = torch.randint(0, 10, (batch, NPTS), generator=g).to(dev)
+    i_gt = torch.randint(-1, 12, (batch, NPTS), generator=g).to(dev)
+    off_gt = (torch.randn(batch, NPTS, 3, generator=g) * 0.05).to(dev)
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        o = net(pts, nrm)
+        loss = nll_loss(o["type_per_point"], t_gt) + 10.0 * offset_l1_loss(o["pt_offsets"], i_gt, off_gt)
+        loss.backward()
+        return loss
+
+    before = gb._cabi.launch_count()
+    ms = _median_ms(step, reps=steps, warm=3)
+    launches = (gb._cabi.launch_count() - before) // (steps + 3)
+    loss = float(step().detach())
+    del net
+    torch.cuda.empty_cache()
+    return {"workload": f"per-point GCANet step fwd+bwd, B={batch} x 10k pts, k=50, mode 5: stack + tail + heads + normals EdgeConv + "
+                        "offset block + NLL / offset-L1 losses (no proposal grouping / spconv head); median of 10 steps",
+            "ms_per_step": round(ms, 3), "clouds_per_s": round(batch / (ms / 1e3), 1), "library_launches_per_step": int(launches),
+            "loss": round(loss, 4)}
 
 
 # ---------------------------------------------------------------------------- GPU path
@@ -380,6 +416,30 @@ def run_ours(args):
         differ = (torch.stack(gathered).std(0).max() > 0).float().reshape(1)      # ranks really hold different gradients
         allreduce_check = {"max_rel_err": float(err[0]), "ranks_differ": bool(differ[0] > 0), "floats": int(mine.numel())}
 
+    # --- BASELINE configs[3], literal split: a FIXED global batch of 128 clouds sharded over the ranks (128 / N per GPU),
+    # same stack step + gradient all-reduce; strong scaling, reported beside the weak-scaling headline
+    fixed = None
+    if not args.no_extras and 128 % world == 0:
+        per = 128 // world
+        xf = torch.from_numpy(abc_like_batch(per, NPTS, seed=1234, first_cloud=rank * per)).to(dev)
+        cotf = [torch.randn(per, c, NPTS, generator=gen).to(dev) for c in (64, 64, 128)]
+
+        def step_fixed():
+            for p in hot:
+                p.grad = None
+            outs = enc.edge_stack(xf)
+            torch.autograd.backward(outs, cotf)
+            if bucket is not None:
+                bucket.all_reduce_mean()
+
+        for _ in range(3):
+            step_fixed()
+        ms_f, med_f = timed(step_fixed, 5)
+        fixed = {"global_batch": 128, "batch_per_gpu": per, "ms_per_step": ms_f / 5, "ms_per_step_median": med_f,
+                 "value": 128 / (ms_f / 5 / 1e3), "unit": UNIT, "scaling": "strong", "steps": 5}
+        del xf, cotf
+        torch.cuda.empty_cache()
+
     extras = {}
     if world == 1 and not args.no_extras:
         extras = extra_configs(enc, dev, G)
@@ -455,6 +515,7 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "gpu_reference": gpu_reference,
         "allreduce_check": allreduce_check,
+        "config4_fixed_global_batch": fixed,
     }
     line.update(extras)
     print(json.dumps(line), flush=True)

@@ -100,3 +100,39 @@ def test_encoder_forward_is_reference_layout_and_differentiable():
         assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0, name
     with pytest.raises(RuntimeError):
         G.global_feature(torch.zeros(1, 10, 128, device=DEV), enc.mlp1.weight, enc.mlp1.bias, enc.bnmlp1.weight, enc.bnmlp1.bias)
+
+
+def test_per_point_model_step_and_folded_global_bias():
+    """PrimitivesEmbeddingPerPoint (BASELINE config 4 in this environment): one forward + backward at small size, the
+    shapes the reference's losses consume, finite gradients on every parameter that takes part, and the identity the
+    model uses instead of building [B, 1280, N]: conv1(cat(repeat(x4), x_features)) == conv1_local(x_features) + W_g x4."""
+    from gcanet_b200.model import PrimitivesEmbeddingPerPoint, nll_loss, offset_l1_loss
+    from gcanet_b200.synth import abc_like_batch
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    B, N = 2, 1500
+    net = PrimitivesEmbeddingPerPoint(mode=5, nn_nb=20).to(DEV)
+    c = torch.from_numpy(abc_like_batch(B, N, seed=11, with_normals=True)).to(DEV)
+    pts, nrm = c[:, :3].transpose(1, 2).contiguous(), c[:, 3:].transpose(1, 2).contiguous()
+    o = net(pts, nrm)
+    assert o["type_per_point"].shape == (B, N, 10) and o["param_per_point"].shape == (B, N, 22)
+    assert o["pt_offsets"].shape == (B, N, 3) and o["output_feats"].shape == (B, N, 64)
+    assert torch.allclose(o["type_per_point"].exp().sum(-1), torch.ones(B, N, device=DEV), atol=1e-4)
+    g = torch.Generator().manual_seed(1)
+    t_gt = torch.randint(-1, 10, (B, N), generator=g).to(DEV)
+    i_gt = torch.randint(-1, 5, (B, N), generator=g).to(DEV)
+    loss = nll_loss(o["type_per_point"], t_gt) + 10 * offset_l1_loss(o["pt_offsets"], i_gt, torch.zeros(B, N, 3, device=DEV))
+    loss.backward()
+    unused = {"encoder.bn4.weight", "encoder.bn4.bias", "encoder.bn5.weight", "encoder.bn5.bias",      # M4:466-467
+              "mlp_param_prob2.weight", "mlp_param_prob2.bias"}                                         # param loss not in this step
+    for name, p in net.named_parameters():
+        if name in unused:
+            continue
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+    # folded global feature
+    with torch.no_grad():
+        x4, xf = net.encoder.forward_global(torch.cat([pts, nrm], -1).permute(0, 2, 1).contiguous())
+        full = net.conv1(torch.cat([x4.unsqueeze(2).expand(-1, -1, N), xf], 1))
+        w1 = net.conv1.weight[:, :, 0]
+        folded = F.conv1d(xf, w1[:, 1024:].unsqueeze(-1)) + F.linear(x4, w1[:, :1024], net.conv1.bias).unsqueeze(-1)
+        assert float((full - folded).abs().max()) <= 1e-4 * float(full.abs().max())
