@@ -245,6 +245,25 @@ def extra_configs(enc, dev, G):
                                             "activations of this encoder; nearest-first int64 lists; median of 7 calls",
                                 "results": sweep}
     del x1, x2, x3
+    # bf16-storage mode of the same stack step ("bf16 on 1xB200" of configs[1]); fp32 stays the headline (parity mode)
+    cot = [torch.randn(B_PER_GPU, c, NPTS, device=dev) for c in (64, 64, 128)]
+    hot16 = [p for n, p in enc.named_parameters() if n.split(".")[0] in ("conv1", "conv2", "conv3", "bn1", "bn2", "bn3")]
+
+    def step16():
+        for p in hot16:
+            p.grad = None
+        torch.autograd.backward(enc.edge_stack(x), cot)
+
+    enc.storage = "bf16"
+    ms16 = _median_ms(step16, reps=15, warm=3)
+    enc.storage = "fp32"
+    ms32 = _median_ms(step16, reps=15, warm=3)
+    out["bf16_storage_mode"] = {"workload": "the headline stack step with the projected operand [P|Q] of the three EdgeConv layers stored "
+                                            "in bf16 (tolerance 2e-2 of the activation scale, tests/test_gpu_bf16.py); median of 15 steps",
+                                "dtype": "bf16 storage of [P|Q], fp32 accumulate / statistics / gradients",
+                                "ms_per_step": round(ms16, 4), "clouds_per_s": round(B_PER_GPU / (ms16 / 1e3), 1),
+                                "fp32_ms_per_step_same_loop": round(ms32, 4)}
+    del cot
     # config 5
     B5, N5 = 4, 100000
     x5 = torch.from_numpy(abc_like_batch(B5, N5, seed=555)).to(dev)

@@ -20,7 +20,7 @@ c_int, c_size_t, c_void_p, c_float = ctypes.c_int, ctypes.c_size_t, ctypes.c_voi
 
 class EdgeConvDesc(ctypes.Structure):
     _fields_ = [("B", c_int), ("N", c_int), ("C", c_int), ("ldx", c_int), ("Cout", c_int), ("k", c_int),
-                ("groups", c_int), ("eps", c_float), ("slope", c_float)]
+                ("groups", c_int), ("eps", c_float), ("slope", c_float), ("storage_bf16", c_int)]
 
 
 _DESC_P = ctypes.POINTER(EdgeConvDesc)
@@ -111,7 +111,7 @@ def lib() -> ctypes.CDLL:
                     fn = getattr(L, name)          # AttributeError if the symbol is not exported
                     fn.restype = res
                     fn.argtypes = args
-                if L.gcanet_abi_version() != 1:
+                if L.gcanet_abi_version() != 2:
                     raise RuntimeError("libgcanet_b200.so ABI version mismatch")
                 _lib = L
     return _lib

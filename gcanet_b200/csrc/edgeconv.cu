@@ -21,13 +21,16 @@
 // 2*B*N*C*2Cout FLOP, k times fewer than the per-edge formulation.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 #include <cstdlib>
 #include <math_constants.h>
 
 namespace gcanet {
 
 // gemm_tc.cu: C[M][N] = A[M][K] Bt[N][K]^T on the tensor cores; -1 = shape not covered, use the CUDA-core GEMM
-int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K, cudaStream_t st);
+int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K, cudaStream_t st,
+                int out_bf16 = 0);
 int gemm_tn_tc_try(const float *X, int ldx, const float *Y, int ldy, float *part, int M, int N, int K, int max_splits, int *splits_out,
                    cudaStream_t st);
 
@@ -410,8 +413,34 @@ struct VecIO<8> {
     static __device__ __forceinline__ void red(float *p, const float *v) { VecIO<4>::red(p, v); VecIO<4>::red(p + 4, v + 4); }
 };
 
+// VEC consecutive bf16 -> fp32 (exact: a shift)
+template <int VEC>
+__device__ __forceinline__ void ld_bf16(const __nv_bfloat16 *p, float *v) {
+    if constexpr (VEC == 1) {
+        v[0] = __bfloat162float(*p);
+    } else if constexpr (VEC == 2) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(p));
+        v[0] = __uint_as_float(w << 16); v[1] = __uint_as_float(w & 0xffff0000u);
+    } else if constexpr (VEC == 4) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(p));
+        v[0] = __uint_as_float(w.x << 16); v[1] = __uint_as_float(w.x & 0xffff0000u);
+        v[2] = __uint_as_float(w.y << 16); v[3] = __uint_as_float(w.y & 0xffff0000u);
+    } else {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(p));
+        v[0] = __uint_as_float(w.x << 16); v[1] = __uint_as_float(w.x & 0xffff0000u);
+        v[2] = __uint_as_float(w.y << 16); v[3] = __uint_as_float(w.y & 0xffff0000u);
+        v[4] = __uint_as_float(w.z << 16); v[5] = __uint_as_float(w.z & 0xffff0000u);
+        v[6] = __uint_as_float(w.w << 16); v[7] = __uint_as_float(w.w & 0xffff0000u);
+    }
+}
+template <int VEC, bool BF16>
+__device__ __forceinline__ void ld_pq(const void *base, size_t elem, float *v) {
+    if constexpr (BF16) ld_bf16<VEC>(reinterpret_cast<const __nv_bfloat16 *>(base) + elem, v);
+    else VecIO<VEC>::ld(reinterpret_cast<const float *>(base) + elem, v);
+}
+
 struct FwdArgs {
-    const float *pq;       // [B][N][2*Cout]
+    const void *pq;        // [B][N][2*Cout] fp32, or bf16 in the bf16-storage mode
     const int32_t *idx;    // [B][N][k]
     const float *gamma;    // [Cout]  only its sign is used: the extreme that survives max_k(LReLU(GN(.)))
     float *ysel, *ysum;    // [B][N][Cout]  selected pre-norm value (max_k y if gamma >= 0 else min_k y), sum_k y
@@ -449,17 +478,16 @@ __device__ __forceinline__ void edge_accumulate(const float *p, const float *sg,
     }
 }
 
-template <int VEC>
+template <int VEC, bool BF16 = false>
 __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArgs a) {
     __shared__ double red[kGWarps * 32][2];
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Cout = a.Cout, k = a.k;
     const int c0 = lane * VEC;
-    const float *pq = a.pq + (size_t)b * a.N * 2 * Cout;
     // rows are addressed with 32-bit element offsets inside the cloud's [N][2 Cout] matrix (N * 2 Cout < 2^30, checked
     // by check_desc): two instructions per edge instead of a seven-instruction 64-bit multiply
-    const float *pq_c0 = pq + c0;
+    const size_t cloud0 = (size_t)b * a.N * 2 * Cout;
     const unsigned row_stride = 2u * (unsigned)Cout;
     double s1 = 0.0, s2 = 0.0;
     float sg[VEC];
@@ -475,7 +503,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
         // sg * sum_k z and y^2 = z^2 -- one instruction per edge and channel less than forming y first
         float q[VEC], zmax[VEC], vsum[VEC], vsq[VEC];
         int kbest[VEC];
-        VecIO<VEC>::ld(pq + (size_t)i * 2 * Cout + Cout + c0, q);
+        ld_pq<VEC, BF16>(a.pq, cloud0 + (size_t)i * 2 * Cout + Cout + c0, q);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { zmax[v] = -CUDART_INF_F; vsum[v] = 0.f; vsq[v] = 0.f; kbest[v] = 0; q[v] *= sg[v]; }
         const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
@@ -488,7 +516,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     int j = __shfl_sync(FULLM, myj, t + u);
-                    VecIO<VEC>::ld(pq_c0 + (unsigned)j * row_stride, p[u]);
+                    ld_pq<VEC, BF16>(a.pq, cloud0 + c0 + (unsigned)j * row_stride, p[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) edge_accumulate<VEC>(p[u], sg, q, zmax, kbest, vsum, vsq, base + t + u);
@@ -496,7 +524,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
             for (; t < cnt; ++t) {
                 float p[VEC];
                 int j = __shfl_sync(FULLM, myj, t);
-                VecIO<VEC>::ld(pq_c0 + (unsigned)j * row_stride, p);
+                ld_pq<VEC, BF16>(a.pq, cloud0 + c0 + (unsigned)j * row_stride, p);
                 edge_accumulate<VEC>(p, sg, q, zmax, kbest, vsum, vsq, base + t);
             }
         }
@@ -629,8 +657,19 @@ __global__ void __launch_bounds__(256) edge_finish_wide_kernel(const float *__re
 // ---------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------
+// four consecutive elements of [P|Q], stored fp32 or bf16
+__device__ __forceinline__ float4 ld4_pq(const void *base, size_t elem, int bf16) {
+    if (bf16) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const __nv_bfloat16 *>(base) + elem));
+        return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                           __uint_as_float(w.y & 0xffff0000u));
+    }
+    return *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(base) + elem);
+}
+
 struct BwdArgs {
-    const float *pq, *ysel, *ysum, *stats, *gamma, *beta, *gout;
+    const void *pq;        // [B][N][2*Cout] fp32, or bf16 when pq_bf16
+    const float *ysel, *ysum, *stats, *gamma, *beta, *gout;
     const unsigned char *arg;
     const int32_t *idx;
     float *part;       // [B][nblk][Cout][2]  per-CTA sums of du, du*yhat
@@ -641,6 +680,7 @@ struct BwdArgs {
     float slope;
     const float *x_nc; // [B][N][LDX]  small-C variant only
     float *xt;         // [B][N][LDX]  small-C variant only: sum of x_i over the in-edges (i -> j)
+    int pq_bf16;
 };
 
 template <int VEC>
@@ -754,7 +794,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_kernel(BwdArgs 
     VecIO<VEC>::ld(a.gamma + c0, gm);
     VecIO<VEC>::ld(a.beta + c0, bt);
     float *dpq = a.dpq + (size_t)b * a.N * 2 * Cout;
-    const float *pq = a.pq + (size_t)b * a.N * 2 * Cout;
+    const size_t cloud0 = (size_t)b * a.N * 2 * Cout;
     float *dpq_c0 = dpq + c0;                              // 32-bit row offsets, as in the gather
     const unsigned row_stride = 2u * (unsigned)Cout;
     for (int pi = 0; pi < kPtsPerWarp; ++pi) {
@@ -766,7 +806,8 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_kernel(BwdArgs 
         VecIO<VEC>::ld(a.ysel + o, ys);
         VecIO<VEC>::ld(a.gout + o, gg);
         VecIO<VEC>::ld(a.ysum + o, ysum);
-        VecIO<VEC>::ld(pq + (size_t)i * 2 * Cout + Cout + c0, q);
+        if (a.pq_bf16) ld_pq<VEC, true>(a.pq, cloud0 + (size_t)i * 2 * Cout + Cout + c0, q);
+        else ld_pq<VEC, false>(a.pq, cloud0 + (size_t)i * 2 * Cout + Cout + c0, q);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             ak[v] = a.arg[o + v];
@@ -851,7 +892,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_small_kernel(Bw
 
 // dP[j][c] += deg_j (A_g + K_g P[j][c]) + K_g sum_c' Wq[c'][c] X~_j[c'],  Wq[c'][c] = wcatT[Cout + c][c']
 template <int LDX>
-__global__ void edge_bwd_degfix_small_kernel(float *__restrict__ dpq, const float *__restrict__ pq, const int *__restrict__ deg,
+__global__ void edge_bwd_degfix_small_kernel(float *__restrict__ dpq, const void *__restrict__ pq, int pq_bf16, const int *__restrict__ deg,
                                              const float *__restrict__ coef, const float *__restrict__ xt,
                                              const float *__restrict__ wcatT, int N, int Cout, int G, long long total4) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -868,7 +909,7 @@ __global__ void edge_bwd_degfix_small_kernel(float *__restrict__ dpq, const floa
         float4 v = *reinterpret_cast<const float4 *>(xt + bn * LDX + q4 * 4);
         x[q4 * 4] = v.x; x[q4 * 4 + 1] = v.y; x[q4 * 4 + 2] = v.z; x[q4 * 4 + 3] = v.w;
     }
-    float4 p = *reinterpret_cast<const float4 *>(pq + bn * 2 * Cout + c);
+    float4 p = ld4_pq(pq, bn * 2 * Cout + c, pq_bf16);
     float4 *o = reinterpret_cast<float4 *>(dpq + bn * 2 * Cout + c);
     float4 v = *o;
     const float pv[4] = {p.x, p.y, p.z, p.w};
@@ -942,7 +983,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_mid_kernel(BwdA
 }
 
 // dP[j][c] += deg_j (A_g + K_g P[j][c]) + K_g (X~ Wq^T)[j][c]
-__global__ void edge_bwd_degfix_mid_kernel(float *__restrict__ dpq, const float *__restrict__ pq, const int *__restrict__ deg,
+__global__ void edge_bwd_degfix_mid_kernel(float *__restrict__ dpq, const void *__restrict__ pq, int pq_bf16, const int *__restrict__ deg,
                                            const float *__restrict__ coef, const float *__restrict__ xq, int N, int Cout,
                                            int G, long long total4) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -953,7 +994,7 @@ __global__ void edge_bwd_degfix_mid_kernel(float *__restrict__ dpq, const float 
     int b = (int)(bn / N);
     const float Ag = coef[((size_t)b * G + c / (Cout / G)) * 2 + 0], Kg = coef[((size_t)b * G + c / (Cout / G)) * 2 + 1];
     const float dg = (float)deg[bn];
-    float4 p = *reinterpret_cast<const float4 *>(pq + bn * 2 * Cout + c);
+    float4 p = ld4_pq(pq, bn * 2 * Cout + c, pq_bf16);
     float4 x = *reinterpret_cast<const float4 *>(xq + bn * Cout + c);
     float4 *o = reinterpret_cast<float4 *>(dpq + bn * 2 * Cout + c);
     float4 v = *o;
@@ -965,7 +1006,7 @@ __global__ void edge_bwd_degfix_mid_kernel(float *__restrict__ dpq, const float 
 }
 
 // dP[j][c] += deg_j * K_g * P[j][c]
-__global__ void edge_bwd_degfix_kernel(float *__restrict__ dpq, const float *__restrict__ pq, const int *__restrict__ deg,
+__global__ void edge_bwd_degfix_kernel(float *__restrict__ dpq, const void *__restrict__ pq, int pq_bf16, const int *__restrict__ deg,
                                        const float *__restrict__ coef, int N, int Cout, int G, long long total4) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total4) return;
@@ -975,7 +1016,7 @@ __global__ void edge_bwd_degfix_kernel(float *__restrict__ dpq, const float *__r
     int b = (int)(bn / N);
     const float Kg = coef[((size_t)b * G + c / (Cout / G)) * 2 + 1];
     const float d = (float)deg[bn] * Kg;
-    float4 p = *reinterpret_cast<const float4 *>(pq + bn * 2 * Cout + c);
+    float4 p = ld4_pq(pq, bn * 2 * Cout + c, pq_bf16);
     float4 *o = reinterpret_cast<float4 *>(dpq + bn * 2 * Cout + c);
     float4 v = *o;
     v.x = fmaf(d, p.x, v.x); v.y = fmaf(d, p.y, v.y); v.z = fmaf(d, p.z, v.z); v.w = fmaf(d, p.w, v.w);
@@ -986,14 +1027,14 @@ __global__ void edge_bwd_degfix_kernel(float *__restrict__ dpq, const float *__r
 // buffer plans
 // ---------------------------------------------------------------------------------
 struct Saved {
-    float *pq, *ysel, *ysum, *stats;
+    float *pq, *ysel, *ysum, *stats;      // pq: fp32, or bf16 (half the bytes) when d->storage_bf16
     unsigned char *arg;
 };
 
 static size_t plan_saved(const gcanet_edgeconv_desc *d, void *base, Saved *s) {
     Carver cv(base);
     size_t bn = (size_t)d->B * d->N;
-    float *pq = cv.take<float>(bn * 2 * d->Cout);
+    float *pq = d->storage_bf16 ? reinterpret_cast<float *>(cv.take<__nv_bfloat16>(bn * 2 * d->Cout)) : cv.take<float>(bn * 2 * d->Cout);
     float *ysel = cv.take<float>(bn * d->Cout);
     float *ysum = cv.take<float>(bn * d->Cout);
     unsigned char *arg = cv.take<unsigned char>(bn * d->Cout);
@@ -1005,6 +1046,7 @@ static size_t plan_saved(const gcanet_edgeconv_desc *d, void *base, Saved *s) {
 struct FwdWs {
     float *wcat, *wcatT;
     double *part;
+    float *pq32;       // bf16 storage: fp32 staging of [P|Q] where the projection runs on the CUDA cores (xyz layer)
 };
 
 static size_t plan_fwd(const gcanet_edgeconv_desc *d, void *base, FwdWs *w) {
@@ -1013,7 +1055,8 @@ static size_t plan_fwd(const gcanet_edgeconv_desc *d, void *base, FwdWs *w) {
     float *wcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
     float *wcatT = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
     double *part = cv.take<double>((size_t)d->B * nblk * d->groups * 2);
-    if (w) { w->wcat = wcat; w->wcatT = wcatT; w->part = part; }
+    float *pq32 = cv.take<float>(d->storage_bf16 ? (size_t)d->B * d->N * 2 * d->Cout : 0);
+    if (w) { w->wcat = wcat; w->wcatT = wcatT; w->part = part; w->pq32 = pq32; }
     return cv.off;
 }
 
@@ -1071,6 +1114,14 @@ static int check_desc(const gcanet_edgeconv_desc *d) {
     return GCANET_OK;
 }
 
+// [P|Q] staging for the bf16-storage mode (xyz layer, whose projection runs on the CUDA cores): four floats -> four bf16
+__global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2 *>(dst)[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+}
 template <int VEC>
 static int run_forward(const gcanet_edgeconv_desc *d, const float *x_nc, const int32_t *idx, const float *weight,
                        const float *gamma, const float *beta, float *out_nc, float *out_cn, const Saved &sv,
@@ -1080,12 +1131,21 @@ static int run_forward(const gcanet_edgeconv_desc *d, const float *x_nc, const i
     prep_wcat_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, w.wcat, w.wcatT, d->C, d->ldx, Cout);
     GCANET_LAUNCH_OK("prep_wcat_kernel");
     // [P|Q] = X Wcat: tensor cores (bf16x3 split, fp32-accurate) for the feature layers, CUDA cores for the xyz layer
-    int rc = gemm_tc_try(x_nc, d->ldx, w.wcatT, d->ldx, sv.pq, 2 * Cout, M, 2 * Cout, d->ldx, st);
-    if (rc > 0) rc = launch_sgemm_nn(x_nc, w.wcat, sv.pq, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, 2 * Cout, st);
+    int rc = gemm_tc_try(x_nc, d->ldx, w.wcatT, d->ldx, sv.pq, 2 * Cout, M, 2 * Cout, d->ldx, st, d->storage_bf16);
+    if (rc > 0) {
+        float *dst = d->storage_bf16 ? w.pq32 : sv.pq;
+        rc = launch_sgemm_nn(x_nc, w.wcat, dst, M, 2 * Cout, d->ldx, d->ldx, 2 * Cout, 2 * Cout, st);
+        if (rc == GCANET_OK && d->storage_bf16) {
+            const long long n4 = (long long)M * 2 * Cout / 4;
+            f32_to_bf16_kernel<<<(unsigned)ceil_div64(n4, 256), 256, 0, st>>>(w.pq32, reinterpret_cast<__nv_bfloat16 *>(sv.pq), n4);
+            GCANET_LAUNCH_OK("f32_to_bf16_kernel");
+        }
+    }
     if (rc) return rc;
     FwdArgs fa{sv.pq, idx, gamma, sv.ysel, sv.ysum, sv.arg, w.part, d->N, Cout, d->k, d->groups};
     const int nblk = ceil_div(d->N, kPtsPerCta);
-    edge_gather_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(fa);
+    if (d->storage_bf16) edge_gather_reduce_kernel<VEC, true><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(fa);
+    else edge_gather_reduce_kernel<VEC, false><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(fa);
     GCANET_LAUNCH_OK("edge_gather_reduce_kernel");
     double count = (double)(Cout / d->groups) * d->N * d->k;
     gn_stats_kernel<<<d->B, 32 * d->groups, 0, st>>>(w.part, sv.stats, nblk, d->groups, count, d->eps);
@@ -1120,8 +1180,10 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     const bool small = d->ldx == 4 || d->ldx == 8;
     const bool mid = bwd_mid_path(d);
     if (small || mid) GCANET_CUDA_OK(cudaMemsetAsync(w.xt, 0, bn * d->ldx * sizeof(float), st));
-    BwdArgs ba{sv.pq, sv.ysel, sv.ysum, sv.stats, gamma, beta, gout, sv.arg, idx, w.part, w.coef, w.dpq, w.deg,
-               d->N, Cout, d->k, d->groups, d->slope, x_nc, w.xt};
+    const void *pq32 = sv.pq;                 // the backward kernels read [P|Q] per point, in the precision it was saved in
+    const int pqb = d->storage_bf16;
+    BwdArgs ba{pq32, sv.ysel, sv.ysum, sv.stats, gamma, beta, gout, sv.arg, idx, w.part, w.coef, w.dpq, w.deg,
+               d->N, Cout, d->k, d->groups, d->slope, x_nc, w.xt, pqb};
     edge_bwd_reduce_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
     GCANET_LAUNCH_OK("edge_bwd_reduce_kernel");
     double count = (double)(Cout / d->groups) * d->N * d->k;
@@ -1137,10 +1199,10 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
         else edge_bwd_scatter_small_kernel<VEC, 8><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
         GCANET_LAUNCH_OK("edge_bwd_scatter_small_kernel");
         if (d->ldx == 4)
-            edge_bwd_degfix_small_kernel<4><<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, w.xt, w.wcatT,
+            edge_bwd_degfix_small_kernel<4><<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, pq32, pqb, w.deg, w.coef, w.xt, w.wcatT,
                                                                                            d->N, Cout, d->groups, total4);
         else
-            edge_bwd_degfix_small_kernel<8><<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, w.xt, w.wcatT,
+            edge_bwd_degfix_small_kernel<8><<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, pq32, pqb, w.deg, w.coef, w.xt, w.wcatT,
                                                                                            d->N, Cout, d->groups, total4);
         GCANET_LAUNCH_OK("edge_bwd_degfix_small_kernel");
     } else if (mid) {
@@ -1151,14 +1213,14 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
             int rq = gemm_tc_try(w.xt, d->ldx, w.wcatT + (size_t)Cout * d->ldx, d->ldx, w.xq, Cout, M, Cout, d->ldx, st);
             if (rq > 0) rq = launch_sgemm_nn(w.xt, w.wcat + Cout, w.xq, M, Cout, d->ldx, d->ldx, 2 * Cout, Cout, st);
             if (rq) return rq;
-            edge_bwd_degfix_mid_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, w.xq, d->N,
+            edge_bwd_degfix_mid_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, pq32, pqb, w.deg, w.coef, w.xq, d->N,
                                                                                         Cout, d->groups, total4);
             GCANET_LAUNCH_OK("edge_bwd_degfix_mid_kernel");
         }
     } else {
         edge_bwd_scatter_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
         GCANET_LAUNCH_OK("edge_bwd_scatter_kernel");
-        edge_bwd_degfix_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, sv.pq, w.deg, w.coef, d->N, Cout,
+        edge_bwd_degfix_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(w.dpq, pq32, pqb, w.deg, w.coef, d->N, Cout,
                                                                                 d->groups, total4);
         GCANET_LAUNCH_OK("edge_bwd_degfix_kernel");
     }

@@ -60,7 +60,8 @@ __device__ __forceinline__ void split_store4(uint8_t *hi_tile, uint8_t *lo_tile,
 template <int K, int N>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ Bt, int ldb, float *__restrict__ C, int ldc, int M,
-               long long batch_a, long long batch_b, long long batch_c, const float *__restrict__ cbias, int batch_bias) {
+               long long batch_a, long long batch_b, long long batch_c, const float *__restrict__ cbias, int batch_bias,
+               int out_bf16) {
     // batched use (blockIdx.y = batch): every batch has its own M x K rows of A, its own weights and, optionally, a row
     // vector cbias[batch][N] added to every output row; element strides between batches are passed in
     A += (size_t)blockIdx.y * batch_a;
@@ -200,12 +201,25 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * N;
             float *crow = C + (size_t)row * ldc;
+            __nv_bfloat16 *hrow = reinterpret_cast<__nv_bfloat16 *>(C) + (size_t)row * ldc;     // out_bf16: C is a bf16 matrix
 #pragma unroll 1
             for (int ch = 0; ch < N / 32; ++ch) {
                 uint32_t v[32];
                 tmem_ld32(taddr + ch * 32, v);
                 tmem_ld_wait();
-                if (row < M) {
+                if (row < M && out_bf16) {
+                    // rounded to bf16 where it is produced: 32 columns = 64 bytes = four 16-byte stores
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+                            w[e] = *reinterpret_cast<const uint32_t *>(&h2);
+                        }
+                        *reinterpret_cast<uint4 *>(hrow + ch * 32 + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                } else if (row < M) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         float4 o = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
@@ -236,7 +250,7 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
 template <int K, int N>
 static int launch_gemm_tc(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, cudaStream_t st,
                           int batches = 1, long long batch_a = 0, long long batch_b = 0, long long batch_c = 0,
-                          const float *cbias = nullptr, int batch_bias = 0) {
+                          const float *cbias = nullptr, int batch_bias = 0, int out_bf16 = 0) {
     constexpr int KCH = K / GT_KB;
     constexpr int GT_STAGES = gt_stages(K, N);
     const size_t smem = 1024 + (size_t)2 * KCH * N * 128 + (size_t)GT_STAGES * 2 * GT_BM * 128 + 32 * sizeof(uint64_t);
@@ -245,7 +259,7 @@ static int launch_gemm_tc(const float *A, int lda, const float *Bt, int ldb, flo
     const int ntiles = ceil_div(M, GT_BM);
     int ctas = ntiles < kNumSMs ? ntiles : kNumSMs;
     if (batches > 1) ctas = ctas < ceil_div(2 * kNumSMs, batches) ? ctas : ceil_div(2 * kNumSMs, batches);
-    kern<<<dim3(ctas, batches), GT_THREADS, smem, st>>>(A, lda, Bt, ldb, C, ldc, M, batch_a, batch_b, batch_c, cbias, batch_bias);
+    kern<<<dim3(ctas, batches), GT_THREADS, smem, st>>>(A, lda, Bt, ldb, C, ldc, M, batch_a, batch_b, batch_c, cbias, batch_bias, out_bf16);
     GCANET_LAUNCH_OK("gemm_tc_kernel");
     return GCANET_OK;
 }
@@ -254,11 +268,13 @@ static int launch_gemm_tc(const float *A, int lda, const float *Bt, int ldb, flo
 // (K, N in {64, 128, 256}, 16-byte aligned rows); returns +1 (GEMM_TC_NOT_COVERED, never a
 // negative gcanet_status) when the shape is not covered and the caller should use the CUDA-core GEMM; a negative return is
 // a real error and must be propagated.
-int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K, cudaStream_t st) {
-    if (M < 1024 || lda % 4 || ldb % 4 || ldc % 4) return 1;
+// out_bf16 != 0: C is a bf16 matrix [M][ldc] (ldc in elements, a multiple of 8), written rounded to nearest.
+int gemm_tc_try(const float *A, int lda, const float *Bt, int ldb, float *C, int ldc, int M, int N, int K, cudaStream_t st,
+                int out_bf16) {
+    if (M < 1024 || lda % 4 || ldb % 4 || ldc % (out_bf16 ? 8 : 4)) return 1;
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt) | reinterpret_cast<uintptr_t>(C)) & 15) return 1;
     if (GCANET_AID_ENV("GCANET_NO_TC_GEMM")) return 1;        // measurement aid
-#define GT_CASE(KK, NN) if (K == KK && N == NN) return launch_gemm_tc<KK, NN>(A, lda, Bt, ldb, C, ldc, M, st)
+#define GT_CASE(KK, NN) if (K == KK && N == NN) return launch_gemm_tc<KK, NN>(A, lda, Bt, ldb, C, ldc, M, st, 1, 0, 0, 0, nullptr, 0, out_bf16)
     GT_CASE(64, 128);
     GT_CASE(64, 256);
     GT_CASE(128, 128);

@@ -344,7 +344,7 @@ class _EdgeConv(torch.autograd.Function):
     """out_nc, out_cn = EdgeConv(x_nc, idx32, weight [Cout, 2C], gamma, beta)."""
 
     @staticmethod
-    def forward(ctx, x_nc, idx32, weight, gamma, beta, C, groups, eps, slope, want_cn):
+    def forward(ctx, x_nc, idx32, weight, gamma, beta, C, groups, eps, slope, want_cn, storage_bf16):
         require_cuda(x_nc, "x_nc", torch.float32)
         require_cuda(idx32, "idx", torch.int32)
         weight = weight.contiguous()
@@ -358,7 +358,7 @@ class _EdgeConv(torch.autograd.Function):
             raise RuntimeError(f"weight must be [Cout, {2 * C}] (got {tuple(weight.shape)})")
         if tuple(idx32.shape[:2]) != (B, N):
             raise RuntimeError(f"idx must be [B, N, k] (got {tuple(idx32.shape)})")
-        desc = EdgeConvDesc(B, N, C, ldx, Cout, k, groups, eps, slope)
+        desc = EdgeConvDesc(B, N, C, ldx, Cout, k, groups, eps, slope, 1 if storage_bf16 else 0)
         L = _cabi.lib()
         with torch.cuda.device(x_nc.device):
             saved_bytes = L.gcanet_edgeconv_saved_bytes(_ct.byref(desc))
@@ -398,18 +398,23 @@ class _EdgeConv(torch.autograd.Function):
             with _timed(f"edgeconv_bwd[C={desc.C},Cout={desc.Cout}]"):
                 call("gcanet_edgeconv_backward", _ct.byref(desc), ptr(x_nc), ptr(idx32), ptr(weight), ptr(gamma),
                      ptr(beta), ptr(g), ptr(saved), ptr(gx), ptr(gw), ptr(gg), ptr(gb), ptr(ws), ws.numel(), stream())
-        return gx, None, gw, gg, gb, None, None, None, None, None
+        return gx, None, gw, gg, gb, None, None, None, None, None, None
 
 
-def edgeconv(x_nc, idx32, weight, gamma, beta, C, groups=2, eps=1e-5, slope=0.2, want_cn=True):
+def edgeconv(x_nc, idx32, weight, gamma, beta, C, groups=2, eps=1e-5, slope=0.2, want_cn=True, storage="fp32"):
     """Fused replacement of ``get_graph_feature(x, idx=idx) -> Conv2d(2C, Cout, 1, bias=False) ->
     GroupNorm(groups, Cout) -> LeakyReLU(slope) -> max over k`` (M4:469-481, M4:494-505).
 
     x_nc [B, N, ld] point-major (``to_point_major``), idx32 [B, N, k] int32, weight [Cout, 2C]
     (or the conv's [Cout, 2C, 1, 1]).  Returns (out_nc [B, N, Cout], out_cn [B, Cout, N] or None);
-    differentiable in x_nc, weight, gamma, beta."""
+    differentiable in x_nc, weight, gamma, beta.  ``storage="bf16"`` keeps the projected operand [P|Q] in bf16 (the
+    "bf16 activations" mode of BASELINE configs[1]: half the gather traffic and half the saved bytes, outputs within bf16
+    rounding of the pre-norm activation); the default "fp32" is the parity mode."""
+    if storage not in ("fp32", "bf16"):
+        raise ValueError("storage must be 'fp32' or 'bf16'")
     w2 = weight.reshape(weight.shape[0], -1)
-    return _EdgeConv.apply(x_nc, idx32, w2, gamma, beta, int(C), int(groups), float(eps), float(slope), bool(want_cn))
+    return _EdgeConv.apply(x_nc, idx32, w2, gamma, beta, int(C), int(groups), float(eps), float(slope), bool(want_cn),
+                           storage == "bf16")
 
 
 class _NormalEdgeConv(torch.autograd.Function):

@@ -49,6 +49,9 @@ class DGCNNEncoderGn(nn.Module):
         # layers used, order unspecified) in last_graphs: the parity tests feed them to the oracle's idx= argument
         self.keep_graphs = False
         self.last_graphs = []
+        # "fp32" (parity mode, default) or "bf16": storage precision of the projected operand [P|Q] of the three EdgeConv
+        # layers (functional.edgeconv); set after construction, it is not part of the reference's signature
+        self.storage = "fp32"
 
     # -- hot path ------------------------------------------------------------------
     def _block(self, x_nc, x_cn, conv, C, metric):
@@ -58,7 +61,7 @@ class DGCNNEncoderGn(nn.Module):
             self.last_graphs.append(idx32)
         gn = conv[1]
         return G.edgeconv(x_nc, idx32, conv[0].weight, gn.weight, gn.bias, C, groups=gn.num_groups, eps=gn.eps,
-                          slope=conv[2].negative_slope, want_cn=True)
+                          slope=conv[2].negative_slope, want_cn=True, storage=self.storage)
 
     def _stack(self, x):
         """x [B, C, N] -> ((x1, x2, x3) channel-major, (x1_nc, x2_nc, x3_nc) point-major)."""

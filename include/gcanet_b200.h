@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GCANET_ABI_VERSION 1
+#define GCANET_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GCANET_API __attribute__((visibility("default")))
@@ -184,6 +184,11 @@ typedef struct {
     int B, N, C, ldx, Cout, k, groups;
     float eps;   /* GroupNorm epsilon, reference 1e-5 */
     float slope; /* LeakyReLU negative slope, reference 0.2 */
+    /* 0: the projected operand [P|Q] is kept in fp32 (parity mode, default).  1: it is rounded to bf16 where the projection
+     * GEMM writes it ("bf16 activations" of BASELINE configs[1]): the gather reads half the bytes, the saved tensor is half
+     * the size; accumulation, GroupNorm statistics and every gradient stay fp32.  Outputs then agree with the reference
+     * to bf16 rounding of the pre-norm activation (2^-9 relative), see tests/test_gpu_bf16.py. */
+    int storage_bf16;
 } gcanet_edgeconv_desc;
 
 GCANET_API size_t gcanet_edgeconv_saved_bytes(const gcanet_edgeconv_desc *d);

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_status_strings():
     L = _cabi.lib()
-    assert L.gcanet_abi_version() == 1
+    assert L.gcanet_abi_version() == 2
     assert L.gcanet_status_string(0) == b"ok"
     assert b"workspace" in L.gcanet_status_string(-2)
 

@@ -54,8 +54,9 @@ def test_offset_module_golden_fixture(golden_dir):
     print(f"forward: max {float(d.max()):.2e}, points above 2e-4: {float((d.amax(dim=1) > 2e-4).float().mean()):.2%}")
     assert float((d.amax(dim=1) > 2e-4).float().mean()) < 0.02
     (out * _t(fx["cot"]).to(DEV)).sum().backward()
-    _compare_points("grad feature", feat.grad, _t(fx["grad.feature"]))
-    _compare_points("grad inst", inst.grad, _t(fx["grad.inst"]))
+    # 120 of the fixture's 300 points per cloud are keys: one swapped neighbour shifts the rows of the keys involved
+    _compare_points("grad feature", feat.grad, _t(fx["grad.feature"]), max_frac=0.05)
+    _compare_points("grad inst", inst.grad, _t(fx["grad.inst"]), max_frac=0.05)
     for name, p in mod.named_parameters():
         _compare(f"grad {name}", p.grad, _t(fx[f"grad.{name}"]), 5e-2, 5e-4)
     assert torch.equal(mod.key_index(300, DEV).cpu().long(), orc.offset_key_indices(300, 120))
