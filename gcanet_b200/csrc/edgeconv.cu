@@ -438,6 +438,14 @@ __device__ __forceinline__ void ld_pq(const void *base, size_t elem, float *v) {
     if constexpr (BF16) ld_bf16<VEC>(reinterpret_cast<const __nv_bfloat16 *>(base) + elem, v);
     else VecIO<VEC>::ld(reinterpret_cast<const float *>(base) + elem, v);
 }
+// row j of a matrix whose rows are `stride_bytes` apart, from a byte pointer to row 0: one IMAD.WIDE.U32 per address
+// (a typed pointer plus a 32-bit element offset costs five instructions: multiply, add, carry, shift, high word)
+template <int VEC, bool BF16>
+__device__ __forceinline__ void ld_pq_row(const char *row0, unsigned j, unsigned stride_bytes, float *v) {
+    const char *p = row0 + (unsigned long long)j * stride_bytes;
+    if constexpr (BF16) ld_bf16<VEC>(reinterpret_cast<const __nv_bfloat16 *>(p), v);
+    else VecIO<VEC>::ld(reinterpret_cast<const float *>(p), v);
+}
 
 struct FwdArgs {
     const void *pq;        // [B][N][2*Cout] fp32, or bf16 in the bf16-storage mode
@@ -488,7 +496,10 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
     // rows are addressed with 32-bit element offsets inside the cloud's [N][2 Cout] matrix (N * 2 Cout < 2^30, checked
     // by check_desc): two instructions per edge instead of a seven-instruction 64-bit multiply
     const size_t cloud0 = (size_t)b * a.N * 2 * Cout;
-    const unsigned row_stride = 2u * (unsigned)Cout;
+    constexpr unsigned ELEM = BF16 ? 2u : 4u;
+    const char *row0 = reinterpret_cast<const char *>(a.pq) + (cloud0 + c0) * ELEM;      // channel c0 of the cloud's first row
+    asm volatile("" : "+l"(row0));        // one 64-bit register pair: keeps the compiler from re-adding the kernel argument per edge
+    const unsigned stride_b = 2u * (unsigned)Cout * ELEM;
     double s1 = 0.0, s2 = 0.0;
     float sg[VEC];
     VecIO<VEC>::ld(a.gamma + c0, sg);
@@ -516,7 +527,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     int j = __shfl_sync(FULLM, myj, t + u);
-                    ld_pq<VEC, BF16>(a.pq, cloud0 + c0 + (unsigned)j * row_stride, p[u]);
+                    ld_pq_row<VEC, BF16>(row0, (unsigned)j, stride_b, p[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) edge_accumulate<VEC>(p[u], sg, q, zmax, kbest, vsum, vsq, base + t + u);
@@ -524,7 +535,7 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
             for (; t < cnt; ++t) {
                 float p[VEC];
                 int j = __shfl_sync(FULLM, myj, t);
-                ld_pq<VEC, BF16>(a.pq, cloud0 + c0 + (unsigned)j * row_stride, p);
+                ld_pq_row<VEC, BF16>(row0, (unsigned)j, stride_b, p);
                 edge_accumulate<VEC>(p, sg, q, zmax, kbest, vsum, vsq, base + t);
             }
         }
@@ -795,7 +806,9 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_scatter_kernel(BwdArgs 
     VecIO<VEC>::ld(a.beta + c0, bt);
     float *dpq = a.dpq + (size_t)b * a.N * 2 * Cout;
     const size_t cloud0 = (size_t)b * a.N * 2 * Cout;
-    float *dpq_c0 = dpq + c0;                              // 32-bit row offsets, as in the gather
+    // (the one-instruction byte addressing of the gather was tried here: the vector reductions then issue faster than the
+    // L2 atomic units retire them and the kernel got SLOWER, 0.36 -> 0.51 ms; the typed form stays)
+    float *dpq_c0 = dpq + c0;                              // 32-bit row offsets
     const unsigned row_stride = 2u * (unsigned)Cout;
     for (int pi = 0; pi < kPtsPerWarp; ++pi) {
         const int i = blockIdx.x * kPtsPerCta + warp * kPtsPerWarp + pi;
