@@ -58,6 +58,19 @@ class _timed:
         return False
 
 
+# Gradient sinks (gcanet_b200.parallel.GradBucket.attach_sinks): parameter storage address -> the slice of a flat
+# all-reduce bucket shaped like the parameter.  A fused backward that finds a sink writes the parameter's gradient
+# straight into the bucket, so nothing has to be packed before the collective or copied back after it.
+_grad_sinks: dict = {}
+
+
+def _grad_buffer(param_like: torch.Tensor) -> torch.Tensor:
+    sink = _grad_sinks.get(param_like.data_ptr())
+    if sink is not None and sink.numel() == param_like.numel() and sink.device == param_like.device:
+        return sink.view(param_like.shape)
+    return torch.empty_like(param_like)
+
+
 def _as_f32_contig(x: torch.Tensor, name: str) -> torch.Tensor:
     require_cuda(x, name, contiguous=False)
     if x.dtype != torch.float32:
@@ -391,9 +404,7 @@ class _EdgeConv(torch.autograd.Function):
                 g = torch.zeros((desc.B, desc.N, desc.Cout), dtype=torch.float32, device=x_nc.device)
             need_x = ctx.needs_input_grad[0]
             gx = torch.empty_like(x_nc) if need_x else None
-            gw = torch.empty_like(weight)
-            gg = torch.empty_like(gamma)
-            gb = torch.empty_like(beta)
+            gw, gg, gb = _grad_buffer(weight), _grad_buffer(gamma), _grad_buffer(beta)
             ws = workspace(L.gcanet_edgeconv_workspace_bytes(_ct.byref(desc)), x_nc.device)
             with _timed(f"edgeconv_bwd[C={desc.C},Cout={desc.Cout}]"):
                 call("gcanet_edgeconv_backward", _ct.byref(desc), ptr(x_nc), ptr(idx32), ptr(weight), ptr(gamma),

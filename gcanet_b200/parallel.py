@@ -81,6 +81,25 @@ class GradBucket:
         self._zeros = None
         self._flag_cache = {}
 
+    def attach_sinks(self):
+        """Let the fused backward kernels write parameter gradients directly into this bucket (functional._grad_sinks):
+        autograd then adopts the bucket slice as ``p.grad`` and ``all_reduce_mean`` finds nothing to pack or to copy
+        back.  Safe with any caller: a gradient that did not land in its slice (another code path, accumulation into an
+        existing ``.grad``) is packed and scattered back the ordinary way.  Callers must reset ``p.grad = None`` before
+        each backward -- accumulating into the slice a kernel is about to overwrite would double-count."""
+        from . import functional as G
+        for p, o in zip(self.params, self.offsets):
+            G._grad_sinks[p.data_ptr()] = self.flat[o:o + p.numel()]
+        return self
+
+    def detach_sinks(self):
+        from . import functional as G
+        for p in self.params:
+            G._grad_sinks.pop(p.data_ptr(), None)
+
+    def _in_place(self, p, o):
+        return p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr() + 4 * o and p.grad.is_contiguous()
+
     def _flags(self, present):
         key = tuple(present)
         t = self._flag_cache.get(key)
@@ -97,8 +116,12 @@ class GradBucket:
         if self._zeros is None:
             self._zeros = [torch.zeros(p.numel(), dtype=torch.float32, device=self.flat.device) for p in self.params]
         present = [p.grad is not None for p in self.params]
-        srcs = [z if p.grad is None else p.grad.reshape(-1) for p, z in zip(self.params, self._zeros)]
-        torch.cat(srcs + [self._flags(present)], out=self.flat)
+        if all(self._in_place(p, o) for p, o in zip(self.params, self.offsets)):
+            # every gradient was written into its slice by the backward kernels (attach_sinks): only the flags are set
+            self.flat[self.numel:].copy_(self._flags(present))
+        else:
+            srcs = [z if p.grad is None else p.grad.reshape(-1) for p, z in zip(self.params, self._zeros)]
+            torch.cat(srcs + [self._flags(present)], out=self.flat)
         in_collective = dist.get_backend(group) == "nccl"
         op = dist.ReduceOp.AVG if in_collective else dist.ReduceOp.SUM
         work = dist.all_reduce(self.flat, op=op, group=group, async_op=async_op)
@@ -120,6 +143,8 @@ class GradBucket:
             if not some:
                 continue
             view = self.flat[o:o + p.numel()].view_as(p)
+            if here and self._in_place(p, o):
+                continue                                # p.grad IS the slice: the collective already averaged it
             if here:
                 dsts.append(p.grad)
                 views.append(view.view_as(p.grad))
