@@ -5,6 +5,9 @@ all compute is in libgcanet_b200.so behind the C-ABI of include/gcanet_b200.h.
 """
 from .functional import (  # noqa: F401
     KNN,
+    affinity_ball_query,
+    ball_query,
+    compute_batch_adjacency_matrix,
     GroupingOperation,
     edgeconv,
     get_graph_feature,

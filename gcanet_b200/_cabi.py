@@ -90,6 +90,14 @@ SIGNATURES = {
     "gcanet_offset_pred_workspace_bytes": (c_size_t, [_ODESC_P]),
     "gcanet_offset_pred_forward": (c_int, [_ODESC_P] + [c_void_p] * 14 + [c_size_t, c_void_p]),
     "gcanet_offset_pred_backward": (c_int, [_ODESC_P] + [c_void_p] * 23 + [c_size_t, c_void_p]),
+    "gcanet_affinity_workspace_bytes": (c_size_t, [c_int]),
+    "gcanet_pairwise_max_distance": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gcanet_affinity_matrix": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gcanet_ball_query_dense": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_float, c_float, c_void_p,
+                                        ctypes.c_longlong, c_void_p, c_void_p, c_void_p]),
+    "gcanet_affinity_ball_query": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_int, c_float,
+                                           c_float, c_float, c_void_p, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_size_t,
+                                           c_void_p]),
 }
 
 _lib = None

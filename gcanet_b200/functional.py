@@ -596,3 +596,92 @@ def offset_pred(points, feature, instance_feature, key_index, conv_w, gamma, bet
                              conv_w.reshape(conv_w.shape[0], -1), gamma, beta, att_w1.reshape(att_w1.shape[0], -1),
                              att_w2.reshape(att_w2.shape[0], -1), off_w.reshape(off_w.shape[0], -1), off_b, int(k), int(groups),
                              float(eps), float(slope))
+
+
+# ----------------------------------------------------------------------------------
+# dense affinity + gated ball query (front end of the proposal grouping, M4:210-233, M4:1215-1233)
+# ----------------------------------------------------------------------------------
+def compute_batch_adjacency_matrix(batch_point_clouds, radius=0, dist_state=True, sigma=1.0):
+    """Replaces ``compute_batch_adjacency_matrix`` (M4:210-233) for the way the model calls it (``dist_state=True`` on one
+    [M, C] cloud, M4:1215-1217): exp(-(d / d_max)^2 / (2 sigma^2)) with a zero diagonal, as a dense [M, M] (or [1, M, M])
+    matrix.  The fused ``affinity_ball_query`` answers the same question without building it."""
+    if not dist_state:
+        raise NotImplementedError("dist_state=False (thresholded adjacency) is not used by the model and not built")
+    x = batch_point_clouds
+    squeeze = x.dim() == 2
+    if x.dim() == 3:
+        if x.shape[0] != 1:
+            raise NotImplementedError("one cloud per call (the reference normalises over the whole batch tensor; its call sites pass one)")
+        x = x[0]
+    require_cuda(x, "batch_point_clouds", contiguous=False)
+    x = x.float().contiguous()
+    M, C = x.shape
+    L = _cabi.lib()
+    with torch.cuda.device(x.device):
+        adj = torch.empty((M, M), dtype=torch.float32, device=x.device)
+        ws = workspace(L.gcanet_affinity_workspace_bytes(1) + 256, x.device)
+        call("gcanet_affinity_matrix", ptr(x), M, C, float(sigma), ptr(adj), ptr(ws), ws.numel(), stream())
+    return adj if squeeze else adj.unsqueeze(0)
+
+
+def _run_ball_query(launch, n, mean_active, device):
+    """The reference's retry loop (softgroup/ops/functions.py:460-472): allocate n * meanActive slots, re-run larger if the
+    neighbours found do not fit; returns (idx [nActive] int32, start_len [n, 2] int32)."""
+    total = torch.zeros(1, dtype=torch.int64, device=device)
+    while True:
+        cap = int(n) * int(mean_active)
+        idx = torch.zeros(max(cap, 1), dtype=torch.int32, device=device)
+        start_len = torch.zeros((n, 2), dtype=torch.int32, device=device)
+        launch(idx, cap, start_len, total)
+        n_active = int(total.item())
+        if n_active <= cap:
+            return idx[:n_active], start_len
+        mean_active = n_active // n + 1
+
+
+def ball_query(coords, batch_idxs, batch_offsets, adj_mat_inst, similarity_threshold_inst, adj_mat_para,
+               similarity_threshold_para, radius, mean_active, with_octree=False):
+    """Replaces ``ball_query`` / ``ballquery_batch_p`` (softgroup/ops/functions.py:93-104, 436-477) with the dense matrices the
+    reference passes: (idx [nActive] int32, start_len [n, 2] int32).  Lists come in point order (the reference's order is
+    whatever its atomicAdd produced), each in ascending neighbour index, capped at 3000 entries per point."""
+    if with_octree:
+        raise NotImplementedError("octree_ball_query is disabled in the reference (with_octree=False, M4:1161)")
+    require_cuda(coords, "coords", torch.float32)
+    require_cuda(batch_offsets, "batch_offsets", torch.int32)
+    require_cuda(adj_mat_inst, "adj_mat_inst", torch.float32)
+    require_cuda(adj_mat_para, "adj_mat_para", torch.float32)
+    n = coords.shape[0]
+    segs = batch_offsets.numel() - 1
+
+    def launch(idx, cap, start_len, total):
+        with torch.cuda.device(coords.device):
+            call("gcanet_ball_query_dense", ptr(coords), ptr(batch_offsets), n, segs, ptr(adj_mat_inst),
+                 float(similarity_threshold_inst), ptr(adj_mat_para), float(similarity_threshold_para), float(radius), ptr(idx),
+                 cap, ptr(start_len), ptr(total), stream())
+
+    return _run_ball_query(launch, n, mean_active, coords.device)
+
+
+def affinity_ball_query(coords, batch_offsets, feat_inst, similarity_threshold_inst, feat_para, similarity_threshold_para,
+                        radius, mean_active=300, sigma=1.0):
+    """The fused form of the three calls at M4:1215-1233 -- two ``compute_batch_adjacency_matrix`` and the gated
+    ``ball_query`` -- without the two n x n matrices: coords [n, 3], feat_inst [n, Ci], feat_para [n, Cp], batch_offsets
+    [S + 1] int32 (each segment is normalised by its own largest pairwise distance, i.e. one reference call per segment).
+    Returns (idx, start_len) like ``ball_query``."""
+    for t, nme in ((coords, "coords"), (feat_inst, "feat_inst"), (feat_para, "feat_para")):
+        require_cuda(t, nme, torch.float32)
+    require_cuda(batch_offsets, "batch_offsets", torch.int32)
+    n = coords.shape[0]
+    segs = batch_offsets.numel() - 1
+    sizes = (batch_offsets[1:] - batch_offsets[:-1])
+    max_seg = int(sizes.max().item())
+    L = _cabi.lib()
+    ws = workspace(L.gcanet_affinity_workspace_bytes(segs), coords.device)
+
+    def launch(idx, cap, start_len, total):
+        with torch.cuda.device(coords.device):
+            call("gcanet_affinity_ball_query", ptr(coords), ptr(batch_offsets), n, segs, max_seg, ptr(feat_inst), feat_inst.shape[1],
+                 float(similarity_threshold_inst), ptr(feat_para), feat_para.shape[1], float(similarity_threshold_para),
+                 float(sigma), float(radius), ptr(idx), cap, ptr(start_len), ptr(total), ptr(ws), ws.numel(), stream())
+
+    return _run_ball_query(launch, n, mean_active, coords.device)

@@ -288,6 +288,32 @@ GCANET_API int gcanet_offset_pred_backward(const gcanet_offset_desc *d, const fl
                                            float *grad_att_w2, float *grad_off_w, float *grad_off_b, void *ws, size_t ws_bytes,
                                            gcanet_stream_t stream);
 
+/* ------------------------------------------------------------------ dense affinity + gated ball query (grouping front end)
+ * compute_batch_adjacency_matrix (M4:210-233) and ballquery_batch_p (softgroup/ops/src/bfs_cluster/bfs_cluster.cpp:20-46,
+ * kernel bfs_cluster.cu:18-77; Python loop softgroup/ops/functions.py:460-472).  All pointers are device pointers.
+ *
+ * gcanet_affinity_matrix        adj [n][n] = exp(-(d_ik / d_max)^2 / (2 sigma^2)), zero diagonal, d = Euclidean distance of the
+ *                               rows of x [n][C], d_max its largest value (the reference's global min is the zero diagonal).
+ * gcanet_ball_query_dense       the reference kernel's contract on the dense matrices it is given: per point the neighbours k of
+ *                               its own batch segment with |p_i - p_k|^2 < radius^2, adj_inst[i][k] > thr_inst, adj_para[i][k] >
+ *                               thr_para; ascending k, at most 3000; start_len [n][2] = (start, length), lists in point order
+ *                               (the reference: atomicAdd order); *total = neighbours found (re-run with more capacity if larger).
+ * gcanet_affinity_ball_query    the three calls fused, no n x n matrix: one pass per feature space for d_max per segment, then the
+ *                               radius search evaluates feature distances only for spatial neighbours.
+ * gcanet_pairwise_max_distance  dmax2 [segments] = largest squared pairwise distance inside each segment. */
+GCANET_API size_t gcanet_affinity_workspace_bytes(int segments);
+GCANET_API int gcanet_pairwise_max_distance(const float *x, const int32_t *seg, int n, int C, int segments, int max_segment,
+                                            float *dmax2, gcanet_stream_t stream);
+GCANET_API int gcanet_affinity_matrix(const float *x, int n, int C, float sigma, float *adj, void *ws, size_t ws_bytes,
+                                      gcanet_stream_t stream);
+GCANET_API int gcanet_ball_query_dense(const float *xyz, const int32_t *batch_offsets, int n, int segments, const float *adj_inst,
+                                       float thr_inst, const float *adj_para, float thr_para, float radius, int32_t *idx,
+                                       long long capacity, int32_t *start_len, long long *total, gcanet_stream_t stream);
+GCANET_API int gcanet_affinity_ball_query(const float *xyz, const int32_t *batch_offsets, int n, int segments, int max_segment,
+                                          const float *f_inst, int Ci, float thr_inst, const float *f_para, int Cp, float thr_para,
+                                          float sigma, float radius, int32_t *idx, long long capacity, int32_t *start_len,
+                                          long long *total, void *ws, size_t ws_bytes, gcanet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

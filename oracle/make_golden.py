@@ -211,6 +211,22 @@ def make_offset_fixture(ref_root, out_dir):
     np.savez_compressed(os.path.join(out_dir, "offset_small.npz"), **fix)
 
 
+def check_adjacency_oracle(ref_root):
+    """compute_batch_adjacency_matrix: the reference's text (M4:210-233) against oracle.native's restatement (no fixture:
+    the function is a few torch calls; tests compare the device path with the restatement directly)."""
+    print("[dense affinity]")
+    from oracle import native as nat
+    with open(os.path.join(ref_root, M4)) as f:
+        lines = f.read().split("\n")
+    ns = {"torch": torch, "np": np, "nn": nn, "F": F}
+    exec(compile("\n".join(lines[209:233]) + "\n", os.path.join(ref_root, M4), "exec"), ns)
+    g = torch.Generator().manual_seed(12)
+    for shape in ((257, 64), (300, 22), (1, 90, 7)):
+        x = torch.randn(*shape, generator=g)
+        same(nat.compute_batch_adjacency_matrix(x, radius=0, dist_state=True), ns["compute_batch_adjacency_matrix"](x, radius=0, dist_state=True),
+             f"compute_batch_adjacency_matrix {shape}")
+
+
 def extract_search_knn_golden(ref_root, out_dir):
     print("[search_knn.py hand-written golden vectors]")
     path = os.path.join(ref_root, "models/search_knn.py")
@@ -245,6 +261,7 @@ def main():
     make_encoder_fixture(ns, out_dir)
     make_normal_head_fixture(ns, out_dir)
     make_offset_fixture(args.reference, out_dir)
+    check_adjacency_oracle(args.reference)
     extract_search_knn_golden(args.reference, out_dir)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "threads": 1,
             "reference_files": [M4 + ":30-205", M4 + ":326-452", M4 + ":455-534", "models/search_knn.py:180-244"]}

@@ -42,6 +42,9 @@ def lib():
         L.oracle_group_points.restype = ctypes.c_int
         L.oracle_group_points_grad.argtypes = [ctypes.c_int] * 5 + [fp, ip, fp]
         L.oracle_group_points_grad.restype = ctypes.c_int
+        L.oracle_ballquery_batch_p.argtypes = [ctypes.c_int, ctypes.c_float, fp, ip, ip, fp, ctypes.c_float, fp, ctypes.c_float,
+                                               ip, ip]
+        L.oracle_ballquery_batch_p.restype = ctypes.c_longlong
         _lib = L
     return _lib
 
@@ -176,3 +179,39 @@ class SoftProjection(torch.nn.Module):
         if action == "project_and_propagate":
             return self.project_and_propagate(point_cloud, point_features, query_cloud)
         raise ValueError("action should be one of the following: 'project', 'propagate', 'project_and_propagate'")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# dense affinity + gated ball query (front end of the proposal grouping)
+# ---------------------------------------------------------------------------------------------------------
+def compute_batch_adjacency_matrix(batch_point_clouds, radius=0, dist_state=True, sigma=1.0):
+    """Restates ``compute_batch_adjacency_matrix`` (models/dgcnn-hais-concat-direct-4.py:210-233): pairwise Euclidean
+    distances (torch.cdist), zero diagonal, normalisation by the GLOBAL min / max of the tensor, exp(-d^2 / 2 sigma^2),
+    zero diagonal again.  Bit-identical to the reference text (oracle/make_golden.py asserts it)."""
+    d = torch.cdist(batch_point_clouds, batch_point_clouds)
+    adj = d if dist_state else (d <= radius).float()
+    adj = adj - torch.diag_embed(torch.diagonal(adj, dim1=-2, dim2=-1))
+    lo, hi = adj.min(), adj.max()
+    adj = (adj - lo) / (hi - lo)
+    adj = torch.exp(-adj ** 2 / (2 * sigma ** 2))
+    return adj - torch.diag_embed(torch.diagonal(adj, dim1=-2, dim2=-1))
+
+
+def ball_query(coords, batch_idxs, batch_offsets, adj_mat_inst, thr_inst, adj_mat_para, thr_para, radius, mean_active=300):
+    """Restates ``ball_query`` -> ``ballquery_batch_p`` (softgroup/ops/functions.py:93-104, 436-477; kernel
+    bfs_cluster.cu:18-77) on CPU tensors: (idx [nActive] int32, start_len [n, 2] int32), lists in point order."""
+    xyz = np.ascontiguousarray(coords.numpy(), np.float32)
+    bi = np.ascontiguousarray(batch_idxs.numpy(), np.int32)
+    bo = np.ascontiguousarray(batch_offsets.numpy(), np.int32)
+    ai = np.ascontiguousarray(adj_mat_inst.numpy(), np.float32)
+    ap = np.ascontiguousarray(adj_mat_para.numpy(), np.float32)
+    n = xyz.shape[0]
+    ipt = ctypes.POINTER(ctypes.c_int32)
+    sl = np.zeros((n, 2), np.int32)
+    L = lib()
+    total = L.oracle_ballquery_batch_p(n, float(radius), _fp(xyz), bi.ctypes.data_as(ipt), bo.ctypes.data_as(ipt), _fp(ai),
+                                       float(thr_inst), _fp(ap), float(thr_para), None, sl.ctypes.data_as(ipt))
+    idx = np.zeros(max(int(total), 1), np.int32)
+    L.oracle_ballquery_batch_p(n, float(radius), _fp(xyz), bi.ctypes.data_as(ipt), bo.ctypes.data_as(ipt), _fp(ai),
+                               float(thr_inst), _fp(ap), float(thr_para), idx.ctypes.data_as(ipt), sl.ctypes.data_as(ipt))
+    return torch.from_numpy(idx[:int(total)]), torch.from_numpy(sl)

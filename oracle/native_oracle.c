@@ -100,3 +100,40 @@ int oracle_group_points_grad(int b, int c, int n, int npoints, int nsample,
                 }
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Gated ball query: restates ballquery_batch_p_cuda_ (softgroup/ops/src/bfs_cluster/bfs_cluster.cu:18-77).
+ * One "thread" per point, in point order: candidates k of the point's own batch segment in ascending order,
+ * kept iff d2 < radius^2 (same expression order, no contraction: built with -ffp-contract=off) and both dense
+ * affinities exceed their thresholds; at most 3000 per point (the kernel's idx_temp[3000] stops the scan at the
+ * 3001st hit); lists are concatenated in point order (the kernel: in the order its atomicAdd happens to run).
+ * start_len [n][2] = (start, length); returns the total number of neighbours, idx must hold that many (call once
+ * with idx == NULL to size it). */
+long long oracle_ballquery_batch_p(int n, float radius, const float *xyz, const int32_t *batch_idxs,
+                                   const int32_t *batch_offsets, const float *adj_inst, float thr_inst,
+                                   const float *adj_para, float thr_para, int32_t *idx, int32_t *start_len)
+{
+    const float radius2 = radius * radius;
+    long long total = 0;
+    for (int p = 0; p < n; ++p) {
+        const float ox = xyz[p * 3 + 0], oy = xyz[p * 3 + 1], oz = xyz[p * 3 + 2];
+        const int b = batch_idxs[p];
+        const int start = batch_offsets[b], end = batch_offsets[b + 1];
+        int cnt = 0;
+        for (int k = start; k < end; ++k) {
+            const float x = xyz[k * 3 + 0], y = xyz[k * 3 + 1], z = xyz[k * 3 + 2];
+            const float d2 = (ox - x) * (ox - x) + (oy - y) * (oy - y) + (oz - z) * (oz - z);
+            if (d2 < radius2 && adj_inst[(size_t)p * n + k] > thr_inst && adj_para[(size_t)p * n + k] > thr_para) {
+                if (cnt < 3000) {
+                    if (idx) idx[total + cnt] = k;
+                } else {
+                    break;
+                }
+                ++cnt;
+            }
+        }
+        if (start_len) { start_len[p * 2] = (int32_t)total; start_len[p * 2 + 1] = cnt; }
+        total += cnt;
+    }
+    return total;
+}

@@ -206,3 +206,18 @@ def test_native_grouping_forward_backward():
     (out * cot).sum().backward()
     gw, = torch.autograd.grad((want * cot).sum(), feats)
     torch.testing.assert_close(feats.grad, gw, rtol=1e-6, atol=1e-6)
+
+
+def test_native_ball_query_restatement_small_case():
+    """oracle_ballquery_batch_p on a hand-checkable case: three collinear points per segment, dense gates."""
+    xyz = torch.tensor([[0.0, 0, 0], [0.01, 0, 0], [0.05, 0, 0], [0.0, 0, 0], [0.01, 0, 0]])
+    bidx = torch.tensor([0, 0, 0, 1, 1], dtype=torch.int32)
+    off = torch.tensor([0, 3, 5], dtype=torch.int32)
+    adj = torch.ones(5, 5) - torch.eye(5)
+    adj[0, 1] = 0.2                                             # gate closes 0 -> 1 but not 1 -> 0
+    idx, sl = nat.ball_query(xyz, bidx, off, adj, 0.5, adj, 0.5, 0.03)
+    assert sl.tolist() == [[0, 0], [0, 1], [1, 0], [1, 1], [2, 1]]
+    assert idx.tolist() == [0, 4, 3]
+    x = torch.randn(40, 5, generator=torch.Generator().manual_seed(0))
+    a = nat.compute_batch_adjacency_matrix(x)
+    assert float(a.diagonal().abs().max()) == 0 and float(a.max()) <= 1.0 and float(a[a > 0].min()) >= np.exp(-0.5) - 1e-6
