@@ -48,6 +48,14 @@ class OffsetDesc(ctypes.Structure):
 
 _ODESC_P = ctypes.POINTER(OffsetDesc)
 
+
+class PrepareDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("n_raw", c_int), ("n_sub", c_int), ("max_labels", c_int), ("min_points", c_int),
+                ("num_primitives", c_int)]
+
+
+_PDESC_P = ctypes.POINTER(PrepareDesc)
+
 # name -> (restype, argtypes); mirrors include/gcanet_b200.h one to one
 SIGNATURES = {
     "gcanet_abi_version": (c_int, []),
@@ -90,6 +98,7 @@ SIGNATURES = {
     "gcanet_offset_pred_workspace_bytes": (c_size_t, [_ODESC_P]),
     "gcanet_offset_pred_forward": (c_int, [_ODESC_P] + [c_void_p] * 14 + [c_size_t, c_void_p]),
     "gcanet_offset_pred_backward": (c_int, [_ODESC_P] + [c_void_p] * 23 + [c_size_t, c_void_p]),
+    "gcanet_prepare_samples": (c_int, [_PDESC_P] + [c_void_p] * 18),
     "gcanet_affinity_workspace_bytes": (c_size_t, [c_int]),
     "gcanet_pairwise_max_distance": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gcanet_affinity_matrix": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),

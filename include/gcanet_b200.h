@@ -314,6 +314,27 @@ GCANET_API int gcanet_affinity_ball_query(const float *xyz, const int32_t *batch
                                           float sigma, float radius, int32_t *idx, long long capacity, int32_t *start_len,
                                           long long *total, void *ws, size_t ws_bytes, gcanet_stream_t stream);
 
+/* ------------------------------------------------------------------ input side: batch preparation on the device
+ * Replaces, for a batch of raw samples resident in device memory, what ABCDataset.__getitem__ does after reading a sample
+ * (dataloader/ABCDataset_new.py:77-141), getInstanceInfo (:157-178) and collate_fn's stacking (:182-295): small instances
+ * (<= min_points raw points) become background, kept ones are renumbered in order of first appearance, the subsample is
+ * gathered, per-instance centroids give the offset labels.
+ *   points, normals [B][n_raw][3];  labels, prim [B][n_raw] int32 (labels in [0, max_labels));  t_param [B][n_raw][22]
+ *   sub_index [B][n_sub] int32: the subsample (the reference draws it with np.random.choice(..., replace=False), :120)
+ *   cloud_cn [B][6][n_sub] (reference layout, xyz then normals), cloud_nc [B][n_sub][8] (xyz | normal | 0 0, point-major)
+ *   i_gt, t_gt, i_gt_clean [B][n_sub] int32;  t_param_out [B][n_sub][22];  pt_offset_label [B][n_sub][3]
+ *   inst_num [B];  inst_pointnum, inst_cls [B][max_labels] (first inst_num[b] entries valid);  status [B]: 0 ok,
+ *   1 = a label outside [0, max_labels) (nothing else is written for that cloud). */
+typedef struct {
+    int B, n_raw, n_sub, max_labels, min_points, num_primitives;
+} gcanet_prepare_desc;
+
+GCANET_API int gcanet_prepare_samples(const gcanet_prepare_desc *d, const float *points, const float *normals, const int32_t *labels,
+                                      const int32_t *prim, const float *t_param, const int32_t *sub_index, float *cloud_cn,
+                                      float *cloud_nc, int32_t *i_gt, int32_t *t_gt, int32_t *i_gt_clean, float *t_param_out,
+                                      float *pt_offset_label, int32_t *inst_num, int32_t *inst_pointnum, int32_t *inst_cls,
+                                      int32_t *status, gcanet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

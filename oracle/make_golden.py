@@ -227,6 +227,46 @@ def check_adjacency_oracle(ref_root):
              f"compute_batch_adjacency_matrix {shape}")
 
 
+def check_dataset_oracle(ref_root):
+    """ABCDataset.__getitem__ after the file read + getInstanceInfo (dataloader/ABCDataset_new.py:77-141, 157-178): the
+    reference's text, executed on a synthetic raw sample, against oracle/dataset_oracle.py."""
+    print("[input side: sample preparation]")
+    import textwrap
+    from collections import Counter
+    from oracle import dataset_oracle as dso
+    with open(os.path.join(ref_root, "dataloader/ABCDataset_new.py")) as f:
+        lines = f.read().split("\n")
+    body = "\n".join(lines[76:141])                      # ret_dict['gt_pc'] = points ... ret_dict['pt_offset_label'] = ...
+    info = textwrap.dedent("\n".join(lines[156:178]))    # def getInstanceInfo(self, ...)
+    src = ("def ref_item(self, points, normals, labels, primitives, primitive_param, index=0):\n    ret_dict = {}\n"
+           + textwrap.indent(textwrap.dedent(body), "    ") + "\n    return ret_dict\n")
+    ns = {"np": np, "Counter": Counter}
+    exec(compile(info, "ABCDataset_new.py:157-178", "exec"), ns)
+    exec(compile(src, "ABCDataset_new.py:77-141", "exec"), ns)
+
+    class FakeSelf:
+        data_list = ["sample"]
+        def getInstanceInfo(self, *a):
+            return ns["getInstanceInfo"](self, *a)
+
+    for num_prims, seed in ((10, 0), (7, 1)):
+        pts, nrm, lab, prim, tp = dso.synthetic_raw_sample(8000, seed)
+        me = FakeSelf()
+        me.num_primitives = num_prims
+        np.random.seed(77 + seed)
+        ref = ns["ref_item"](me, pts.copy(), nrm.copy(), lab.copy(), prim.copy(), tp.copy())
+        np.random.seed(77 + seed)
+        subidx = np.random.choice(range(8000), 7000, replace=False)
+        mine = dso.prepare_sample(pts, nrm, lab, prim, tp, subidx, num_primitives=num_prims)
+        for key in ("gt_pc", "gt_normal", "T_gt", "T_param", "I_gt", "I_gt_clean", "pt_offset_label"):
+            a, b = np.asarray(mine[key]), np.asarray(ref[key])
+            assert a.shape == b.shape and np.array_equal(a, b), key
+        assert mine["inst_num"] == ref["inst_num"] and list(mine["inst_pointnum"]) == list(ref["inst_pointnum"])
+        assert [int(v) for v in mine["inst_cls"]] == [int(v) for v in ref["inst_cls"]]
+        print(f"  oracle == reference   sample preparation, {num_prims} primitive classes: {ref['inst_num']} instances kept, "
+              f"{int((np.asarray(ref['I_gt']) == -1).sum())} background points")
+
+
 def extract_search_knn_golden(ref_root, out_dir):
     print("[search_knn.py hand-written golden vectors]")
     path = os.path.join(ref_root, "models/search_knn.py")
@@ -262,9 +302,11 @@ def main():
     make_normal_head_fixture(ns, out_dir)
     make_offset_fixture(args.reference, out_dir)
     check_adjacency_oracle(args.reference)
+    check_dataset_oracle(args.reference)
     extract_search_knn_golden(args.reference, out_dir)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "threads": 1,
-            "reference_files": [M4 + ":30-205", M4 + ":326-452", M4 + ":455-534", "models/search_knn.py:180-244"]}
+            "reference_files": [M4 + ":30-205", M4 + ":326-452", M4 + ":455-534", "models/search_knn.py:180-244",
+                                "dataloader/ABCDataset_new.py:77-141,157-178"]}
     with open(os.path.join(out_dir, "META.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("done ->", out_dir)
