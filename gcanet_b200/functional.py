@@ -58,16 +58,20 @@ class _timed:
         return False
 
 
-# Gradient sinks (gcanet_b200.parallel.GradBucket.attach_sinks): parameter storage address -> the slice of a flat
-# all-reduce bucket shaped like the parameter.  A fused backward that finds a sink writes the parameter's gradient
-# straight into the bucket, so nothing has to be packed before the collective or copied back after it.
+# Gradient sinks (gcanet_b200.parallel.GradBucket.attach_sinks): parameter storage address -> [slice of a flat all-reduce
+# bucket shaped like the parameter, handed-out flag].  A fused backward that finds an unused sink writes the parameter's
+# gradient straight into the bucket, so nothing has to be packed before the collective or copied back after it.  A sink
+# is handed out once per step (the bucket clears the flags when it reduces): a second backward call for the same
+# parameter in the same step -- weight sharing, or a batch split over two streams -- gets an ordinary buffer, which
+# autograd then ADDS into the slice that already is ``p.grad``.
 _grad_sinks: dict = {}
 
 
 def _grad_buffer(param_like: torch.Tensor) -> torch.Tensor:
-    sink = _grad_sinks.get(param_like.data_ptr())
-    if sink is not None and sink.numel() == param_like.numel() and sink.device == param_like.device:
-        return sink.view(param_like.shape)
+    entry = _grad_sinks.get(param_like.data_ptr())
+    if entry is not None and not entry[1] and entry[0].numel() == param_like.numel() and entry[0].device == param_like.device:
+        entry[1] = True
+        return entry[0].view(param_like.shape)
     return torch.empty_like(param_like)
 
 

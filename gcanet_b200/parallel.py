@@ -79,6 +79,7 @@ class GradBucket:
         # gradients, then one presence flag per parameter
         self.flat = torch.zeros(n + len(self.params), dtype=torch.float32, device=dev)
         self._zeros = None
+        self._has_sinks = False
         self._flag_cache = {}
 
     def attach_sinks(self):
@@ -89,8 +90,17 @@ class GradBucket:
         each backward -- accumulating into the slice a kernel is about to overwrite would double-count."""
         from . import functional as G
         for p, o in zip(self.params, self.offsets):
-            G._grad_sinks[p.data_ptr()] = self.flat[o:o + p.numel()]
+            G._grad_sinks[p.data_ptr()] = [self.flat[o:o + p.numel()], False]
+        self._has_sinks = True
         return self
+
+    def release_sinks(self):
+        """Start of a new step: every sink may be handed out again (``all_reduce_mean`` does this itself)."""
+        from . import functional as G
+        for p in self.params:
+            e = G._grad_sinks.get(p.data_ptr())
+            if e is not None:
+                e[1] = False
 
     def detach_sinks(self):
         from . import functional as G
@@ -110,6 +120,8 @@ class GradBucket:
 
     def all_reduce_mean(self, group=None, async_op: bool = False):
         world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self._has_sinks:
+            self.release_sinks()
         if world == 1:
             return _Done() if async_op else None
         # pack with one kernel (absent gradients go in as zeros), average inside the collective where the backend can
