@@ -407,17 +407,16 @@ __global__ void op_bwd_affine_kernel(const double *__restrict__ sbc, float *__re
     dgamma[c] = (float)s2;
 }
 
-// pass 2: the edges again.  One warp per point; key-side gradients accumulate in shared memory and are flushed per CTA.
+// pass 2: the edges again.  One warp per point.  Key-side gradients (dT, d k^) go straight to global memory as vector
+// reductions (red.global.add.v4.f32 / v2.f32, resolved in L2): fp32 atomicAdd on SHARED memory is a compare-and-swap loop,
+// and with 120 keys shared by all points it made this kernel 16 % of the whole training step (959 M instructions, ncu).
 __global__ void __launch_bounds__(OP_WARPS * 32) op_bwd_main_kernel(OpBwdArgs p) {
     const OpArgs &a = p.f;
     extern __shared__ __align__(16) float op_sm[];
+    __shared__ float s_red[OP_WARPS][2 * OP_KMAX + 1];
     const OpSmem sm = op_carve(op_sm, a.S, a.E, a.k);
-    float *s_dT = sm.wsc + OP_WARPS * sm.per_warp;          // [S][128]
-    float *s_dkn = s_dT + a.S * OP_F;                       // [S][E]
-    float *s_dw = s_dkn + a.S * a.E;                        // [2][k][k] then [128][3]
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     op_load_tables(a, sm, b);
-    for (int e = threadIdx.x; e < a.S * OP_F + a.S * a.E + 2 * a.k * a.k + OP_F * 3; e += blockDim.x) s_dT[e] = 0.f;
     __syncthreads();
     float *ws = sm.wsc + warp * sm.per_warp;
     float *ssim = ws, *su = ws + OP_SMAX, *sd = su + a.E, *sa = sd + 32, *sh = sa + 32;
@@ -432,6 +431,12 @@ __global__ void __launch_bounds__(OP_WARPS * 32) op_bwd_main_kernel(OpBwdArgs p)
 #pragma unroll
         for (int d = 0; d < 3; ++d) { wp[v][d] = a.cw[(size_t)(c0 + v) * (OP_F + 3) + OP_F + d]; dwp[v][d] = 0.f; }
     }
+    // attention-weight gradients: lane r keeps row r of dW2 (dpre_r h_c) and row r of dW1 (dz_r d_c) in registers
+    float dw1r[OP_KMAX], dw2r[OP_KMAX];
+#pragma unroll
+    for (int c = 0; c < OP_KMAX; ++c) { dw1r[c] = 0.f; dw2r[c] = 0.f; }
+    float *dT = p.dT + (size_t)b * a.S * OP_F + c0;
+    float *dkn = p.dkn + (size_t)b * a.S * a.E;
     const int per_warp = OP_PTS_BWD / OP_WARPS;
     for (int pi = 0; pi < per_warp; ++pi) {
         const int i = blockIdx.x * OP_PTS_BWD + warp * per_warp + pi;
@@ -472,16 +477,16 @@ __global__ void __launch_bounds__(OP_WARPS * 32) op_bwd_main_kernel(OpBwdArgs p)
             const int j = sj[kk];
             const float4 t4 = *reinterpret_cast<const float4 *>(sm.T + j * OP_F + c0);
             const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
-            float dap = 0.f;
+            float dap = 0.f, adt[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
                 const float t = tv[v] - q[v];
                 const float dy = (ak[v] == kk ? sv[v] : 0.f) + fmaf(Kg, at * t, Ag);
                 dap = fmaf(dy, t, dap);
-                const float adt = at * dy;
-                atomicAdd(s_dT + j * OP_F + c0 + v, adt);
-                dq[v] -= adt;
+                adt[v] = at * dy;
+                dq[v] -= adt[v];
             }
+            atomicAdd(reinterpret_cast<float4 *>(dT + (size_t)j * OP_F), make_float4(adt[0], adt[1], adt[2], adt[3]));
             for (int o = 16; o; o >>= 1) dap += __shfl_xor_sync(OFULL, dap, o);
             if (lane == kk) da_mine = dap;
         }
@@ -496,8 +501,8 @@ __global__ void __launch_bounds__(OP_WARPS * 32) op_bwd_main_kernel(OpBwdArgs p)
         float dot = at * da_mine;
         for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(OFULL, dot, o);
         const float dpre = at * (da_mine - dot);
-        // MLP backward: dh = W2^T dpre, dz = dh [z > 0], dd = W1^T dz; weight gradients accumulate in shared memory
-        ssim[lane] = dpre;                                   // reuse the similarity scratch: [0, 32) dpre, [32, 64) dz
+        // MLP backward: dh = W2^T dpre, dz = dh [z > 0], dd = W1^T dz
+        ssim[lane] = dpre;                                   // similarity scratch reused: [0, 32) dpre, [32, 64) dz, [64, 96) dd
         __syncwarp();
         float dh = 0.f;
         if (lane < a.k)
@@ -506,50 +511,66 @@ __global__ void __launch_bounds__(OP_WARPS * 32) op_bwd_main_kernel(OpBwdArgs p)
         ssim[32 + lane] = dz;
         __syncwarp();
         float dd = 0.f;
-        if (lane < a.k) {
+        if (lane < a.k)
             for (int c = 0; c < a.k; ++c) dd = fmaf(sm.w1[c * (a.k + 1) + lane], ssim[32 + c], dd);
-            for (int c = 0; c < a.k; ++c) {
-                atomicAdd(s_dw + a.k * a.k + lane * a.k + c, dpre * sh[c]);       // dW2[r = lane][c]
-                atomicAdd(s_dw + lane * a.k + c, dz * sd[c]);                      // dW1[c' = lane][m = c]
-            }
+#pragma unroll
+        for (int c = 0; c < OP_KMAX; ++c) {                  // (lanes >= k carry dpre = dz = 0, columns >= k carry sh = sd = 0)
+            dw2r[c] = fmaf(dpre, sh[c], dw2r[c]);
+            dw1r[c] = fmaf(dz, sd[c], dw1r[c]);
         }
         ssim[64 + lane] = dd;                                // gradient w.r.t. the similarity of the lane-th neighbour
         __syncwarp();
-        // cosine similarity backward: sim_j = u^ . k^_j - 1.  A lane owns the components c = lane + 32 e of the instance
-        // feature (E <= 256: at most 8); d u^ = sum_k dd_k k^_{j_k}, and every key collects dd_k u^ in shared memory
-        float dun[8];
+        // cosine similarity backward: sim_j = u^ . k^_j - 1.  A lane owns the component pairs (64 e + 2 lane, + 1) of the
+        // instance feature (E <= 256: at most 4 pairs); d u^ = sum_k dd_k k^_{j_k}; every key collects dd_k u^ (one
+        // two-float reduction per lane, key and pair)
+        float dun[4][2];
         float dotu = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = lane + 32 * e;
-            dun[e] = 0.f;
+        for (int e = 0; e < 4; ++e) {
+            const int c = 64 * e + 2 * lane;
+            dun[e][0] = 0.f; dun[e][1] = 0.f;
             if (c < a.E) {
+                const float u0 = su[c], u1 = su[c + 1];
                 for (int kk = 0; kk < a.k; ++kk) {
                     const float ddk = ssim[64 + kk];
-                    dun[e] = fmaf(ddk, sm.keyn[sj[kk] * (a.E + 1) + c], dun[e]);
-                    atomicAdd(s_dkn + sj[kk] * a.E + c, ddk * su[c]);
+                    const float *kr = sm.keyn + sj[kk] * (a.E + 1) + c;
+                    dun[e][0] = fmaf(ddk, kr[0], dun[e][0]);
+                    dun[e][1] = fmaf(ddk, kr[1], dun[e][1]);
+                    atomicAdd(reinterpret_cast<float2 *>(dkn + (size_t)sj[kk] * a.E + c), make_float2(ddk * u0, ddk * u1));
                 }
-                dotu = fmaf(dun[e], su[c], dotu);
+                dotu = fmaf(dun[e][0], u0, fmaf(dun[e][1], u1, dotu));
             }
         }
         for (int o = 16; o; o >>= 1) dotu += __shfl_xor_sync(OFULL, dotu, o);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = lane + 32 * e;
-            if (c < a.E) p.dinst[row * a.E + c] = (dun[e] - dotu * su[c]) / nrm;      // (I - u^ u^T) d u^ / |u|
+        for (int e = 0; e < 4; ++e) {
+            const int c = 64 * e + 2 * lane;
+            if (c < a.E)                                     // (I - u^ u^T) d u^ / |u|
+                *reinterpret_cast<float2 *>(p.dinst + row * a.E + c) =
+                    make_float2((dun[e][0] - dotu * su[c]) / nrm, (dun[e][1] - dotu * su[c + 1]) / nrm);
         }
         __syncwarp();
     }
-    // per-thread accumulators of the position columns -> shared memory
+    // per-thread accumulators -> global (one reduction per thread and entry, after a cross-warp sum for the k x k matrices)
 #pragma unroll
     for (int v = 0; v < 4; ++v)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) atomicAdd(s_dw + 2 * a.k * a.k + (c0 + v) * 3 + d, dwp[v][d]);
-    __syncthreads();
-    for (int e = threadIdx.x; e < a.S * OP_F; e += blockDim.x) { const float v = s_dT[e]; if (v != 0.f) atomicAdd(p.dT + (size_t)b * a.S * OP_F + e, v); }
-    for (int e = threadIdx.x; e < a.S * a.E; e += blockDim.x) { const float v = s_dkn[e]; if (v != 0.f) atomicAdd(p.dkn + (size_t)b * a.S * a.E + e, v); }
-    for (int e = threadIdx.x; e < a.k * a.k; e += blockDim.x) { atomicAdd(p.dw1 + e, s_dw[e]); atomicAdd(p.dw2 + e, s_dw[a.k * a.k + e]); }
-    for (int e = threadIdx.x; e < OP_F * 3; e += blockDim.x) atomicAdd(p.dwp + e, s_dw[2 * a.k * a.k + e]);
+        for (int d = 0; d < 3; ++d) atomicAdd(p.dwp + (c0 + v) * 3 + d, dwp[v][d]);
+#pragma unroll 1
+    for (int c = 0; c < a.k; ++c) {
+        float v1 = 0.f, v2 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < OP_KMAX; ++cc) { if (cc == c) { v1 = dw1r[cc]; v2 = dw2r[cc]; } }
+        __syncthreads();
+        if (lane < a.k) { s_red[warp][lane] = v1; s_red[warp][OP_KMAX + lane] = v2; }
+        __syncthreads();
+        if (warp == 0 && lane < a.k) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int w = 0; w < OP_WARPS; ++w) { t1 += s_red[w][lane]; t2 += s_red[w][OP_KMAX + lane]; }
+            atomicAdd(p.dw1 + lane * a.k + c, t1);          // dW1[row = lane][col = c]
+            atomicAdd(p.dw2 + lane * a.k + c, t2);
+        }
+    }
 }
 
 // key-side epilogue: gradients that reached the key tables go back to the key points' rows.   grid (S, B), block 128
@@ -729,7 +750,7 @@ extern "C" int gcanet_offset_pred_backward(const gcanet_offset_desc *d, const fl
     GCANET_LAUNCH_OK("op_bwd_coef_kernel");
     op_bwd_affine_kernel<<<1, OP_F, 0, st>>>(w.sbc, grad_gamma, grad_beta, d->B);
     GCANET_LAUNCH_OK("op_bwd_affine_kernel");
-    const size_t smem = (op_smem_floats(d->S, d->E, d->k) + (size_t)d->S * OP_F + (size_t)d->S * d->E + 2 * d->k * d->k + OP_F * 3) * sizeof(float);
+    const size_t smem = op_smem_floats(d->S, d->E, d->k) * sizeof(float);
     GCANET_REQUIRE(smem <= 227 * 1024, "offset_pred_backward: S=%d, E=%d need %zu bytes of shared memory", d->S, d->E, smem);
     GCANET_CUDA_OK(cudaFuncSetAttribute(op_bwd_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     op_bwd_main_kernel<<<dim3(ceil_div(d->N, OP_PTS_BWD), d->B), OP_WARPS * 32, smem, st>>>(p);

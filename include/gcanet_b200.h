@@ -267,8 +267,8 @@ GCANET_API int gcanet_global_feature_backward(const gcanet_global_feature_desc *
  *   key_index [S] int32;  conv_w [128][131];  gamma, beta [128];  att_w1, att_w2 [k][k];  off_w [3][256];  off_b [3]
  *   out [B][3][N]
  * backward: grad_out [B][3][N] -> grad_feature [B][N][128], grad_inst [B][N][E] and all parameter gradients (overwritten);
- * points are data.  Constraints: S % 4 == 0, S <= 128, k <= min(32, S), E % 4 == 0, E <= 256 (E <= 64 for the backward's
- * shared-memory budget at S = 120). */
+ * points are data.  Constraints: S % 4 == 0, S <= 128, k <= min(32, S), E % 4 == 0, E <= 256 (the key tables of a cloud
+ * must fit in shared memory: S * (E + 129) floats). */
 typedef struct {
     int B, N, S, k, E, groups;
     float eps, slope;

@@ -129,10 +129,11 @@ def test_per_point_model_step_and_folded_global_bias():
         if name in unused:
             continue
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
-    # folded global feature
+    # folded global feature (in fp64: cuDNN may run the fp32 1x1 convolutions in TF32, which is not what is checked here)
     with torch.no_grad():
         x4, xf = net.encoder.forward_global(torch.cat([pts, nrm], -1).permute(0, 2, 1).contiguous())
-        full = net.conv1(torch.cat([x4.unsqueeze(2).expand(-1, -1, N), xf], 1))
-        w1 = net.conv1.weight[:, :, 0]
-        folded = F.conv1d(xf, w1[:, 1024:].unsqueeze(-1)) + F.linear(x4, w1[:, :1024], net.conv1.bias).unsqueeze(-1)
-        assert float((full - folded).abs().max()) <= 1e-4 * float(full.abs().max())
+        x4, xf = x4.double(), xf.double()
+        w1, b1 = net.conv1.weight[:, :, 0].double(), net.conv1.bias.double()
+        full = F.conv1d(torch.cat([x4.unsqueeze(2).expand(-1, -1, N), xf], 1), w1.unsqueeze(-1), b1)
+        folded = F.conv1d(xf, w1[:, 1024:].unsqueeze(-1)) + F.linear(x4, w1[:, :1024], b1).unsqueeze(-1)
+        assert float((full - folded).abs().max()) <= 1e-9 * float(full.abs().max())
