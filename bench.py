@@ -491,6 +491,27 @@ def run_ours(args):
     if graph is not None:
         static_x.copy_(x_dev)
 
+    # --- N > 1: where the multi-GPU step's extra time goes.  Every rank times its own replay WITHOUT the collective (no
+    # barrier between steps); the synchronous step costs the slowest rank's time plus the all-reduce, so
+    # `ms_per_step - max(per-rank)` is the collective with its stream hand-offs and `max - mean` the spread between ranks
+    # (their clouds differ, so the pruned kNN scans do different amounts of work)
+    multi_gpu = None
+    if world > 1 and graph is not None:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        barrier()
+        evs[0].record()
+        for _ in range(args.steps):
+            graph.replay()
+        evs[1].record()
+        torch.cuda.synchronize()
+        own = torch.tensor([evs[0].elapsed_time(evs[1]) / args.steps], device=dev)
+        allr = [torch.empty_like(own) for _ in range(world)]
+        dist.all_gather(allr, own)
+        per_rank = [round(float(t[0]), 4) for t in allr]
+        multi_gpu = {"per_rank_ms_without_collective": per_rank,
+                     "rank_spread_ms": round(max(per_rank) - sum(per_rank) / world, 4),
+                     "collective_ms": round(ms_step - max(per_rank), 4)}
+
     # --- N > 1: the collective itself, checked on the hardware (outside the timed regions): every rank's own gradients
     # are all-gathered and averaged with torch ops, and must equal what GradBucket.all_reduce_mean left in p.grad
     allreduce_check = None
@@ -610,7 +631,7 @@ def run_ours(args):
         "breakdown_ms_per_step": breakdown,
         "cpu_baseline": cpu_baseline,
         "gpu_reference": gpu_reference,
-        "allreduce_check": allreduce_check,
+        "allreduce_check": allreduce_check, "multi_gpu": multi_gpu,
         "config4_fixed_global_batch": fixed,
     }
     line.update(extras)

@@ -41,6 +41,13 @@ class GlobalFeatureDesc(ctypes.Structure):
 _GDESC_P = ctypes.POINTER(GlobalFeatureDesc)
 
 
+class GroupNormDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("C", c_int), ("N", c_int), ("groups", c_int), ("eps", c_float), ("act", c_int)]
+
+
+_GNDESC_P = ctypes.POINTER(GroupNormDesc)
+
+
 class OffsetDesc(ctypes.Structure):
     _fields_ = [("B", c_int), ("N", c_int), ("S", c_int), ("k", c_int), ("E", c_int), ("groups", c_int),
                 ("eps", c_float), ("slope", c_float)]
@@ -94,6 +101,9 @@ SIGNATURES = {
     "gcanet_global_feature_workspace_bytes": (c_size_t, [_GDESC_P]),
     "gcanet_global_feature_forward": (c_int, [_GDESC_P] + [c_void_p] * 8 + [c_size_t, c_void_p]),
     "gcanet_global_feature_backward": (c_int, [_GDESC_P] + [c_void_p] * 13 + [c_size_t, c_void_p]),
+    "gcanet_group_norm_workspace_bytes": (c_size_t, [_GNDESC_P]),
+    "gcanet_group_norm_forward": (c_int, [_GNDESC_P] + [c_void_p] * 6 + [c_size_t, c_void_p]),
+    "gcanet_group_norm_backward": (c_int, [_GNDESC_P] + [c_void_p] * 9 + [c_size_t, c_void_p]),
     "gcanet_offset_pred_saved_bytes": (c_size_t, [_ODESC_P]),
     "gcanet_offset_pred_workspace_bytes": (c_size_t, [_ODESC_P]),
     "gcanet_offset_pred_forward": (c_int, [_ODESC_P] + [c_void_p] * 14 + [c_size_t, c_void_p]),

@@ -13,7 +13,7 @@ import ctypes as _ct
 import torch
 
 from . import _cabi
-from ._cabi import EdgeConvDesc, GlobalFeatureDesc, NormalEdgeDesc, OffsetDesc, call, ptr, require_cuda, stream, workspace
+from ._cabi import EdgeConvDesc, GlobalFeatureDesc, GroupNormDesc, NormalEdgeDesc, OffsetDesc, call, ptr, require_cuda, stream, workspace
 
 METRIC_L2 = 0
 METRIC_POINTS_NORMALS = 1
@@ -543,6 +543,62 @@ def global_feature(x_nc, weight, bias, gamma, beta, groups=8, eps=1e-5):
     concatenation of x1 | x2 | x3, weight [1024, 256] (or the Conv1d's [1024, 256, 1]), bias [1024] or None.
     Returns x4 [B, Cout]; differentiable in x_nc, weight, bias, gamma, beta.  The [B, Cout, N] activation is never formed."""
     return _GlobalFeature.apply(x_nc, weight.reshape(weight.shape[0], -1), bias, gamma, beta, int(groups), float(eps))
+
+
+# ----------------------------------------------------------------------------------
+# GroupNorm + ReLU of the per-point heads (M4:644-713), channel-major
+# ----------------------------------------------------------------------------------
+class _GroupNormAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, act):
+        require_cuda(x, "x", torch.float32)
+        if x.dim() != 3:
+            raise RuntimeError(f"group_norm_act: x must be [B, C, N] (got {tuple(x.shape)})")
+        x = x.contiguous()
+        gamma, beta = gamma.contiguous(), beta.contiguous()
+        B, C, N = x.shape
+        if gamma.numel() != C or beta.numel() != C:
+            raise RuntimeError(f"group_norm_act: weight / bias must have C = {C} elements")
+        desc = GroupNormDesc(B, C, N, groups, eps, act)
+        L = _cabi.lib()
+        with torch.cuda.device(x.device):
+            ws_bytes = L.gcanet_group_norm_workspace_bytes(_ct.byref(desc))
+            if ws_bytes == 0:
+                raise RuntimeError(f"group_norm_act: groups = {groups} must divide C = {C}")
+            ws = workspace(ws_bytes, x.device)
+            y = torch.empty_like(x)
+            stats = torch.empty((B, groups, 2), dtype=torch.float32, device=x.device)
+            with _timed("group_norm_fwd"):
+                call("gcanet_group_norm_forward", _ct.byref(desc), ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), ptr(ws),
+                     ws.numel(), stream())
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.desc = desc
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, beta, stats = ctx.saved_tensors
+        desc = ctx.desc
+        L = _cabi.lib()
+        with torch.cuda.device(x.device):
+            gy = gy.contiguous().float()
+            gx, gg, gb = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(beta)
+            ws = workspace(L.gcanet_group_norm_workspace_bytes(_ct.byref(desc)), x.device)
+            with _timed("group_norm_bwd"):
+                call("gcanet_group_norm_backward", _ct.byref(desc), ptr(x), ptr(gamma), ptr(beta), ptr(stats), ptr(gy), ptr(gx),
+                     ptr(gg), ptr(gb), ptr(ws), ws.numel(), stream())
+        return gx, gg, gb, None, None, None
+
+
+def group_norm_relu(x, weight, bias, groups, eps=1e-5):
+    """``F.relu(GroupNorm(groups, C)(x))`` on channel-major x [B, C, N] (M4:644-645, 650, 661, 698, 713): one statistics
+    pass spread over the whole GPU, one normalise + ReLU pass; backward in three passes.  Differentiable in x, weight, bias."""
+    return _GroupNormAct.apply(x, weight, bias, int(groups), float(eps), 1)
+
+
+def group_norm(x, weight, bias, groups, eps=1e-5):
+    """``GroupNorm(groups, C)(x)`` on channel-major x [B, C, N], same kernels without the activation."""
+    return _GroupNormAct.apply(x, weight, bias, int(groups), float(eps), 0)
 
 
 # ----------------------------------------------------------------------------------

@@ -256,6 +256,26 @@ GCANET_API int gcanet_global_feature_backward(const gcanet_global_feature_desc *
                                               float *grad_gamma, float *grad_beta, void *ws, size_t ws_bytes,
                                               gcanet_stream_t stream);
 
+/* ------------------------------------------------------------------ GroupNorm + ReLU of the per-point heads
+ * Replaces F.relu(GroupNorm(x)) on channel-major activations -- F.relu(self.bn1(self.conv1(x))) and its siblings,
+ * M4:644-645, 650, 661, 698, 713 -- and its autograd backward.  A group's values are contiguous in [B][C][N], so the
+ * statistics are split over many CTAs (fp64 partials, fixed-order finalize: deterministic).
+ *   x, y, grad_y, grad_x  [B][C][N];  gamma, beta, grad_gamma, grad_beta [C];  stats [B][groups][2] (mean, rstd): written by
+ *   forward, read by backward (the only saved state; y is recomputed from x where the ReLU mask is needed)
+ *   act: 0 = none, 1 = ReLU.   y may alias x (in place) in forward only when backward is not needed. */
+typedef struct {
+    int B, C, N, groups;
+    float eps;
+    int act;
+} gcanet_group_norm_desc;
+
+GCANET_API size_t gcanet_group_norm_workspace_bytes(const gcanet_group_norm_desc *d);
+GCANET_API int gcanet_group_norm_forward(const gcanet_group_norm_desc *d, const float *x, const float *gamma, const float *beta,
+                                         float *y, float *stats, void *ws, size_t ws_bytes, gcanet_stream_t stream);
+GCANET_API int gcanet_group_norm_backward(const gcanet_group_norm_desc *d, const float *x, const float *gamma, const float *beta,
+                                          const float *stats, const float *grad_y, float *grad_x, float *grad_gamma,
+                                          float *grad_beta, void *ws, size_t ws_bytes, gcanet_stream_t stream);
+
 /* ------------------------------------------------------------------ offset-prediction block
  * Replaces OFFSET_PRED_MODULE.forward with KPAM and cos_dist (M4:326-452) and its autograd backward: per cloud S key
  * points (the caller passes their indices; the reference re-seeds numpy with 1234 and takes the first S of a shuffle,
