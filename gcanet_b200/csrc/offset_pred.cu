@@ -9,8 +9,8 @@
 // Here:  W [a (f_j ; p_j - p_i)] = a (T_j - q_i)  with  T_j = W_f f_j + W_p p_j  (120 x 128 per cloud, kept in shared
 // memory) and q_i = W_p p_i, so one warp per point does similarity, ranking, attention and the 30 edges out of shared
 // memory; GroupNorm + LeakyReLU commute with the max as in edgeconv.cu (sign of gamma picks max or min).  Nothing of
-// size N x k x C or N x S x C is ever stored.  Backward recomputes the edges, accumulates the key-side gradients
-// (dT, d k^) in shared memory and flushes them once per CTA.
+// size N x k x C or N x S x C is ever stored.  Backward recomputes the edges; the key-side gradients (dT, d k^) are
+// vector reductions into global memory (resolved in L2).
 #include "common.cuh"
 
 #include <math_constants.h>
@@ -24,6 +24,8 @@ constexpr int OP_PTS = 64;           // points per CTA (forward / reduce passes)
 constexpr int OP_PTS_BWD = 128;      // points per CTA in the main backward pass (amortises the flush of the key gradients)
 constexpr int OP_SMAX = 128;         // keys per cloud <= 128 (4 per lane)
 constexpr int OP_KMAX = 32;          // neighbours per point <= 32 (one per lane)
+constexpr int OP_KS = 4;             // padding of a key row in shared memory: rows of E + 4 floats stay 16-byte aligned and a quarter
+                                     // warp reading four consecutive floats of eight different rows touches 32 different banks
 
 struct OpArgs {
     const float *points;   // [B][N][3]
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(128) op_keys_kernel(OpArgs a) {
 
 // shared-memory layout shared by the forward and backward point kernels
 struct OpSmem {
-    float *keyn;   // [S][E + 1]
+    float *keyn;   // [S][E + OP_KS]
     float *T;      // [S][128]
     float *w1, *w2;  // [k][k + 1]
     float *wsc;    // per warp: sims[128] | u[E] | seld[32] | sela[32] | sh[32] | selj[32] (as int)
@@ -84,17 +86,17 @@ struct OpSmem {
 __device__ __forceinline__ OpSmem op_carve(float *base, int S, int E, int k) {
     OpSmem s;
     s.keyn = base;
-    s.T = s.keyn + S * (E + 1);
+    s.T = s.keyn + S * (E + OP_KS);
     s.w1 = s.T + S * OP_F;
     s.w2 = s.w1 + k * (k + 1);
     s.wsc = s.w2 + k * (k + 1);
     s.per_warp = OP_SMAX + E + 4 * 32;
     return s;
 }
-static size_t op_smem_floats(int S, int E, int k) { return (size_t)S * (E + 1) + (size_t)S * OP_F + 2 * k * (k + 1) + OP_WARPS * (OP_SMAX + E + 4 * 32); }
+static size_t op_smem_floats(int S, int E, int k) { return (size_t)S * (E + OP_KS) + (size_t)S * OP_F + 2 * k * (k + 1) + OP_WARPS * (OP_SMAX + E + 4 * 32); }
 
 __device__ __forceinline__ void op_load_tables(const OpArgs &a, const OpSmem &sm, int b) {
-    for (int e = threadIdx.x; e < a.S * a.E; e += blockDim.x) sm.keyn[(e / a.E) * (a.E + 1) + e % a.E] = a.keyn[(size_t)b * a.S * a.E + e];
+    for (int e = threadIdx.x; e < a.S * a.E; e += blockDim.x) sm.keyn[(e / a.E) * (a.E + OP_KS) + e % a.E] = a.keyn[(size_t)b * a.S * a.E + e];
     for (int e = threadIdx.x; e < a.S * OP_F; e += blockDim.x) sm.T[e] = a.T[(size_t)b * a.S * OP_F + e];
     for (int e = threadIdx.x; e < a.k * a.k; e += blockDim.x) {
         sm.w1[(e / a.k) * (a.k + 1) + e % a.k] = a.w1[e];
@@ -120,24 +122,80 @@ __device__ __forceinline__ float op_select_attend(const OpArgs &a, const OpSmem 
         const int key = lane + 32 * t;
         float v = -CUDART_INF_F;
         if (key < a.S) {
-            const float *kr = sm.keyn + key * (a.E + 1);
+            const float4 *kr = reinterpret_cast<const float4 *>(sm.keyn + key * (a.E + OP_KS));
+            const float4 *ur = reinterpret_cast<const float4 *>(su);
             float dot = 0.f;
-            for (int c = 0; c < a.E; ++c) dot = fmaf(su[c], kr[c], dot);
+            for (int c = 0; c < a.E / 4; ++c) {                 // same summation order as a scalar loop over the channels
+                const float4 u4 = ur[c], k4 = kr[c];
+                dot = fmaf(u4.x, k4.x, dot); dot = fmaf(u4.y, k4.y, dot); dot = fmaf(u4.z, k4.z, dot); dot = fmaf(u4.w, k4.w, dot);
+            }
             v = -(1.f - dot);                                  // M4:340-341
         }
         mine[t] = v;
-        ssim[key] = v;
+    }
+    // The k most similar keys, descending, ties by key index.  Ranking every key against all S costs S x 4 compares per
+    // lane; instead: the k-th largest similarity V by bisection over the order-preserving bit patterns (the warp counts
+    // with one redux per probe and stops as soon as exactly k keys lie at or above the probe), the keys above V plus the
+    // lowest-index ties are compacted into the k slots, and only those k are ranked against each other.
+    unsigned key4[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const unsigned u = __float_as_uint(mine[t]);
+        key4[t] = (lane + 32 * t < a.S) ? ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) : 0u;   // absent keys sort below everything
+    }
+    unsigned klo, khi;                                           // count(key >= klo) >= k > count(key >= khi)
+    {
+        unsigned mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (lane + 32 * t < a.S) { mn = min(mn, key4[t]); mx = max(mx, key4[t]); }
+        klo = __reduce_min_sync(OFULL, mn);
+        khi = __reduce_max_sync(OFULL, mx) + 1u;                 // (similarities are finite: no wrap-around)
+    }
+    int c_hi = 0;                                                // count(key >= khi)
+    while (khi - klo > 1u) {
+        const unsigned km = klo + ((khi - klo) >> 1);
+        const int c = __reduce_add_sync(OFULL, (key4[0] >= km) + (key4[1] >= km) + (key4[2] >= km) + (key4[3] >= km));
+        if (c >= a.k) { klo = km; if (c == a.k) break; } else { khi = km; c_hi = c; }
+    }
+    // klo: every key >= klo is selected when exactly k of them exist; otherwise klo is the k-th largest value itself
+    // (khi = klo + 1), the c_hi keys above it are selected and the remaining k - c_hi come from the ties, lowest index first
+    {
+        const int cnt_ge = __reduce_add_sync(OFULL, (key4[0] >= klo) + (key4[1] >= klo) + (key4[2] >= klo) + (key4[3] >= klo));
+        const bool exact = cnt_ge == a.k;
+        int base = 0, ties_left = exact ? 0 : a.k - c_hi;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const bool valid = lane + 32 * t < a.S;
+            const bool above = valid && (exact ? key4[t] >= klo : key4[t] > klo);
+            const bool tie = valid && !exact && key4[t] == klo;
+            const unsigned mt = __ballot_sync(OFULL, tie);
+            const bool take_tie = tie && __popc(mt & ((1u << lane) - 1)) < ties_left;
+            ties_left = max(0, ties_left - __popc(mt));
+            const bool sel = above || take_tie;
+            const unsigned ms = __ballot_sync(OFULL, sel);
+            if (sel) {
+                const int p = base + __popc(ms & ((1u << lane) - 1));
+                ssim[p] = mine[t];                               // similarity scratch reused: the selected values ...
+                sj[p] = lane + 32 * t;                           // ... and their keys, unordered
+            }
+            base += __popc(ms);
+        }
     }
     __syncwarp();
-    int rank[4] = {0, 0, 0, 0};
-    for (int j = 0; j < a.S; ++j) {
-        const float o = ssim[j];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) rank[t] += (o > mine[t] || (o == mine[t] && j < lane + 32 * t)) ? 1 : 0;
+    {
+        float v = 0.f;
+        int j = 0, rank = 0;
+        if (lane < a.k) {
+            v = ssim[lane]; j = sj[lane];
+            for (int e = 0; e < a.k; ++e) {
+                const float o = ssim[e];
+                const int oj = sj[e];
+                rank += (o > v || (o == v && oj < j)) ? 1 : 0;
+            }
+        }
+        __syncwarp();
+        if (lane < a.k) { sd[rank] = v; sj[rank] = j; }
     }
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-        if (lane + 32 * t < a.S && rank[t] < a.k) { sj[rank[t]] = lane + 32 * t; sd[rank[t]] = mine[t]; }
     __syncwarp();
     // attention (KPAM, M4:351-373): softmax over the k neighbours of W2 relu(W1 d)
     float z = 0.f;
@@ -163,7 +221,6 @@ __device__ __forceinline__ float op_select_attend(const OpArgs &a, const OpSmem 
 // forward: one warp per point.  grid (ceil(N / OP_PTS), B), block 256, dynamic smem op_smem_floats
 __global__ void __launch_bounds__(OP_WARPS * 32) op_forward_kernel(OpArgs a) {
     extern __shared__ __align__(16) float op_sm[];
-    __shared__ double red[OP_WARPS * 32][2];
     const OpSmem sm = op_carve(op_sm, a.S, a.E, a.k);
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     op_load_tables(a, sm, b);
@@ -216,15 +273,17 @@ __global__ void __launch_bounds__(OP_WARPS * 32) op_forward_kernel(OpArgs a) {
         for (int v = 0; v < 4; ++v) { s1 += (double)vs[v]; s2 += (double)vq[v]; }
         __syncwarp();
     }
-    red[threadIdx.x][0] = s1;
-    red[threadIdx.x][1] = s2;
+    // per-group sums: the lanes of a group are contiguous (channels of a lane never straddle a group)
+    const int lpg = 32 / a.G;
+    for (int o = 1; o < lpg; o <<= 1) { s1 += __shfl_xor_sync(OFULL, s1, o); s2 += __shfl_xor_sync(OFULL, s2, o); }
+    __syncwarp();
+    double *wred = reinterpret_cast<double *>(ws);               // the warp's similarity scratch (128 floats) is free now
+    if (lane % lpg == 0) { wred[(lane / lpg) * 2] = s1; wred[(lane / lpg) * 2 + 1] = s2; }
     __syncthreads();
     if (threadIdx.x < a.G * 2) {
         const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
-        const int lpg = 32 / a.G;
         double s = 0.0;
-        for (int w = 0; w < OP_WARPS; ++w)
-            for (int l = g * lpg; l < (g + 1) * lpg; ++l) s += red[w * 32 + l][which];
+        for (int w = 0; w < OP_WARPS; ++w) s += reinterpret_cast<const double *>(sm.wsc + w * sm.per_warp)[g * 2 + which];
         a.part[(((size_t)b * gridDim.x + blockIdx.x) * a.G + g) * 2 + which] = s;
     }
 }
@@ -356,22 +415,12 @@ __global__ void __launch_bounds__(OP_WARPS * 32) op_bwd_reduce_kernel(OpBwdArgs 
     }
 }
 
-// per cloud: (A_g, K_g); over clouds: dgamma, dbeta; over all CTAs: d(W_o), d(b_o).   grid B + 1 CTAs of 256 threads
+// per cloud: (A_g, K_g) and the per-channel sums behind dgamma, dbeta.   grid B CTAs of 256 threads
 __global__ void __launch_bounds__(256) op_bwd_coef_kernel(OpBwdArgs p, float *__restrict__ dgamma, float *__restrict__ dbeta,
                                                           float *__restrict__ dow, float *__restrict__ dob, double *__restrict__ sbc,
                                                           int nblk) {
     const OpArgs &a = p.f;
     __shared__ double gs[2][32];
-    if ((int)blockIdx.x == a.B) {
-        // d(W_o), d(b_o): fixed-order sum of the per-CTA partials
-        const int total = a.B * nblk;
-        for (int e = threadIdx.x; e < 6 * OP_F + 3; e += blockDim.x) {
-            double s = 0.0;
-            for (int i = 0; i < total; ++i) s += (double)p.owpart[(size_t)i * (6 * OP_F + 3) + e];
-            if (e < 6 * OP_F) dow[e] = (float)s; else dob[e - 6 * OP_F] = (float)s;
-        }
-        return;
-    }
     const int b = blockIdx.x;
     for (int e = threadIdx.x; e < 2 * 32; e += blockDim.x) gs[e / 32][e % 32] = 0.0;
     __syncthreads();
@@ -396,7 +445,24 @@ __global__ void __launch_bounds__(256) op_bwd_coef_kernel(OpBwdArgs p, float *__
         p.coef[((size_t)b * a.G + g) * 2] = (float)(-rstd * m1 + rstd * rstd * m2 * mean);
         p.coef[((size_t)b * a.G + g) * 2 + 1] = (float)(-rstd * rstd * m2);
     }
-    (void)dgamma; (void)dbeta;
+    (void)dgamma; (void)dbeta; (void)dow; (void)dob;
+}
+
+// d(W_o), d(b_o): sum of the per-CTA partials in a fixed order.  block (32 entries, 32 slices of the partial list)
+__global__ void __launch_bounds__(1024) op_bwd_ow_kernel(const float *__restrict__ owpart, int total, float *__restrict__ dow,
+                                                         float *__restrict__ dob) {
+    __shared__ double red[32][33];
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (e < 6 * OP_F + 3)
+        for (int i = threadIdx.y; i < total; i += 32) s += (double)owpart[(size_t)i * (6 * OP_F + 3) + e];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < 6 * OP_F + 3) {
+        double t = 0.0;
+        for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+        if (e < 6 * OP_F) dow[e] = (float)t; else dob[e - 6 * OP_F] = (float)t;
+    }
 }
 
 __global__ void op_bwd_affine_kernel(const double *__restrict__ sbc, float *__restrict__ dgamma, float *__restrict__ dbeta, int B) {
@@ -410,7 +476,7 @@ __global__ void op_bwd_affine_kernel(const double *__restrict__ sbc, float *__re
 // pass 2: the edges again.  One warp per point.  Key-side gradients (dT, d k^) go straight to global memory as vector
 // reductions (red.global.add.v4.f32 / v2.f32, resolved in L2): fp32 atomicAdd on SHARED memory is a compare-and-swap loop,
 // and with 120 keys shared by all points it made this kernel 16 % of the whole training step (959 M instructions, ncu).
-__global__ void __launch_bounds__(OP_WARPS * 32) op_bwd_main_kernel(OpBwdArgs p) {
+__global__ void __launch_bounds__(OP_WARPS * 32, 2) op_bwd_main_kernel(OpBwdArgs p) {
     const OpArgs &a = p.f;
     extern __shared__ __align__(16) float op_sm[];
     __shared__ float s_red[OP_WARPS][2 * OP_KMAX + 1];
@@ -471,24 +537,53 @@ __global__ void __launch_bounds__(OP_WARPS * 32) op_bwd_main_kernel(OpBwdArgs p)
             sv[v] = rstd * gm[v] * duv[v];
             dq[v] = 0.f;
         }
+        // d(attention): da_k = sum over the 128 channels of dy t.  One butterfly reduction per edge is a chain of five
+        // dependent shuffles (150 per point); eight edges at a time are reduce-scattered instead: 7 + 2 shuffles per
+        // chunk, after which lane l holds the total of edge 8 chunk + (l & 7)
         float da_mine = 0.f;
-        for (int kk = 0; kk < a.k; ++kk) {
-            const float at = sa[kk];
-            const int j = sj[kk];
-            const float4 t4 = *reinterpret_cast<const float4 *>(sm.T + j * OP_F + c0);
-            const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
-            float dap = 0.f, adt[4];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const float t = tv[v] - q[v];
-                const float dy = (ak[v] == kk ? sv[v] : 0.f) + fmaf(Kg, at * t, Ag);
-                dap = fmaf(dy, t, dap);
-                adt[v] = at * dy;
-                dq[v] -= adt[v];
+        for (int ch = 0; ch < OP_KMAX / 8; ++ch) {
+            if (ch * 8 >= a.k) break;
+            float dv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int kk = ch * 8 + u;
+                dv[u] = 0.f;
+                if (kk < a.k) {
+                    const float at = sa[kk];
+                    const int j = sj[kk];
+                    const float4 t4 = *reinterpret_cast<const float4 *>(sm.T + j * OP_F + c0);
+                    const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+                    float dap = 0.f, adt[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float t = tv[v] - q[v];
+                        const float dy = (ak[v] == kk ? sv[v] : 0.f) + fmaf(Kg, at * t, Ag);
+                        dap = fmaf(dy, t, dap);
+                        adt[v] = at * dy;
+                        dq[v] -= adt[v];
+                    }
+                    atomicAdd(reinterpret_cast<float4 *>(dT + (size_t)j * OP_F), make_float4(adt[0], adt[1], adt[2], adt[3]));
+                    dv[u] = dap;
+                }
             }
-            atomicAdd(reinterpret_cast<float4 *>(dT + (size_t)j * OP_F), make_float4(adt[0], adt[1], adt[2], adt[3]));
-            for (int o = 16; o; o >>= 1) dap += __shfl_xor_sync(OFULL, dap, o);
-            if (lane == kk) da_mine = dap;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float send = (lane & 4) ? dv[i] : dv[i + 4], keep = (lane & 4) ? dv[i + 4] : dv[i];
+                dv[i] = keep + __shfl_xor_sync(OFULL, send, 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float send = (lane & 2) ? dv[i] : dv[i + 2], keep = (lane & 2) ? dv[i + 2] : dv[i];
+                dv[i] = keep + __shfl_xor_sync(OFULL, send, 2);
+            }
+            {
+                const float send = (lane & 1) ? dv[0] : dv[1], keep = (lane & 1) ? dv[1] : dv[0];
+                dv[0] = keep + __shfl_xor_sync(OFULL, send, 1);
+            }
+            dv[0] += __shfl_xor_sync(OFULL, dv[0], 8);
+            dv[0] += __shfl_xor_sync(OFULL, dv[0], 16);
+            if ((lane >> 3) == ch) da_mine = dv[0];
         }
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -533,7 +628,7 @@ __global__ void __launch_bounds__(OP_WARPS * 32) op_bwd_main_kernel(OpBwdArgs p)
                 const float u0 = su[c], u1 = su[c + 1];
                 for (int kk = 0; kk < a.k; ++kk) {
                     const float ddk = ssim[64 + kk];
-                    const float *kr = sm.keyn + sj[kk] * (a.E + 1) + c;
+                    const float *kr = sm.keyn + sj[kk] * (a.E + OP_KS) + c;
                     dun[e][0] = fmaf(ddk, kr[0], dun[e][0]);
                     dun[e][1] = fmaf(ddk, kr[1], dun[e][1]);
                     atomicAdd(reinterpret_cast<float2 *>(dkn + (size_t)sj[kk] * a.E + c), make_float2(ddk * u0, ddk * u1));
@@ -599,24 +694,40 @@ __global__ void __launch_bounds__(128) op_bwd_keys_kernel(OpBwdArgs p) {
     for (int c = t; c < a.E; c += 128) p.dinst[row * a.E + c] += (dk[c] - dot * kn[c]) / nrm;
 }
 
-// d conv weight [128][131]: columns f < 128 and the p_j part of the position columns from dT, the -p_i part from dwp
-__global__ void __launch_bounds__(OP_F + 3) op_bwd_convw_kernel(OpBwdArgs p, float *__restrict__ dcw) {
+// d conv weight [128][131]: columns f < 128 and the p_j part of the position columns from dT, the -p_i part from dwp.
+// dcw[c][f] = sum over (cloud, key) of dT[c] * [feature ; position][f]: grid (16 channel blocks, B), thread = column f;
+// the per-cloud partials are summed in a fixed order by op_bwd_convw_sum_kernel.
+__global__ void __launch_bounds__(OP_F + 3) op_bwd_convw_kernel(OpBwdArgs p, float *__restrict__ part) {
     const OpArgs &a = p.f;
+    __shared__ int rows[OP_SMAX];
+    __shared__ float dts[OP_SMAX][8];
+    const int cb = blockIdx.x, b = blockIdx.y, f = threadIdx.x;
+    for (int j = f; j < a.S; j += OP_F + 3) rows[j] = a.sub[j];
+    for (int e = f; e < a.S * 8; e += OP_F + 3) dts[e >> 3][e & 7] = p.dT[((size_t)b * a.S + (e >> 3)) * OP_F + cb * 8 + (e & 7)];
+    __syncthreads();
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int j = 0; j < a.S; ++j) {
+        const size_t row = (size_t)b * a.N + rows[j];
+        const float x = f < OP_F ? a.feat[row * OP_F + f] : a.points[row * 3 + f - OP_F];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = fmaf(dts[j][u], x, acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) part[((size_t)b * OP_F + cb * 8 + u) * (OP_F + 3) + f] = acc[u];
+}
+
+__global__ void __launch_bounds__(OP_F + 3) op_bwd_convw_sum_kernel(OpBwdArgs p, const float *__restrict__ part, float *__restrict__ dcw) {
     const int c = blockIdx.x, f = threadIdx.x;
     double acc = 0.0;
-    for (int b = 0; b < a.B; ++b)
-        for (int j = 0; j < a.S; ++j) {
-            const size_t row = (size_t)b * a.N + a.sub[j];
-            const float x = f < OP_F ? a.feat[row * OP_F + f] : a.points[row * 3 + f - OP_F];
-            acc += (double)p.dT[((size_t)b * a.S + j) * OP_F + c] * x;
-        }
+    for (int b = 0; b < p.f.B; ++b) acc += (double)part[((size_t)b * OP_F + c) * (OP_F + 3) + f];
     if (f >= OP_F) acc += (double)p.dwp[c * 3 + f - OP_F];
     dcw[(size_t)c * (OP_F + 3) + f] = (float)acc;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 struct OpSaved { float *T, *keyn, *knorm, *seld, *sela, *ysel, *stats; unsigned char *selj, *arg; };
-struct OpWs { double *part, *sbc; float *du, *rpart, *owpart, *coef, *dT, *dkn, *dw, *dwp; };
+struct OpWs { double *part, *sbc; float *du, *rpart, *owpart, *coef, *cwpart, *dT, *dkn, *dw, *dwp; };
 
 static int op_check(const gcanet_offset_desc *d) {
     GCANET_REQUIRE(d != nullptr, "offset_pred: null descriptor");
@@ -652,9 +763,10 @@ static size_t op_plan_ws(const gcanet_offset_desc *d, void *base, OpWs *w) {
     float *rpart = cv.take<float>((size_t)d->B * nblk * OP_F * 2);
     float *owpart = cv.take<float>((size_t)d->B * nblk * (6 * OP_F + 3));
     float *coef = cv.take<float>((size_t)d->B * d->groups * 2);
+    float *cwpart = cv.take<float>((size_t)d->B * OP_F * (OP_F + 3));
     // zeroed in one memset: dT | dkn | dw1 | dw2 | dwp
     float *dT = cv.take<float>(bs * OP_F + bs * d->E + 2 * d->k * d->k + OP_F * 3);
-    if (w) { w->part = part; w->sbc = sbc; w->du = du; w->rpart = rpart; w->owpart = owpart; w->coef = coef; w->dT = dT;
+    if (w) { w->part = part; w->sbc = sbc; w->du = du; w->rpart = rpart; w->owpart = owpart; w->coef = coef; w->cwpart = cwpart; w->dT = dT;
              w->dkn = dT + bs * OP_F; w->dw = w->dkn + bs * d->E; w->dwp = w->dw + 2 * d->k * d->k; }
     return cv.off;
 }
@@ -746,8 +858,10 @@ extern "C" int gcanet_offset_pred_backward(const gcanet_offset_desc *d, const fl
     const int nblk = ceil_div(d->N, OP_PTS);
     op_bwd_reduce_kernel<<<dim3(nblk, d->B), OP_WARPS * 32, 0, st>>>(p);
     GCANET_LAUNCH_OK("op_bwd_reduce_kernel");
-    op_bwd_coef_kernel<<<d->B + 1, 256, 0, st>>>(p, grad_gamma, grad_beta, grad_off_w, grad_off_b, w.sbc, nblk);
+    op_bwd_coef_kernel<<<d->B, 256, 0, st>>>(p, grad_gamma, grad_beta, grad_off_w, grad_off_b, w.sbc, nblk);
     GCANET_LAUNCH_OK("op_bwd_coef_kernel");
+    op_bwd_ow_kernel<<<ceil_div(6 * OP_F + 3, 32), dim3(32, 32), 0, st>>>(w.owpart, d->B * nblk, grad_off_w, grad_off_b);
+    GCANET_LAUNCH_OK("op_bwd_ow_kernel");
     op_bwd_affine_kernel<<<1, OP_F, 0, st>>>(w.sbc, grad_gamma, grad_beta, d->B);
     GCANET_LAUNCH_OK("op_bwd_affine_kernel");
     const size_t smem = op_smem_floats(d->S, d->E, d->k) * sizeof(float);
@@ -757,8 +871,10 @@ extern "C" int gcanet_offset_pred_backward(const gcanet_offset_desc *d, const fl
     GCANET_LAUNCH_OK("op_bwd_main_kernel");
     op_bwd_keys_kernel<<<dim3(d->S, d->B), 128, 0, st>>>(p);
     GCANET_LAUNCH_OK("op_bwd_keys_kernel");
-    op_bwd_convw_kernel<<<OP_F, OP_F + 3, 0, st>>>(p, grad_conv_w);
+    op_bwd_convw_kernel<<<dim3(OP_F / 8, d->B), OP_F + 3, 0, st>>>(p, w.cwpart);
     GCANET_LAUNCH_OK("op_bwd_convw_kernel");
+    op_bwd_convw_sum_kernel<<<OP_F, OP_F + 3, 0, st>>>(p, w.cwpart, grad_conv_w);
+    GCANET_LAUNCH_OK("op_bwd_convw_sum_kernel");
     GCANET_CUDA_OK(cudaMemcpyAsync(grad_att_w1, p.dw1, (size_t)d->k * d->k * sizeof(float), cudaMemcpyDeviceToDevice, st));
     GCANET_CUDA_OK(cudaMemcpyAsync(grad_att_w2, p.dw2, (size_t)d->k * d->k * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return GCANET_OK;
