@@ -1283,7 +1283,7 @@ struct NFwdArgs {
 template <int VEC>
 __global__ void __launch_bounds__(kGWarps * 32) normal_edge_forward_kernel(NFwdArgs a) {
     __shared__ double red[kGWarps * 32][2];
-    __shared__ float s_e[kGWarps][8];
+    __shared__ float4 s_edge[kGWarps][64];
     __shared__ double s_mom[kGWarps][kNMom];
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1296,21 +1296,13 @@ __global__ void __launch_bounds__(kGWarps * 32) normal_edge_forward_kernel(NFwdA
         for (int f = 0; f < kNF; ++f) w[v][f] = a.weight[(size_t)(c0 + v) * kNF + f];
         sg[v] = a.gamma[c0 + v] < 0.f ? -1.f : 1.f;
     }
-    // moment slots of this lane: item `lane` and, for lanes 0..2, item 32 + lane
-    // items 0..6 = E1[f]; items 7.. = E2 pairs (f <= g) in row-major order
-    int f1[2], g1[2];
+    // Edges are staged 64 at a time: lane l loads the neighbour index and normal of edges l and 32 + l (two independent
+    // loads per lane instead of a chain of k dependent ones), forms (angle, n_j) and adds its edges' 35 feature moments
+    // (7 first + 28 second, items in row-major order of the pairs f <= g) to its own registers; the channel loop then
+    // reads the staged edges back as broadcasts.  The moments are summed over the lanes once, at the end.
+    float macc[kNMom];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        int item = lane + 32 * t;
-        f1[t] = -1; g1[t] = -1;
-        if (item < kNF) { f1[t] = item; }
-        else if (item < kNMom) {
-            int r = item - kNF, f = 0;
-            while (r >= kNF - f) { r -= kNF - f; ++f; }
-            f1[t] = f; g1[t] = f + r;
-        }
-    }
-    float macc[2] = {0.f, 0.f};
+    for (int m = 0; m < kNMom; ++m) macc[m] = 0.f;
     double s1 = 0.0, s2 = 0.0;
 
     for (int pi = 0; pi < kPtsPerWarp; ++pi) {
@@ -1326,28 +1318,41 @@ __global__ void __launch_bounds__(kGWarps * 32) normal_edge_forward_kernel(NFwdA
             zmax[v] = -CUDART_INF_F; vsum[v] = 0.f; vsq[v] = 0.f; kbest[v] = 0;
         }
         const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
-        for (int kk = 0; kk < k; ++kk) {
-            const int j = ip[kk];                                   // same address in every lane
-            const float b0 = xb[(size_t)j * a.ldx + 3], b1 = xb[(size_t)j * a.ldx + 4], b2 = xb[(size_t)j * a.ldx + 5];
-            const float ang = normal_angle(a0, a1, a2, b0, b1, b2);
+        for (int k0 = 0; k0 < k; k0 += 64) {
+            const int kn = min(64, k - k0);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                float y = fmaf(w[v][0], ang, base[v]);
-                y = fmaf(w[v][1], b0, y);
-                y = fmaf(w[v][2], b1, y);
-                y = fmaf(w[v][3], b2, y);
-                const float z = sg[v] * y;
-                if (z > zmax[v]) { zmax[v] = z; kbest[v] = kk; }
-                vsum[v] += y;
-                vsq[v] = fmaf(y, y, vsq[v]);
+            for (int t = 0; t < 2; ++t) {
+                const int kk = lane + 32 * t;
+                if (kk < kn) {
+                    const int j = ip[k0 + kk];
+                    const float b0 = xb[(size_t)j * a.ldx + 3], b1 = xb[(size_t)j * a.ldx + 4], b2 = xb[(size_t)j * a.ldx + 5];
+                    const float ang = normal_angle(a0, a1, a2, b0, b1, b2);
+                    s_edge[warp][kk] = make_float4(ang, b0, b1, b2);
+                    const float e[kNF] = {ang, b0 - a0, b1 - a1, b2 - a2, a0, a1, a2};
+                    int m = kNF;
+#pragma unroll
+                    for (int f = 0; f < kNF; ++f) {
+                        macc[f] += e[f];
+#pragma unroll
+                        for (int g = f; g < kNF; ++g) { macc[m] = fmaf(e[f], e[g], macc[m]); ++m; }
+                    }
+                }
             }
-            // feature moments: every lane owns up to two of the 35 sums
-            const float e[kNF] = {ang, b0 - a0, b1 - a1, b2 - a2, a0, a1, a2};
-            if (lane < kNF) s_e[warp][lane] = lane == 0 ? e[0] : (lane == 1 ? e[1] : (lane == 2 ? e[2] : (lane == 3 ? e[3] : (lane == 4 ? e[4] : (lane == 5 ? e[5] : e[6])))));
             __syncwarp();
+            for (int kk = 0; kk < kn; ++kk) {
+                const float4 nb = s_edge[warp][kk];
 #pragma unroll
-            for (int t = 0; t < 2; ++t)
-                if (f1[t] >= 0) macc[t] += g1[t] >= 0 ? s_e[warp][f1[t]] * s_e[warp][g1[t]] : s_e[warp][f1[t]];
+                for (int v = 0; v < VEC; ++v) {
+                    float y = fmaf(w[v][0], nb.x, base[v]);
+                    y = fmaf(w[v][1], nb.y, y);
+                    y = fmaf(w[v][2], nb.z, y);
+                    y = fmaf(w[v][3], nb.w, y);
+                    const float z = sg[v] * y;
+                    if (z > zmax[v]) { zmax[v] = z; kbest[v] = k0 + kk; }
+                    vsum[v] += y;
+                    vsq[v] = fmaf(y, y, vsq[v]);
+                }
+            }
             __syncwarp();
         }
         const size_t o = ((size_t)b * a.N + i) * Cout + c0;
@@ -1364,9 +1369,10 @@ __global__ void __launch_bounds__(kGWarps * 32) normal_edge_forward_kernel(NFwdA
     red[threadIdx.x][0] = s1;
     red[threadIdx.x][1] = s2;
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        int item = lane + 32 * t;
-        if (item < kNMom) s_mom[warp][item] = (double)macc[t];
+    for (int m = 0; m < kNMom; ++m) {
+        double v = (double)macc[m];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULLM, v, o);
+        if (lane == 0) s_mom[warp][m] = v;
     }
     __syncthreads();
     if (threadIdx.x < a.G * 2) {
@@ -1467,16 +1473,25 @@ __global__ void __launch_bounds__(kGWarps * 32) normal_edge_bwd_kernel(NBwdArgs 
 }
 
 // dW[c][f] = sum_{b,blk} dw_part + sum_b (A_g E1_b[f] + K_g sum_f' W[c][f'] E2_b[f'][f])
-__global__ void normal_edge_dw_kernel(const float *__restrict__ dw_part, const float *__restrict__ coef,
-                                      const float *__restrict__ mom, const float *__restrict__ weight,
-                                      float *__restrict__ dW, int B, int nblk, int Cout, int G) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= Cout * kNF) return;
+// block (32 entries, 32 slices of the partial list): the partials are summed slice by slice, then across the slices, in a
+// fixed order
+__global__ void __launch_bounds__(1024) normal_edge_dw_kernel(const float *__restrict__ dw_part, const float *__restrict__ coef,
+                                                              const float *__restrict__ mom, const float *__restrict__ weight,
+                                                              float *__restrict__ dW, int B, int nblk, int Cout, int G) {
+    __shared__ double red[32][33];
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    const bool live = e < Cout * kNF;
+    double s = 0.0;
+    if (live)
+        for (int i = threadIdx.y; i < B * nblk; i += 32) s += (double)dw_part[(size_t)i * Cout * kNF + e];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y != 0 || !live) return;
+    s = 0.0;
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
     const int c = e / kNF, f = e % kNF;
     const int g = c / (Cout / G);
-    double s = 0.0;
     for (int b = 0; b < B; ++b) {
-        for (int i = 0; i < nblk; ++i) s += (double)dw_part[((size_t)b * nblk + i) * Cout * kNF + e];
         const float Ag = coef[((size_t)b * G + g) * 2 + 0], Kg = coef[((size_t)b * G + g) * 2 + 1];
         const float *m = mom + b * 56;
         double we2 = 0.0;
@@ -1571,7 +1586,7 @@ static int run_nbackward(const gcanet_normal_edge_desc *d, const float *x_nc, co
     NBwdArgs na{x_nc, idx, sv.ysel, sv.stats, gamma, beta, gout, sv.arg, w.dw_part, d->N, d->ldx, Cout, d->k, d->groups, d->slope};
     normal_edge_bwd_kernel<VEC><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(na);
     GCANET_LAUNCH_OK("normal_edge_bwd_kernel");
-    normal_edge_dw_kernel<<<ceil_div(Cout * kNF, 128), 128, 0, st>>>(w.dw_part, w.coef, sv.mom, weight, grad_weight, d->B,
+    normal_edge_dw_kernel<<<ceil_div(Cout * kNF, 32), dim3(32, 32), 0, st>>>(w.dw_part, w.coef, sv.mom, weight, grad_weight, d->B,
                                                                      nblk, Cout, d->groups);
     GCANET_LAUNCH_OK("normal_edge_dw_kernel");
     return GCANET_OK;
