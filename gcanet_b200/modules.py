@@ -114,7 +114,13 @@ class SoftProjection(nn.Module):
     """Drop-in for ``SoftProjection`` (models/search_knn.py:44-174): soft nearest-neighbour
     projection / feature propagation on top of ``knn_point`` + ``grouping_operation``; same
     constructor, ``forward(point_cloud, query_cloud, point_features=None, action=...)``,
-    ``project`` / ``propagate`` / ``project_and_propagate`` and ``sigma()``."""
+    ``project`` / ``propagate`` / ``project_and_propagate`` and ``sigma()``.
+
+    This class is a SHIM, not a kernel: the two native calls underneath (``knn_point`` -> ``gcanet_knn_cuda``,
+    ``grouping_operation`` -> ``gcanet_group_points``) are the hot path; the soft-max weighting around them is the
+    reference's own handful of elementwise torch ops on [B, C, Nq, k] tensors with k = 1..3 and stays on torch.  It
+    exists so that ``models/search_knn.py``'s own tests (the golden vectors of search_knn.py:180-304) run unchanged
+    against this package."""
 
     def __init__(self, group_size, initial_temperature=1.0, is_temperature_trainable=True, min_sigma=1e-4):
         super().__init__()
