@@ -9,8 +9,9 @@ ABC-shaped clouds: B = 16 clouds x 10 000 points, k = 50, mode 0 (configs[1] of
 BASELINE.json) per GPU; with N > 1 the batch is sharded by cloud (weak scaling: 16
 clouds per GPU) and the weight gradients are all-reduced once per step over NCCL.
 
-The timed step is one CUDA-graph replay of forward + backward (same kernels as the eager call sequence; `--no-graph`
-times the eager sequence, whose per-call breakdown is reported either way), followed by the all-reduce when N > 1.
+The timed step is one CUDA-graph replay of forward + backward (same kernels as the eager call sequence, run as
+`--streams` half-batch branches on separate streams inside the graph; `--no-graph` times the eager sequence, whose
+per-call breakdown is reported either way), followed by the all-reduce when N > 1.
 
 Prints ONE JSON line (rank 0).  `value` = clouds/s with inputs resident in HBM, timed with
 CUDA events, max over ranks; `e2e` = the same step driven from pinned HOST buffers through
@@ -18,6 +19,12 @@ the public API (H2D of the batch and D2H of the loss inside the timed region);
 `roofline` = the dominant kernel (feature-space kNN) against the measured tensor peak;
 `cpu_baseline` = the oracle (a torch-CPU restatement of the reference path) on this box's
 host cores, on a bounded sample.  `--impl reference` times that CPU path alone.
+
+Extra keys on the same line (skipped with `--no-extras`, all outside the timed region of the headline):
+`gpu_reference` (the oracle's torch path on this GPU), `config3_knn_sweep`, `config4_full_step` (per-point training
+step, mode 5), `config4_fixed_global_batch` (128 clouds over N GPUs), `config5_large_clouds` (4 x 100 k points),
+`bf16_storage_mode`, and for N > 1 `allreduce_check` (the collective checked against an all-gather) and `multi_gpu`
+(every rank's own step time, the spread between ranks, what remains for the collective).
 """
 from __future__ import annotations
 
