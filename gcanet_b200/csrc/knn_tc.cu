@@ -1097,6 +1097,7 @@ struct TcpScanArgs {
     int N, k, tiles, pre, P;  // P = tiles rounded up to a power of two (sort width)
     int qtiles;
     long long *prof;        // [B * qtiles][16] per-CTA cycle counters (measurement builds, GCANET_TC_PROF=1), else null
+    int refresh0, refresh_mul, refresh_max;   // pass A publishes its bound after refresh0 tiles, then every refresh_mul times as many, up to refresh_max
 };
 
 #ifdef GCANET_MEASUREMENT_AIDS
@@ -1493,7 +1494,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
             float m[32 * SM];
 #pragma unroll
             for (int s = 0; s < 32 * SM; ++s) m[s] = CUDART_INF_F;
-            int done = 0, refresh_at = 12;
+            int done = 0, refresh_at = a.refresh0;
             for (;; ++seq) {
                 { TCP_PROF_T0(); mbar_wait(&t_full[acc], accphase); TCP_PROF_ADD(pw0); }
                 if (seq == s_end[0]) break;
@@ -1533,7 +1534,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
                 if (++done == refresh_at) {
                     // let the producer start skipping: publish the bound reached so far (after 12 and 36 tiles: each
                     // refresh costs about as much as six tiles of this pass)
-                    refresh_at = refresh_at < 36 ? refresh_at * 3 : 0x7fffffff;
+                    refresh_at = refresh_at < a.refresh_max ? refresh_at * a.refresh_mul : 0x7fffffff;
                     TCP_PROF_T0();
                     const float bd = row_bound(m, 6);
                     TCP_PROF_ADD(prof_refresh);
@@ -1922,7 +1923,10 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         }
         long long *prof = GCANET_AID_ENV("GCANET_TC_PROF") ? prof_buf : nullptr;
         if (prof) GCANET_CUDA_OK(cudaMemsetAsync(prof, 0, (size_t)B * qtiles * 16 * sizeof(long long), st));
-        TcpScanArgs sa{norm_pad, Npad, xs, kext, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, structured, N, k2, tiles, pre, P, qtiles, prof};
+        int r0 = 12, rmul = 3, rmax = 36;
+        if (const char *e = GCANET_AID_ENV("GCANET_TC_REFRESH")) sscanf(e, "%d,%d,%d", &r0, &rmul, &rmax);   // measurement aid
+        TcpScanArgs sa{norm_pad, Npad, xs, kext, nmax, boxes, boxes32, perm, cand, cand_cnt, overflow, visited, work, structured, N, k2, tiles, pre, P, qtiles, prof,
+                       r0, rmul, rmax};
         RerankArgs ra{x_nc, norm, nmax, cand, cand_cnt, overflow, idx64, idx32, N, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2),
                       (unordered && k1 == k2) ? 1 : 0, perm, TCP_CAP, 1, big_list, big_count, fb_list, fb_count};
         int fstride = (int)(tiles * 0.381966f);

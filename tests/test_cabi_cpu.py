@@ -108,3 +108,23 @@ def test_encoder_state_dict_keys_match_reference_layout():
     ref = orc.DGCNNEncoderGn(mode=5, nn_nb=80, input_channels=6)
     assert list(ref.state_dict()) == list(sd)
     enc.load_state_dict(ref.state_dict())
+
+
+def test_dispatcher_ops_registered_with_shape_inference():
+    """gcanet_b200.torch_ops: the operators exist under torch.ops.gcanet_b200 and their fake implementations infer the
+    reference's shapes / dtypes on meta tensors (no kernel runs, no GPU needed)."""
+    import torch
+    import gcanet_b200.torch_ops  # noqa: F401
+    ops = torch.ops.gcanet_b200
+    x = torch.empty(2, 64, 1000, device="meta")
+    idx = ops.knn_graph(x, 10, 40, 0, True)
+    assert idx.shape == (2, 1000, 10) and idx.dtype == torch.int64
+    d, i = ops.knn_cuda(torch.empty(2, 3, 500, device="meta"), torch.empty(2, 3, 70, device="meta"), 4)
+    assert d.shape == (2, 4, 70) and i.dtype == torch.int64
+    g = ops.group_points(torch.empty(2, 16, 500, device="meta"), torch.empty(2, 70, 4, dtype=torch.int32, device="meta"))
+    assert g.shape == (2, 16, 70, 4)
+    o_nc, o_cn, saved = ops.edgeconv_forward(torch.empty(2, 1000, 64, device="meta"),
+                                             torch.empty(2, 1000, 20, dtype=torch.int32, device="meta"),
+                                             torch.empty(128, 128, device="meta"), torch.empty(128, device="meta"),
+                                             torch.empty(128, device="meta"), 64, 2, 1e-5, 0.2)
+    assert o_nc.shape == (2, 1000, 128) and o_cn.shape == (2, 128, 1000) and saved.dtype == torch.uint8 and saved.numel() > 0

@@ -173,3 +173,31 @@ def test_group_norm_relu_vs_torch(B, C, N, groups):
             assert float(err.max()) <= 2e-5 * float(want.abs().max()), f"{name} relu={relu}: {float(err.max()):.3e}"
     with pytest.raises(RuntimeError):
         G.group_norm_relu(torch.zeros(2, 10, 8, device=DEV), torch.ones(10, device=DEV), torch.zeros(10, device=DEV), 4)
+
+
+def test_dispatcher_ops_equal_functional_and_pass_opcheck():
+    """torch.ops.gcanet_b200.* (gcanet_b200/torch_ops.py) are the same kernels behind the PyTorch dispatcher: equal results
+    and gradients to the functional API, and torch.library.opcheck (schema, fake tensor, autograd registration) passes."""
+    import gcanet_b200.torch_ops as T
+    from gcanet_b200.synth import abc_like_batch
+    torch.manual_seed(0)
+    x = torch.from_numpy(abc_like_batch(2, 1500, seed=5)).to(DEV)
+    i64 = torch.ops.gcanet_b200.knn_graph(x, 20, 20, 0, True)
+    assert torch.equal(i64, G.knn(x, 20, 20))
+    feat = torch.randn(2, 64, 1500, device=DEV)
+    x_nc = G.to_point_major(feat)
+    _, idx32 = G.knn_graph(feat, 20, 20, want64=False, want32=True)
+    w = (torch.randn(128, 128, device=DEV) * 0.1).requires_grad_(True)
+    gm, bt = torch.randn(128, device=DEV).requires_grad_(True), torch.randn(128, device=DEV).requires_grad_(True)
+    xa, xb = x_nc.clone().requires_grad_(True), x_nc.clone().requires_grad_(True)
+    o1, c1 = G.edgeconv(xa, idx32, w, gm, bt, C=64)
+    g1 = torch.autograd.grad((o1.square().sum() + c1.sum()), (xa, w, gm, bt))
+    o2, c2 = T.edgeconv(xb, idx32, w, gm, bt, C=64)
+    g2 = torch.autograd.grad((o2.square().sum() + c2.sum()), (xb, w, gm, bt))
+    assert torch.equal(o1, o2) and torch.equal(c1, c2)
+    for a, b in zip(g1, g2):          # atomics in the scatter: equal up to summation order
+        assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max())
+    f = torch.randn(2, 8, 1500, device=DEV, requires_grad=True)
+    gi = idx32[:, :100, :4].contiguous()
+    torch.library.opcheck(torch.ops.gcanet_b200.group_points.default, (f, gi))
+    torch.library.opcheck(torch.ops.gcanet_b200.knn_graph.default, (x, 20, 20, 0, True), test_utils=("test_schema", "test_faketensor"))
