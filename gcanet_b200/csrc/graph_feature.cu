@@ -10,24 +10,59 @@
 namespace gcanet {
 
 // out[b][i][kk][0:C] = x_j - x_i, out[b][i][kk][C:2C] = x_i          (M4:120-123)
-__global__ void edge_diff_center_kernel(const float *__restrict__ x_nc, const int64_t *__restrict__ idx,
-                                        float *__restrict__ out, int C, int N, int k, long long rows) {
-    // one warp per (b, i, kk) row of 2C floats, grid-stride over rows
+// C % 64 == 0: one warp per output row, four rows in flight; a lane moves 16 bytes per access (at C = 64 the row is exactly
+// one 16-byte load pair and one 16-byte store per lane); rows < 2^31 (32-bit index arithmetic, checked by the caller)
+__global__ void __launch_bounds__(256) edge_diff_center_kernel(const float *__restrict__ x_nc, const int64_t *__restrict__ idx,
+                                                               float *__restrict__ out, int C, int N, int k, unsigned rows) {
     const int lane = threadIdx.x & 31;
-    long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (; w < rows; w += nw) {
-        long long bi = w / k;                 // b * N + i
-        long long b = bi / N;
-        long long j = idx[w];
-        const float *xi = x_nc + bi * C;
-        const float *xj = x_nc + (b * N + j) * C;
-        float *o = out + w * 2 * C;
-        for (int c = lane; c < C; c += 32) {
-            float ci = xi[c];
-            o[c] = xj[c] - ci;
-            o[C + c] = ci;
+    const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w0 < rows; w0 += 4 * nw) {
+        const float *xi[4], *xj[4];
+        unsigned row[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            row[u] = min(w0 + u * nw, rows - 1);                     // (clamped rows are recomputed, not written)
+            const unsigned bi = row[u] / (unsigned)k, b = bi / (unsigned)N;
+            xi[u] = x_nc + (size_t)bi * C;
+            xj[u] = x_nc + ((size_t)b * N + (size_t)idx[row[u]]) * C;
         }
+        for (int o4 = lane * 4; o4 < 2 * C; o4 += 128) {              // o4: offset inside the 2C-float output row
+            const bool diff = o4 < C;
+            const int c4 = diff ? o4 : o4 - C;
+            float4 ci[4], cj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ci[u] = __ldg(reinterpret_cast<const float4 *>(xi[u] + c4));
+                if (diff) cj[u] = __ldg(reinterpret_cast<const float4 *>(xj[u] + c4));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (w0 + u * nw >= rows) continue;
+                float4 v = ci[u];
+                if (diff) v = make_float4(cj[u].x - ci[u].x, cj[u].y - ci[u].y, cj[u].z - ci[u].z, cj[u].w - ci[u].w);
+                *reinterpret_cast<float4 *>(out + (size_t)row[u] * 2 * C + o4) = v;
+            }
+        }
+    }
+}
+
+// any other C (the xyz layers, C = 3 / 6): one thread per output element, so a warp writes 128 contiguous bytes spanning
+// several rows
+template <typename I>
+__global__ void __launch_bounds__(256) edge_diff_center_small_kernel(const float *__restrict__ x_nc, const int64_t *__restrict__ idx,
+                                                                     float *__restrict__ out, int C, int N, int k, I total) {
+    const I w2 = 2 * C, nt = (I)gridDim.x * blockDim.x;
+    for (I t = (I)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nt) {
+        const I row = t / w2;
+        const int c2 = (int)(t - row * w2);
+        const I bi = row / (I)k;
+        const float ci = x_nc[(size_t)bi * C + (c2 < C ? c2 : c2 - C)];
+        float v = ci;
+        if (c2 < C) {
+            const I b = bi / (I)N;
+            v = x_nc[((size_t)b * N + (size_t)idx[row]) * C + c2] - ci;
+        }
+        out[t] = v;
     }
 }
 
@@ -109,30 +144,45 @@ __global__ void edge_normal_angle_grad_kernel(const float *__restrict__ go, cons
 }
 
 // out[b][c][j][s] = points[b][c][idx[b][j][s]]          (group_points_gpu.cu:20-27)
-__global__ void group_points_kernel(const float *__restrict__ points, const int32_t *__restrict__ idx,
-                                    float *__restrict__ out, int c, int n, long long ms, long long total) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per V consecutive (j, s) slots of a batch element: it reads its V indices once and walks the channels, so
+// the index array is read once instead of once per channel, the stores are V-wide and coalesced across the warp, and the
+// inner loop has no division.  (The reference launches one CTA per batch element.)
+template <int V>
+__global__ void __launch_bounds__(256) group_points_kernel(const float *__restrict__ points, const int32_t *__restrict__ idx,
+                                                           float *__restrict__ out, int c, int n, long long ms, long long work) {
+    const long long per_b = ms / V;
     const long long nt = (long long)gridDim.x * blockDim.x;
-    for (; t < total; t += nt) {
-        long long e = t % ms;              // j * nsample + s
-        long long bc = t / ms;             // b * c + l
-        long long b = bc / c;
-        int ii = idx[b * ms + e];
-        out[t] = points[bc * n + ii];
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += nt) {
+        const long long b = t / per_b, e = (t - b * per_b) * V;
+        int ii[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) ii[v] = idx[b * ms + e + v];
+        const float *src = points + b * c * n;
+        float *dst = out + b * c * ms + e;
+#pragma unroll 4
+        for (int l = 0; l < c; ++l) {
+            if constexpr (V == 4) {
+                *reinterpret_cast<float4 *>(dst + (long long)l * ms) =
+                    make_float4(__ldg(src + (long long)l * n + ii[0]), __ldg(src + (long long)l * n + ii[1]),
+                                __ldg(src + (long long)l * n + ii[2]), __ldg(src + (long long)l * n + ii[3]));
+            } else {
+                dst[(long long)l * ms] = __ldg(src + (long long)l * n + ii[0]);
+            }
+        }
     }
 }
 
 // grad_points[b][c][idx[b][j][s]] += grad_out[b][c][j][s]   (group_points_gpu.cu:56-62)
-__global__ void group_points_grad_kernel(const float *__restrict__ go, const int32_t *__restrict__ idx,
-                                         float *__restrict__ gp, int c, int n, long long ms, long long total) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) group_points_grad_kernel(const float *__restrict__ go, const int32_t *__restrict__ idx,
+                                                                float *__restrict__ gp, int c, int n, long long ms, long long work) {
     const long long nt = (long long)gridDim.x * blockDim.x;
-    for (; t < total; t += nt) {
-        long long e = t % ms;
-        long long bc = t / ms;
-        long long b = bc / c;
-        int ii = idx[b * ms + e];
-        atomicAdd(gp + bc * n + ii, go[t]);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += nt) {
+        const long long b = t / ms, e = t - b * ms;
+        const int ii = idx[t];
+        const float *src = go + b * c * ms + e;
+        float *dst = gp + b * c * n + ii;
+#pragma unroll 4
+        for (int l = 0; l < c; ++l) atomicAdd(dst + (long long)l * n, __ldg(src + (long long)l * ms));
     }
 }
 
@@ -187,7 +237,13 @@ extern "C" int gcanet_graph_feature(const float *x, const int64_t *idx, float *o
     if (rc) return rc;
     long long rows = (long long)B * N * k;
     if (variant == GCANET_EDGE_DIFF_CENTER) {
-        edge_diff_center_kernel<<<grid_for(rows, 8), 256, 0, st>>>(x_nc, idx, out, C, N, k, rows);
+        const long long total = rows * 2 * C;
+        if (C % 64 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && rows < 2147483647ll)
+            edge_diff_center_kernel<<<grid_for(rows, 32), 256, 0, st>>>(x_nc, idx, out, C, N, k, (unsigned)rows);
+        else if (total < 4294967295ll)
+            edge_diff_center_small_kernel<unsigned><<<grid_for(total, 256), 256, 0, st>>>(x_nc, idx, out, C, N, k, (unsigned)total);
+        else
+            edge_diff_center_small_kernel<long long><<<grid_for(total, 256), 256, 0, st>>>(x_nc, idx, out, C, N, k, total);
         GCANET_LAUNCH_OK("edge_diff_center_kernel");
     } else {
         edge_normal_angle_kernel<<<grid_for(rows, 256), 256, 0, st>>>(x_nc, idx, out, N, k, rows);
@@ -231,8 +287,14 @@ extern "C" int gcanet_group_points(int b, int c, int n, int npoints, int nsample
                                    const int32_t *idx, float *out, gcanet_stream_t stream) {
     GCANET_REQUIRE(points && idx && out, "group_points: null pointer");
     GCANET_REQUIRE(b >= 1 && c >= 1 && n >= 1 && npoints >= 1 && nsample >= 1, "group_points: bad shape");
-    long long ms = (long long)npoints * nsample, total = (long long)b * c * ms;
-    group_points_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(points, idx, out, c, n, ms, total);
+    const long long ms = (long long)npoints * nsample;
+    if (ms % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+        const long long work = (long long)b * (ms / 4);
+        group_points_kernel<4><<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(points, idx, out, c, n, ms, work);
+    } else {
+        const long long work = (long long)b * ms;
+        group_points_kernel<1><<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(points, idx, out, c, n, ms, work);
+    }
     GCANET_LAUNCH_OK("group_points_kernel");
     return GCANET_OK;
 }
@@ -243,8 +305,8 @@ extern "C" int gcanet_group_points_grad(int b, int c, int n, int npoints, int ns
     GCANET_REQUIRE(b >= 1 && c >= 1 && n >= 1 && npoints >= 1 && nsample >= 1, "group_points_grad: bad shape");
     cudaStream_t st = as_stream(stream);
     GCANET_CUDA_OK(cudaMemsetAsync(grad_points, 0, (size_t)b * c * n * sizeof(float), st));
-    long long ms = (long long)npoints * nsample, total = (long long)b * c * ms;
-    group_points_grad_kernel<<<grid_for(total, 256), 256, 0, st>>>(grad_out, idx, grad_points, c, n, ms, total);
+    const long long ms = (long long)npoints * nsample, work = (long long)b * ms;
+    group_points_grad_kernel<<<grid_for(work, 256), 256, 0, st>>>(grad_out, idx, grad_points, c, n, ms, work);
     GCANET_LAUNCH_OK("group_points_grad_kernel");
     return GCANET_OK;
 }
