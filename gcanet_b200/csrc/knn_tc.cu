@@ -1934,7 +1934,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         auto gcd2 = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
         while (gcd2(fstride, tiles) != 1) ++fstride;
         TcScanArgs fa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, 0, fstride, structured, TCP_CAP, 1};
-        if (k2 <= TC_BN) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, fa, ra, B, st);
+        if (k2 <= TC_BN && !GCANET_AID_ENV("GCANET_TC_SM2")) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, fa, ra, B, st);
         else rc = C == 64 ? launch_tcp<64, 2>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 2>(tmap_q, tmap_k, sa, fa, ra, B, st);
         if (rc) return rc;
         if (prof) {                                // measurement aid: synchronises; mean cycles per CTA and role
