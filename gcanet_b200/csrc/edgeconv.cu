@@ -938,6 +938,162 @@ __global__ void edge_bwd_degfix_small_kernel(float *__restrict__ dpq, const void
     *o = make_float4(out[0], out[1], out[2], out[3]);
 }
 
+// Small-C layer whose input needs NO gradient (layer 1: the input cloud is data): only dW is wanted, and
+//   dWp[c] = sum_i sum_k dy_ikc x_j^T,   dy_ikc = [k = k*] s_ic + A_g + K_g (P_jc + Q_ic),   P_j = Wp x_j
+// needs no scatter at all -- every term is a sum over the edges of a point or collapses onto per-cloud moments:
+//   dWp[c] = sum_i s_ic x_{j*(i,c)}^T + K_g sum_i Q_ic Xbar_i^T + A_g (sum_i Xbar_i)^T + K_g (Wp S)[c],
+//   Xbar_i = sum_k x_j,  S = sum_i sum_k x_j x_j^T (LDX x LDX per cloud),      dWq[c] = sum_i dQ_ic x_i^T.
+// One warp per point stages its k neighbour rows (16 / 32 bytes each) in shared memory; nothing is written per point and
+// there is no atomic: per-CTA partials of dWcat, summed in a fixed order by edge_bwd_dw_small_sum_kernel.  Replaces the
+// X~ scatter, its degree fix-up, the [N][2 Cout] gradient buffer (and its memset) and the X^T dPQ product for this layer.
+constexpr int kDwPts = 16;             // points per warp
+template <int VEC, int LDX>
+__global__ void __launch_bounds__(kGWarps * 32) edge_bwd_dw_small_kernel(BwdArgs a, const float *__restrict__ wcatT,
+                                                                         float *__restrict__ part) {
+    constexpr int COUT = 32 * VEC;
+    __shared__ __align__(16) float s_red[kGWarps][2 * COUT][LDX];      // first the staged neighbour rows, then the reduction
+    __shared__ float s_mom[kGWarps][LDX * LDX + LDX];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = a.k, c0 = lane * VEC;
+    const int cpg = COUT / a.G;
+    const int g = c0 / cpg;
+    const float mean = a.stats[((size_t)b * a.G + g) * 2 + 0], rstd = a.stats[((size_t)b * a.G + g) * 2 + 1];
+    const float Ag = a.coef[((size_t)b * a.G + g) * 2 + 0], Kg = a.coef[((size_t)b * a.G + g) * 2 + 1];
+    float gm[VEC], bt[VEC];
+    VecIO<VEC>::ld(a.gamma + c0, gm);
+    VecIO<VEC>::ld(a.beta + c0, bt);
+    const float *xb = a.x_nc + (size_t)b * a.N * LDX;
+    const size_t cloud0 = (size_t)b * a.N * 2 * COUT;
+    float (*stage)[LDX] = reinterpret_cast<float (*)[LDX]>(&s_red[warp][0][0]);   // [64][LDX] of this warp (2 COUT >= 64 rows)
+    float dwp[VEC][LDX], dwq[VEC][LDX], S[LDX][LDX], xtot[LDX];
+#pragma unroll
+    for (int cc = 0; cc < LDX; ++cc) {
+        xtot[cc] = 0.f;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { dwp[v][cc] = 0.f; dwq[v][cc] = 0.f; }
+#pragma unroll
+        for (int c2 = 0; c2 < LDX; ++c2) S[cc][c2] = 0.f;
+    }
+    for (int pi = 0; pi < kDwPts; ++pi) {
+        const int i = (blockIdx.x * kGWarps + warp) * kDwPts + pi;
+        if (i >= a.N) break;
+        const size_t o = ((size_t)b * a.N + i) * COUT + c0;
+        float ys[VEC], gg[VEC], ysum[VEC], q[VEC], sv[VEC], dq[VEC];
+        int ak[VEC];
+        VecIO<VEC>::ld(a.ysel + o, ys);
+        VecIO<VEC>::ld(a.gout + o, gg);
+        VecIO<VEC>::ld(a.ysum + o, ysum);
+        if (a.pq_bf16) ld_pq<VEC, true>(a.pq, cloud0 + (size_t)i * 2 * COUT + COUT + c0, q);
+        else ld_pq<VEC, false>(a.pq, cloud0 + (size_t)i * 2 * COUT + COUT + c0, q);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            ak[v] = a.arg[o + v];
+            const float yh = (ys[v] - mean) * rstd;
+            const float u = yh * gm[v] + bt[v];
+            const float du = u > 0.f ? gg[v] : gg[v] * a.slope;
+            sv[v] = rstd * gm[v] * du;
+            dq[v] = sv[v] + (float)k * Ag + Kg * ysum[v];
+        }
+        float xi[LDX], xs[LDX];
+#pragma unroll
+        for (int c4 = 0; c4 < LDX / 4; ++c4) VecIO<4>::ld(xb + (size_t)i * LDX + c4 * 4, xi + c4 * 4);
+#pragma unroll
+        for (int cc = 0; cc < LDX; ++cc) xs[cc] = 0.f;
+        const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int kk = lane + 32 * t;
+            if (kk < k) {
+                const int j = ip[kk];
+                float xj[LDX];
+#pragma unroll
+                for (int c4 = 0; c4 < LDX / 4; ++c4) {
+                    VecIO<4>::ld(xb + (size_t)j * LDX + c4 * 4, xj + c4 * 4);
+                    VecIO<4>::st(&stage[kk][c4 * 4], xj + c4 * 4);
+                }
+#pragma unroll
+                for (int cc = 0; cc < LDX; ++cc) {
+                    xs[cc] += xj[cc];
+#pragma unroll
+                    for (int c2 = 0; c2 < LDX; ++c2) S[cc][c2] = fmaf(xj[cc], xj[c2], S[cc][c2]);
+                }
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < LDX; ++cc) {
+            for (int off = 16; off; off >>= 1) xs[cc] += __shfl_xor_sync(FULLM, xs[cc], off);
+            xtot[cc] += xs[cc];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float kq = Kg * q[v];
+#pragma unroll
+            for (int cc = 0; cc < LDX; ++cc) {
+                dwp[v][cc] = fmaf(sv[v], stage[ak[v]][cc], fmaf(kq, xs[cc], dwp[v][cc]));
+                dwq[v][cc] = fmaf(dq[v], xi[cc], dwq[v][cc]);
+            }
+        }
+        __syncwarp();
+    }
+    // per-warp moments: S over the lanes (every lane saw different edges), sum of Xbar (already uniform)
+#pragma unroll
+    for (int cc = 0; cc < LDX; ++cc)
+#pragma unroll
+        for (int c2 = 0; c2 < LDX; ++c2) {
+            float v = S[cc][c2];
+            for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(FULLM, v, off);
+            if (lane == 0) s_mom[warp][cc * LDX + c2] = v;
+        }
+    if (lane == 0) {
+#pragma unroll
+        for (int cc = 0; cc < LDX; ++cc) s_mom[warp][LDX * LDX + cc] = xtot[cc];
+    }
+    __syncthreads();                                   // every warp is done with its staging rows
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+        for (int cc = 0; cc < LDX; ++cc) { s_red[warp][c0 + v][cc] = dwp[v][cc]; s_red[warp][COUT + c0 + v][cc] = dwq[v][cc]; }
+    __syncthreads();
+    float *out = part + ((size_t)b * gridDim.x + blockIdx.x) * 2 * COUT * LDX;
+    for (int e = threadIdx.x; e < 2 * COUT * LDX; e += blockDim.x) {
+        const int n = e / LDX, cc = e % LDX;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kGWarps; ++w) v += s_red[w][n][cc];
+        if (n < COUT) {                                // cloud-level terms of dWp, from this CTA's share of the moments
+            const int gg2 = n / cpg;
+            const float A2 = a.coef[((size_t)b * a.G + gg2) * 2 + 0], K2 = a.coef[((size_t)b * a.G + gg2) * 2 + 1];
+            float xt = 0.f, ws = 0.f;
+            for (int w = 0; w < kGWarps; ++w) {
+                xt += s_mom[w][LDX * LDX + cc];
+#pragma unroll
+                for (int c2 = 0; c2 < LDX; ++c2) ws = fmaf(wcatT[(size_t)n * LDX + c2], s_mom[w][c2 * LDX + cc], ws);
+            }
+            v += A2 * xt + K2 * ws;
+        }
+        out[e] = v;
+    }
+}
+
+// dwcat[cc][n] = sum over the CTAs of part[cta][n][cc], fixed order.  block (32 entries, 32 slices of the CTA list)
+__global__ void __launch_bounds__(1024) edge_bwd_dw_small_sum_kernel(const float *__restrict__ part, float *__restrict__ dwcat,
+                                                                     int ctas, int n2, int ldx) {
+    __shared__ double red[32][33];
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (e < n2 * ldx)
+        for (int i = threadIdx.y; i < ctas; i += 32) s += (double)part[(size_t)i * n2 * ldx + e];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < n2 * ldx) {
+        double t = 0.0;
+        for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+        dwcat[(size_t)(e % ldx) * n2 + e / ldx] = (float)t;
+    }
+}
+
 // C = 64 feeding Cout > 64 (layer 3): the same split as the small-C variant, with the X~ scatter as one 16-byte
 // reduction per lane -- each half-warp owns one edge (16 lanes x 4 floats = the 64-float row of x_i) -- so an edge costs
 // 256 B of L2 reductions instead of 4 Cout, and the dense term comes back as one tensor-core GEMM  X~ Wq^T  whose
@@ -1074,7 +1230,7 @@ static size_t plan_fwd(const gcanet_edgeconv_desc *d, void *base, FwdWs *w) {
 }
 
 struct BwdWs {
-    float *wcatT, *wcat, *dpq, *part, *coef, *dwcat, *dwpart, *xt, *xq;
+    float *wcatT, *wcat, *dpq, *part, *coef, *dwcat, *dwpart, *xt, *xq, *dwsmall;
     int *deg;
     double *sbc;
 };
@@ -1103,7 +1259,9 @@ static size_t plan_bwd(const gcanet_edgeconv_desc *d, void *base, BwdWs *w) {
     float *xt = cv.take<float>(d->ldx <= 8 || mid ? bn * d->ldx : 0);
     float *xq = cv.take<float>(mid ? bn * d->Cout : 0);
     float *wcat = cv.take<float>((size_t)d->ldx * 2 * d->Cout);
-    if (w) { w->xt = xt; w->xq = xq; w->wcat = wcat; w->wcatT = wcatT; w->dpq = dpq; w->deg = deg; w->part = part; w->sbc = sbc; w->coef = coef; w->dwcat = dwcat; w->dwpart = dwpart; }
+    // per-CTA partials of the scatter-free weight gradient (small-C layers whose input needs no gradient)
+    float *dwsmall = cv.take<float>(d->ldx <= 8 && d->Cout <= 64 ? (size_t)d->B * ceil_div(d->N, kGWarps * kDwPts) * 2 * d->Cout * d->ldx : 0);
+    if (w) { w->dwsmall = dwsmall; w->xt = xt; w->xq = xq; w->wcat = wcat; w->wcatT = wcatT; w->dpq = dpq; w->deg = deg; w->part = part; w->sbc = sbc; w->coef = coef; w->dwcat = dwcat; w->dwpart = dwpart; }
     return cv.off;
 }
 
@@ -1187,12 +1345,15 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     int total = d->ldx * 2 * Cout;
     prep_wcat_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight, w.wcat, w.wcatT, d->C, d->ldx, Cout);
     GCANET_LAUNCH_OK("prep_wcat_kernel");
-    GCANET_CUDA_OK(cudaMemsetAsync(w.dpq, 0, bn * 2 * Cout * sizeof(float), st));
-    GCANET_CUDA_OK(cudaMemsetAsync(w.deg, 0, bn * sizeof(int), st));
-
     const bool small = d->ldx == 4 || d->ldx == 8;
     const bool mid = bwd_mid_path(d);
-    if (small || mid) GCANET_CUDA_OK(cudaMemsetAsync(w.xt, 0, bn * d->ldx * sizeof(float), st));
+    // layer 1 in training: the input cloud is data, so only dW is needed and it can be had without any scatter
+    const bool dw_only = small && grad_x_nc == nullptr && VEC <= 2 && d->k <= 64 && !GCANET_AID_ENV("GCANET_NO_DW_ONLY");
+    if (!dw_only) {
+        GCANET_CUDA_OK(cudaMemsetAsync(w.dpq, 0, bn * 2 * Cout * sizeof(float), st));
+        GCANET_CUDA_OK(cudaMemsetAsync(w.deg, 0, bn * sizeof(int), st));
+        if (small || mid) GCANET_CUDA_OK(cudaMemsetAsync(w.xt, 0, bn * d->ldx * sizeof(float), st));
+    }
     const void *pq32 = sv.pq;                 // the backward kernels read [P|Q] per point, in the precision it was saved in
     const int pqb = d->storage_bf16;
     BwdArgs ba{pq32, sv.ysel, sv.ysum, sv.stats, gamma, beta, gout, sv.arg, idx, w.part, w.coef, w.dpq, w.deg,
@@ -1207,6 +1368,20 @@ static int run_backward(const gcanet_edgeconv_desc *d, const float *x_nc, const 
     edge_bwd_affine_kernel<<<ceil_div(Cout, 128), 128, 0, st>>>(w.sbc, grad_gamma, grad_beta, d->B, Cout);
     GCANET_LAUNCH_OK("edge_bwd_affine_kernel");
     long long total4 = (long long)bn * (Cout / 4);
+    if (dw_only) {
+        if constexpr (VEC <= 2) {
+            const int ctas = ceil_div(d->N, kGWarps * kDwPts);
+            if (d->ldx == 4) edge_bwd_dw_small_kernel<VEC, 4><<<dim3(ctas, d->B), kGWarps * 32, 0, st>>>(ba, w.wcatT, w.dwsmall);
+            else edge_bwd_dw_small_kernel<VEC, 8><<<dim3(ctas, d->B), kGWarps * 32, 0, st>>>(ba, w.wcatT, w.dwsmall);
+            GCANET_LAUNCH_OK("edge_bwd_dw_small_kernel");
+            edge_bwd_dw_small_sum_kernel<<<ceil_div(2 * Cout * d->ldx, 32), dim3(32, 32), 0, st>>>(w.dwsmall, w.dwcat, ctas * d->B,
+                                                                                                 2 * Cout, d->ldx);
+            GCANET_LAUNCH_OK("edge_bwd_dw_small_sum_kernel");
+            unprep_dw_kernel<<<ceil_div(Cout * d->C, 256), 256, 0, st>>>(w.dwcat, grad_weight, d->C, Cout);
+            GCANET_LAUNCH_OK("unprep_dw_kernel");
+        }
+        return GCANET_OK;
+    }
     if (small) {
         if (d->ldx == 4) edge_bwd_scatter_small_kernel<VEC, 4><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
         else edge_bwd_scatter_small_kernel<VEC, 8><<<dim3(nblk, d->B), kGWarps * 32, 0, st>>>(ba);
