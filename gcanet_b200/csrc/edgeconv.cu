@@ -948,7 +948,7 @@ __global__ void edge_bwd_degfix_small_kernel(float *__restrict__ dpq, const void
 // X~ scatter, its degree fix-up, the [N][2 Cout] gradient buffer (and its memset) and the X^T dPQ product for this layer.
 constexpr int kDwPts = 16;             // points per warp
 template <int VEC, int LDX>
-__global__ void __launch_bounds__(kGWarps * 32) edge_bwd_dw_small_kernel(BwdArgs a, const float *__restrict__ wcatT,
+__global__ void __launch_bounds__(kGWarps * 32, LDX == 4 ? 3 : 1) edge_bwd_dw_small_kernel(BwdArgs a, const float *__restrict__ wcatT,
                                                                          float *__restrict__ part) {
     constexpr int COUT = 32 * VEC;
     __shared__ __align__(16) float s_red[kGWarps][2 * COUT][LDX];      // first the staged neighbour rows, then the reduction
@@ -975,9 +975,24 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_dw_small_kernel(BwdArgs
 #pragma unroll
         for (int c2 = 0; c2 < LDX; ++c2) S[cc][c2] = 0.f;
     }
+    // the neighbour ids of the NEXT point are fetched while the current one is processed: ids -> rows is a chain of two
+    // dependent loads per point, and a warp walks its points one after the other
+    const int i0 = (blockIdx.x * kGWarps + warp) * kDwPts;
+    int jn[2] = {0, 0};
+    if (i0 < a.N) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            if (lane + 32 * t < k) jn[t] = a.idx[((size_t)b * a.N + i0) * k + lane + 32 * t];
+    }
     for (int pi = 0; pi < kDwPts; ++pi) {
-        const int i = (blockIdx.x * kGWarps + warp) * kDwPts + pi;
+        const int i = i0 + pi;
         if (i >= a.N) break;
+        const int jc[2] = {jn[0], jn[1]};
+        if (pi + 1 < kDwPts && i + 1 < a.N) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (lane + 32 * t < k) jn[t] = a.idx[((size_t)b * a.N + i + 1) * k + lane + 32 * t];
+        }
         const size_t o = ((size_t)b * a.N + i) * COUT + c0;
         float ys[VEC], gg[VEC], ysum[VEC], q[VEC], sv[VEC], dq[VEC];
         int ak[VEC];
@@ -1000,12 +1015,11 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_bwd_dw_small_kernel(BwdArgs
         for (int c4 = 0; c4 < LDX / 4; ++c4) VecIO<4>::ld(xb + (size_t)i * LDX + c4 * 4, xi + c4 * 4);
 #pragma unroll
         for (int cc = 0; cc < LDX; ++cc) xs[cc] = 0.f;
-        const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const int kk = lane + 32 * t;
             if (kk < k) {
-                const int j = ip[kk];
+                const int j = jc[t];
                 float xj[LDX];
 #pragma unroll
                 for (int c4 = 0; c4 < LDX / 4; ++c4) {
