@@ -14,6 +14,8 @@ from .functional import (  # noqa: F401
     get_graph_feature_with_normals,
     get_graph_feature_with_normals_g,
     global_feature,
+    group_norm,
+    group_norm_relu,
     group_points,
     grouping_operation,
     knn,
@@ -31,4 +33,4 @@ from .functional import (  # noqa: F401
 )
 from .modules import KPAM, OFFSET_PRED_MODULE, DGCNNEncoderGn, NormalEdgeHead, SoftProjection  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
