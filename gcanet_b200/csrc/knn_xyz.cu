@@ -152,14 +152,16 @@ struct XyzArgs {
     int32_t *idx32;
     int *fallback;        // [B] set to 1 when the cloud must take the brute-force path (PN, c <= 0)
     int unordered;        // 1: only the neighbour set is needed, skip the final ordering
+    int aabb_smem;        // 1: the cloud's tile boxes are copied to shared memory; 0: read through L1 (large clouds, where
+                          //    the table would cost the CTA its co-residents)
 };
 
 template <int CDIM, bool PN, int SL>
 __global__ void __launch_bounds__(XW * 32, 3) knn_xyz_kernel(XyzArgs a) {   // 80 registers: three CTAs (24 warps) per SM hide the list latency better than two
     extern __shared__ __align__(16) float smem[];
     constexpr int CAP = 32 * SL;
-    float *s_aabb = smem;                                     // [tiles][6]
-    float *lds = s_aabb + (size_t)a.tiles * 6;                // [XQ][CAP]
+    float *s_aabb = smem;                                     // [tiles][6] (aabb_smem only)
+    float *lds = s_aabb + (a.aabb_smem ? (size_t)a.tiles * 6 : 0);   // [XQ][CAP]
     int *lis = reinterpret_cast<int *>(lds + XQ * CAP);       // [XQ][CAP]
 
     const int b = blockIdx.y;
@@ -181,8 +183,12 @@ __global__ void __launch_bounds__(XW * 32, 3) knn_xyz_kernel(XyzArgs a) {   // 8
     const float abs_slack = 1e-6f * ext * ext + 2e-5f * fmaxf(fmaxf(bb[3] * bb[3], bb[0] * bb[0]),
                                                               fmaxf(fmaxf(bb[4] * bb[4], bb[1] * bb[1]), fmaxf(bb[5] * bb[5], bb[2] * bb[2])));
 
-    for (int e = threadIdx.x; e < tiles * 6; e += XW * 32) s_aabb[e] = a.aabb[(size_t)b * tiles * 6 + e];
-    __syncthreads();
+    const float *boxes = a.aabb + (size_t)b * tiles * 6;
+    if (a.aabb_smem) {
+        for (int e = threadIdx.x; e < tiles * 6; e += XW * 32) s_aabb[e] = boxes[e];
+        __syncthreads();
+        boxes = s_aabb;
+    }
 
     // my queries: sorted positions q0 .. q0+3
     const int q0 = tile0 * XT + warp * XR;
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(XW * 32, 3) knn_xyz_kernel(XyzArgs a) {   // 8
             const bool mine = t < tiles && (pass == 0 ? in_window : !in_window);
             float lb = -CUDART_INF_F;                                  // pass 0: always scanned
             if (mine && pass == 1) {
-                const float *bx = s_aabb + t * 6;
+                const float *bx = boxes + t * 6;
                 float acc = 0.f;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -373,16 +379,19 @@ static int launch_xyz(XyzArgs a, cudaStream_t st) {
     dim3 grid(a.tiles, a.B);
     auto go = [&](auto slc) -> int {
         constexpr int SL = decltype(slc)::value;
-        size_t smem = ((size_t)a.tiles * 6 + 2 * (size_t)XQ * 32 * SL) * sizeof(float);
+        size_t smem = ((a.aabb_smem ? (size_t)a.tiles * 6 : 0) + 2 * (size_t)XQ * 32 * SL) * sizeof(float);
         auto kern = knn_xyz_kernel<CDIM, PN, SL>;
         if (smem > 48 * 1024) GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, XW * 32, smem, st>>>(a);
         GCANET_LAUNCH_OK("knn_xyz_kernel");
         return GCANET_OK;
     };
-    if (a.k <= 40) return go(std::integral_constant<int, 4>{});
-    if (a.k <= 72) return go(std::integral_constant<int, 5>{});
-    if (a.k <= 104) return go(std::integral_constant<int, 6>{});
+    // list capacity 32 * SL per query: a shrink must leave room for a tile (k + 8 <= 32 (SL - 1)); the roomier choice
+    // (fewer shrinks) measures best
+    const int sl = a.k <= 40 ? 4 : (a.k <= 72 ? 5 : (a.k <= 104 ? 6 : 8));
+    if (sl == 4) return go(std::integral_constant<int, 4>{});
+    if (sl == 5) return go(std::integral_constant<int, 5>{});
+    if (sl == 6) return go(std::integral_constant<int, 6>{});
     return go(std::integral_constant<int, 8>{});
 }
 
@@ -420,7 +429,7 @@ int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metri
     GCANET_LAUNCH_OK("xyz_gather_kernel");
 
     XyzArgs a{sc, sn, perm, aabb, bbox, B, N, tiles, k2, k2 / k1, gcanet_knn_graph_columns(k1, k2), idx64, idx32, fallback,
-              (unordered && k1 == k2) ? 1 : 0};
+              (unordered && k1 == k2) ? 1 : 0, tiles * 24 <= 16 * 1024 ? 1 : 0};
     rc = metric == GCANET_METRIC_L2 ? launch_xyz<3, false>(a, st) : launch_xyz<6, true>(a, st);
     if (rc) return rc;
     *norm_out = norm;
