@@ -631,6 +631,7 @@ int knn_graph_xyz(const float *x, int B, int C, int N, int k1, int k2, int metri
 // knn_tc.cu
 size_t knn_tc_workspace_bytes(int B, int C, int N);
 bool knn_tc_supported(int C, int N, int k2);
+bool knn_tc_xyz_supported(int B, int N, int k2);
 int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, int64_t *idx64, int32_t *idx32,
                            void *ws, int unordered, int no_prune, cudaStream_t st);
 
@@ -644,14 +645,19 @@ extern "C" int gcanet_knn_graph_columns(int k1, int k2) {
     return (k2 + step - 1) / step;
 }
 
-static bool use_tensor_cores(int C, int N, int k2, int metric) {
+static bool use_tensor_cores(int B, int C, int N, int k2, int metric) {
+    const bool no_prune = (metric & GCANET_KNN_FLAG_NO_PRUNE) != 0;
     metric &= ~(GCANET_KNN_FLAG_UNORDERED | GCANET_KNN_FLAG_NO_PRUNE);
-    return metric == GCANET_METRIC_L2 && knn_tc_supported(C, N, k2);   // the brute-force flag makes this false
+    if (metric != GCANET_METRIC_L2) return false;                      // the brute-force flag makes this false
+    // xyz clouds: one MMA per key tile on the box-pruned scan; with GCANET_KNN_FLAG_NO_PRUNE (A/B tests) and outside that
+    // scan's limits the CUDA-core kernel of knn_xyz.cu takes them
+    if (C == 3) return !no_prune && knn_tc_xyz_supported(B, N, k2);
+    return knn_tc_supported(C, N, k2);
 }
 
 extern "C" size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric) {
     if (B < 1 || C < 1 || N < 1) return 0;
-    if (use_tensor_cores(C, N, k2, metric)) return knn_tc_workspace_bytes(B, C, N);
+    if (use_tensor_cores(B, C, N, k2, metric)) return knn_tc_workspace_bytes(B, C, N);
     if (knn_xyz_supported(C, N, k2, metric & ~(GCANET_KNN_FLAG_UNORDERED | GCANET_KNN_FLAG_NO_PRUNE))) return knn_xyz_workspace_bytes(B, C, N);
     return align_up((size_t)B * N * sizeof(float));
 }
@@ -681,7 +687,7 @@ extern "C" int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int
         set_error("knn_graph: workspace too small or misaligned (%zu bytes given)", ws_bytes);
         return GCANET_ERR_WORKSPACE;
     }
-    if (flags == 0 && use_tensor_cores(C, N, k2, metric))
+    if (flags == 0 && use_tensor_cores(B, C, N, k2, metric | (no_prune ? GCANET_KNN_FLAG_NO_PRUNE : 0)))
         return knn_graph_tensor_cores(x, B, C, N, k1, k2, idx64, idx32, ws, unordered, no_prune, as_stream(stream));
     if (flags == 0 && knn_xyz_supported(C, N, k2, metric)) {
         float *norms = nullptr;

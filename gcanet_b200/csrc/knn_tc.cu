@@ -31,6 +31,7 @@
 #include <cuda_bf16.h>
 #include <math_constants.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace gcanet {
 
@@ -576,7 +577,18 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
     // 2. exact fp32 distances of the m survivors, 32 / LPC at a time: LPC lanes share a candidate, each with 16 channels
     //    as four 16-byte loads (the lanes of a candidate read LPC * 16 contiguous bytes per load), the query's matching
     //    channels stay in registers, log2(LPC) shuffles finish the dot product
-    {
+    if constexpr (C == 3) {
+        // xyz clouds: rows of (x, y, z, 0), one lane per candidate, the arithmetic of the brute-force scan
+        // (knn_select.cu: fl(q0 r0), two fused steps, then fl(fl(|x_j|^2 - 2 t) + |x_i|^2))
+        for (int e = lane; e < m; e += 32) {
+            const int j = sl[e];
+            const float4 r = __ldg(reinterpret_cast<const float4 *>(xb) + j);
+            float t = __fmul_rn(qv[0], r.x);
+            t = fmaf(qv[1], r.y, t);
+            t = fmaf(qv[2], r.z, t);
+            sd[e] = __fadd_rn(fmaf(-2.f, t, nb[j]), qn);
+        }
+    } else {
         constexpr int CPP = 32 / LPC;                   // candidates per pass
         const int u = lane / LPC, w = lane % LPC;
         for (int e0 = 0; e0 < m; e0 += CPP) {
@@ -659,12 +671,13 @@ __device__ __forceinline__ void rerank_row(const RerankArgs &a, const uint2 *can
 template <int C, bool BIG>
 __global__ void __launch_bounds__(256, BIG ? 1 : 6) knn_tc_rerank_kernel(RerankArgs a) {
     constexpr int LPC = C / 16;
+    constexpr int XS = C == 3 ? 4 : C;                  // row stride of x_nc (xyz clouds: padded to 16 bytes)
     constexpr int SCAP = BIG ? TCP_CAP : TC_CAP;
     __shared__ unsigned long long s_key[8][SCAP];       // per warp: survivors' ids | exact distances, then the packed keys
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int *perm = a.perm ? a.perm + (size_t)b * a.N : nullptr;
-    const float *xb = a.x_nc + (size_t)b * a.N * C;
+    const float *xb = a.x_nc + (size_t)b * a.N * XS;
     const float *nb = a.norm + (size_t)b * a.N;
     const int rows = BIG ? a.big_count[b] : a.N;
     for (int slot = blockIdx.x * 8 + warp; slot < rows; slot += gridDim.x * 8) {
@@ -679,10 +692,15 @@ __global__ void __launch_bounds__(256, BIG ? 1 : 6) knn_tc_rerank_kernel(RerankA
         const size_t grow = (size_t)b * a.N + q;
         const int ovf = BIG ? 0 : a.overflow[grow];
         float qv[16];                                    // this lane's 16 channels of the query (layout of the exact pass)
+        if constexpr (C == 3) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(xb) + q);
+            qv[0] = t.x; qv[1] = t.y; qv[2] = t.z;
+        } else {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)q * C) + it * LPC + lane % LPC);
-            qv[it * 4] = t.x; qv[it * 4 + 1] = t.y; qv[it * 4 + 2] = t.z; qv[it * 4 + 3] = t.w;
+            for (int it = 0; it < 4; ++it) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(xb + (size_t)q * C) + it * LPC + lane % LPC);
+                qv[it * 4] = t.x; qv[it * 4 + 1] = t.y; qv[it * 4 + 2] = t.z; qv[it * 4 + 3] = t.w;
+            }
         }
         const float qn = nb[q];
         if (ovf) {                                        // the fallback kernel writes this row
@@ -728,10 +746,11 @@ constexpr int TCP_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epil
 constexpr int TCP_HCAP = TCP_CAP / 2; // each of a row's two epilogue threads owns half of its candidate list
 // TMEM accumulator stages (64 columns each) behind the query tile, which lives in TMEM as well (C columns: hi | lo):
 // C = 64: 64 + 3 x 64 = 256 columns, so two CTAs still share an SM's 512; C = 128: 128 + 4 x 64 = 384 (one CTA per SM)
-__host__ __device__ constexpr int tcp_acc(int C) { return C == 64 ? 3 : 4; }
-__host__ __device__ constexpr int tcp_tmem_cols(int C) { return C == 64 ? 256 : 512; }
+// C = 3 (xyz clouds): the query tile is one K = 16 step = 8 columns (32 reserved): 32 + 3 x 64 = 224 of 256
+__host__ __device__ constexpr int tcp_acc(int C) { return C == 128 ? 4 : 3; }
+__host__ __device__ constexpr int tcp_tmem_cols(int C) { return C == 128 ? 512 : 256; }
 constexpr int TCP_NRING = 16;         // key-norm ring: the producer runs at most STAGES + ACC + 1 tiles ahead of the epilogue
-__host__ __device__ constexpr int tcp_stages(int C) { return C == 64 ? 4 : 3; }
+__host__ __device__ constexpr int tcp_stages(int C) { return C == 128 ? 3 : 4; }
 
 // part[b][sp][C*C + C] = (sum_n x x^T | sum_n x) over the sp-th slice of a strided subsample of the cloud's points
 // (every `stride`-th point, Ns of them: the directions only steer the pruning, a sample is enough)
@@ -898,15 +917,6 @@ __global__ void __launch_bounds__(256) tcp_pca_kernel(const float *__restrict__ 
     if (tid == 3) o[3 * C + 3] = s_ok ? fmaxf(s_lambda[0], fmaxf(s_lambda[1], s_lambda[2])) : 0.f;   // = sigma_1^2 (largest |cov v|)
 }
 
-__device__ __forceinline__ unsigned tcp_spread10(unsigned v) {   // 10 bits -> every third bit
-    v &= 0x3ffu;
-    v = (v | (v << 16)) & 0x030000ffu;
-    v = (v | (v << 8)) & 0x0300f00fu;
-    v = (v | (v << 4)) & 0x030c30c3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-
 // proj[i][b][n] = v_i . x_n ; sort key = (cloud, 30-bit Morton code of the projections in a +-4 sigma_1 cube)
 template <int C>
 __global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restrict__ x, const float *__restrict__ pca,
@@ -934,14 +944,15 @@ __global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restric
     const float sig = sqrtf(fmaxf(V[3 * C + 3], 0.f));
     const float sc = sig > 0.f ? 1024.f / (8.f * sig) : 0.f;
     const float pv[3] = {p0, p1, p2};
-    unsigned code = 0;
+    unsigned cell[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         float t = (pv[i] - V[3 * C + i]) * sc + 512.f;
         t = t == t ? t : 0.f;                                   // NaN -> 0
-        code |= tcp_spread10(((unsigned)fminf(fmaxf(t, 0.f), 1023.f)) >> (10 - bits)) << i;
+        cell[i] = ((unsigned)fminf(fmaxf(t, 0.f), 1023.f)) >> (10 - bits);
     }
-    keys[o] = ((unsigned)b << (3 * bits)) | code;              // cloud | Morton code with `bits` bits per axis
+    const unsigned code = hilbert3(cell[0], cell[1], cell[2], bits);
+    keys[o] = ((unsigned)b << (3 * bits)) | code;              // cloud | Hilbert-curve position with `bits` bits per axis
     vals[o] = n;
 }
 
@@ -954,13 +965,21 @@ __host__ __device__ __forceinline__ uint32_t tcp_kext_offset(int r, int chunk) {
 
 // one warp per 64-key tile of the sorted order: perm / inverse permutation, sorted key norms (+inf padding),
 // tile AABB in the projected space
+//
+// XYZ (C = 3 clouds, the coordinates themselves are the "projections"): `proj` is the cloud x[B][C][N]; the K = 16 operand
+// row of a key holds the whole bf16 x 3 product AND the norm -- (hi, lo, hi, |k|^2 hi, mid, lo, 0 ...) against the query
+// row -2 (hi, hi, lo), 1, 1, 1 -- so ONE MMA per key tile yields |k|^2 - 2 q.k; x4[b][o] = (x, y, z, 0) in the original
+// order feeds the exact re-rank, and every cloud is flagged structured.
+template <bool XYZ>
 __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ sorted_vals, const float *__restrict__ norm,
                                                         const float *__restrict__ proj, int *__restrict__ perm,
                                                         int *__restrict__ inv, float *__restrict__ norm_pad,
                                                         float *__restrict__ boxes, float *__restrict__ boxes32,
                                                         unsigned *__restrict__ nmax_bits, uint8_t *__restrict__ kext,
-                                                        int B, int N, int Npad, int tiles) {
+                                                        int B, int N, int Npad, int tiles, int C, float4 *__restrict__ x4,
+                                                        int *__restrict__ structured) {
     const int b = blockIdx.y;
+    if (XYZ && blockIdx.x == 0 && threadIdx.x == 0) structured[b] = 1;
     const int wl = threadIdx.x >> 5;
     const int t = blockIdx.x * 8 + wl, lane = threadIdx.x & 31;
     float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -981,10 +1000,11 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
             nm = fmaxf(nm, nv);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const float p = proj[(size_t)i * B * N + (size_t)b * N + o];
+                const float p = XYZ ? proj[((size_t)b * C + i) * N + o] : proj[(size_t)i * B * N + (size_t)b * N + o];
                 hmn[i] = p;
                 hmx[i] = p;
             }
+            if (XYZ) x4[(size_t)b * N + o] = make_float4(hmn[0], hmn[1], hmn[2], 0.f);
         } else if (s < Npad) {
             norm_pad[(size_t)b * Npad + s] = CUDART_INF_F;
         }
@@ -999,13 +1019,31 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
                 e1 = __float2bfloat16_rn(r1);
                 e2 = __float2bfloat16_rn(r1 - __bfloat162float(e1));
             }
-            uint4 c0;
-            c0.x = (unsigned)__bfloat16_as_ushort(e0) | ((unsigned)__bfloat16_as_ushort(e1) << 16);
-            c0.y = (unsigned)__bfloat16_as_ushort(e2);
-            c0.z = 0u; c0.w = 0u;
+            uint4 c0, c1 = make_uint4(0u, 0u, 0u, 0u);
+            if (XYZ) {
+                // columns 0-2 hi, 3-5 lo, 6-8 hi, 9-11 the norm; keys past N: zero coordinates (hmn is +inf there), norm +inf
+                unsigned h[3], l[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float v = s < N ? hmn[i] : 0.f;        // hmn still holds this point's own coordinates here
+                    const __nv_bfloat16 vh = __float2bfloat16_rn(v);
+                    h[i] = __bfloat16_as_ushort(vh);
+                    l[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(vh)));
+                }
+                c0.x = h[0] | (h[1] << 16);
+                c0.y = h[2] | (l[0] << 16);
+                c0.z = l[1] | (l[2] << 16);
+                c0.w = h[0] | (h[1] << 16);
+                c1.x = h[2] | ((unsigned)__bfloat16_as_ushort(e0) << 16);
+                c1.y = (unsigned)__bfloat16_as_ushort(e1) | ((unsigned)__bfloat16_as_ushort(e2) << 16);
+            } else {
+                c0.x = (unsigned)__bfloat16_as_ushort(e0) | ((unsigned)__bfloat16_as_ushort(e1) << 16);
+                c0.y = (unsigned)__bfloat16_as_ushort(e2);
+                c0.z = 0u; c0.w = 0u;
+            }
             uint8_t *img = kext + ((size_t)b * tiles + t) * TCP_KEXT_BYTES;
             *reinterpret_cast<uint4 *>(img + tcp_kext_offset(r, 0)) = c0;
-            *reinterpret_cast<uint4 *>(img + tcp_kext_offset(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(img + tcp_kext_offset(r, 1)) = c1;
         }
         // box of this 32-point half (the rows one epilogue warp of the scan owns), then merged into the tile's box
 #pragma unroll
@@ -1112,18 +1150,23 @@ struct TcpScanArgs {
 
 // SM = 1: k <= 64, one minimum per column slot.  SM = 2: k <= 128, the two smallest per slot (128 distinct keys; the
 // 64 extra registers cost the second resident CTA).
+//
+// C = 3 (XYZ): the cloud's own coordinates take the place of the principal directions, and the whole distance is ONE
+// K = 16 MMA per key tile -- the 2 KB operand image written by tcp_tiles_kernel<true> holds the bf16 x 3 split of the
+// three coordinates and the norm; no tensor map, no swizzled operand blocks, the query row is built from the same image.
 template <int C, int SM>
-__global__ void __launch_bounds__(TCP_THREADS, C == 64 ? 2 : 1)
+__global__ void __launch_bounds__(TCP_THREADS, C == 128 ? 1 : 2)
 knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
-    constexpr int NBLK = 2 * C / TC_KB;
-    constexpr int NH = C / TC_KB;
+    constexpr bool XYZ = (C == 3);
+    constexpr int NBLK = XYZ ? 0 : 2 * C / TC_KB;
+    constexpr int NH = XYZ ? 0 : C / TC_KB;
     constexpr int BLK_BYTES = TC_BN * 128;
     constexpr int TILE_BYTES = NBLK * BLK_BYTES;
     // The hand-offs (TMA -> MMA -> epilogue -> MMA -> TMA) each cost a barrier round trip of ~1 us under load, so the
     // rings are deep: the epilogue should never wait for an accumulator.  C = 64: 32 + 4*16 KB -> two CTAs per SM.
     constexpr int STAGES = tcp_stages(C);
     constexpr int ACC = tcp_acc(C);
-    constexpr int ACOLS = C;                                // TMEM columns of the query tile: C/2 hi, C/2 lo (two bf16 each)
+    constexpr int ACOLS = XYZ ? 32 : C;                     // TMEM columns of the query tile: C/2 hi, C/2 lo (two bf16 each)
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1166,7 +1209,7 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
     const int pre = a.pre;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_k);
+        if constexpr (!XYZ) tma_prefetch_desc(&tmap_k);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
         mbar_init(thr_ready, 8);
@@ -1374,6 +1417,14 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
                     continue;
                 }
                 tc_fence_after();
+                if constexpr (XYZ) {
+                    if (elect_one_sync()) {
+                        // products and norm in one K = 16 step: A = the query rows in TMEM columns [0, 8)
+                        umma_bf16_ts(tmem_base + ACOLS + acc * TC_BN, tmem_base, desc_advance(k_desc0, stage * TCP_KEXT_BYTES), kIdesc, 0u);
+                        umma_commit(&empty[stage]);
+                        umma_commit(&t_full[acc]);
+                    }
+                } else
                 if (elect_one_sync()) {
                     const uint64_t b_desc = desc_advance(b_desc0, stage * TILE_BYTES);
                     const uint32_t d_tmem = tmem_base + ACOLS + acc * TC_BN;
@@ -1426,7 +1477,31 @@ knn_tcp_scan_kernel(const __grid_constant__ CUtensorMap tmap_k, TcpScanArgs a) {
         // the query tile: one thread per row (the column-half-0 warps; a warp owns the TMEM lanes of its quarter) reads
         // the row's hi | lo operand (2C bf16), multiplies by -2 (exact: a sign and an exponent step) so that the MMAs
         // accumulate -2 q.k, and stores it into TMEM columns [0, C): one 32-bit column = two consecutive bf16 along K
-        if (hf == 0) {
+        if (hf == 0 && XYZ) {
+            // the row's own key image (hi | lo | hi | norm) rearranged into -2 (hi, hi, lo), 1, 1, 1, 0 ...
+            const __nv_bfloat162 m2 = __float2bfloat162_rn(-2.f);
+            uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (active) {
+                const uint8_t *img = a.kext + ((size_t)b * tiles + (q >> 6)) * TCP_KEXT_BYTES;
+                uint4 t = __ldg(reinterpret_cast<const uint4 *>(img + tcp_kext_offset(q & 63, 0)));
+                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+#pragma unroll
+                for (int e = 0; e < 3; ++e) h[e] = __hmul2(h[e], m2);
+                const uint32_t n0 = t.x, n1 = t.y, n2 = t.z;      // -2 (h0, h1), -2 (h2, l0), -2 (l1, l2)
+                w[0] = n0;
+                w[1] = (n1 & 0xffffu) | (n0 << 16);                // -2 (h2, h0)
+                w[2] = (n0 >> 16) | (n1 << 16);                    // -2 (h1, h2)
+                w[3] = (n1 >> 16) | (n2 << 16);                    // -2 (l0, l1)
+                w[4] = (n2 >> 16) | 0x3F800000u;                   // (-2 l2, 1)
+                w[5] = 0x3F803F80u;                                // (1, 1)
+            }
+            tmem_st8(tmem_base + ((uint32_t)(lg * 32) << 16), w);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        }
+        if (hf == 0 && !XYZ) {
             const __nv_bfloat162 m2 = __float2bfloat162_rn(-2.f);
             const uint4 *src = reinterpret_cast<const uint4 *>(a.xs + ((size_t)b * a.N + (active ? q : 0)) * 2 * C);
 #pragma unroll
@@ -1711,7 +1786,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     size_t t = 0;
     // pruned path
     t += align_up((size_t)B * TCP_SPLIT * (C * C + C) * sizeof(float));   // partial moments
-    t += align_up((size_t)B * (3 * C + 4) * sizeof(float));               // pca
+    t += align_up((size_t)B * (3 * C + 4) * sizeof(float));               // pca (xyz clouds: the bounding boxes, 8 floats each)
     t += align_up((size_t)B * sizeof(int));                               // structured flags
     t += align_up(3 * bn * sizeof(float));                                // projections
     t += 2 * align_up(bn * sizeof(unsigned));                             // keys in/out
@@ -1724,7 +1799,7 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
     t += align_up((size_t)B * ceil_div(N, TC_BM) * 16 * sizeof(long long)); // per-CTA cycle counters (measurement builds)
     t += 2 * align_up(bn * sizeof(int)) + align_up(2 * (size_t)B * sizeof(int));  // fallback / wide re-rank row lists + counts
     t += align_up(bn * 2 * C * sizeof(__nv_bfloat16));   // xs
-    t += align_up(bn * C * sizeof(float));               // x_nc
+    t += align_up(bn * (C == 3 ? 4 : C) * sizeof(float)); // x_nc (xyz clouds: rows padded to 16 bytes)
     t += align_up(bn * sizeof(float));                   // norm
     t += align_up((size_t)B * (ceil_div(N, TC_BN) * TC_BN) * sizeof(float));   // norm_pad
     t += align_up((size_t)B * ceil_div(N, TC_BN) * TCP_KEXT_BYTES);            // key norms as an operand step
@@ -1738,6 +1813,12 @@ size_t knn_tc_workspace_bytes(int B, int C, int N) {
 bool knn_tc_supported(int C, int N, int k2) {
     return (C == 64 || C == 128) && k2 <= 128 && N >= TC_BM && k2 + TC_SLACK + 64 <= TC_CAP;
 }
+// xyz clouds (C = 3, L2): only the box-pruned scan exists for them (one K = 16 MMA per key tile); everything it does not
+// cover stays with knn_xyz.cu
+bool knn_tc_xyz_supported(int B, int N, int k2) { return tcp_supported(B, N, k2) && k2 + TC_SLACK + 64 <= TC_CAP; }
+
+// knn_xyz.cu: bbox[b][8], keys = (cloud << 3 ab) | Morton code with `ab` bits per axis, vals = point index
+int launch_xyz_sort_keys(const float *x, float *bbox, unsigned *keys, int *vals, int B, int C, int N, int ab, cudaStream_t st);
 
 // declared in knn_select.cu
 int launch_sqnorm_public(const float *x, float *out, int B, int C, int Cuse, int N, cudaStream_t st);
@@ -1765,7 +1846,7 @@ static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcSca
 template <int C, int SM>
 static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpScanArgs sa, TcScanArgs fa, RerankArgs ra, int B,
                       cudaStream_t st) {
-    constexpr int NBLK = 2 * C / TC_KB;
+    constexpr int NBLK = C == 3 ? 0 : 2 * C / TC_KB;
     constexpr int STAGES = tcp_stages(C);
     const size_t smem = 1024 + (size_t)STAGES * NBLK * TC_BN * 128 +
                         (size_t)STAGES * TCP_KEXT_BYTES + 256 + 32 * sizeof(uint64_t) + 6 * TC_BM * sizeof(float) + (size_t)sa.P * 16;
@@ -1774,7 +1855,7 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
     dim3 grid(ceil_div(sa.N, TC_BM) * B);
     kern<<<grid, TCP_THREADS, smem, st>>>(tmap_k, sa);
     GCANET_LAUNCH_OK("knn_tcp_scan_kernel");
-    {
+    if constexpr (C != 3) {
         // clouds without low-dimensional structure (their sorted order is the original order): single-pass full scan
         constexpr int FS_STAGES = 2;
         const size_t fsmem = 1024 + (size_t)NBLK * TC_BM * 128 + (size_t)FS_STAGES * NBLK * TC_BN * 128 +
@@ -1815,6 +1896,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { set_error("knn_graph: cuTensorMapEncodeTiled is not available from the driver"); return GCANET_ERR_CUDA; }
     const size_t bn = (size_t)B * N;
+    const bool xyz = C == 3;                               // xyz clouds: pruned scan only (the caller checked knn_tc_xyz_supported)
     Carver cv(ws);
     float *part = cv.take<float>((size_t)B * TCP_SPLIT * (C * C + C));
     float *pca = cv.take<float>((size_t)B * (3 * C + 4));
@@ -1841,9 +1923,9 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     int *big_count = fb_count + B;
     GCANET_CUDA_OK(cudaMemsetAsync(fb_count, 0, 2 * B * sizeof(int), st));
     const char *env_np = GCANET_AID_ENV("GCANET_TC_NO_PRUNE");
-    const bool prune = !no_prune && tcp_supported(B, N, k2) && !(env_np && env_np[0] == '1') && !GCANET_AID_ENV("GCANET_TC_DEBUG");
+    const bool prune = xyz || (!no_prune && tcp_supported(B, N, k2) && !(env_np && env_np[0] == '1') && !GCANET_AID_ENV("GCANET_TC_DEBUG"));
     __nv_bfloat16 *xs = cv.take<__nv_bfloat16>(bn * 2 * C);
-    float *x_nc = cv.take<float>(bn * C);
+    float *x_nc = cv.take<float>(bn * (xyz ? 4 : C));
     float *norm = cv.take<float>(bn);
     const int Npad = ceil_div(N, TC_BN) * TC_BN;
     float *norm_pad = cv.take<float>((size_t)B * Npad);
@@ -1860,18 +1942,30 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     int rc = launch_sqnorm_public(x, norm, B, C, C, N, st);
     if (rc) return rc;
     const int tiles = ceil_div(N, TC_BN);
-    if (prune) {
+    if (xyz) {
+        // sort key = (cloud, Morton code of the coordinates inside the cloud's bounding box); `pca` holds the boxes
+        rc = launch_xyz_sort_keys(x, pca, keys_in, vals_in, B, C, N, tcp_axis_bits(B), st);
+        if (rc) return rc;
+        GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
+        count_launch();
+        GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
+        tcp_tiles_kernel<true><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, x, perm, inv, norm_pad, boxes, boxes32,
+                                                                            reinterpret_cast<unsigned *>(nmax), kext, B, N, Npad, tiles, C,
+                                                                            reinterpret_cast<float4 *>(x_nc), structured);
+        GCANET_LAUNCH_OK("tcp_tiles_kernel");
+    } else if (prune) {
         rc = C == 64 ? launch_tcp_prep<64>(x, part, pca, structured, proj, keys_in, vals_in, B, N, st)
                      : launch_tcp_prep<128>(x, part, pca, structured, proj, keys_in, vals_in, B, N, st);
         if (rc) return rc;
         GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
         count_launch();
         GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
-        tcp_tiles_kernel<<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes, boxes32,
-                                                                      reinterpret_cast<unsigned *>(nmax), kext, B, N, Npad, tiles);
+        tcp_tiles_kernel<false><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes, boxes32,
+                                                                             reinterpret_cast<unsigned *>(nmax), kext, B, N, Npad, tiles, C,
+                                                                             nullptr, nullptr);
         GCANET_LAUNCH_OK("tcp_tiles_kernel");
     }
-    {
+    if (!xyz) {
         const uintptr_t bases = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(x_nc);
         if (N % 4 == 0 && C % 64 == 0 && (bases & 15) == 0) {
             tc_prep_wide_kernel<<<dim3(ceil_div(N, 64), C / 64, B), 256, 0, st>>>(x, xs, x_nc, prune ? inv : nullptr, C, N);
@@ -1890,15 +1984,19 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     // 3-D tensor map over xs: (K = 2C bf16, N rows, B clouds), box = (64, 128, 1), 128-byte swizzle;
     // rows past N are zero-filled, so a partial last tile never reads the next cloud.
     CUtensorMap tmap_q, tmap_k;
+    memset(&tmap_q, 0, sizeof(tmap_q));
+    memset(&tmap_k, 0, sizeof(tmap_k));
     cuuint64_t gdim[3] = {(cuuint64_t)(2 * C), (cuuint64_t)N, (cuuint64_t)B};
     cuuint64_t gstride[2] = {(cuuint64_t)(2 * C) * sizeof(__nv_bfloat16), (cuuint64_t)N * 2 * C * sizeof(__nv_bfloat16)};
     cuuint32_t estride[3] = {1, 1, 1};
     cuuint32_t box_q[3] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_BM, 1};
     cuuint32_t box_k[3] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_BN, 1};
-    CUresult cr = encode(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, xs, gdim, gstride, box_q, estride,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr == CUDA_SUCCESS)
+    CUresult cr = CUDA_SUCCESS;                            // (xyz clouds need no tensor map: their operand is one bulk copy per tile)
+    if (!xyz)
+        cr = encode(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, xs, gdim, gstride, box_q, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (!xyz && cr == CUDA_SUCCESS)
         cr = encode(&tmap_k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, xs, gdim, gstride, box_k, estride,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1934,7 +2032,8 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         auto gcd2 = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
         while (gcd2(fstride, tiles) != 1) ++fstride;
         TcScanArgs fa{norm_pad, Npad, norm, nmax, cand, cand_cnt, overflow, N, k2, tiles, 0, fstride, structured, TCP_CAP, 1};
-        if (k2 <= TC_BN && !GCANET_AID_ENV("GCANET_TC_SM2")) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, fa, ra, B, st);
+        if (xyz) rc = k2 <= TC_BN ? launch_tcp<3, 1>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<3, 2>(tmap_q, tmap_k, sa, fa, ra, B, st);
+        else if (k2 <= TC_BN && !GCANET_AID_ENV("GCANET_TC_SM2")) rc = C == 64 ? launch_tcp<64, 1>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 1>(tmap_q, tmap_k, sa, fa, ra, B, st);
         else rc = C == 64 ? launch_tcp<64, 2>(tmap_q, tmap_k, sa, fa, ra, B, st) : launch_tcp<128, 2>(tmap_q, tmap_k, sa, fa, ra, B, st);
         if (rc) return rc;
         if (prof) {                                // measurement aid: synchronises; mean cycles per CTA and role

@@ -69,16 +69,7 @@ __global__ void xyz_bbox_kernel(const float *__restrict__ x, float *__restrict__
     }
 }
 
-__device__ __forceinline__ unsigned spread10(unsigned v) {   // 10 bits -> every third bit
-    v &= 0x3ffu;
-    v = (v | (v << 16)) & 0x030000ffu;
-    v = (v | (v << 8)) & 0x0300f00fu;
-    v = (v | (v << 4)) & 0x030c30c3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-
-// key = (cloud << 3*ab) | Morton code with `ab` bits per axis: fits a 32-bit radix key (four 8-bit passes at B = 16,
+// key = (cloud << 3*ab) | Hilbert-curve position (common.cuh) with `ab` bits per axis: fits a 32-bit radix key (four 8-bit passes at B = 16,
 // ab = 9, instead of five over 64-bit keys); 512 cells per axis are far finer than the point spacing of a 10 k cloud,
 // and the order only shapes the tiles -- exactness rests on their AABBs
 __global__ void xyz_code_kernel(const float *__restrict__ x, const float *__restrict__ bbox,
@@ -91,13 +82,13 @@ __global__ void xyz_code_kernel(const float *__restrict__ x, const float *__rest
     const float ext = fmaxf(fmaxf(bb[3] - bb[0], bb[4] - bb[1]), fmaxf(bb[5] - bb[2], 1e-30f));
     const float top = (float)((1 << ab) - 1);
     const float sc = top / ext;
-    unsigned code = 0;
+    unsigned q[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float t = (p[(size_t)c * N + n] - bb[c]) * sc;
-        unsigned q = (unsigned)fminf(fmaxf(t, 0.f), top);
-        code |= spread10(q) << c;
+        q[c] = (unsigned)fminf(fmaxf(t, 0.f), top);
     }
+    const unsigned code = hilbert3(q[0], q[1], q[2], ab);
     keys[(size_t)b * N + n] = ((unsigned)b << (3 * ab)) | code;
     vals[(size_t)b * N + n] = n;
 }
@@ -393,6 +384,15 @@ static int launch_xyz(XyzArgs a, cudaStream_t st) {
     if (sl == 5) return go(std::integral_constant<int, 5>{});
     if (sl == 6) return go(std::integral_constant<int, 6>{});
     return go(std::integral_constant<int, 8>{});
+}
+
+// the sort keys alone, for the tensor-core scan of xyz clouds (knn_tc.cu)
+int launch_xyz_sort_keys(const float *x, float *bbox, unsigned *keys, int *vals, int B, int C, int N, int ab, cudaStream_t st) {
+    xyz_bbox_kernel<<<B, 1024, 0, st>>>(x, bbox, C, N);
+    GCANET_LAUNCH_OK("xyz_bbox_kernel");
+    xyz_code_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(x, bbox, keys, vals, C, N, ab);
+    GCANET_LAUNCH_OK("xyz_code_kernel");
+    return GCANET_OK;
 }
 
 // Returns GCANET_OK; *fallback_flags (device, [B]) tells the caller which clouds need the brute-force scan.

@@ -64,7 +64,11 @@ for kind in ("abc", "uniform", "grid", "dup", "same"):
     for metric in (G.METRIC_L2, G.METRIC_POINTS_NORMALS):
         for (k1, k2, ordered) in ((50, 50, False), (50, 50, True), (20, 20, True), (64, 64, False), (10, 40, True), (1, 1, True)):
             ok &= check(kind, 2, 3000 if kind != "same" else 600, k1, k2, metric, ordered)
+ok &= check("same", 2, 2048, 50, 50, G.METRIC_L2, False)       # every row overflows: the per-row fallback
+ok &= check("grid", 2, 4096, 50, 50, G.METRIC_L2, True)
+ok &= check("abc", 2, 5000, 80, 80, G.METRIC_L2, True)          # 64 < k <= 128: two slot minima per column
 ok &= check("abc", 16, 10000, 50, 50, G.METRIC_L2, False)
+ok &= check("abc", 16, 10000, 50, 50, G.METRIC_L2, True)
 ok &= check("abc", 16, 10000, 50, 50, G.METRIC_POINTS_NORMALS, False)
 ok &= check("abc", 3, 1037, 20, 20, G.METRIC_L2, True)
 ok &= check("abc", 2, 257, 20, 20, G.METRIC_L2, True)
@@ -78,6 +82,8 @@ for name, x, m in (("L2 C=3", x3, G.METRIC_L2), ("PN C=6", x6, G.METRIC_POINTS_N
     for k in (20, 50):
         t = timeit(lambda: G.knn_graph(x, k, k, m, want64=False, want32=True, ordered=False))
         t2 = timeit(lambda: G.knn_graph(x, k, k, m, want64=True, want32=False, ordered=True))
-        print(f"{name} k={k}: unordered int32 {t:.3f} ms, ordered int64 {t2:.3f} ms per call (B=16 x 10k)")
+        t3 = timeit(lambda: G.knn_graph(x, k, k, m, want64=False, want32=True, ordered=False, prune=False))
+        print(f"{name} k={k}: unordered int32 {t:.3f} ms, ordered int64 {t2:.3f} ms per call (B=16 x 10k); CUDA-core kernel (prune=False) {t3:.3f} ms")
 xl = torch.from_numpy(abc_like_batch(4, 100000, seed=2, with_normals=False)).cuda()
-print(f"L2 C=3 k=50 B=4 x 100k: {timeit(lambda: G.knn_graph(xl, 50, 50, G.METRIC_L2, want64=False, want32=True, ordered=False), 5):.3f} ms")
+print(f"L2 C=3 k=50 B=4 x 100k: {timeit(lambda: G.knn_graph(xl, 50, 50, G.METRIC_L2, want64=False, want32=True, ordered=False), 5):.3f} ms"
+      f" (CUDA-core kernel: {timeit(lambda: G.knn_graph(xl, 50, 50, G.METRIC_L2, want64=False, want32=True, ordered=False, prune=False), 5):.3f} ms)")
