@@ -135,7 +135,7 @@ def test_knn_tensor_core_path_on_activations_and_ties():
 @pytest.mark.parametrize("C,N,k,B,k1", [(3, 257, 20, 2, 20), (3, 10000, 50, 3, 50), (3, 10000, 80, 1, 80), (3, 5000, 20, 2, 10),
                                         (6, 10000, 50, 2, 50), (6, 3001, 80, 2, 80), (3, 100000, 50, 1, 50), (3, 4000, 150, 1, 150)])
 def test_knn_xyz_pruned_path_equals_brute_force(C, N, k, B, k1):
-    """Morton sort + AABB pruning evaluates a fraction of the pairs but uses the same fp32 distance
+    """Spatial sort + AABB pruning evaluates a fraction of the pairs but decides with the same fp32 distance
     arithmetic and the same (distance, index) ranking: the lists must be IDENTICAL to the brute-force scan."""
     x = _t(abc_like_batch(B, N, seed=N + k, with_normals=(C == 6)))
     x[:, :, 11] = x[:, :, 5]                                   # coincident points: index tie-break
@@ -144,6 +144,32 @@ def test_knn_xyz_pruned_path_equals_brute_force(C, N, k, B, k1):
     fast = G.knn_graph(xd, k1, k, metric)[0]
     slow = G.knn_graph(xd, k1, k, metric, brute_force=True)[0]
     assert torch.equal(fast, slow)
+
+
+@pytest.mark.parametrize("kind,N,k,B", [("abc", 10000, 50, 3), ("abc", 1024, 64, 2), ("abc", 6000, 100, 2), ("grid", 4096, 50, 2),
+                                       ("dup", 3000, 20, 2), ("same", 2048, 50, 1), ("abc", 1100, 1, 17)])
+def test_knn_xyz_both_pruned_paths_equal_brute_force(kind, N, k, B):
+    """xyz clouds of 1 024 .. 32 767 points take the tensor-core scan (one K = 16 MMA per key tile: bf16 x 3 products and the
+    norm, exact fp32 re-rank), ``prune=False`` keeps them on the CUDA-core kernel of knn_xyz.cu: both must return the
+    brute-force lists element for element -- on surfaces, on a lattice (massive exact ties), with every point present
+    four times, and with all points in one place (every row overflows into the per-row fallback)."""
+    g = torch.Generator().manual_seed(N + k)
+    if kind == "abc":
+        x = _t(abc_like_batch(B, N, seed=N + k))
+    elif kind == "grid":
+        m = int(round(N ** (1 / 3))) + 1
+        ax = torch.arange(m, dtype=torch.float32) / m
+        x = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), 0).reshape(3, -1)[:, :N].unsqueeze(0).repeat(B, 1, 1)
+    elif kind == "dup":
+        x = torch.rand(B, 3, N // 4, generator=g).repeat(1, 1, 4)[:, :, torch.randperm(N, generator=g)]
+    else:
+        x = torch.ones(B, 3, N) * 0.3
+    xd = x.contiguous().to(DEV)
+    ref = G.knn_graph(xd, k, k, brute_force=True)[0]
+    assert torch.equal(G.knn_graph(xd, k, k)[0], ref)
+    assert torch.equal(G.knn_graph(xd, k, k, prune=False)[0], ref)
+    sets = G.knn_graph(xd, k, k, want64=False, want32=True, ordered=False)[1]
+    assert torch.equal(sets.sort(dim=2)[0].long(), ref.sort(dim=2)[0])
 
 
 def test_knn_xyz_pruned_path_degenerate_inputs():
