@@ -87,6 +87,11 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
     uint64_t *t_full = bars + 2 * GT_STAGES;            // [2] MMA -> epilogue
     uint64_t *t_empty = t_full + 2;                     // [2] epilogue -> MMA       (4 arrivals)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+    // [4 epilogue warps][32 rows][32 floats] staging of the output rows (16-byte chunks XOR-swizzled by the row), 1 KB-aligned
+    // behind the barrier block: the accumulator hands every thread ONE row, and thirty-two threads storing 16 bytes each to
+    // thirty-two different rows cost the load/store unit 32 cycles per instruction (8.4 tiles x 128 such stores per SM were
+    // 17 of the kernel's 39 us); through this buffer a store instruction covers four rows x 128 contiguous bytes
+    float *sOut = reinterpret_cast<float *>(sA + GT_STAGES * A_STAGE + 1024);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (M + GT_BM - 1) / GT_BM;
@@ -219,17 +224,27 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
                         }
                         *reinterpret_cast<uint4 *>(hrow + ch * 32 + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
-                } else if (row < M) {
+                } else if (!out_bf16) {
+                    // own row -> staging buffer (chunk q of row `lane` at physical chunk q ^ (lane & 7): conflict-free both ways)
+                    float4 *st4 = reinterpret_cast<float4 *>(sOut + ew * 1024);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 o = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                                               __uint_as_float(v[q * 4 + 3]));
-                        if (cbias) {
-                            const float4 cb = __ldg(reinterpret_cast<const float4 *>(cbias + ch * 32 + q * 4));
-                            o.x += cb.x; o.y += cb.y; o.z += cb.z; o.w += cb.w;
-                        }
-                        *reinterpret_cast<float4 *>(crow + ch * 32 + q * 4) = o;
+                    for (int q = 0; q < 8; ++q)
+                        st4[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                                         __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                    __syncwarp();
+                    // eight lanes per row: one instruction stores four complete 128-byte row segments
+                    const int cq = lane & 7;
+                    float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cbias) cb = __ldg(reinterpret_cast<const float4 *>(cbias + ch * 32 + cq * 4));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + (lane >> 3);
+                        float4 o = st4[r * 8 + (cq ^ (r & 7))];
+                        o.x += cb.x; o.y += cb.y; o.z += cb.z; o.w += cb.w;
+                        const int grow_ = tile * GT_BM + ew * 32 + r;
+                        if (grow_ < M) *reinterpret_cast<float4 *>(C + (size_t)grow_ * ldc + ch * 32 + cq * 4) = o;
                     }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -253,7 +268,7 @@ static int launch_gemm_tc(const float *A, int lda, const float *Bt, int ldb, flo
                           const float *cbias = nullptr, int batch_bias = 0, int out_bf16 = 0) {
     constexpr int KCH = K / GT_KB;
     constexpr int GT_STAGES = gt_stages(K, N);
-    const size_t smem = 1024 + (size_t)2 * KCH * N * 128 + (size_t)GT_STAGES * 2 * GT_BM * 128 + 32 * sizeof(uint64_t);
+    const size_t smem = 1024 + (size_t)2 * KCH * N * 128 + (size_t)GT_STAGES * 2 * GT_BM * 128 + 1024 + 4 * 32 * 32 * sizeof(float);
     auto kern = gemm_tc_kernel<K, N>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = ceil_div(M, GT_BM);
