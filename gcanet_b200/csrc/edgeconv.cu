@@ -21,6 +21,8 @@
 // 2*B*N*C*2Cout FLOP, k times fewer than the per-edge formulation.
 #include "common.cuh"
 
+#include <type_traits>
+
 #include <cuda_bf16.h>
 
 #include <cstdlib>
@@ -486,6 +488,14 @@ __device__ __forceinline__ void edge_accumulate(const float *p, const float *sg,
     }
 }
 
+template <int I, int N, typename F>
+__device__ __forceinline__ void gather_static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        gather_static_for<I + 1, N>(f);
+    }
+}
+
 template <int VEC, bool BF16 = false>
 __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArgs a) {
     __shared__ double red[kGWarps * 32][2];
@@ -518,7 +528,25 @@ __global__ void __launch_bounds__(kGWarps * 32) edge_gather_reduce_kernel(FwdArg
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { zmax[v] = -CUDART_INF_F; vsum[v] = 0.f; vsq[v] = 0.f; kbest[v] = 0; q[v] *= sg[v]; }
         const int32_t *ip = a.idx + ((size_t)b * a.N + i) * k;
-        for (int base = 0; base < k; base += 32) {
+        int base = 0;
+        if (k >= 32) {
+            // the first 32 edges with compile-time lane and slot numbers: the shuffle's source lane and the slot written
+            // into kbest are immediates (one VIADD each per edge in the generic loop below; the kernel is issue-bound)
+            const int myj = ip[lane];
+            gather_static_for<0, 4>([&](auto tb) {
+                constexpr int t = decltype(tb)::value * 8;
+                float p[8][VEC];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    int j = __shfl_sync(FULLM, myj, t + u);
+                    ld_pq_row<VEC, BF16>(row0, (unsigned)j, stride_b, p[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) edge_accumulate<VEC>(p[u], sg, q, zmax, kbest, vsum, vsq, t + u);
+            });
+            base = 32;
+        }
+        for (; base < k; base += 32) {
             const int cnt = min(32, k - base);
             const int myj = lane < cnt ? ip[base + lane] : 0;
             int t = 0;
