@@ -619,7 +619,7 @@ def run_ours(args):
         achieved = flop / (avg_ms * 1e-3) / 1e12
         peak = float(peaks["bf16_tflops_sustained"])
         roofline = {"bound": "tensor",
-                    "kernel": "feature-space kNN C=64: PCA/Morton prep + knn_tcp_scan_kernel (tcgen05, box-pruned) + exact "
+                    "kernel": "feature-space kNN C=64: PCA / Hilbert-order prep + knn_tcp_scan_kernel (tcgen05, box-pruned) + exact "
                               "re-rank, algorithmic 2*N^2*C FLOP per cloud",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_source, "ms_per_launch": avg_ms, "launches_per_step": len(knn_ms) / n_eager,
