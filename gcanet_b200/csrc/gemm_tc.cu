@@ -205,7 +205,6 @@ gemm_tc_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B
             mbar_wait(&t_full[acc], accphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * N;
-            float *crow = C + (size_t)row * ldc;
             __nv_bfloat16 *hrow = reinterpret_cast<__nv_bfloat16 *>(C) + (size_t)row * ldc;     // out_bf16: C is a bf16 matrix
 #pragma unroll 1
             for (int ch = 0; ch < N / 32; ++ch) {

@@ -109,8 +109,11 @@ GCANET_API int gcanet_cn_to_nc_add(const float *x_cn, const float *add_nc, float
  * pruned on the tensor cores (tcgen05, bf16x3 split) and the survivors re-ranked in exact
  * fp32 -- for N >= 1024 after sorting the cloud along its three leading principal
  * directions, so that key tiles whose bounding box cannot hold a neighbour are never read
- * (GCANET_KNN_FLAG_NO_PRUNE scans every tile); xyz clouds (C = 3 L2, C = 6 points x normals,
- * N >= 256) are Morton-sorted and scanned with AABB pruning; every other shape runs the
+ * (GCANET_KNN_FLAG_NO_PRUNE scans every tile); xyz clouds (C = 3, L2, 1024 <= N < 32768,
+ * k2 <= 128) take the same tensor-core scan with one K = 16 MMA per key tile (products of the
+ * bf16x3 split and the norm in one step); the other xyz clouds (C = 3 outside those limits or
+ * with GCANET_KNN_FLAG_NO_PRUNE, C = 6 points x normals; N >= 256) are sorted along a Hilbert
+ * curve and scanned on the CUDA cores with AABB pruning; every other shape runs the
  * brute-force CUDA-core scan.  The result does not depend on the path. */
 GCANET_API int gcanet_knn_graph_columns(int k1, int k2);
 GCANET_API size_t gcanet_knn_graph_workspace_bytes(int B, int C, int N, int k2, int metric);
