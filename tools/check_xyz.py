@@ -1,6 +1,7 @@
-"""xyz kNN (pruned, query-per-thread for k <= 64) against the brute-force scan: the lists must be identical -- ordered
-lists element for element, unordered lists as sets -- on smooth clouds, uniform noise, grids (ties) and duplicates;
-then timings.  Usage: python tools/check_xyz.py [quick]"""
+"""xyz kNN -- the tensor-core scan (C = 3, 1 024 <= N < 32 768) and the CUDA-core pruned kernel (`prune=False`, points x
+normals, other sizes) -- against the brute-force scan: the lists must be identical -- ordered lists element for element,
+unordered lists as sets -- on smooth clouds, uniform noise, grids (ties) and duplicates; then timings of both.
+Usage: python tools/check_xyz.py [quick]"""
 import sys
 
 import numpy as np
