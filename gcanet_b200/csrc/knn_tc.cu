@@ -27,6 +27,7 @@
 #include "tc_ptx.cuh"
 
 #include <cuda.h>
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -1143,6 +1144,35 @@ __global__ void __launch_bounds__(256) tcp_work_order_kernel(const unsigned *__r
     if (lane == 0) work[rank] = i;
 }
 
+// Clouds of at most 10 240 points: one CTA sorts a cloud's (code, point) pairs in shared memory -- five 4-bit passes of
+// cub::BlockRadixSort over the 18 code bits, ~20 us for sixteen clouds on sixteen SMs -- instead of the device-wide
+// sort's histogram + scan + three onesweep passes over all clouds (45 us: latency-bound at 160 000 keys).  Both are stable
+// LSD sorts of the same keys, so the permutation is the same; padding keys carry all-ones code bits and, being last in
+// the input, stay behind every real key.
+constexpr int TCP_SORT_ITEMS = 10;
+constexpr int TCP_SORT_MAX_N = 1024 * TCP_SORT_ITEMS;
+__global__ void __launch_bounds__(1024) tcp_sort_cloud_kernel(const unsigned *__restrict__ keys, int *__restrict__ vals_out, int N,
+                                                              int code_bits) {
+    using Sort = cub::BlockRadixSort<unsigned, 1024, TCP_SORT_ITEMS, int>;
+    __shared__ typename Sort::TempStorage temp;
+    const int b = blockIdx.x;
+    const unsigned mask = code_bits >= 32 ? 0xffffffffu : ((1u << code_bits) - 1u);
+    unsigned k[TCP_SORT_ITEMS];
+    int v[TCP_SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < TCP_SORT_ITEMS; ++i) {
+        const int n = threadIdx.x * TCP_SORT_ITEMS + i;                 // blocked arrangement = input order
+        k[i] = n < N ? (keys[(size_t)b * N + n] & mask) : 0xffffffffu;
+        v[i] = n;
+    }
+    Sort(temp).Sort(k, v, 0, code_bits);
+#pragma unroll
+    for (int i = 0; i < TCP_SORT_ITEMS; ++i) {
+        const int p = threadIdx.x * TCP_SORT_ITEMS + i;
+        if (p < N) vals_out[(size_t)b * N + p] = v[i];
+    }
+}
+
 struct TcpScanArgs {
     const float *norm_pad;  // [B][Npad] key norms in sorted order, +inf past N
     int Npad;
@@ -1791,6 +1821,22 @@ static size_t tcp_cub_temp_bytes(size_t n, int end_bit) {
                                     (const int *)nullptr, (int *)nullptr, (int)n, 0, end_bit);
     return bytes;
 }
+static int tcp_cloud_bits(int B);
+static int tcp_axis_bits(int B);
+// sorted point indices per cloud (vals_out[b][rank] = point) from keys = (cloud << 3 bits) | code
+static int tcp_sort_clouds(void *temp, size_t temp_bytes, unsigned *keys_in, unsigned *keys_out, int *vals_in, int *vals_out, int B, int N,
+                           cudaStream_t st) {
+    const int code_bits = 3 * tcp_axis_bits(B);
+    if (N <= TCP_SORT_MAX_N && !GCANET_AID_ENV("GCANET_TC_DEVICE_SORT")) {
+        tcp_sort_cloud_kernel<<<B, 1024, 0, st>>>(keys_in, vals_out, N, code_bits);
+        GCANET_LAUNCH_OK("tcp_sort_cloud_kernel");
+        return GCANET_OK;
+    }
+    GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)((size_t)B * N), 0,
+                                                   tcp_cloud_bits(B) + code_bits, st));
+    count_launch();
+    return GCANET_OK;
+}
 static int tcp_cloud_bits(int B) {
     int bits = 0;
     while ((1 << bits) < B) ++bits;
@@ -1975,8 +2021,8 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         // sort key = (cloud, Morton code of the coordinates inside the cloud's bounding box); `pca` holds the boxes
         rc = launch_xyz_sort_keys(x, pca, keys_in, vals_in, B, C, N, tcp_axis_bits(B), st);
         if (rc) return rc;
-        GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
-        count_launch();
+        rc = tcp_sort_clouds(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, B, N, st);
+        if (rc) return rc;
         GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
         tcp_tiles_kernel<true><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, x, perm, inv, norm_pad, boxes, boxes32,
                                                                             reinterpret_cast<unsigned *>(nmax), kext, B, N, Npad, tiles, C,
@@ -1986,8 +2032,8 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         rc = C == 64 ? launch_tcp_prep<64>(x, part, pca, structured, proj, keys_in, vals_in, B, N, st)
                      : launch_tcp_prep<128>(x, part, pca, structured, proj, keys_in, vals_in, B, N, st);
         if (rc) return rc;
-        GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
-        count_launch();
+        rc = tcp_sort_clouds(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, B, N, st);
+        if (rc) return rc;
         GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
         tcp_tiles_kernel<false><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes, boxes32,
                                                                              reinterpret_cast<unsigned *>(nmax), kext, B, N, Npad, tiles, C,
