@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(256) tcp_pca_kernel(const float *__restrict__ 
 template <int C>
 __global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restrict__ x, const float *__restrict__ pca,
                                                           float *__restrict__ proj, unsigned *__restrict__ keys,
-                                                          int *__restrict__ vals, int B, int N, int bits) {
+                                                          int *__restrict__ vals, float *__restrict__ norm, int B, int N, int bits) {
     __shared__ float V[3 * C + 4];
     const int b = blockIdx.y;
     for (int e = threadIdx.x; e < 3 * C + 4; e += 128) V[e] = pca[(size_t)b * (3 * C + 4) + e];
@@ -956,15 +956,17 @@ __global__ void __launch_bounds__(128) tcp_project_kernel(const float *__restric
     const int n = blockIdx.x * 128 + threadIdx.x;
     if (n >= N) return;
     const float *xb = x + (size_t)b * C * N + n;
-    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, sq = 0.f;
 #pragma unroll 8
     for (int c = 0; c < C; ++c) {
         const float v = xb[(size_t)c * N];
         p0 = fmaf(V[c], v, p0);
         p1 = fmaf(V[C + c], v, p1);
         p2 = fmaf(V[2 * C + c], v, p2);
+        sq = __fadd_rn(sq, __fmul_rn(v, v));                    // |x|^2 in sqnorm_kernel's order (the point is read here anyway)
     }
     const size_t o = (size_t)b * N + n;
+    norm[o] = sq;
     proj[o] = p0;
     proj[(size_t)B * N + o] = p1;
     proj[2 * (size_t)B * N + o] = p2;
@@ -997,21 +999,33 @@ __host__ __device__ __forceinline__ uint32_t tcp_kext_offset(int r, int chunk) {
 // row of a key holds the whole bf16 x 3 product AND the norm -- (hi, lo, hi, |k|^2 hi, mid, lo, 0 ...) against the query
 // row -2 (hi, hi, lo), 1, 1, 1 -- so ONE MMA per key tile yields |k|^2 - 2 q.k; x4[b][o] = (x, y, z, 0) in the original
 // order feeds the exact re-rank, and every cloud is flagged structured.
+struct TcpTileArgs {
+    const int *sorted_vals;   // [B][N] point of every sorted position
+    const float *norm;        // [B][N]
+    const float *proj;        // projections [3][B][N], or (XYZ) the cloud itself [B][C][N]
+    int *perm, *inv;
+    float *norm_pad, *boxes, *boxes32;
+    unsigned *nmax_bits;
+    uint8_t *kext;
+    int B, N, Npad, tiles, C;
+    float4 *x4;               // XYZ: [B][N] (x, y, z, 0) in the original order
+    int *structured;          // XYZ: every cloud is flagged
+};
+
+// one warp, one 64-key tile t of cloud b
 template <bool XYZ>
-__global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ sorted_vals, const float *__restrict__ norm,
-                                                        const float *__restrict__ proj, int *__restrict__ perm,
-                                                        int *__restrict__ inv, float *__restrict__ norm_pad,
-                                                        float *__restrict__ boxes, float *__restrict__ boxes32,
-                                                        unsigned *__restrict__ nmax_bits, uint8_t *__restrict__ kext,
-                                                        int B, int N, int Npad, int tiles, int C, float4 *__restrict__ x4,
-                                                        int *__restrict__ structured) {
-    const int b = blockIdx.y;
-    if (XYZ && blockIdx.x == 0 && threadIdx.x == 0) structured[b] = 1;
-    const int wl = threadIdx.x >> 5;
-    const int t = blockIdx.x * 8 + wl, lane = threadIdx.x & 31;
+__device__ __forceinline__ void tcp_tile_work(const TcpTileArgs &a, int b, int t, int lane) {
+    const int *sorted_vals = a.sorted_vals;
+    const float *norm = a.norm, *proj = a.proj;
+    int *perm = a.perm, *inv = a.inv;
+    float *norm_pad = a.norm_pad, *boxes = a.boxes, *boxes32 = a.boxes32;
+    unsigned *nmax_bits = a.nmax_bits;
+    uint8_t *kext = a.kext;
+    const int B = a.B, N = a.N, Npad = a.Npad, tiles = a.tiles, C = a.C;
+    float4 *x4 = a.x4;
     float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     float nm = 0.f;
-    if (t < tiles) {
+    {
 #pragma unroll
     for (int h = 0; h < TC_BN / 32; ++h) {
         const int s = t * TC_BN + h * 32 + lane;
@@ -1096,17 +1110,22 @@ __global__ void __launch_bounds__(256) tcp_tiles_kernel(const int *__restrict__ 
     }
 }
 
+template <bool XYZ>
+__global__ void __launch_bounds__(256) tcp_tiles_kernel(TcpTileArgs a) {
+    const int b = blockIdx.y;
+    if (XYZ && blockIdx.x == 0 && threadIdx.x == 0) a.structured[b] = 1;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t < a.tiles) tcp_tile_work<XYZ>(a, b, t, threadIdx.x & 31);
+}
+
 // work[rank] = i for query tile i = b * qtiles + qt, ranked by the squared diagonal of its bounding box in the
 // projected space (wkey, written by tcp_tiles_kernel), largest first.  Every thread ranks one tile against all.
 constexpr int TCP_MAX_WORK = 65536;
 // wkey[b * qtiles + qt] = estimate of the work of a query tile: the number of key tiles whose lower bound lies within
 // a quarter of the squared diagonal of the query tile's own box (rank correlation with the tiles it ends up visiting:
 // 0.96 on layer activations; the diagonal alone: 0.7-0.8), ties by the diagonal.  One warp per query tile.
-__global__ void __launch_bounds__(256) tcp_work_key_kernel(const float *__restrict__ boxes, unsigned *__restrict__ wkey,
-                                                           int tiles, int qtiles) {
-    const int b = blockIdx.y;
-    const int qt = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (qt >= qtiles) return;
+__device__ __forceinline__ void tcp_work_key_one(const float *__restrict__ boxes, unsigned *__restrict__ wkey, int tiles, int qtiles,
+                                                 int b, int qt, int lane) {
     const float *bx = boxes + (size_t)b * tiles * 6;
     const int t0 = 2 * qt, t1 = min(t0 + 1, tiles - 1);
     float qlo[3], qhi[3], d2 = 0.f;
@@ -1130,6 +1149,11 @@ __global__ void __launch_bounds__(256) tcp_work_key_kernel(const float *__restri
     cnt = __reduce_add_sync(FULLW, cnt);
     if (lane == 0) wkey[(size_t)b * qtiles + qt] = ((unsigned)min(cnt, 65535) << 16) | (__float_as_uint(d2) >> 16);
 }
+__global__ void __launch_bounds__(256) tcp_work_key_kernel(const float *__restrict__ boxes, unsigned *__restrict__ wkey,
+                                                           int tiles, int qtiles) {
+    const int qt = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (qt < qtiles) tcp_work_key_one(boxes, wkey, tiles, qtiles, blockIdx.y, qt, threadIdx.x & 31);
+}
 
 __global__ void __launch_bounds__(256) tcp_work_order_kernel(const unsigned *__restrict__ wkey, int *__restrict__ work, int n) {
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;    // one warp per tile
@@ -1144,33 +1168,113 @@ __global__ void __launch_bounds__(256) tcp_work_order_kernel(const unsigned *__r
     if (lane == 0) work[rank] = i;
 }
 
-// Clouds of at most 10 240 points: one CTA sorts a cloud's (code, point) pairs in shared memory -- five 4-bit passes of
-// cub::BlockRadixSort over the 18 code bits, ~20 us for sixteen clouds on sixteen SMs -- instead of the device-wide
-// sort's histogram + scan + three onesweep passes over all clouds (45 us: latency-bound at 160 000 keys).  Both are stable
-// LSD sorts of the same keys, so the permutation is the same; padding keys carry all-ones code bits and, being last in
-// the input, stay behind every real key.
+// Clouds of at most 10 240 points: ONE CTA sorts a cloud's (code, point) pairs in shared memory -- five 4-bit passes of
+// cub::BlockRadixSort over the 18 code bits instead of the device-wide sort's histogram + scan + three onesweep passes
+// over all clouds (25 us against 45: those are latency-bound at 160 000 keys) -- and does the small per-cloud chores that
+// used to be launches of their own on the way: zeroing the per-cloud counters and, for xyz clouds, the squared norms, the
+// bounding box and the curve positions themselves.  Both sorts are stable LSD sorts of the same keys, so the permutation
+// is the same; padding keys carry all-ones code bits and, being last in the input, stay behind every real key.
 constexpr int TCP_SORT_ITEMS = 10;
 constexpr int TCP_SORT_MAX_N = 1024 * TCP_SORT_ITEMS;
-__global__ void __launch_bounds__(1024) tcp_sort_cloud_kernel(const unsigned *__restrict__ keys, int *__restrict__ vals_out, int N,
-                                                              int code_bits) {
+struct TcpCloudPrepArgs {
+    TcpTileArgs t;
+    const unsigned *keys;     // feature clouds: (cloud << code_bits) | code from tcp_project_kernel; xyz clouds: unused
+    float *norm_out;          // xyz clouds: [B][N] squared norms (reference order), written here
+    int *vals_out;            // [B][N] = t.sorted_vals
+    int *fb_count, *big_count;  // [B] each, zeroed here
+    int code_bits, axis_bits;
+};
+template <bool XYZ>
+__global__ void __launch_bounds__(1024) tcp_cloud_prep_kernel(TcpCloudPrepArgs a) {
     using Sort = cub::BlockRadixSort<unsigned, 1024, TCP_SORT_ITEMS, int>;
     __shared__ typename Sort::TempStorage temp;
-    const int b = blockIdx.x;
-    const unsigned mask = code_bits >= 32 ? 0xffffffffu : ((1u << code_bits) - 1u);
+    __shared__ float s_red[6][32];
+    __shared__ float s_bb[6];
+    const int b = blockIdx.x, N = a.t.N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        a.t.nmax_bits[b] = 0u;
+        a.fb_count[b] = 0;
+        a.big_count[b] = 0;
+        if (XYZ) a.t.structured[b] = 1;
+    }
     unsigned k[TCP_SORT_ITEMS];
     int v[TCP_SORT_ITEMS];
+    if constexpr (XYZ) {
+        // squared norms (sqnorm_kernel's order), bounding box, then the Hilbert-curve position inside it (xyz_code_kernel)
+        const float *xb = a.t.proj + (size_t)b * a.t.C * N;
+        float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
 #pragma unroll
-    for (int i = 0; i < TCP_SORT_ITEMS; ++i) {
-        const int n = threadIdx.x * TCP_SORT_ITEMS + i;                 // blocked arrangement = input order
-        k[i] = n < N ? (keys[(size_t)b * N + n] & mask) : 0xffffffffu;
-        v[i] = n;
+        for (int i = 0; i < TCP_SORT_ITEMS; ++i) {
+            const int n = threadIdx.x * TCP_SORT_ITEMS + i;
+            if (n < N) {
+                float sq = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float x = xb[(size_t)c * N + n];
+                    sq = __fadd_rn(sq, __fmul_rn(x, x));
+                    mn[c] = fminf(mn[c], x);
+                    mx[c] = fmaxf(mx[c], x);
+                }
+                a.norm_out[(size_t)b * N + n] = sq;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            for (int o = 16; o; o >>= 1) {
+                mn[c] = fminf(mn[c], __shfl_xor_sync(FULLW, mn[c], o));
+                mx[c] = fmaxf(mx[c], __shfl_xor_sync(FULLW, mx[c], o));
+            }
+            if (lane == 0) { s_red[c][warp] = mn[c]; s_red[3 + c][warp] = mx[c]; }
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                float r = s_red[c][lane];
+                for (int o = 16; o; o >>= 1) {
+                    const float w = __shfl_xor_sync(FULLW, r, o);
+                    r = c < 3 ? fminf(r, w) : fmaxf(r, w);
+                }
+                if (lane == 0) s_bb[c] = r;
+            }
+        }
+        __syncthreads();
+        const float ext = fmaxf(fmaxf(s_bb[3] - s_bb[0], s_bb[4] - s_bb[1]), fmaxf(s_bb[5] - s_bb[2], 1e-30f));
+        const float top = (float)((1 << a.axis_bits) - 1);
+        const float sc = top / ext;
+#pragma unroll
+        for (int i = 0; i < TCP_SORT_ITEMS; ++i) {
+            const int n = threadIdx.x * TCP_SORT_ITEMS + i;
+            k[i] = 0xffffffffu;
+            v[i] = n;
+            if (n < N) {
+                unsigned q[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float t = (xb[(size_t)c * N + n] - s_bb[c]) * sc;
+                    q[c] = (unsigned)fminf(fmaxf(t, 0.f), top);
+                }
+                k[i] = hilbert3(q[0], q[1], q[2], a.axis_bits);
+            }
+        }
+    } else {
+        const unsigned mask = a.code_bits >= 32 ? 0xffffffffu : ((1u << a.code_bits) - 1u);
+#pragma unroll
+        for (int i = 0; i < TCP_SORT_ITEMS; ++i) {
+            const int n = threadIdx.x * TCP_SORT_ITEMS + i;                 // blocked arrangement = input order
+            k[i] = n < N ? (a.keys[(size_t)b * N + n] & mask) : 0xffffffffu;
+            v[i] = n;
+        }
     }
-    Sort(temp).Sort(k, v, 0, code_bits);
+    Sort(temp).Sort(k, v, 0, a.code_bits);
 #pragma unroll
     for (int i = 0; i < TCP_SORT_ITEMS; ++i) {
         const int p = threadIdx.x * TCP_SORT_ITEMS + i;
-        if (p < N) vals_out[(size_t)b * N + p] = v[i];
+        if (p < N) a.vals_out[(size_t)b * N + p] = v[i];
     }
+    // (the tile pass stays a kernel of its own: 157 tiles of dependent gathers on ONE CTA per cloud took 60 us, spread over
+    // the GPU they take 9)
 }
 
 struct TcpScanArgs {
@@ -1821,22 +1925,6 @@ static size_t tcp_cub_temp_bytes(size_t n, int end_bit) {
                                     (const int *)nullptr, (int *)nullptr, (int)n, 0, end_bit);
     return bytes;
 }
-static int tcp_cloud_bits(int B);
-static int tcp_axis_bits(int B);
-// sorted point indices per cloud (vals_out[b][rank] = point) from keys = (cloud << 3 bits) | code
-static int tcp_sort_clouds(void *temp, size_t temp_bytes, unsigned *keys_in, unsigned *keys_out, int *vals_in, int *vals_out, int B, int N,
-                           cudaStream_t st) {
-    const int code_bits = 3 * tcp_axis_bits(B);
-    if (N <= TCP_SORT_MAX_N && !GCANET_AID_ENV("GCANET_TC_DEVICE_SORT")) {
-        tcp_sort_cloud_kernel<<<B, 1024, 0, st>>>(keys_in, vals_out, N, code_bits);
-        GCANET_LAUNCH_OK("tcp_sort_cloud_kernel");
-        return GCANET_OK;
-    }
-    GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)((size_t)B * N), 0,
-                                                   tcp_cloud_bits(B) + code_bits, st));
-    count_launch();
-    return GCANET_OK;
-}
 static int tcp_cloud_bits(int B) {
     int bits = 0;
     while ((1 << bits) < B) ++bits;
@@ -1950,7 +2038,7 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
 
 template <int C>
 static int launch_tcp_prep(const float *x, float *part, float *pca, int *structured, float *proj, unsigned *keys, int *vals,
-                           int B, int N, cudaStream_t st) {
+                           float *norm, int B, int N, cudaStream_t st) {
     int stride = N / 1024;
     stride = stride < 1 ? 1 : (stride > 8 ? 8 : stride);
     const int Ns = (N + stride - 1) / stride;
@@ -1961,7 +2049,7 @@ static int launch_tcp_prep(const float *x, float *part, float *pca, int *structu
     if (smem > 48 * 1024) GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B, 256, smem, st>>>(part, pca, structured, Ns, N);
     GCANET_LAUNCH_OK("tcp_pca_kernel");
-    tcp_project_kernel<C><<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(x, pca, proj, keys, vals, B, N, tcp_axis_bits(B));
+    tcp_project_kernel<C><<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(x, pca, proj, keys, vals, norm, B, N, tcp_axis_bits(B));
     GCANET_LAUNCH_OK("tcp_project_kernel");
     return GCANET_OK;
 }
@@ -1996,9 +2084,13 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     int *big_list = cv.take<int>(bn);
     int *fb_count = cv.take<int>(2 * (size_t)B);          // fallback rows | wide re-rank rows
     int *big_count = fb_count + B;
-    GCANET_CUDA_OK(cudaMemsetAsync(fb_count, 0, 2 * B * sizeof(int), st));
     const char *env_np = GCANET_AID_ENV("GCANET_TC_NO_PRUNE");
     const bool prune = xyz || (!no_prune && tcp_supported(B, N, k2) && !(env_np && env_np[0] == '1') && !GCANET_AID_ENV("GCANET_TC_DEBUG"));
+    // small clouds: one CTA per cloud sorts and does the whole per-cloud preparation (tcp_cloud_prep_kernel)
+    const bool cloud_prep = prune && N <= TCP_SORT_MAX_N && !GCANET_AID_ENV("GCANET_TC_DEVICE_SORT");
+    const int qtiles_all = ceil_div(N, TC_BM);
+    const bool want_order = prune && B * qtiles_all <= TCP_MAX_WORK && !GCANET_AID_ENV("GCANET_TC_NO_ORDER");
+    if (!cloud_prep) GCANET_CUDA_OK(cudaMemsetAsync(fb_count, 0, 2 * B * sizeof(int), st));
     __nv_bfloat16 *xs = cv.take<__nv_bfloat16>(bn * 2 * C);
     float *x_nc = cv.take<float>(bn * (xyz ? 4 : C));
     float *norm = cv.take<float>(bn);
@@ -2014,30 +2106,39 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
     int *cand_cnt = cv.take<int>(2 * bn);
     int *overflow = cv.take<int>(bn);
 
-    int rc = launch_sqnorm_public(x, norm, B, C, C, N, st);
-    if (rc) return rc;
+    int rc = GCANET_OK;
     const int tiles = ceil_div(N, TC_BN);
-    if (xyz) {
-        // sort key = (cloud, Morton code of the coordinates inside the cloud's bounding box); `pca` holds the boxes
-        rc = launch_xyz_sort_keys(x, pca, keys_in, vals_in, B, C, N, tcp_axis_bits(B), st);
+    TcpTileArgs ta{vals_out, norm, xyz ? x : proj, perm, inv, norm_pad, boxes, boxes32, reinterpret_cast<unsigned *>(nmax), kext,
+                   B, N, Npad, tiles, C, reinterpret_cast<float4 *>(x_nc), structured};
+    TcpCloudPrepArgs ca{ta, keys_in, norm, vals_out, fb_count, big_count, 3 * tcp_axis_bits(B), tcp_axis_bits(B)};
+    // squared norms: the projection kernel (feature clouds) and the per-cloud kernel (xyz clouds) compute them on the way
+    if (!prune || (xyz && !cloud_prep)) {
+        rc = launch_sqnorm_public(x, norm, B, C, C, N, st);
         if (rc) return rc;
-        rc = tcp_sort_clouds(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, B, N, st);
+    }
+    if (prune && !xyz) {
+        rc = C == 64 ? launch_tcp_prep<64>(x, part, pca, structured, proj, keys_in, vals_in, norm, B, N, st)
+                     : launch_tcp_prep<128>(x, part, pca, structured, proj, keys_in, vals_in, norm, B, N, st);
         if (rc) return rc;
-        GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
-        tcp_tiles_kernel<true><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, x, perm, inv, norm_pad, boxes, boxes32,
-                                                                            reinterpret_cast<unsigned *>(nmax), kext, B, N, Npad, tiles, C,
-                                                                            reinterpret_cast<float4 *>(x_nc), structured);
+    }
+    if (cloud_prep) {
+        if (xyz) tcp_cloud_prep_kernel<true><<<B, 1024, 0, st>>>(ca);
+        else tcp_cloud_prep_kernel<false><<<B, 1024, 0, st>>>(ca);
+        GCANET_LAUNCH_OK("tcp_cloud_prep_kernel");
+        if (xyz) tcp_tiles_kernel<true><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(ta);
+        else tcp_tiles_kernel<false><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(ta);
         GCANET_LAUNCH_OK("tcp_tiles_kernel");
     } else if (prune) {
-        rc = C == 64 ? launch_tcp_prep<64>(x, part, pca, structured, proj, keys_in, vals_in, B, N, st)
-                     : launch_tcp_prep<128>(x, part, pca, structured, proj, keys_in, vals_in, B, N, st);
-        if (rc) return rc;
-        rc = tcp_sort_clouds(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, B, N, st);
-        if (rc) return rc;
+        if (xyz) {
+            // sort key = (cloud, curve position of the coordinates inside the cloud's bounding box); `pca` holds the boxes
+            rc = launch_xyz_sort_keys(x, pca, keys_in, vals_in, B, C, N, tcp_axis_bits(B), st);
+            if (rc) return rc;
+        }
+        GCANET_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)bn, 0, end_bit, st));
+        count_launch();
         GCANET_CUDA_OK(cudaMemsetAsync(nmax, 0, B * sizeof(float), st));
-        tcp_tiles_kernel<false><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(vals_out, norm, proj, perm, inv, norm_pad, boxes, boxes32,
-                                                                             reinterpret_cast<unsigned *>(nmax), kext, B, N, Npad, tiles, C,
-                                                                             nullptr, nullptr);
+        if (xyz) tcp_tiles_kernel<true><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(ta);
+        else tcp_tiles_kernel<false><<<dim3(ceil_div(tiles, 8), B), 256, 0, st>>>(ta);
         GCANET_LAUNCH_OK("tcp_tiles_kernel");
     }
     if (!xyz) {
@@ -2087,7 +2188,7 @@ int knn_graph_tensor_cores(const float *x, int B, int C, int N, int k1, int k2, 
         const int qtiles = ceil_div(N, TC_BM);
         if (GCANET_AID_ENV("GCANET_TC_STATS")) GCANET_CUDA_OK(cudaMemsetAsync(visited, 0, (size_t)B * qtiles * sizeof(int), st));
         const int *work = nullptr;
-        if (B * qtiles <= TCP_MAX_WORK && !GCANET_AID_ENV("GCANET_TC_NO_ORDER")) {
+        if (want_order) {
             tcp_work_key_kernel<<<dim3(ceil_div(qtiles, 8), B), 256, 0, st>>>(boxes, wkey, tiles, qtiles);
             GCANET_LAUNCH_OK("tcp_work_key_kernel");
             tcp_work_order_kernel<<<ceil_div(B * qtiles, 8), 256, 0, st>>>(wkey, work_buf, B * qtiles);
