@@ -18,8 +18,14 @@ def main():
     rows = list(csv.DictReader(lines))
     names = [r["Kernel Name"] for r in rows]
     vals = [float(r["Metric Value"].replace(",", "")) for r in rows]
-    starts = [i for i, n in enumerate(names) if "sqnorm" in n]       # 3 kNN graphs per step
-    a, b = starts[3 * step], starts[3 * (step + 1)]
+    # a step starts with the xyz kNN graph: its first kernel is the per-cloud preparation of xyz clouds (older launch
+    # lists: the squared norms, three kNN graphs per step)
+    starts = [i for i, n in enumerate(names) if "tcp_cloud_prep_kernel<1>" in n or "tcp_cloud_prep_kernel<true>" in n]
+    if len(starts) > step + 1:
+        a, b = starts[step], starts[step + 1]
+    else:
+        starts = [i for i, n in enumerate(names) if "sqnorm" in n]
+        a, b = starts[3 * step], starts[3 * (step + 1)]
     agg = collections.OrderedDict()
     for n, v in zip(names[a:b], vals[a:b]):
         key = re.sub(r"\(.*", "", n).replace("void ", "")
