@@ -77,6 +77,8 @@ SIGNATURES = {
     "gcanet_knn_graph_workspace_bytes": (c_size_t, [c_int] * 5),
     "gcanet_knn_graph": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),
+    "gcanet_knn_probe_arm": (c_int, [c_int]),
+    "gcanet_knn_probe_read": (c_int, [ctypes.POINTER(c_float)]),
     "gcanet_knn_cuda_workspace_bytes": (c_size_t, [c_int] * 5),
     "gcanet_knn_cuda": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_size_t, c_void_p]),

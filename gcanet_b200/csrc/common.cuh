@@ -12,6 +12,10 @@ namespace gcanet {
 
 void set_error(const char *fmt, ...);
 void count_launch();   // statistics only: bumps the counter gcanet_launch_count() reports
+// measurement probe (gcanet_knn_probe_arm): no-ops unless the calling thread armed it; the first begin / end pair after
+// arming records the thread's two timing events on `st`
+void probe_scan_begin(cudaStream_t st);
+void probe_scan_end(cudaStream_t st);
 
 #define GCANET_REQUIRE(cond, ...)                         \
     do {                                                  \

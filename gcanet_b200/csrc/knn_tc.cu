@@ -1997,8 +1997,10 @@ static int launch_tc(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcSca
     auto kern = knn_tc_scan_kernel<C, MODE>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(sa.N, TC_BM), B);
+    probe_scan_begin(st);
     kern<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_k, sa);
     GCANET_LAUNCH_OK("knn_tc_scan_kernel");
+    probe_scan_end(st);
     if (sa.debug_no_append) return GCANET_OK;      // measurement aid: scan pipeline only
     dim3 rgrid(ceil_div(sa.N, 8), B);
     knn_tc_rerank_kernel<C, false><<<rgrid, 256, 0, st>>>(ra);
@@ -2016,8 +2018,10 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
     auto kern = knn_tcp_scan_kernel<C, SM>;
     GCANET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(sa.N, TC_BM) * B);
+    probe_scan_begin(st);
     kern<<<grid, TCP_THREADS, smem, st>>>(tmap_k, sa);
     GCANET_LAUNCH_OK("knn_tcp_scan_kernel");
+    if (C == 3) probe_scan_end(st);
     if constexpr (C != 3) {
         // clouds without low-dimensional structure (their sorted order is the original order): single-pass full scan
         constexpr int FS_STAGES = 2;
@@ -2027,6 +2031,7 @@ static int launch_tcp(const CUtensorMap &tmap_q, const CUtensorMap &tmap_k, TcpS
         GCANET_CUDA_OK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         fkern<<<dim3(ceil_div(sa.N, TC_BM), B), TC_THREADS, fsmem, st>>>(tmap_q, tmap_k, fa);
         GCANET_LAUNCH_OK("knn_tc_scan_kernel");
+        probe_scan_end(st);
     }
     dim3 rgrid(ceil_div(sa.N, 8), B);
     knn_tc_rerank_kernel<C, false><<<rgrid, 256, 0, st>>>(ra);

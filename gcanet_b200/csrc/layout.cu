@@ -12,6 +12,23 @@ static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Measurement probe (gcanet_knn_probe_arm / _read): per-thread pair of timing events around the kNN scan kernel(s).
+struct ScanProbe {
+    cudaEvent_t begin = nullptr, end = nullptr;
+    bool armed = false, open = false, fired = false;
+};
+static thread_local ScanProbe g_probe;
+
+void probe_scan_begin(cudaStream_t st) {
+    if (!g_probe.armed || g_probe.open) return;
+    if (cudaEventRecord(g_probe.begin, st) == cudaSuccess) g_probe.open = true;
+}
+void probe_scan_end(cudaStream_t st) {
+    if (!g_probe.open) return;
+    g_probe.fired = cudaEventRecord(g_probe.end, st) == cudaSuccess;
+    g_probe.open = g_probe.armed = false;
+}
+
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -131,6 +148,24 @@ extern "C" int gcanet_abi_version(void) { return GCANET_ABI_VERSION; }
 extern "C" const char *gcanet_last_error(void) { return g_err; }
 
 extern "C" unsigned long long gcanet_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int gcanet_knn_probe_arm(int on) {
+    if (on && g_probe.begin == nullptr) {
+        GCANET_CUDA_OK(cudaEventCreate(&g_probe.begin));
+        GCANET_CUDA_OK(cudaEventCreate(&g_probe.end));
+    }
+    g_probe.armed = on != 0;
+    g_probe.open = g_probe.fired = false;
+    return GCANET_OK;
+}
+
+extern "C" int gcanet_knn_probe_read(float *scan_ms) {
+    GCANET_REQUIRE(scan_ms != nullptr, "knn_probe_read: null pointer");
+    GCANET_REQUIRE(g_probe.fired, "knn_probe_read: no tensor-core scan has run on this thread since the probe was armed");
+    GCANET_CUDA_OK(cudaEventSynchronize(g_probe.end));
+    GCANET_CUDA_OK(cudaEventElapsedTime(scan_ms, g_probe.begin, g_probe.end));
+    return GCANET_OK;
+}
 
 extern "C" const char *gcanet_status_string(int status) {
     switch (status) {

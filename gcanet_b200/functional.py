@@ -40,6 +40,24 @@ def kernel_timings_ms() -> dict:
     return out
 
 
+# With `scan_probe=True` the per-call timing also asks the library (gcanet_knn_probe_arm / _read) for the time of the
+# tensor-core distance-scan kernel(s) inside each kNN call -- the dominant kernel of the step -- and records it under
+# the call's tag + ":scan_kernel".  The read waits for the device after every kNN call: breakdown passes only.
+_scan_probe = False
+_scan_ms: dict = {}
+
+
+def enable_scan_probe(flag: bool = True) -> None:
+    global _scan_probe
+    _scan_probe = bool(flag)
+    _scan_ms.clear()
+
+
+def scan_kernel_timings_ms() -> dict:
+    """{kNN call tag: [ms of its scan kernel(s), ...]} recorded while the scan probe was on."""
+    return {k: list(v) for k, v in _scan_ms.items()}
+
+
 class _timed:
     def __init__(self, tag):
         self.tag = tag
@@ -117,8 +135,17 @@ def knn_graph(x: torch.Tensor, k1: int, k2: int, metric: int = METRIC_L2, want64
         i32 = torch.empty((B, N, kout), dtype=torch.int32, device=x.device) if want32 else None
         ws_bytes = L.gcanet_knn_graph_workspace_bytes(B, C, N, k2, metric)
         ws = workspace(ws_bytes, x.device)
-        with _timed(f"knn_graph[C={C},metric={metric & 0xff}]"):
+        tag = f"knn_graph[C={C},metric={metric & 0xff}]"
+        probe = _scan_probe and not torch.cuda.is_current_stream_capturing()
+        if probe:
+            call("gcanet_knn_probe_arm", 1)
+        with _timed(tag):
             call("gcanet_knn_graph", ptr(x), B, C, N, k1, k2, metric, ptr(i64), ptr(i32), ptr(ws), ws.numel(), stream())
+        if probe:
+            ms = _ct.c_float(0.0)
+            if L.gcanet_knn_probe_read(_ct.byref(ms)) == 0:       # non-zero: this call took a path without a tensor-core scan
+                _scan_ms.setdefault(tag, []).append(float(ms.value))
+            call("gcanet_knn_probe_arm", 0)
     return i64, i32
 
 

@@ -121,6 +121,16 @@ GCANET_API int gcanet_knn_graph(const float *x, int B, int C, int N, int k1, int
                      int64_t *idx64, int32_t *idx32, void *ws, size_t ws_bytes,
                      gcanet_stream_t stream);
 
+/* Measurement probe for the roofline line of bench.py -- not a data-path call and the only entry points that create
+ * CUDA objects or wait for the device.  gcanet_knn_probe_arm(1) arms the calling thread: the next gcanet_knn_graph call
+ * of that thread which takes a tensor-core scan brackets its distance-scan kernel(s) (knn_tcp_scan_kernel, plus the
+ * full-scan launch for clouds without structure; NOT the preparation and NOT the exact re-rank) with a pair of CUDA
+ * events on the call's stream, then disarms.  gcanet_knn_probe_read waits for that pair and stores the elapsed
+ * milliseconds; it returns GCANET_ERR_INVALID_ARGUMENT when no scan has been bracketed since the thread was armed.
+ * The events are created on the current device the first time a thread arms.  Never arm during stream capture. */
+GCANET_API int gcanet_knn_probe_arm(int on);
+GCANET_API int gcanet_knn_probe_read(float *scan_ms);
+
 /* ------------------------------------------------------------------ kNN (KNN_CUDA path)
  * Replaces knn_device(ref,ref_nb,query,query_nb,dim,k,dist,ind,stream) KNN/csrc/cuda/knn.cpp:11-21
  * (kernels knn.cu:29-183) and the Python batch loop around it (KNN/__init__.py:41-74):

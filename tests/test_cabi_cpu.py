@@ -39,6 +39,15 @@ def test_abi_version_and_status_strings():
     assert b"workspace" in L.gcanet_status_string(-2)
 
 
+def test_scan_probe_read_without_a_bracketed_scan_is_an_error():
+    L = _cabi.lib()
+    ms = ctypes.c_float(0.0)
+    assert L.gcanet_knn_probe_arm(0) == 0                      # disarming creates nothing and needs no device
+    assert L.gcanet_knn_probe_read(ctypes.byref(ms)) == -1
+    assert b"probe" in L.gcanet_last_error()
+    assert L.gcanet_knn_probe_read(None) == -1
+
+
 def test_knn_columns_follow_reference_dilation():
     L = _cabi.lib()
     import numpy as np

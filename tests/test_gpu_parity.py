@@ -686,6 +686,35 @@ def test_knn_and_edgeconv_are_graph_capturable():
         assert torch.allclose(out_g, out_e, rtol=1e-5, atol=1e-6)
 
 
+def test_scan_probe_brackets_only_tensor_core_scans():
+    """gcanet_knn_probe_arm / _read (bench.py's roofline leg): a feature-space call reports a positive scan time that is
+    no longer than the whole call, the neighbour lists are the same with and without the probe, a call on a path without
+    a tensor-core scan (brute force) leaves the probe unfired, and a read without an armed call is an error."""
+    from gcanet_b200 import _cabi
+    import ctypes
+    L = _cabi.lib()
+    ms = ctypes.c_float(-1.0)
+    L.gcanet_knn_probe_arm(0)
+    assert L.gcanet_knn_probe_read(ctypes.byref(ms)) == -1
+    x1, _ = _layer_activations(2, 4000, seed=5)
+    x = x1.to(DEV)
+    ref = G.knn_graph(x, 20, 20, want64=False, want32=True)[1]
+    G.enable_kernel_timing(True)
+    G.enable_scan_probe(True)
+    try:
+        got = G.knn_graph(x, 20, 20, want64=False, want32=True)[1]
+        G.knn_graph(x, 20, 20, want64=False, want32=True, brute_force=True)
+        torch.cuda.synchronize()
+        calls, scans = G.kernel_timings_ms(), G.scan_kernel_timings_ms()
+    finally:
+        G.enable_scan_probe(False)
+        G.enable_kernel_timing(False)
+    assert torch.equal(got, ref)
+    tag = "knn_graph[C=64,metric=0]"
+    assert list(scans) == [tag] and len(scans[tag]) == 1          # the brute-force call bracketed nothing
+    assert 0.0 < scans[tag][0] <= calls[tag][0]
+
+
 def test_normal_edge_head_golden(golden_dir):
     """conv_normal head (M4:584-587, 691-693) against the fixture made from the reference's
     get_graph_feature_with_normals_g; forward 1e-4, weight gradients 2e-3 relative."""
