@@ -467,7 +467,7 @@ def run_ours(args):
     try:
         G.enable_scan_probe(True)
         for _ in range(min(args.steps, 10)):
-            step(x_dev)
+            step_core(x_dev)                            # no collective here: a probe failure must not desynchronise ranks
         torch.cuda.synchronize()
         scan_ms = G.scan_kernel_timings_ms()
     except Exception as exc:                            # noqa: BLE001 -- the roofline then falls back to the whole call, and says so
@@ -655,7 +655,8 @@ def run_ours(args):
                         "timed_by": "CUDA events recorded by the library around the kernel on the launching stream "
                                     "(gcanet_knn_probe_arm / gcanet_knn_probe_read), eager pass",
                         "launches_per_step": len(knn_ms) / n_eager, "call": call,
-                        "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)"}
+                        "peak_source": f"{peaks['_source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                        "frac_of_burst_peak": (achieved / float(peaks["bf16_tflops"])) if "bf16_tflops" in peaks else None}
         else:
             roofline = {"bound": "tensor",
                         "kernel": "feature-space kNN C=64, WHOLE CALL (scan-kernel probe unavailable: "
