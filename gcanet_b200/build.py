@@ -5,6 +5,10 @@
 Each csrc/*.cu is compiled with nvcc to an object file (in parallel) and linked into
 gcanet_b200/lib/libgcanet_b200.so.  The library has no PyTorch dependency; it is
 loaded with ctypes (gcanet_b200/_cabi.py).  nvcc cross-compiles without a GPU.
+
+csrc_ext/torch_ext.cpp -- the PyTorch C++ extension over that C-ABI, the counterpart of the reference's pybind modules --
+is compiled with g++ against the installed torch's headers into gcanet_b200/lib/gcanet_b200_ext.so (build_extension,
+loaded by gcanet_b200/native_ext.py).
 """
 from __future__ import annotations
 
@@ -96,6 +100,65 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
     return LIB
 
 
+EXT_SRC = os.path.join(HERE, "csrc_ext", "torch_ext.cpp")
+EXT = os.path.join(HERE, "lib", "gcanet_b200_ext.so")
+EXT_NAME = "gcanet_b200_ext"
+
+
+def build_extension(force: bool = False, verbose: bool = False) -> str:
+    """g++ build of the PyTorch C++ extension (pybind module + TORCH_LIBRARY registration) that wraps the C-ABI.  It links
+    against libgcanet_b200.so (found next to it through $ORIGIN) and the torch libraries of the running interpreter,
+    which are already loaded whenever the module is imported (native_ext.py imports torch first)."""
+    import sysconfig
+
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    if not os.path.exists(LIB):
+        raise RuntimeError("build libgcanet_b200.so first (build_library)")
+    stamp = EXT + ".torch"                              # rebuilt when the torch it was compiled against changes
+    same_torch = os.path.exists(stamp) and open(stamp).read() == torch.__version__
+    if not force and same_torch and not _newer([EXT_SRC, os.path.join(INCLUDE, "gcanet_b200.h"), LIB], EXT):
+        return EXT
+    cuda_home = os.environ.get("CUDA_HOME") or "/usr/local/cuda"
+    args = ["-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+            f"-DTORCH_EXTENSION_NAME={EXT_NAME}", "-DTORCH_API_INCLUDE_EXTENSION_H",
+            f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    for inc in [*ce.include_paths(), os.path.join(cuda_home, "include"), sysconfig.get_paths()["include"], INCLUDE]:
+        args += ["-I", inc]
+    args += [EXT_SRC, "-o", EXT]
+    for lp in ce.library_paths():
+        args += ["-L", lp]
+    args += ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
+             "-L", os.path.dirname(LIB), "-lgcanet_b200", "-Wl,-rpath,$ORIGIN"]
+    # The module must share the process's libstdc++.so.6 with torch: a toolchain whose libstdc++.so is missing links
+    # libstdc++.a into the module instead, and that private copy (its own, never initialised locale / iostream state)
+    # crashes the first time an error message formats a number.  So: the system compiler first, and the result is checked.
+    problems = []
+    for cxx in dict.fromkeys(["/usr/bin/g++", "g++", os.environ.get("CXX") or "g++"]):
+        cmd = [cxx, *args]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True)
+        except OSError as exc:
+            problems.append(f"{cxx}: {exc}")
+            continue
+        if r.returncode != 0:
+            problems.append(f"{cxx} failed on {EXT_SRC}:\n{r.stdout}\n{r.stderr}")
+            continue
+        with open(EXT, "rb") as f:
+            if b"libstdc++.so.6" in f.read():             # DT_NEEDED entry present
+                break
+        problems.append(f"{cxx} linked libstdc++ statically into {EXT}")
+        os.remove(EXT)
+    else:
+        raise RuntimeError("could not build the PyTorch extension:\n" + "\n".join(problems))
+    with open(stamp, "w") as f:
+        f.write(torch.__version__)
+    return EXT
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
@@ -108,3 +171,4 @@ if __name__ == "__main__":
     if a.aids:
         extra.append("-DGCANET_MEASUREMENT_AIDS")
     print(build_library(force=a.force or a.ptxas_v or a.aids, verbose=a.verbose or a.ptxas_v, extra_flags=extra))
+    print(build_extension(force=a.force, verbose=a.verbose))
