@@ -31,6 +31,7 @@ from .functional import (  # noqa: F401
     to_channel_major,
     to_point_major,
 )
-from .modules import KPAM, OFFSET_PRED_MODULE, DGCNNEncoderGn, NormalEdgeHead, SoftProjection  # noqa: F401
+from .modules import (KPAM, OFFSET_PRED_MODULE, DGCNNEncoderGn, NormalEdgeHead, SoftProjection,  # noqa: F401
+                      SppnetDGCNNEncoderGn)
 
 __version__ = "0.2.0"

@@ -110,6 +110,20 @@ class DGCNNEncoderGn(nn.Module):
         return torch.cat([x4.unsqueeze(2).expand(-1, -1, x_features.shape[2]), x_features], 1)
 
 
+class SppnetDGCNNEncoderGn(DGCNNEncoderGn):
+    """Drop-in for the encoder of ``models/sppnet.py`` (``DGCNNEncoderGn``, sppnet.py:148-217): the same three EdgeConv
+    layers and tail, with that file's conventions -- constructor ``(mode=0, input_channels=3, nn_nb=80)`` where
+    ``input_channels`` counts the channels of a POINT (conv1 takes ``2 * input_channels``, sppnet.py:163), and
+    ``forward(x) -> (x4 [B, 1024], x_features [B, 256, N])`` instead of the [B, 1280, N] concat.  Same ``state_dict`` keys."""
+
+    def __init__(self, mode=0, input_channels=3, nn_nb=80):
+        # the base class takes the EDGE channel count in mode 0 and the point channel count in mode 5 (M4:455-470)
+        super().__init__(mode=mode, nn_nb=nn_nb, input_channels=input_channels if mode == 5 else 2 * input_channels)
+
+    def forward(self, x):
+        return self.forward_global(x)
+
+
 class SoftProjection(nn.Module):
     """Drop-in for ``SoftProjection`` (models/search_knn.py:44-174): soft nearest-neighbour
     projection / feature propagation on top of ``knn_point`` + ``grouping_operation``; same

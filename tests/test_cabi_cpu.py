@@ -137,3 +137,14 @@ def test_dispatcher_ops_registered_with_shape_inference():
                                              torch.empty(128, 128, device="meta"), torch.empty(128, device="meta"),
                                              torch.empty(128, device="meta"), 64, 2, 1e-5, 0.2)
     assert o_nc.shape == (2, 1000, 128) and o_cn.shape == (2, 128, 1000) and saved.dtype == torch.uint8 and saved.numel() > 0
+
+
+def test_sppnet_encoder_variant_keeps_that_files_constructor_and_keys():
+    """models/sppnet.py:148-175: (mode, input_channels, nn_nb), conv1 takes 2 * input_channels, same parameter names."""
+    enc = gb.SppnetDGCNNEncoderGn(0, 3, 40)
+    assert enc.k == 40 and enc.mode == 0 and enc.conv1[0].weight.shape == (64, 6, 1, 1)
+    enc5 = gb.SppnetDGCNNEncoderGn(mode=5, input_channels=6, nn_nb=80)
+    assert enc5.conv1[0].weight.shape == (64, 12, 1, 1)
+    assert set(enc.state_dict()) == set(gb.DGCNNEncoderGn(mode=0, nn_nb=40, input_channels=6).state_dict())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        enc(torch.zeros(1, 3, 64))

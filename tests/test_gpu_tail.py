@@ -102,6 +102,32 @@ def test_encoder_forward_is_reference_layout_and_differentiable():
         G.global_feature(torch.zeros(1, 10, 128, device=DEV), enc.mlp1.weight, enc.mlp1.bias, enc.bnmlp1.weight, enc.bnmlp1.bias)
 
 
+@pytest.mark.parametrize("mode,cin", [(0, 3), (5, 6)])
+def test_sppnet_encoder_variant_vs_oracle(mode, cin):
+    """``SppnetDGCNNEncoderGn`` (models/sppnet.py:148-217): constructor (mode, input_channels, nn_nb) with input_channels
+    counting point channels, forward -> (x4, x_features).  Against the oracle's stack and tail on the same neighbour
+    lists: x_features within 5e-4 of the activation scale on 99.5 % of the outputs (the oracle builds its own graphs: tie rows, as in
+    smoke()), x4 within 1e-3 of its scale against the oracle's tail applied to OUR features."""
+    from gcanet_b200.synth import abc_like_batch
+    from oracle import dgcnn_oracle as orc
+    torch.manual_seed(1)
+    k = 20
+    ref = orc.DGCNNEncoderGn(mode=mode, nn_nb=k, input_channels=cin if mode == 5 else 2 * cin)
+    enc = gb.SppnetDGCNNEncoderGn(mode=mode, input_channels=cin, nn_nb=k)
+    assert enc.conv1[0].weight.shape == (64, 2 * cin, 1, 1)
+    enc.load_state_dict(ref.state_dict())
+    enc.to(DEV)
+    x = torch.from_numpy(abc_like_batch(2, 1200, seed=9, with_normals=(mode == 5)))
+    x4, feats = enc(x.to(DEV))
+    assert x4.shape == (2, 1024) and feats.shape == (2, 256, 1200)
+    with torch.no_grad():
+        want = torch.cat(ref.edge_stack(x), 1)
+        d = (feats.cpu() - want).abs()
+        assert float((d > 5e-4 * float(want.abs().max())).float().mean()) < 5e-3
+        t = torch.relu(ref.bnmlp1(ref.mlp1(feats.cpu()))).max(dim=2)[0]            # the tail on OUR features (M4:507-510)
+        assert float((x4.cpu() - t).abs().max()) <= 1e-3 * float(t.abs().max())
+
+
 def test_per_point_model_step_and_folded_global_bias():
     """PrimitivesEmbeddingPerPoint (BASELINE config 4 in this environment): one forward + backward at small size, the
     shapes the reference's losses consume, finite gradients on every parameter that takes part, and the identity the
