@@ -211,9 +211,9 @@ def make_offset_fixture(ref_root, out_dir):
     np.savez_compressed(os.path.join(out_dir, "offset_small.npz"), **fix)
 
 
-def check_adjacency_oracle(ref_root):
-    """compute_batch_adjacency_matrix: the reference's text (M4:210-233) against oracle.native's restatement (no fixture:
-    the function is a few torch calls; tests compare the device path with the restatement directly)."""
+def check_adjacency_oracle(ref_root, out_dir):
+    """compute_batch_adjacency_matrix: the reference's text (M4:210-233) against oracle.native's restatement; the
+    reference's outputs on the two small inputs are written to tests/golden/affinity_small.npz."""
     print("[dense affinity]")
     from oracle import native as nat
     with open(os.path.join(ref_root, M4)) as f:
@@ -221,13 +221,19 @@ def check_adjacency_oracle(ref_root):
     ns = {"torch": torch, "np": np, "nn": nn, "F": F}
     exec(compile("\n".join(lines[209:233]) + "\n", os.path.join(ref_root, M4), "exec"), ns)
     g = torch.Generator().manual_seed(12)
+    fix = {}
     for shape in ((257, 64), (300, 22), (1, 90, 7)):
         x = torch.randn(*shape, generator=g)
-        same(nat.compute_batch_adjacency_matrix(x, radius=0, dist_state=True), ns["compute_batch_adjacency_matrix"](x, radius=0, dist_state=True),
-             f"compute_batch_adjacency_matrix {shape}")
+        ref = ns["compute_batch_adjacency_matrix"](x, radius=0, dist_state=True)
+        same(nat.compute_batch_adjacency_matrix(x, radius=0, dist_state=True), ref, f"compute_batch_adjacency_matrix {shape}")
+        if x.numel() <= 300 * 22:                         # the two small cases travel as a fixture (the reference's own outputs)
+            tag = "x".join(str(v) for v in shape)
+            fix[f"x.{tag}"] = x.numpy()
+            fix[f"adj.{tag}"] = ref.numpy()
+    np.savez_compressed(os.path.join(out_dir, "affinity_small.npz"), **fix)
 
 
-def check_dataset_oracle(ref_root):
+def check_dataset_oracle(ref_root, out_dir):
     """ABCDataset.__getitem__ after the file read + getInstanceInfo (dataloader/ABCDataset_new.py:77-141, 157-178): the
     reference's text, executed on a synthetic raw sample, against oracle/dataset_oracle.py."""
     print("[input side: sample preparation]")
@@ -249,6 +255,7 @@ def check_dataset_oracle(ref_root):
         def getInstanceInfo(self, *a):
             return ns["getInstanceInfo"](self, *a)
 
+    fix = {}
     for num_prims, seed in ((10, 0), (7, 1)):
         pts, nrm, lab, prim, tp = dso.synthetic_raw_sample(8000, seed)
         me = FakeSelf()
@@ -263,8 +270,21 @@ def check_dataset_oracle(ref_root):
             assert a.shape == b.shape and np.array_equal(a, b), key
         assert mine["inst_num"] == ref["inst_num"] and list(mine["inst_pointnum"]) == list(ref["inst_pointnum"])
         assert [int(v) for v in mine["inst_cls"]] == [int(v) for v in ref["inst_cls"]]
+        # fixture: the reference's own outputs.  The raw sample is regenerated from its seed (numpy's legacy generator is
+        # stable), the gathered copies of the inputs travel as fp64 checksums, everything computed travels in full.
+        fix[f"p{num_prims}.raw_seed"] = np.int64(seed)
+        fix[f"p{num_prims}.subidx"] = np.asarray(subidx, np.int32)
+        for key in ("T_gt", "I_gt", "I_gt_clean"):
+            fix[f"p{num_prims}.{key}"] = np.asarray(ref[key]).astype(np.int32)
+        fix[f"p{num_prims}.pt_offset_label"] = np.asarray(ref["pt_offset_label"], np.float32)
+        for key in ("gt_pc", "gt_normal", "T_param"):
+            fix[f"p{num_prims}.sum.{key}"] = np.asarray(ref[key], np.float64).sum(axis=0)
+        fix[f"p{num_prims}.inst_num"] = np.int64(ref["inst_num"])
+        fix[f"p{num_prims}.inst_pointnum"] = np.asarray(ref["inst_pointnum"], np.int64)
+        fix[f"p{num_prims}.inst_cls"] = np.asarray([int(v) for v in ref["inst_cls"]], np.int64)
         print(f"  oracle == reference   sample preparation, {num_prims} primitive classes: {ref['inst_num']} instances kept, "
               f"{int((np.asarray(ref['I_gt']) == -1).sum())} background points")
+    np.savez_compressed(os.path.join(out_dir, "dataset_small.npz"), **fix)
 
 
 def extract_search_knn_golden(ref_root, out_dir):
@@ -301,12 +321,12 @@ def main():
     make_encoder_fixture(ns, out_dir)
     make_normal_head_fixture(ns, out_dir)
     make_offset_fixture(args.reference, out_dir)
-    check_adjacency_oracle(args.reference)
-    check_dataset_oracle(args.reference)
+    check_adjacency_oracle(args.reference, out_dir)
+    check_dataset_oracle(args.reference, out_dir)
     extract_search_knn_golden(args.reference, out_dir)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "threads": 1,
             "reference_files": [M4 + ":30-205", M4 + ":326-452", M4 + ":455-534", "models/search_knn.py:180-244",
-                                "dataloader/ABCDataset_new.py:77-141,157-178"]}
+                                "dataloader/ABCDataset_new.py:77-141,157-178", M4 + ":210-233"]}
     with open(os.path.join(out_dir, "META.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("done ->", out_dir)

@@ -221,3 +221,42 @@ def test_native_ball_query_restatement_small_case():
     x = torch.randn(40, 5, generator=torch.Generator().manual_seed(0))
     a = nat.compute_batch_adjacency_matrix(x)
     assert float(a.diagonal().abs().max()) == 0 and float(a.max()) <= 1.0 and float(a[a > 0].min()) >= np.exp(-0.5) - 1e-6
+
+
+# ------------------------------------------------------------------------------ next rows: affinity, input side
+def test_adjacency_oracle_matches_reference_fixture(golden_dir):
+    """compute_batch_adjacency_matrix (M4:210-233): the restatement against the outputs of the reference's own text
+    (tests/golden/affinity_small.npz, written by oracle/make_golden.py)."""
+    fx = dict(np.load(os.path.join(golden_dir, "affinity_small.npz")))
+    tags = sorted(k[2:] for k in fx if k.startswith("x."))
+    assert tags == ["1x90x7", "300x22"]
+    for tag in tags:
+        got = nat.compute_batch_adjacency_matrix(_t(fx[f"x.{tag}"]), radius=0, dist_state=True)
+        want = _t(fx[f"adj.{tag}"])
+        # torch.cdist may pick another kernel with another thread count; everything after it is elementwise
+        assert got.shape == want.shape and float((got - want).abs().max()) <= 2e-6
+        assert float(got.diagonal(dim1=-2, dim2=-1).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("num_prims", [10, 7])
+def test_dataset_oracle_matches_reference_fixture(golden_dir, num_prims):
+    """ABCDataset.__getitem__ after the file read + getInstanceInfo (dataloader/ABCDataset_new.py:77-141, 157-178): the numpy
+    restatement against the outputs of the reference's own text on the same raw sample and subsample
+    (tests/golden/dataset_small.npz).  Integer outputs exactly; offsets exactly (same numpy arithmetic)."""
+    from oracle import dataset_oracle as dso
+    fx = dict(np.load(os.path.join(golden_dir, "dataset_small.npz")))
+    p = f"p{num_prims}."
+    pts, nrm, lab, prim, tp = dso.synthetic_raw_sample(8000, int(fx[p + "raw_seed"]))
+    subidx = fx[p + "subidx"].astype(np.int64)
+    assert subidx.shape == (7000,) and len(np.unique(subidx)) == 7000            # drawn without replacement (:120-126)
+    mine = dso.prepare_sample(pts, nrm, lab, prim, tp, subidx, num_primitives=num_prims)
+    for key in ("T_gt", "I_gt", "I_gt_clean"):
+        assert np.array_equal(np.asarray(mine[key]).astype(np.int32), fx[p + key]), key
+    assert np.array_equal(np.asarray(mine["pt_offset_label"], np.float32), fx[p + "pt_offset_label"])
+    for key in ("gt_pc", "gt_normal", "T_param"):
+        np.testing.assert_allclose(np.asarray(mine[key], np.float64).sum(axis=0), fx[p + "sum." + key], rtol=0, atol=1e-9)
+    assert int(mine["inst_num"]) == int(fx[p + "inst_num"])
+    assert [int(v) for v in mine["inst_pointnum"]] == fx[p + "inst_pointnum"].tolist()
+    assert [int(v) for v in mine["inst_cls"]] == fx[p + "inst_cls"].tolist()
+    if num_prims == 7:                                                             # the 7-class remap (:94-97)
+        assert not np.isin(fx[p + "T_gt"], (7, 8, 9)).any()
