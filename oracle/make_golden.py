@@ -287,6 +287,110 @@ def check_dataset_oracle(ref_root, out_dir):
     np.savez_compressed(os.path.join(out_dir, "dataset_small.npz"), **fix)
 
 
+BFS_CU = "softgroup/ops/src/bfs_cluster/bfs_cluster.cu"
+
+_BALL_HARNESS = r"""
+// Host harness around the TEXT of the reference kernel ballquery_batch_p_cuda_ (bfs_cluster.cu:18-77), generated by
+// oracle/make_golden.py into a temporary directory and never committed: the kernel body is plain per-thread C, so with
+// the CUDA built-ins below it runs on the CPU, one "thread" after the other in point order (the order in which the
+// restatement concatenates the lists; on a GPU the atomicAdd order is arbitrary).
+#include <stdint.h>
+#define __global__
+struct Dim3 { int x, y, z; };
+static Dim3 blockIdx, blockDim, threadIdx;
+static int atomicAdd(int *p, int v) { int old = *p; *p += v; return old; }
+%s
+extern "C" int run_ballquery(int n, int meanActive, float radius, const float *xyz, const int *batch_idxs,
+                             const int *batch_offsets, const float *adj_inst, float thr_inst, const float *adj_para,
+                             float thr_para, int *idx, int *start_len) {
+    int cumsum = 0;                                        // ballquery_batch_p_cuda, bfs_cluster.cu:102-119
+    blockDim.x = 1024;
+    for (int p = 0; p < n; ++p) {
+        blockIdx.x = p / 1024;
+        threadIdx.x = p %% 1024;
+        ballquery_batch_p_cuda_(n, meanActive, radius, xyz, batch_idxs, batch_offsets, adj_inst, thr_inst, adj_para, thr_para,
+                                idx, start_len, &cumsum);
+    }
+    return cumsum;
+}
+"""
+
+
+def check_ball_query_oracle(ref_root, out_dir):
+    """ballquery_batch_p: the reference kernel's own text (bfs_cluster.cu:18-77), compiled for the host with shims for the
+    CUDA built-ins and driven by the reference's retry loop (softgroup/ops/functions.py:460-475), against
+    oracle/native_oracle.c's restatement.  Writes tests/golden/ballquery_small.npz."""
+    print("[gated ball query]")
+    import ctypes
+    import subprocess
+    import tempfile
+    from oracle import native as nat
+    with open(os.path.join(ref_root, BFS_CU)) as f:
+        lines = f.read().split("\n")
+    kernel = "\n".join(lines[17:77])
+    assert kernel.lstrip().startswith("__global__ void ballquery_batch_p_cuda_(") and kernel.rstrip().endswith("}")
+    assert "ballquery_batch_p_cuda(" not in kernel.replace("ballquery_batch_p_cuda_(", "")
+    tmp = tempfile.mkdtemp(prefix="gcanet_ballref_")
+    src, so = os.path.join(tmp, "ballref.cpp"), os.path.join(tmp, "libballref.so")
+    with open(src, "w") as f:
+        f.write(_BALL_HARNESS % kernel)
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
+    ref = ctypes.CDLL(so).run_ballquery
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    ref.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_float, fp, ip, ip, fp, ctypes.c_float, fp, ctypes.c_float, ip, ip]
+    ref.restype = ctypes.c_int
+
+    def reference_ball_query(xyz, bidx, boff, ai, ti, ap, tp, radius, mean_active):
+        n = xyz.shape[0]
+        calls = 0
+        while True:                                       # functions.py:460-475
+            idx = np.zeros(n * mean_active, np.int32)
+            sl = np.zeros((n, 2), np.int32)
+            n_active = ref(n, mean_active, radius, xyz.ctypes.data_as(fp), bidx.ctypes.data_as(ip), boff.ctypes.data_as(ip),
+                           ai.ctypes.data_as(fp), ti, ap.ctypes.data_as(fp), tp, idx.ctypes.data_as(ip), sl.ctypes.data_as(ip))
+            calls += 1
+            if n_active <= n * mean_active:
+                break
+            mean_active = int(n_active // n + 1)
+        return idx[:n_active], sl, calls
+
+    fix = {}
+    cases = [("two_segments", 400, (0, 250, 400), 0.12, 0.45, 0.30, 300),
+             ("retry_loop", 300, (0, 300), 0.30, 0.20, 0.20, 2),           # more neighbours than n * meanActive: second call
+             ("cap_3000", 3300, (0, 3300), 10.0, -1.0, -1.0, 300)]          # every point sees > 3000 neighbours: the idx_temp cap
+    for seed, (name, n, offs, radius, ti, tp, mean_active) in enumerate(cases, start=5):
+        # inputs from a seeded legacy numpy generator (stable across versions): the fixture ships the seed, not 2 n^2 floats;
+        # tests/test_oracle_golden.py::_ball_case draws them the same way
+        rs = np.random.RandomState(seed)
+        xyz = np.ascontiguousarray(rs.rand(n, 3).astype(np.float32))
+        boff = np.asarray(offs, np.int32)
+        bidx = np.repeat(np.arange(len(offs) - 1), np.diff(offs)).astype(np.int32)
+        if name == "cap_3000":
+            ai = ap = np.ones((n, n), np.float32)
+        else:
+            ai = np.ascontiguousarray(rs.rand(n, n).astype(np.float32))
+            ap = np.ascontiguousarray(rs.rand(n, n).astype(np.float32))
+        r_idx, r_sl, calls = reference_ball_query(xyz, bidx, boff, ai, ti, ap, tp, radius, mean_active)
+        o_idx, o_sl = nat.ball_query(torch.from_numpy(xyz), torch.from_numpy(bidx), torch.from_numpy(boff), torch.from_numpy(ai), ti,
+                                     torch.from_numpy(ap), tp, radius, mean_active)
+        assert np.array_equal(o_sl.numpy(), r_sl), f"ball query {name}: start_len differs"
+        assert np.array_equal(o_idx.numpy(), r_idx), f"ball query {name}: idx differs"
+        print(f"  oracle == reference   ballquery_batch_p {name:14s} n={n} neighbours={len(r_idx)} "
+              f"longest list={int(r_sl[:, 1].max())} kernel calls={calls}")
+        if name == "retry_loop":
+            assert calls == 2
+        if name == "cap_3000":
+            assert int(r_sl[:, 1].max()) == 3000 and int(r_sl[:, 1].min()) == 3000
+            continue                                      # 40 MB of gates: checked here, not shipped
+        for k, v in (("seed", np.int64(seed)), ("batch_offsets", boff), ("xyz_checksum", np.float64(xyz.astype(np.float64).sum())),
+                     ("gates_checksum", np.float64(ai.astype(np.float64).sum() + 2.0 * ap.astype(np.float64).sum())),
+                     ("params", np.asarray([radius, ti, tp, mean_active], np.float64)), ("idx", r_idx), ("start_len", r_sl)):
+            fix[f"{name}.{k}"] = v
+    np.savez_compressed(os.path.join(out_dir, "ballquery_small.npz"), **fix)
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def extract_search_knn_golden(ref_root, out_dir):
     print("[search_knn.py hand-written golden vectors]")
     path = os.path.join(ref_root, "models/search_knn.py")
@@ -323,10 +427,11 @@ def main():
     make_offset_fixture(args.reference, out_dir)
     check_adjacency_oracle(args.reference, out_dir)
     check_dataset_oracle(args.reference, out_dir)
+    check_ball_query_oracle(args.reference, out_dir)
     extract_search_knn_golden(args.reference, out_dir)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "threads": 1,
             "reference_files": [M4 + ":30-205", M4 + ":326-452", M4 + ":455-534", "models/search_knn.py:180-244",
-                                "dataloader/ABCDataset_new.py:77-141,157-178", M4 + ":210-233"]}
+                                "dataloader/ABCDataset_new.py:77-141,157-178", M4 + ":210-233", BFS_CU + ":18-77", "softgroup/ops/functions.py:460-475"]}
     with open(os.path.join(out_dir, "META.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("done ->", out_dir)

@@ -108,7 +108,10 @@ int oracle_group_points_grad(int b, int c, int n, int npoints, int nsample,
  * affinities exceed their thresholds; at most 3000 per point (the kernel's idx_temp[3000] stops the scan at the
  * 3001st hit); lists are concatenated in point order (the kernel: in the order its atomicAdd happens to run).
  * start_len [n][2] = (start, length); returns the total number of neighbours, idx must hold that many (call once
- * with idx == NULL to size it). */
+ * with idx == NULL to size it).
+ * Pinned: oracle/make_golden.py runs the reference kernel's own text on the host (same point order) and requires
+ * identical outputs, including the 3000 cap and the retry loop of functions.py:460-475; fixture
+ * tests/golden/ballquery_small.npz. */
 long long oracle_ballquery_batch_p(int n, float radius, const float *xyz, const int32_t *batch_idxs,
                                    const int32_t *batch_offsets, const float *adj_inst, float thr_inst,
                                    const float *adj_para, float thr_para, int32_t *idx, int32_t *start_len)

@@ -260,3 +260,31 @@ def test_dataset_oracle_matches_reference_fixture(golden_dir, num_prims):
     assert [int(v) for v in mine["inst_cls"]] == fx[p + "inst_cls"].tolist()
     if num_prims == 7:                                                             # the 7-class remap (:94-97)
         assert not np.isin(fx[p + "T_gt"], (7, 8, 9)).any()
+
+
+def _ball_case(fx, name):
+    """Inputs of a ball-query fixture case, drawn exactly as oracle/make_golden.py::check_ball_query_oracle draws them."""
+    boff = fx[f"{name}.batch_offsets"].astype(np.int32)
+    n = int(boff[-1])
+    rs = np.random.RandomState(int(fx[f"{name}.seed"]))
+    xyz = np.ascontiguousarray(rs.rand(n, 3).astype(np.float32))
+    bidx = np.repeat(np.arange(len(boff) - 1), np.diff(boff)).astype(np.int32)
+    ai = np.ascontiguousarray(rs.rand(n, n).astype(np.float32))
+    ap = np.ascontiguousarray(rs.rand(n, n).astype(np.float32))
+    assert abs(float(xyz.astype(np.float64).sum()) - float(fx[f"{name}.xyz_checksum"])) < 1e-9
+    assert abs(float(ai.astype(np.float64).sum() + 2.0 * ap.astype(np.float64).sum()) - float(fx[f"{name}.gates_checksum"])) < 1e-6
+    radius, ti, tp, mean_active = fx[f"{name}.params"].tolist()
+    return xyz, bidx, boff, ai, ap, float(radius), float(ti), float(tp), int(mean_active)
+
+
+@pytest.mark.parametrize("name", ["two_segments", "retry_loop"])
+def test_ball_query_oracle_matches_reference_kernel_fixture(golden_dir, name):
+    """oracle_ballquery_batch_p against tests/golden/ballquery_small.npz: the outputs of the reference kernel's own text
+    (bfs_cluster.cu:18-77, run on the host in point order under the reference's retry loop, functions.py:460-475) --
+    written by oracle/make_golden.py, which also checks the 3000-entry cap case without shipping its 40 MB of gates."""
+    fx = dict(np.load(os.path.join(golden_dir, "ballquery_small.npz")))
+    xyz, bidx, boff, ai, ap, radius, ti, tp, mean_active = _ball_case(fx, name)
+    idx, sl = nat.ball_query(_t(xyz), _t(bidx), _t(boff), _t(ai), ti, _t(ap), tp, radius, mean_active)
+    assert np.array_equal(sl.numpy(), fx[f"{name}.start_len"])
+    assert np.array_equal(idx.numpy(), fx[f"{name}.idx"])
+    assert int(sl[:, 1].sum()) == len(idx) and (name != "retry_loop" or len(idx) > len(xyz) * mean_active)
