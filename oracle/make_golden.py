@@ -391,6 +391,83 @@ def check_ball_query_oracle(ref_root, out_dir):
     shutil.rmtree(tmp, ignore_errors=True)
 
 
+PN2_GROUP_CU = "models/Pointnet2_PyTorch-master/pointnet2_ops_lib/pointnet2_ops/_ext-src/src/group_points_gpu.cu"
+
+_GROUP_HARNESS = r"""
+// Host harness around the TEXT of the reference kernels group_points_kernel / group_points_grad_kernel
+// (group_points_gpu.cu:8-28, 43-64); generated by oracle/make_golden.py into a temporary directory, never committed.
+// One CTA of ONE thread per batch element: the kernels' strided loops then visit (channel, point, sample) in ascending
+// order, which is also the summation order of the restatement's gradient.
+#define __global__
+struct Dim3 { int x, y, z; };
+static Dim3 blockIdx, blockDim, threadIdx;
+static float atomicAdd(float *p, float v) { float old = *p; *p += v; return old; }
+%s
+%s
+extern "C" void run_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx, float *out) {
+    blockDim.x = blockDim.y = 1; threadIdx.x = threadIdx.y = 0;
+    for (blockIdx.x = 0; blockIdx.x < b; ++blockIdx.x) group_points_kernel(b, c, n, npoints, nsample, points, idx, out);
+}
+extern "C" void run_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int *idx,
+                                      float *grad_points) {
+    blockDim.x = blockDim.y = 1; threadIdx.x = threadIdx.y = 0;
+    for (blockIdx.x = 0; blockIdx.x < b; ++blockIdx.x) group_points_grad_kernel(b, c, n, npoints, nsample, grad_out, idx, grad_points);
+}
+"""
+
+
+def check_grouping_oracle(ref_root, out_dir):
+    """grouping_operation: the reference kernels' own text (PN2 group_points_gpu.cu:8-28, 43-64) run on the host against
+    oracle/native_oracle.c's restatement -- forward and gradient bit-equal.  Writes tests/golden/grouping_small.npz."""
+    print("[PN2 grouping]")
+    import ctypes
+    import shutil
+    import subprocess
+    import tempfile
+    from oracle import native as nat
+    with open(os.path.join(ref_root, PN2_GROUP_CU)) as f:
+        lines = f.read().split("\n")
+
+    def kernel_text(name):
+        first = next(i for i, ln in enumerate(lines) if ln.startswith(f"__global__ void {name}("))
+        last = next(i for i in range(first, len(lines)) if lines[i] == "}")
+        return "\n".join(lines[first:last + 1])
+
+    fwd, bwd = kernel_text("group_points_kernel"), kernel_text("group_points_grad_kernel")
+    assert "<<<" not in fwd + bwd and "atomicAdd(grad_points" in bwd
+    tmp = tempfile.mkdtemp(prefix="gcanet_groupref_")
+    src, so = os.path.join(tmp, "groupref.cpp"), os.path.join(tmp, "libgroupref.so")
+    with open(src, "w") as f:
+        f.write(_GROUP_HARNESS % (fwd, bwd))
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
+    L = ctypes.CDLL(so)
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    for fn in (L.run_group_points, L.run_group_points_grad):
+        fn.argtypes = [ctypes.c_int] * 5 + [fp, ip, fp]
+        fn.restype = None
+    g = torch.Generator().manual_seed(21)
+    fix = {}
+    for tag, (b, c, n, npnt, ns) in (("small", (2, 5, 40, 7, 3)), ("wide", (3, 64, 500, 120, 16))):
+        feats = torch.randn(b, c, n, generator=g)
+        idx = torch.randint(0, n, (b, npnt, ns), generator=g, dtype=torch.int32)
+        idx[0, 0, :] = idx[0, 0, 0]                       # repeated index inside one group: the gradient accumulates
+        cot = torch.randn(b, c, npnt, ns, generator=g)
+        out_ref = np.zeros((b, c, npnt, ns), np.float32)
+        L.run_group_points(b, c, n, npnt, ns, feats.numpy().ctypes.data_as(fp), idx.numpy().ctypes.data_as(ip), out_ref.ctypes.data_as(fp))
+        grad_ref = np.zeros((b, c, n), np.float32)         # torch::zeros in group_points.cpp:49-51
+        L.run_group_points_grad(b, c, n, npnt, ns, cot.numpy().ctypes.data_as(fp), idx.numpy().ctypes.data_as(ip),
+                                grad_ref.ctypes.data_as(fp))
+        f_o = feats.clone().requires_grad_(True)
+        out_o = nat.grouping_operation(f_o, idx)
+        (out_o * cot).sum().backward()
+        same(out_o.detach(), torch.from_numpy(out_ref), f"group_points {tag}")
+        same(f_o.grad, torch.from_numpy(grad_ref), f"group_points_grad {tag}")
+        if tag == "small":
+            fix.update({"features": feats.numpy(), "idx": idx.numpy(), "cot": cot.numpy(), "out": out_ref, "grad": grad_ref})
+    np.savez_compressed(os.path.join(out_dir, "grouping_small.npz"), **fix)
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def extract_search_knn_golden(ref_root, out_dir):
     print("[search_knn.py hand-written golden vectors]")
     path = os.path.join(ref_root, "models/search_knn.py")
@@ -428,10 +505,12 @@ def main():
     check_adjacency_oracle(args.reference, out_dir)
     check_dataset_oracle(args.reference, out_dir)
     check_ball_query_oracle(args.reference, out_dir)
+    check_grouping_oracle(args.reference, out_dir)
     extract_search_knn_golden(args.reference, out_dir)
     meta = {"torch": torch.__version__, "numpy": np.__version__, "threads": 1,
             "reference_files": [M4 + ":30-205", M4 + ":326-452", M4 + ":455-534", "models/search_knn.py:180-244",
-                                "dataloader/ABCDataset_new.py:77-141,157-178", M4 + ":210-233", BFS_CU + ":18-77", "softgroup/ops/functions.py:460-475"]}
+                                "dataloader/ABCDataset_new.py:77-141,157-178", M4 + ":210-233", BFS_CU + ":18-77", "softgroup/ops/functions.py:460-475",
+                                PN2_GROUP_CU + ":8-28,43-64"]}
     with open(os.path.join(out_dir, "META.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("done ->", out_dir)

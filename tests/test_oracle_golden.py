@@ -288,3 +288,15 @@ def test_ball_query_oracle_matches_reference_kernel_fixture(golden_dir, name):
     assert np.array_equal(sl.numpy(), fx[f"{name}.start_len"])
     assert np.array_equal(idx.numpy(), fx[f"{name}.idx"])
     assert int(sl[:, 1].sum()) == len(idx) and (name != "retry_loop" or len(idx) > len(xyz) * mean_active)
+
+
+def test_grouping_oracle_matches_reference_kernel_fixture(golden_dir):
+    """oracle_group_points / _grad against tests/golden/grouping_small.npz: the outputs of the reference kernels' own text
+    (PN2 group_points_gpu.cu:8-28, 43-64, run on the host by oracle/make_golden.py), a repeated index inside one group
+    included.  Bit-equal, forward and gradient."""
+    fx = dict(np.load(os.path.join(golden_dir, "grouping_small.npz")))
+    feats = _t(fx["features"]).clone().requires_grad_(True)
+    out = nat.grouping_operation(feats, _t(fx["idx"]))
+    assert torch.equal(out.detach(), _t(fx["out"]))
+    (out * _t(fx["cot"])).sum().backward()
+    assert torch.equal(feats.grad, _t(fx["grad"]))
