@@ -9,8 +9,10 @@
  *   - the library never allocates, frees or synchronises: outputs and scratch
  *     (`ws`, sized by the matching *_workspace_bytes) are passed in by the caller,
  *     kernels are enqueued on `stream` and the call returns immediately, so every
- *     function may be captured in a CUDA graph;
- *   - re-entrant, no mutable global state, uses the calling thread's current device;
+ *     function may be captured in a CUDA graph (the one exception is the measurement
+ *     probe gcanet_knn_probe_arm / _read, which says so where it is declared);
+ *   - re-entrant, no mutable global state (per thread: the last error message and the
+ *     probe's event pair), uses the calling thread's current device;
  *   - returns GCANET_OK (0) or a negative gcanet_status; gcanet_last_error() gives
  *     the message for the calling thread.  Nothing here ever exits the process (the
  *     reference's PN2 wrapper does: _ext-src/include/cuda_utils.h:30-39);
